@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the Needleman-Wunsch score-table fill on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json): config 3, one pair of 100,000 x 100,000 synthetic DNA
+(SplitMix64 seeds 0x5EED0030/31), m=k=d=1 -- the configuration the target
+("the 100k x 100k fill at >= 50% of the INT/DPX issue roofline") is quoted on.
+A step = one fill of the whole table (scores in registers, every arrow set
+written as 4-bit codes).  At N > 1 the table is cut into column strips across
+the ranks (boundary columns stream rank-to-rank through CUDA-IPC peer memory
+over NVLink), total work fixed -> "scaling": "strong".
+
+value  = interior cells / device time, strings resident in HBM (CUDA events on
+         the launching stream, max over ranks);
+e2e    = the same through the public C-ABI plan calls with HOST strings:
+         upload (H2D) + fill + summary (D2H) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GCUPS (giga cell updates/sec), NW score-table fill"
+A = B = 100_000
+SEED = 0x5EED0030
+M_, K_, D_ = 1, 1, 1
+OPS_PER_CELL = 10          # SURVEY.md 8d convention: score + arrows
+SM_MAX_MHZ_FALLBACK = 1965.0
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "config3: single pair 100000x100000 synthetic DNA (seeds 0x5EED0030/31), m=1 k=1 d=1, "
+                        "fill + 4-bit arrow table, no count",
+            "top_len": A, "side_len": B, "m": M_, "k": K_, "d": D_, "cells_per_step": A * B,
+            "parallelism": f"column strips x{n_gpus}" if n_gpus > 1 else "single GPU",
+            "l2": "each step writes a 5.0 GB arrow table (>> 126 MB L2); no explicit flush needed"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args) -> None:
+    """The reference's own CPU fill (oracle/_ref, the unmodified sources compiled
+    by oracle/Makefile), timed on this box's host cores on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    n = 3000  # 9e6 cells per step: ~1.5 s at the reference's ~6 MCUPS, 1.2 GB of its 136 B/cell tables
+    t, s = oracle.generate_pair(SEED, n, n)
+    kind = "reference" if oracle.have_reference() else "port"
+    ncpu = os.cpu_count() or 1
+
+    def one(threads):
+        if kind == "reference":
+            r = oracle.reference_fill(t, s, M_, K_, D_, threads=threads, tflag=False)
+            return r.fill_seconds
+        t0 = time.perf_counter()
+        oracle.fill(t, s, M_, K_, D_)
+        return time.perf_counter() - t0
+
+    # the reference's -p filler stops scaling at 2 threads (README:72-75); probe and keep the best
+    cands = [1] if kind == "port" else sorted({1, 2, min(4, ncpu), ncpu})
+    probe = {T: one(T) for T in cands}
+    best_t = min(probe, key=probe.get)
+    for _ in range(args.warmup):
+        one(best_t)
+    times = [one(best_t) for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    gcups = n * n / sec / 1e9
+    cfg = workload_config(args.gpus)
+    sample = (f"{n}x{n} prefix of the workload's strings per step (the reference needs 136 B/cell: the full "
+              f"100k x 100k table would take 1.36 TB); fill only (compute_table_scores), threads probed {probe}")
+    line = {"impl": "reference", "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": best_t, "kind": kind, "sample": sample,
+                             "host_cores": ncpu},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def cpu_baseline_leg() -> dict:
+    import oracle
+    n = 4000
+    t, s = oracle.generate_pair(SEED, n, n)
+    ncpu = os.cpu_count() or 1
+    if oracle.have_reference():
+        res = {}
+        for T in sorted({1, 2, min(4, ncpu)}):
+            res[T] = oracle.reference_fill(t, s, M_, K_, D_, threads=T, tflag=False).fill_seconds
+        best = min(res, key=res.get)
+        return {"value": n * n / res[best] / 1e9, "unit": "GCUPS", "cores": best, "kind": "reference",
+                "host_cores": ncpu,
+                "sample": f"{n}x{n} prefix of the workload, compute_table_scores() only, unmodified reference "
+                          f"(oracle/_ref), seconds by -p threads: { {k: round(v, 2) for k, v in res.items()} }"}
+    t0 = time.perf_counter()
+    oracle.fill(t, s, M_, K_, D_)
+    dt = time.perf_counter() - t0
+    return {"value": n * n / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "host_cores": ncpu,
+            "sample": f"{n}x{n} prefix of the workload, oracle/nw_oracle.c (scalar C)"}
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    import nw_b200 as nwb
+    import oracle
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available() or nwb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the fill has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t, s = oracle.generate_pair(SEED, A, B)  # input generation only (SURVEY 8d generator)
+    flags = 0
+    plan = nwb.Plan(A, B, flags, device=local, strip_rank=rank, strip_world=world)
+    if world > 1:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, plan.ipc_export())
+        if rank + 1 < world:
+            plan.ipc_attach_right(blobs[rank + 1])
+    plan.upload(t, s)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        if world > 1:
+            plan.reset_inbox(stream)
+            barrier()
+        plan.run(M_, K_, D_, stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    kernel_ms = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        if world > 1:
+            plan.reset_inbox(stream)
+            barrier()
+        ev[i][0].record()
+        plan.run(M_, K_, D_, stream)
+        ev[i][1].record()
+        if world > 1:
+            torch.cuda.synchronize()
+        kernel_ms.append(None)
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    if world > 1:
+        tt = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    last_kernel_ms = plan.kernel_ms()
+    summ = plan.summary()
+
+    # ---- end to end through the public plan API with host strings
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        plan.upload(t, s)            # H2D of this step's inputs
+        if world > 1:
+            plan.reset_inbox(stream)
+            barrier()
+        plan.run(M_, K_, D_, stream)
+        summ = plan.summary()        # D2H of the step's result (waits for the fill)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        cells = A * B
+        ms_per_step = total_ms / args.steps
+        gcups = cells / (ms_per_step * 1e-3) / 1e9
+        e2e_gcups = cells * args.steps / e2e_s / 1e9
+        # INT/DPX issue roofline: P = N_SM * R * f
+        r_per_clk, r_gops = nwb.measure_int_issue(1, local)
+        r16, _ = nwb.measure_int_issue(2, local)
+        rmix, _ = nwb.measure_int_issue(3, local)
+        props = torch.cuda.get_device_properties(local)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        f_mhz = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_FALLBACK))
+        peak_ops = props.multi_processor_count * r_per_clk * f_mhz * 1e6          # thread-results/s at max clock
+        k_ms = last_kernel_ms if world == 1 else ms_per_step
+        achieved_ops = cells * OPS_PER_CELL / (k_ms * 1e-3)
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = cells * 0.5 + A + B
+        line = {
+            "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u16x2" if summ.kernel_kind == 1 else "int32",
+            "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "int_issue", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12,
+                         "unit": "Tops/s (algorithmic INT ops, 10 per cell)", "frac": achieved_ops / peak_ops,
+                         "traffic": None,
+                         "peak_source": f"measured on this GPU: VIMNMX3 {r_per_clk:.1f} thread-results/clk/SM "
+                                        f"(VIMNMX3.U16x2 {r16:.1f} instr/clk/SM, VIMNMX3+IMAD {rmix:.1f}) x "
+                                        f"{props.multi_processor_count} SMs x {f_mhz:.0f} MHz "
+                                        f"({'MEASURED_PEAKS.json' if peaks else 'fallback'} sm_max_mhz)",
+                         "kernel": "nwb_fill_pk_kernel" if summ.kernel_kind == 1 else "nwb_fill_i32_kernel",
+                         "kernel_ms": k_ms},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                             "note": "secondary: 0.5 B/cell arrow write-back + strings; not the binding roofline"},
+            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": A + B, "d2h_bytes_per_step": 24},
+            "gpu_launches": args.steps * world,
+            "clocks": clocks,
+            "result": {"opt_score": summ.opt_score, "branch_count": summ.branch_count, "kernel_kind": summ.kernel_kind},
+            "step_ms": [round(x, 3) for x in step_ms],
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

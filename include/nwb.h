@@ -1,0 +1,222 @@
+/*
+ * nwb.h -- C ABI of the B200-native Needleman-Wunsch score-table fill.
+ *
+ * This is the drop-in boundary for ONE path of skotchandsoda/needleman-wunsch:
+ * the score-table fill.  Each entry point cites the reference interface it
+ * replaces (paths are into the reference repository).  C99-includable,
+ * extern "C", plain pointers and sizes only.
+ *
+ * Orientation (reference naming, computation.c:158-160): the TOP string s1
+ * (length A) indexes columns i in [0,A]; the SIDE string s2 (length B) indexes
+ * rows j in [0,B]; the table is M x N = (A+1) x (B+1); the reference stores
+ * cells[i][j].
+ *
+ * There is no CPU fallback: every fill runs hand-written sm_100a kernels and
+ * fails with NWB_ERR_NO_DEVICE / NWB_ERR_CUDA when no usable GPU is present.
+ *
+ * ARROW TABLE LAYOUT (replaces walk_table_cell_t{diag,left,up}, walk-table.h:48-57,
+ * 32 B/cell, by 4 bits/cell):
+ *   - interior cells only (i in [1,A], j in [1,B]); the borders are implied
+ *     (row 0: LEFT, column 0: UP, (0,0): none -- computation.c:97-124);
+ *   - row-major: row j starts at byte (j-1)*pitch, pitch = nwb_arrow_pitch()
+ *     (a multiple of 16 bytes, >= ceil(A/2));
+ *   - cell (i,j) is the 4-bit code in byte (j-1)*pitch + (i-1)/2, low nibble
+ *     when (i-1) is even: bit0 = DIAG, bit1 = LEFT, bit2 = UP, bit3 = 0.
+ *     Several bits are set when candidates tie (needleman-wunsch.c:485-503
+ *     records EVERY candidate equal to the maximum).
+ *   - bytes/nibbles beyond column A inside the pitch are unspecified.
+ *   The reference's `match` flag (score-table.h:60, written at
+ *   needleman-wunsch.c:432-438, never read back) is derived from the strings by
+ *   nwb_arrows() and returned as NWB_MATCH.
+ */
+#ifndef NWB_H
+#define NWB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- arrow code bits returned by nwb_arrows() ---------------------------- */
+#define NWB_DIAG 1u  /* walk_table_cell_t.diag  */
+#define NWB_LEFT 2u  /* walk_table_cell_t.left  */
+#define NWB_UP 4u    /* walk_table_cell_t.up    */
+#define NWB_MATCH 8u /* score_table_cell_t.match */
+
+/* ---- flags --------------------------------------------------------------- */
+/* Materialise the int32 score matrix (needed by the -t printer,
+ * print-table.c:120-157, and by score-level verification).  O(A*B*4) bytes. */
+#define NWB_WANT_SCORES 0x01u
+/* Fuse the 64-bit optimal-alignment count into the fill (-s; replaces the
+ * exponential enumeration behind get_solution_count(), computation.c:249). */
+#define NWB_WANT_COUNT 0x02u
+/* Copy the arrow table to host memory so nwb_arrows()/nwb_arrow_rows() work
+ * (the walk needs it: needleman-wunsch.c:667 `!q || l || s || t`). */
+#define NWB_WANT_ARROWS_HOST 0x04u
+/* Track max |score| over interior cells (the tflag rule,
+ * needleman-wunsch.c:538-541; score_table_t.greatest_abs_val). */
+#define NWB_TRACK_ABS 0x08u
+/* Always use the general int32 kernel (any m,k,d) instead of the packed
+ * 16x2 difference kernel that is selected automatically for small scores. */
+#define NWB_FORCE_GENERAL 0x10u
+/* Verification aid: materialise the full uint64 count matrix (small inputs). */
+#define NWB_WANT_COUNT_MATRIX 0x20u
+
+/* ---- error codes ---------------------------------------------------------- */
+#define NWB_OK 0
+#define NWB_ERR_INVALID (-1)     /* bad argument                               */
+#define NWB_ERR_NOMEM (-2)       /* host or device allocation failed           */
+#define NWB_ERR_CUDA (-3)        /* a CUDA call or kernel failed               */
+#define NWB_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback   */
+#define NWB_ERR_UNSUPPORTED (-5) /* flag combination not available             */
+
+const char *nwb_strerror(int err);
+/* Text of the last CUDA error seen by this thread ("" if none). */
+const char *nwb_last_cuda_error(void);
+/* Number of usable CUDA devices (0 if none), ABI version. */
+int nwb_device_count(void);
+int nwb_abi_version(void);
+
+/* ========================================================================== *
+ * 1. One pair, host buffers -- replaces the call
+ *        compute_table_scores(C)                 needleman-wunsch.c:583-626
+ *    together with the table set-up it depends on
+ *        init_computation_tables()               computation.c:75-125
+ *        alloc_score_table()/alloc_walk_table()  score-table.c:60, walk-table.c:58
+ *    at the call site needleman_wunsch(), needleman-wunsch.c:654-689.
+ * ========================================================================== */
+typedef struct nwb_table nwb_table; /* opaque; owns device + host buffers */
+
+/* Blocking.  top/side need not be NUL-terminated; arbitrary bytes, compared
+ * for equality (needleman-wunsch.c:432).  m = match bonus, k = mismatch
+ * penalty, d = indel penalty, exactly the reference's operands (may be 0 or
+ * negative).  On success *out owns the results until nwb_free(). */
+int nwb_fill(const char *top, int top_len, const char *side, int side_len,
+             int m, int k, int d, unsigned flags, nwb_table **out);
+/* As nwb_fill, on CUDA device `device`, splitting the table into column
+ * strips over `num_gpus` consecutive devices starting at `device` (boundary
+ * columns are pipelined device-to-device over NVLink peer memory). */
+int nwb_fill_on(const char *top, int top_len, const char *side, int side_len,
+                int m, int k, int d, unsigned flags, int device, int num_gpus,
+                nwb_table **out);
+/* replaces free_computation(), computation.c:200-214 */
+void nwb_free(nwb_table *t);
+
+/* score_table_t.M-1 / N-1 (score-table.h:70-71) */
+int nwb_top_len(const nwb_table *t);
+int nwb_side_len(const nwb_table *t);
+/* cells[M-1][N-1].score, as printed by print_summary(), computation.c:279-280 */
+int32_t nwb_opt_score(const nwb_table *t);
+/* Number of optimal alignments mod 2^64 (NWB_WANT_COUNT).  Its low 32 bits are
+ * what the reference's `unsigned int solution_count` holds (computation.h:65)
+ * and prints with %d (computation.c:277). */
+uint64_t nwb_count_u64(const nwb_table *t);
+/* get_branch_count(), walk-table.c:133-147 (mod 2^32) */
+uint32_t nwb_branch_count(const nwb_table *t);
+/* score_table_t.greatest_abs_val under tflag (NWB_TRACK_ABS), else 0 */
+int32_t nwb_greatest_abs_interior(const nwb_table *t);
+/* cells[i][j].score for any 0<=i<=A, 0<=j<=B (NWB_WANT_SCORES; borders by the
+ * init formula).  Returns INT32_MIN when scores were not requested. */
+int32_t nwb_score(const nwb_table *t, int i, int j);
+/* NWB_DIAG|NWB_LEFT|NWB_UP|NWB_MATCH of cell (i,j), borders included
+ * (NWB_WANT_ARROWS_HOST).  Returns 0xFFFFFFFF when arrows are not on host. */
+unsigned nwb_arrows(const nwb_table *t, int i, int j);
+/* Raw host view of the arrow table (layout above); NULL if not on host. */
+const uint8_t *nwb_arrow_rows(const nwb_table *t);
+size_t nwb_arrow_pitch(const nwb_table *t);
+/* Verification aid (NWB_WANT_COUNT_MATRIX): count of cell (i,j), borders = 1. */
+uint64_t nwb_count_at(const nwb_table *t, int i, int j);
+/* Raw host views of the INTERIOR score / count matrices: element (i,j), i,j>=1,
+ * is rows[(j-1)*(*pitch_elems) + (i-1)].  NULL when not requested. */
+const int32_t *nwb_score_rows(const nwb_table *t, size_t *pitch_elems);
+const uint64_t *nwb_count_rows(const nwb_table *t, size_t *pitch_elems);
+/* Device time of the fill kernel(s) of this table in ms (CUDA events on the
+ * launching stream), and which kernel ran: 0 = general int32, 1 = packed 16x2. */
+float nwb_kernel_ms(const nwb_table *t);
+int nwb_kernel_kind(const nwb_table *t);
+
+/* ========================================================================== *
+ * 2. Device-resident plan -- the same fill with the strings already in HBM and
+ *    the results left there; used for repeated fills and for measurement.
+ *    (No reference counterpart: the reference has no device boundary.)
+ * ========================================================================== */
+typedef struct nwb_plan nwb_plan;
+
+typedef struct nwb_summary {
+    int32_t opt_score;
+    uint32_t branch_count;
+    int32_t greatest_abs;
+    int32_t kernel_kind;
+    uint64_t count;
+} nwb_summary;
+
+/* Allocate device workspace for fills up to max_top x max_side on `device`.
+ * strip_rank/strip_world != (0,1) makes this plan one rank of a column-strip
+ * group: rank r owns columns (r*A/world, (r+1)*A/world]. */
+int nwb_plan_create(int max_top, int max_side, unsigned flags, int device,
+                    int strip_rank, int strip_world, nwb_plan **out);
+void nwb_plan_destroy(nwb_plan *p);
+/* Host -> device copy of the two strings (synchronous on the plan's stream). */
+int nwb_plan_upload(nwb_plan *p, const char *top, int top_len, const char *side, int side_len);
+/* Launch the fill on `stream` (a cudaStream_t; NULL = the plan's own stream).
+ * Asynchronous; inputs and outputs stay on the device. */
+int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream);
+/* Wait for the plan's work and fetch the 24-byte summary (device -> host). */
+int nwb_plan_summary(nwb_plan *p, nwb_summary *out);
+/* Device pointer / pitch of the arrow table (layout above). */
+void *nwb_plan_arrows_device(nwb_plan *p);
+size_t nwb_plan_arrow_pitch(const nwb_plan *p);
+/* Copy arrow rows [row_begin,row_end) (0-based interior rows, j-1) to host. */
+int nwb_plan_download_arrows(nwb_plan *p, uint8_t *dst, size_t dst_pitch, int row_begin, int row_end);
+/* Kernel launches issued by the plan since creation. */
+int64_t nwb_plan_launches(const nwb_plan *p);
+/* Device time (ms, CUDA events on the launching stream) of the last run. */
+float nwb_plan_kernel_ms(nwb_plan *p);
+/* Interior columns [begin,end) (0-based, i-1) this plan's strips cover. */
+int nwb_plan_strip_range(const nwb_plan *p, int *begin_col, int *end_col);
+/* Re-arm the inbound boundary flag before the next run of a strip group
+ * (all ranks must do this, then synchronise, before any rank runs again). */
+int nwb_plan_reset_inbox(nwb_plan *p, void *stream);
+/* Multi-process column strips: export this rank's inbound boundary buffer as
+ * an opaque CUDA IPC blob (nwb_plan_ipc_size() bytes) and attach the right
+ * neighbour's blob so this rank's last strip streams its boundary column
+ * straight into the neighbour's HBM over NVLink. */
+size_t nwb_plan_ipc_size(void);
+int nwb_plan_ipc_export(nwb_plan *p, void *blob);
+int nwb_plan_ipc_attach_right(nwb_plan *p, const void *blob);
+
+/* ========================================================================== *
+ * 3. Batch of independent pairs -- the reference looped per pair
+ *    (alloc/init_computation + compute_table_scores + free_computation per
+ *    pair); one warp per pair, no inter-block sync.
+ * ========================================================================== */
+typedef struct nwb_batch nwb_batch;
+
+/* Pair p has top = tops + top_off[p] .. top_off[p+1], side likewise.
+ * Results per pair: opt score, branch count, count (if NWB_WANT_COUNT), and
+ * with NWB_WANT_ARROWS_HOST each pair's arrow table. */
+int nwb_fill_batch(const char *tops, const int64_t *top_off,
+                   const char *sides, const int64_t *side_off, int64_t n_pairs,
+                   int m, int k, int d, unsigned flags, int device, nwb_batch **out);
+void nwb_batch_free(nwb_batch *b);
+int64_t nwb_batch_size(const nwb_batch *b);
+int32_t nwb_batch_opt_score(const nwb_batch *b, int64_t pair);
+uint32_t nwb_batch_branch_count(const nwb_batch *b, int64_t pair);
+uint64_t nwb_batch_count_u64(const nwb_batch *b, int64_t pair);
+const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair, size_t *pitch);
+float nwb_batch_kernel_ms(const nwb_batch *b);
+
+/* ========================================================================== *
+ * 4. Measurement aid (not on the fill path): INT/DPX issue rate of `device`,
+ *    from independent VIADDMNMX (mode 0) / VIMNMX3 (1) / VIMNMX3.U16x2 (2) /
+ *    VIMNMX3+IMAD (3) chains at full occupancy.  Returns
+ *    thread-instructions per clock per SM (in-kernel clock64) and G/s (events).
+ * ========================================================================== */
+int nwb_measure_int_issue(int device, int mode, double *per_clk_per_sm, double *gops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWB_H */

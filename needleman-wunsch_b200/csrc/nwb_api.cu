@@ -1,0 +1,724 @@
+/*
+ * nwb_api.cu -- the C ABI of include/nwb.h over the sm_100a fill kernels.
+ *
+ * Host side only: geometry, device memory, launches, host<->device copies.
+ * There is no CPU implementation of the fill in this library; without a CUDA
+ * device every entry point fails with NWB_ERR_NO_DEVICE.
+ */
+#include "../../include/nwb.h"
+
+#include <cuda_runtime.h>
+
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "nwb_layout.h"
+#include "nwb_fill_i32.cuh"
+#include "nwb_fill_pk.cuh"
+#include "nwb_batch.cuh"
+#include "nwb_peak.cuh"
+
+#define NWB_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------- */
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorMemoryAllocation) return NWB_ERR_NOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return NWB_ERR_NO_DEVICE;
+    return NWB_ERR_CUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+extern "C" const char *nwb_strerror(int err)
+{
+    switch (err) {
+    case NWB_OK: return "ok";
+    case NWB_ERR_INVALID: return "invalid argument";
+    case NWB_ERR_NOMEM: return "out of memory";
+    case NWB_ERR_CUDA: return "CUDA failure";
+    case NWB_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case NWB_ERR_UNSUPPORTED: return "unsupported flag combination";
+    default: return "unknown error";
+    }
+}
+extern "C" const char *nwb_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int nwb_abi_version(void) { return NWB_ABI_VERSION; }
+extern "C" int nwb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------- */
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0; /* elements */
+    int ensure(size_t n)
+    {
+        if (n <= cap) return NWB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        cap = n;
+        return NWB_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+/* inbox: the boundary stream of the strip left of this plan's first strip */
+struct Inbox {
+    size_t bpitch;      /* elements per array                        */
+    size_t off_s, off_c, off_w, off_flag; /* byte offsets in `base`  */
+    size_t bytes;
+    unsigned char *base;
+};
+
+struct NwbIpcBlob {
+    cudaIpcMemHandle_t handle;
+    unsigned long long bpitch, off_s, off_c, off_w, off_flag, bytes;
+    int device;
+    int pad;
+};
+
+struct nwb_plan {
+    int device = 0;
+    unsigned flags = 0;
+    int maxA = 0, maxB = 0;
+    int rank = 0, world = 1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int A = 0, B = 0;
+    DevBuf<uint8_t> top, side, arrows;
+    DevBuf<int32_t> scores, bnd_s;
+    DevBuf<unsigned long long> cntmat, bnd_c;
+    DevBuf<uint32_t> bnd_w;
+    DevBuf<int> progress;
+    DevBuf<NwbDevSummary> summary;
+    Inbox inbox = {};
+    /* right neighbour's inbox (peer memory), if attached */
+    unsigned char *right_base = nullptr;
+    bool right_is_ipc = false;
+    Inbox right = {};
+    NwbLayout L = {};
+    int strip_begin = 0, strip_end = 0;
+    int kind = NWB_KIND_I32;
+    int64_t launches = 0;
+    NwbDevSummary last = {};
+    bool ran = false;
+    cudaStream_t last_stream = nullptr;
+};
+
+static void make_inbox_layout(Inbox &ib, size_t bpitch)
+{
+    ib.bpitch = bpitch;
+    ib.off_s = 0;
+    ib.off_c = nwb_round_up(ib.off_s + bpitch * sizeof(int32_t), 256);
+    ib.off_w = nwb_round_up(ib.off_c + bpitch * sizeof(unsigned long long), 256);
+    ib.off_flag = nwb_round_up(ib.off_w + bpitch * sizeof(uint32_t), 256);
+    ib.bytes = ib.off_flag + 256;
+}
+
+extern "C" int nwb_plan_create(int max_top, int max_side, unsigned flags, int device,
+                               int strip_rank, int strip_world, nwb_plan **out)
+{
+    if (!out) return NWB_ERR_INVALID;
+    *out = nullptr;
+    if (max_top < 0 || max_side < 0 || strip_world < 1 || strip_rank < 0 || strip_rank >= strip_world)
+        return NWB_ERR_INVALID;
+    if ((flags & (NWB_WANT_SCORES | NWB_WANT_COUNT_MATRIX)) && strip_world > 1) return NWB_ERR_UNSUPPORTED;
+    int ndev = nwb_device_count();
+    if (ndev <= 0) return NWB_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(device));
+    nwb_plan *p = new (std::nothrow) nwb_plan();
+    if (!p) return NWB_ERR_NOMEM;
+    p->device = device;
+    p->flags = flags;
+    p->maxA = max_top;
+    p->maxB = max_side;
+    p->rank = strip_rank;
+    p->world = strip_world;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "plan setup");
+        nwb_plan_destroy(p);
+        return rc;
+    }
+    p->sm_count = prop.multiProcessorCount;
+    int rc = p->summary.ensure(1);
+    if (rc == NWB_OK) rc = p->top.ensure((size_t)max_top + 1024);
+    if (rc == NWB_OK) rc = p->side.ensure((size_t)max_side + 1024);
+    if (rc == NWB_OK && strip_world > 1) {
+        /* inbox sized for the longest side string; allocated once so that it
+         * can be exported through CUDA IPC before any fill */
+        make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64, 32));
+        e = cudaMalloc((void **)&p->inbox.base, p->inbox.bytes);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(inbox)");
+        else e = cudaMemset(p->inbox.base, 0, p->inbox.bytes);
+        if (rc == NWB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaMemset(inbox)");
+    }
+    if (rc != NWB_OK) {
+        nwb_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return NWB_OK;
+}
+
+extern "C" void nwb_plan_destroy(nwb_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    p->top.release(); p->side.release(); p->arrows.release(); p->scores.release();
+    p->bnd_s.release(); p->cntmat.release(); p->bnd_c.release(); p->bnd_w.release();
+    p->progress.release(); p->summary.release();
+    if (p->inbox.base) cudaFree(p->inbox.base);
+    if (p->right_base && p->right_is_ipc) cudaIpcCloseMemHandle(p->right_base);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" int nwb_plan_upload(nwb_plan *p, const char *top, int top_len, const char *side, int side_len)
+{
+    if (!p || top_len < 0 || side_len < 0 || (top_len && !top) || (side_len && !side)) return NWB_ERR_INVALID;
+    if (top_len > p->maxA || side_len > p->maxB) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    if (top_len) CK(cudaMemcpyAsync(p->top.p, top, (size_t)top_len, cudaMemcpyHostToDevice, p->stream));
+    if (side_len) CK(cudaMemcpyAsync(p->side.p, side, (size_t)side_len, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->A = top_len;
+    p->B = side_len;
+    p->ran = false;
+    return NWB_OK;
+}
+
+/* ---- kernel selection -------------------------------------------------------
+ * The packed 16x2 difference kernel needs every per-cell difference to stay
+ * small (nwb_fill_pk.cuh); otherwise, or when scores/abs/count-matrix are
+ * requested, the general int32 kernel runs. */
+static int choose_kind(unsigned flags, int m, int k, int d, NwbPkConsts *pc)
+{
+    if (flags & (NWB_FORCE_GENERAL | NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_WANT_COUNT_MATRIX)) return NWB_KIND_I32;
+    if (!nwb_pk_supported(m, k, d, pc)) return NWB_KIND_I32;
+    return NWB_KIND_PK;
+}
+
+template <typename KernelT>
+static int launch_strip_kernel(KernelT kernel, int grid, int block, size_t smem, cudaStream_t stream,
+                               const NwbStripParams &sp)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    /* cooperative launch: not for grid.sync, only for its guarantee that all
+     * blocks are co-resident (the strips spin-wait on one another) */
+    void *args[] = {(void *)&sp};
+    e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(block), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel");
+    return NWB_OK;
+}
+
+static int run_i32(nwb_plan *p, const NwbStripParams &sp, int grid, cudaStream_t st)
+{
+    const bool C = p->flags & NWB_WANT_COUNT, S = p->flags & NWB_WANT_SCORES, AB = p->flags & NWB_TRACK_ABS,
+               CM = p->flags & NWB_WANT_COUNT_MATRIX;
+    const int block = 32 * NWB_I32_WARPS;
+    const size_t smem = NWB_I32_SMEM_BYTES;
+#define L_(c, s, a, cm) return launch_strip_kernel(nwb_fill_i32_kernel<c, s, a, cm>, grid, block, smem, st, sp)
+    if (CM) {
+        if (S) { if (AB) L_(true, true, true, true); else L_(true, true, false, true); }
+        else { if (AB) L_(true, false, true, true); else L_(true, false, false, true); }
+    }
+    if (C) {
+        if (S) { if (AB) L_(true, true, true, false); else L_(true, true, false, false); }
+        else { if (AB) L_(true, false, true, false); else L_(true, false, false, false); }
+    }
+    if (S) { if (AB) L_(false, true, true, false); else L_(false, true, false, false); }
+    if (AB) L_(false, false, true, false);
+    L_(false, false, false, false);
+#undef L_
+}
+
+static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st);
+
+extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
+{
+    if (!p) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+    p->last_stream = st;
+    const int A = p->A, B = p->B;
+    unsigned flags = p->flags;
+    if (flags & NWB_WANT_COUNT_MATRIX) flags |= NWB_WANT_COUNT;
+
+    NwbPkConsts pc;
+    memset(&pc, 0, sizeof(pc));
+    p->kind = choose_kind(flags, m, k, d, &pc);
+    int strip_w = NWB_I32_STRIP_W, pk_k = 0;
+    if (p->kind == NWB_KIND_PK) {
+        pk_k = nwb_pk_choose_k(A, B, p->sm_count * NWB_PK_WARPS * p->world);
+        strip_w = 64 * pk_k;
+    }
+    p->L = nwb_make_layout(A, B, p->kind, pk_k, strip_w);
+    const NwbLayout &L = p->L;
+
+    /* this rank's strips */
+    const int per = (L.n_strips + p->world - 1) / p->world;
+    p->strip_begin = p->rank * per < L.n_strips ? p->rank * per : L.n_strips;
+    p->strip_end = (p->rank + 1) * per < L.n_strips ? (p->rank + 1) * per : L.n_strips;
+    const int nloc = p->strip_end - p->strip_begin;
+
+    NwbDevSummary init;
+    memset(&init, 0, sizeof(init));
+    init.kernel_kind = p->kind;
+    if (A == 0 || B == 0) {
+        /* no interior cells: borders only (computation.c:97-124) */
+        init.opt_score = (A == 0) ? -B * d : -A * d;
+        init.count = (flags & NWB_WANT_COUNT) ? 1ull : 0ull;
+    }
+    CK(cudaMemcpyAsync(p->summary.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    p->ran = true;
+    p->timed = false;
+    if (A == 0 || B == 0 || nloc <= 0) return NWB_OK;
+
+    int rc = p->arrows.ensure(L.pitch * (size_t)B);
+    if (rc == NWB_OK && (flags & NWB_WANT_SCORES)) rc = p->scores.ensure(L.spitch * (size_t)B);
+    if (rc == NWB_OK && (flags & NWB_WANT_COUNT_MATRIX)) rc = p->cntmat.ensure(L.spitch * (size_t)B);
+    if (rc == NWB_OK) rc = p->progress.ensure((size_t)nloc);
+    if (rc == NWB_OK && p->kind == NWB_KIND_I32) {
+        rc = p->bnd_s.ensure((size_t)nloc * L.bpitch);
+        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * L.bpitch);
+    }
+    if (rc == NWB_OK && p->kind == NWB_KIND_PK) {
+        rc = p->bnd_w.ensure((size_t)nloc * L.bpitch);
+        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * L.bpitch);
+    }
+    if (rc != NWB_OK) return rc;
+    CK(cudaMemsetAsync(p->progress.p, 0, (size_t)nloc * sizeof(int), st));
+
+    NwbStripParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.top = p->top.p;
+    sp.side = p->side.p;
+    sp.A = A; sp.B = B; sp.m = m; sp.k = k; sp.d = d;
+    sp.n_strips = L.n_strips;
+    sp.strip_begin = p->strip_begin;
+    sp.strip_end = p->strip_end;
+    sp.arrows = p->arrows.p;
+    sp.pitch = L.pitch;
+    sp.scores = p->scores.p;
+    sp.cntmat = p->cntmat.p;
+    sp.spitch = L.spitch;
+    sp.bnd_s = p->bnd_s.p;
+    sp.bnd_c = p->bnd_c.p;
+    sp.bnd_w = p->bnd_w.p;
+    sp.bpitch = L.bpitch;
+    sp.progress = p->progress.p;
+    sp.summary = p->summary.p;
+    if (p->strip_begin > 0) {
+        if (!p->inbox.base || L.bpitch > p->inbox.bpitch) return NWB_ERR_INVALID;
+        sp.in_bnd_s = (const int32_t *)(p->inbox.base + p->inbox.off_s);
+        sp.in_bnd_c = (const unsigned long long *)(p->inbox.base + p->inbox.off_c);
+        sp.in_bnd_w = (const uint32_t *)(p->inbox.base + p->inbox.off_w);
+        sp.in_progress = (const int *)(p->inbox.base + p->inbox.off_flag);
+    }
+    if (p->strip_end < L.n_strips) {
+        if (!p->right_base || L.bpitch > p->right.bpitch) return NWB_ERR_INVALID;
+        sp.out_bnd_s = (int32_t *)(p->right_base + p->right.off_s);
+        sp.out_bnd_c = (unsigned long long *)(p->right_base + p->right.off_c);
+        sp.out_bnd_w = (uint32_t *)(p->right_base + p->right.off_w);
+        sp.out_progress = (int *)(p->right_base + p->right.off_flag);
+    }
+
+    const int warps = (p->kind == NWB_KIND_PK) ? NWB_PK_WARPS : NWB_I32_WARPS;
+    int grid = nloc < p->sm_count ? nloc : p->sm_count;
+    (void)warps;
+    CK(cudaEventRecord(p->ev0, st));
+    if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, st);
+    else rc = run_i32(p, sp, grid, st);
+    if (rc != NWB_OK) return rc;
+    CK(cudaEventRecord(p->ev1, st));
+    p->timed = true;
+    p->launches += 1;
+    return NWB_OK;
+}
+
+static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st)
+{
+    return nwb_pk_launch(sp, pc, p->L.pk_k, (p->flags & NWB_WANT_COUNT) != 0, grid, st, cuda_fail);
+}
+
+extern "C" int nwb_plan_reset_inbox(nwb_plan *p, void *stream)
+{
+    if (!p) return NWB_ERR_INVALID;
+    if (!p->inbox.base) return NWB_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+    CK(cudaMemsetAsync(p->inbox.base + p->inbox.off_flag, 0, 256, st));
+    return NWB_OK;
+}
+
+extern "C" int nwb_plan_summary(nwb_plan *p, nwb_summary *out)
+{
+    if (!p || !out) return NWB_ERR_INVALID;
+    if (!p->ran) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpyAsync(&p->last, p->summary.p, sizeof(NwbDevSummary), cudaMemcpyDeviceToHost, p->last_stream));
+    CK(cudaStreamSynchronize(p->last_stream));
+    out->opt_score = p->last.opt_score;
+    out->branch_count = p->last.branch_count;
+    out->greatest_abs = p->last.greatest_abs;
+    out->kernel_kind = p->last.kernel_kind;
+    out->count = p->last.count;
+    return NWB_OK;
+}
+
+extern "C" float nwb_plan_kernel_ms(nwb_plan *p)
+{
+    if (!p || !p->timed) return 0.f;
+    cudaSetDevice(p->device);
+    float ms = 0.f;
+    if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" void *nwb_plan_arrows_device(nwb_plan *p) { return p ? (void *)p->arrows.p : nullptr; }
+extern "C" size_t nwb_plan_arrow_pitch(const nwb_plan *p) { return p ? p->L.pitch : 0; }
+extern "C" int64_t nwb_plan_launches(const nwb_plan *p) { return p ? p->launches : 0; }
+extern "C" int nwb_plan_strip_range(const nwb_plan *p, int *begin_col, int *end_col)
+{
+    if (!p) return NWB_ERR_INVALID;
+    long long b = (long long)p->strip_begin * p->L.strip_w, e = (long long)p->strip_end * p->L.strip_w;
+    if (e > p->A) e = p->A;
+    if (b > p->A) b = p->A;
+    if (begin_col) *begin_col = (int)b;
+    if (end_col) *end_col = (int)e;
+    return NWB_OK;
+}
+
+extern "C" int nwb_plan_download_arrows(nwb_plan *p, uint8_t *dst, size_t dst_pitch, int row_begin, int row_end)
+{
+    if (!p || !dst || row_begin < 0 || row_end > p->B || row_begin > row_end) return NWB_ERR_INVALID;
+    if (row_begin == row_end || p->A == 0) return NWB_OK;
+    if (dst_pitch < (size_t)(p->A + 1) / 2) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->last_stream ? p->last_stream : p->stream));
+    const size_t width = dst_pitch < p->L.pitch ? dst_pitch : p->L.pitch;
+    CK(cudaMemcpy2D(dst, dst_pitch, p->arrows.p + (size_t)row_begin * p->L.pitch, p->L.pitch, width,
+                    (size_t)(row_end - row_begin), cudaMemcpyDeviceToHost));
+    return NWB_OK;
+}
+
+/* ---- multi-process strips: CUDA IPC ---------------------------------------- */
+extern "C" size_t nwb_plan_ipc_size(void) { return sizeof(NwbIpcBlob); }
+
+extern "C" int nwb_plan_ipc_export(nwb_plan *p, void *blob)
+{
+    if (!p || !blob || !p->inbox.base) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    NwbIpcBlob b;
+    memset(&b, 0, sizeof(b));
+    CK(cudaIpcGetMemHandle(&b.handle, p->inbox.base));
+    b.bpitch = p->inbox.bpitch; b.off_s = p->inbox.off_s; b.off_c = p->inbox.off_c;
+    b.off_w = p->inbox.off_w; b.off_flag = p->inbox.off_flag; b.bytes = p->inbox.bytes;
+    b.device = p->device;
+    memcpy(blob, &b, sizeof(b));
+    return NWB_OK;
+}
+
+extern "C" int nwb_plan_ipc_attach_right(nwb_plan *p, const void *blob)
+{
+    if (!p || !blob) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(p->device));
+    NwbIpcBlob b;
+    memcpy(&b, blob, sizeof(b));
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess));
+    p->right_base = (unsigned char *)ptr;
+    p->right_is_ipc = true;
+    p->right.bpitch = b.bpitch; p->right.off_s = b.off_s; p->right.off_c = b.off_c;
+    p->right.off_w = b.off_w; p->right.off_flag = b.off_flag; p->right.bytes = b.bytes;
+    p->right.base = p->right_base;
+    return NWB_OK;
+}
+
+/* same-process variant: `right` lives on another device of this process */
+static int plan_attach_right_local(nwb_plan *p, nwb_plan *right)
+{
+    CK(cudaSetDevice(p->device));
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, p->device, right->device));
+    if (!can) return NWB_ERR_UNSUPPORTED;
+    cudaError_t e = cudaDeviceEnablePeerAccess(right->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    cudaGetLastError();
+    p->right_base = right->inbox.base;
+    p->right_is_ipc = false;
+    p->right = right->inbox;
+    return NWB_OK;
+}
+
+/* ========================================================================== */
+struct nwb_table {
+    int A = 0, B = 0;
+    int m = 0, k = 0, d = 0;
+    unsigned flags = 0;
+    std::vector<nwb_plan *> plans;
+    nwb_summary sum = {};
+    float kernel_ms = 0.f;
+    std::vector<char> top, side;
+    uint8_t *h_arrows = nullptr;
+    size_t pitch = 0;
+    int32_t *h_scores = nullptr;
+    unsigned long long *h_cntmat = nullptr;
+    size_t spitch = 0;
+};
+
+extern "C" void nwb_free(nwb_table *t)
+{
+    if (!t) return;
+    for (nwb_plan *p : t->plans) nwb_plan_destroy(p);
+    free(t->h_arrows);
+    free(t->h_scores);
+    free(t->h_cntmat);
+    delete t;
+}
+
+extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int side_len,
+                           int m, int k, int d, unsigned flags, int device, int num_gpus,
+                           nwb_table **out)
+{
+    if (!out) return NWB_ERR_INVALID;
+    *out = nullptr;
+    if (top_len < 0 || side_len < 0 || (top_len && !top) || (side_len && !side) || num_gpus < 1)
+        return NWB_ERR_INVALID;
+    const int ndev = nwb_device_count();
+    if (ndev <= 0) return NWB_ERR_NO_DEVICE;
+    if (device < 0 || device + num_gpus > ndev) return NWB_ERR_INVALID;
+    if (flags & NWB_WANT_COUNT_MATRIX) flags |= NWB_WANT_COUNT;
+
+    nwb_table *t = new (std::nothrow) nwb_table();
+    if (!t) return NWB_ERR_NOMEM;
+    t->A = top_len; t->B = side_len; t->m = m; t->k = k; t->d = d; t->flags = flags;
+    t->top.assign(top, top + top_len);
+    t->side.assign(side, side + side_len);
+
+    int rc = NWB_OK;
+    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
+        nwb_plan *p = nullptr;
+        rc = nwb_plan_create(top_len, side_len, flags, device + g, g, num_gpus, &p);
+        if (rc == NWB_OK) t->plans.push_back(p);
+    }
+    for (int g = 0; g + 1 < num_gpus && rc == NWB_OK; g++) rc = plan_attach_right_local(t->plans[g], t->plans[g + 1]);
+    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_upload(t->plans[g], top, top_len, side, side_len);
+    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_run(t->plans[g], m, k, d, nullptr);
+    /* summaries: score/count live on the rank that owns column A (the last
+     * non-empty one); branch counts and abs maxima are combined */
+    memset(&t->sum, 0, sizeof(t->sum));
+    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
+        nwb_summary s;
+        rc = nwb_plan_summary(t->plans[g], &s);
+        if (rc != NWB_OK) break;
+        nwb_plan *p = t->plans[g];
+        t->sum.branch_count += s.branch_count;
+        if (s.greatest_abs > t->sum.greatest_abs) t->sum.greatest_abs = s.greatest_abs;
+        t->sum.kernel_kind = s.kernel_kind;
+        const bool owns_last = (top_len == 0 || side_len == 0) ? (g == 0)
+                                                               : (p->strip_end == p->L.n_strips && p->strip_end > p->strip_begin);
+        if (owns_last) {
+            t->sum.opt_score = s.opt_score;
+            t->sum.count = s.count;
+        }
+        const float ms = nwb_plan_kernel_ms(p);
+        if (ms > t->kernel_ms) t->kernel_ms = ms;
+    }
+    if (rc == NWB_OK && top_len > 0 && side_len > 0) {
+        const NwbLayout &L = t->plans[0]->L;
+        t->pitch = L.pitch;
+        t->spitch = L.spitch;
+        if (flags & NWB_WANT_ARROWS_HOST) {
+            t->h_arrows = (uint8_t *)malloc(L.pitch * (size_t)side_len);
+            if (!t->h_arrows) rc = NWB_ERR_NOMEM;
+            for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
+                nwb_plan *p = t->plans[g];
+                if (p->strip_end <= p->strip_begin) continue;
+                const size_t off = (size_t)p->strip_begin * L.strip_w / 2;
+                const size_t width = (size_t)(p->strip_end - p->strip_begin) * L.strip_w / 2;
+                cudaSetDevice(p->device);
+                cudaError_t e = cudaMemcpy2D(t->h_arrows + off, L.pitch, p->arrows.p + off, L.pitch, width,
+                                             (size_t)side_len, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy2D(arrows)");
+            }
+        }
+        if (rc == NWB_OK && (flags & NWB_WANT_SCORES)) {
+            t->h_scores = (int32_t *)malloc(L.spitch * (size_t)side_len * sizeof(int32_t));
+            if (!t->h_scores) rc = NWB_ERR_NOMEM;
+            else {
+                cudaError_t e = cudaMemcpy(t->h_scores, t->plans[0]->scores.p,
+                                           L.spitch * (size_t)side_len * sizeof(int32_t), cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(scores)");
+            }
+        }
+        if (rc == NWB_OK && (flags & NWB_WANT_COUNT_MATRIX)) {
+            t->h_cntmat = (unsigned long long *)malloc(L.spitch * (size_t)side_len * sizeof(unsigned long long));
+            if (!t->h_cntmat) rc = NWB_ERR_NOMEM;
+            else {
+                cudaError_t e = cudaMemcpy(t->h_cntmat, t->plans[0]->cntmat.p,
+                                           L.spitch * (size_t)side_len * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(cntmat)");
+            }
+        }
+    }
+    if (rc != NWB_OK) {
+        nwb_free(t);
+        return rc;
+    }
+    *out = t;
+    return NWB_OK;
+}
+
+extern "C" int nwb_fill(const char *top, int top_len, const char *side, int side_len,
+                        int m, int k, int d, unsigned flags, nwb_table **out)
+{
+    return nwb_fill_on(top, top_len, side, side_len, m, k, d, flags, 0, 1, out);
+}
+
+extern "C" int nwb_top_len(const nwb_table *t) { return t ? t->A : 0; }
+extern "C" int nwb_side_len(const nwb_table *t) { return t ? t->B : 0; }
+extern "C" int32_t nwb_opt_score(const nwb_table *t) { return t ? t->sum.opt_score : 0; }
+extern "C" uint64_t nwb_count_u64(const nwb_table *t) { return t ? t->sum.count : 0; }
+extern "C" uint32_t nwb_branch_count(const nwb_table *t) { return t ? t->sum.branch_count : 0; }
+extern "C" int32_t nwb_greatest_abs_interior(const nwb_table *t) { return t ? t->sum.greatest_abs : 0; }
+extern "C" float nwb_kernel_ms(const nwb_table *t) { return t ? t->kernel_ms : 0.f; }
+extern "C" int nwb_kernel_kind(const nwb_table *t) { return t ? t->sum.kernel_kind : -1; }
+extern "C" const uint8_t *nwb_arrow_rows(const nwb_table *t) { return t ? t->h_arrows : nullptr; }
+extern "C" size_t nwb_arrow_pitch(const nwb_table *t) { return t ? t->pitch : 0; }
+
+extern "C" int32_t nwb_score(const nwb_table *t, int i, int j)
+{
+    if (!t || i < 0 || j < 0 || i > t->A || j > t->B) return INT32_MIN;
+    /* borders: init_computation_tables(), computation.c:97-124 */
+    if (j == 0) return (int32_t)((uint32_t)i * (uint32_t)(-t->d));
+    if (i == 0) return (int32_t)((uint32_t)j * (uint32_t)(-t->d));
+    if (!t->h_scores) return INT32_MIN;
+    return t->h_scores[(size_t)(j - 1) * t->spitch + (size_t)(i - 1)];
+}
+
+extern "C" unsigned nwb_arrows(const nwb_table *t, int i, int j)
+{
+    if (!t || i < 0 || j < 0 || i > t->A || j > t->B) return 0xFFFFFFFFu;
+    if (i == 0 && j == 0) return 0;
+    if (j == 0) return NWB_LEFT;
+    if (i == 0) return NWB_UP;
+    if (!t->h_arrows) return 0xFFFFFFFFu;
+    const uint8_t byte = t->h_arrows[(size_t)(j - 1) * t->pitch + (size_t)((i - 1) >> 1)];
+    unsigned code = ((i - 1) & 1) ? (byte >> 4) : (byte & 0xF);
+    code &= 7u;
+    if (t->top[(size_t)i - 1] == t->side[(size_t)j - 1]) code |= NWB_MATCH;
+    return code;
+}
+
+extern "C" uint64_t nwb_count_at(const nwb_table *t, int i, int j)
+{
+    if (!t || i < 0 || j < 0 || i > t->A || j > t->B) return 0;
+    if (i == 0 || j == 0) return 1;
+    if (!t->h_cntmat) return 0;
+    return t->h_cntmat[(size_t)(j - 1) * t->spitch + (size_t)(i - 1)];
+}
+
+extern "C" const int32_t *nwb_score_rows(const nwb_table *t, size_t *pitch_elems)
+{
+    if (pitch_elems) *pitch_elems = t ? t->spitch : 0;
+    return t ? t->h_scores : nullptr;
+}
+extern "C" const uint64_t *nwb_count_rows(const nwb_table *t, size_t *pitch_elems)
+{
+    if (pitch_elems) *pitch_elems = t ? t->spitch : 0;
+    return t ? (const uint64_t *)t->h_cntmat : nullptr;
+}
+
+/* ---- measurement aid: INT/DPX issue rate ---------------------- */
+extern "C" int nwb_measure_int_issue(int device, int mode, double *per_clk_per_sm, double *gops_per_s)
+{
+    const int ndev = nwb_device_count();
+    if (ndev <= 0) return NWB_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev || mode < 0 || mode > 3) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 4096;
+    int *sink = nullptr;
+    long long *cyc = nullptr;
+    CK(cudaMalloc((void **)&sink, sizeof(int)));
+    CK(cudaMalloc((void **)&cyc, sizeof(long long) * blocks));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    long long max_cyc = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0));
+        switch (mode) {
+        case 0: nwb_peak_kernel<0><<<blocks, threads>>>(iters, 3, -5, sink, cyc); break;
+        case 1: nwb_peak_kernel<1><<<blocks, threads>>>(iters, 3, -5, sink, cyc); break;
+        case 2: nwb_peak_kernel<2><<<blocks, threads>>>(iters, 0x00030004, 0x7fff7ffe, sink, cyc); break;
+        default: nwb_peak_kernel<3><<<blocks, threads>>>(iters, 3, -5, sink, cyc); break;
+        }
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) {
+            best_ms = ms;
+            std::vector<long long> h(blocks);
+            CK(cudaMemcpy(h.data(), cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost));
+            max_cyc = 0;
+            for (long long c : h) if (c > max_cyc) max_cyc = c;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(cyc);
+    /* thread-instructions: 64 per iteration per thread; two resident blocks share an SM */
+    const double per_sm = 2.0 * threads * (double)iters * 64.0;
+    if (per_clk_per_sm) *per_clk_per_sm = max_cyc > 0 ? per_sm / (double)max_cyc : 0.0;
+    if (gops_per_s) *gops_per_s = (double)blocks * threads * (double)iters * 64.0 / (best_ms * 1e-3) / 1e9;
+    return NWB_OK;
+}
+
+/* ========================================================================== */
+#include "nwb_batch_api.inl"

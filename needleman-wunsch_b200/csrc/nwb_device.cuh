@@ -1,0 +1,135 @@
+/*
+ * nwb_device.cuh -- device-side primitives and launch parameter blocks shared
+ * by the fill kernels.  Compiles for sm_100a with nvcc and, with -DNWB_EMU,
+ * for the host under the test-only SIMT emulator (tests/emu/emu_cuda.h).
+ */
+#pragma once
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef NWB_EMU
+#include "emu_cuda.h"
+#define NWB_SMEM_BASE() (emu_smem())
+#else
+#include <cuda_runtime.h>
+extern __shared__ __align__(16) unsigned char nwb_dyn_smem_[];
+#define NWB_SMEM_BASE() (nwb_dyn_smem_)
+#endif
+
+#define NWB_FULL_MASK 0xffffffffu
+
+/* ---- inter-block / inter-GPU flag protocol --------------------------------
+ * Producer: plain stores of the boundary data by ONE thread, then
+ * st.release of the progress word by the same thread.  Consumer: every lane
+ * ld.acquire's the progress word until it is large enough, then reads the
+ * data.  `_sys` variants are used when producer and consumer sit on
+ * different GPUs (peer memory over NVLink). */
+__device__ __forceinline__ int nwb_ld_acquire_gpu(const int *p)
+{
+#ifdef NWB_EMU
+    return *(const volatile int *)p;
+#else
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ int nwb_ld_acquire_sys(const int *p)
+{
+#ifdef NWB_EMU
+    return *(const volatile int *)p;
+#else
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void nwb_st_release_gpu(int *p, int v)
+{
+#ifdef NWB_EMU
+    *(volatile int *)p = v;
+#else
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void nwb_st_release_sys(int *p, int v)
+{
+#ifdef NWB_EMU
+    *(volatile int *)p = v;
+#else
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void nwb_pause()
+{
+    __nanosleep(32);
+}
+
+/* Spin until *flag >= need.  `sys` selects system scope (peer memory). */
+__device__ __forceinline__ void nwb_wait_ge(const int *flag, int need, bool sys)
+{
+    if (sys) {
+        while (nwb_ld_acquire_sys(flag) < need) nwb_pause();
+    } else {
+        while (nwb_ld_acquire_gpu(flag) < need) nwb_pause();
+    }
+}
+
+/* ---- 16x2 helpers (DPX / video SIMD; VIMNMX.U16x2, VIMNMX3.U16x2, VIADD.16x2) */
+__device__ __forceinline__ unsigned nwb_min_u16x2(unsigned a, unsigned b) { return __vminu2(a, b); }
+__device__ __forceinline__ unsigned nwb_min3_u16x2(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ unsigned nwb_max3_u16x2(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
+
+/* ---- results ---------------------------------------------------------------- */
+struct NwbDevSummary {
+    int opt_score;
+    unsigned branch_count;
+    int greatest_abs;
+    int kernel_kind;
+    unsigned long long count;
+    long long rsum; /* packed kernel: sum of bottom-row u differences */
+};
+
+/* ---- launch parameters of the single-pair strip-pipeline kernels ------------
+ * The table is cut into column strips of `strip_w` interior columns; strip c
+ * covers columns i in [c*strip_w + 1, (c+1)*strip_w].  One warp sweeps one
+ * strip top to bottom.  Strip c streams its right boundary column into
+ * bnd_*[c - strip_begin] and publishes in progress[c - strip_begin] how many
+ * rows are final; strip c+1 polls it.  Strips [strip_begin, strip_end) belong
+ * to this launch (this GPU).  When the table starts on another GPU
+ * (strip_begin > 0) the boundary of strip strip_begin-1 arrives in the in_*
+ * "inbox", written by the left-neighbour GPU through peer memory; when the
+ * table continues on another GPU (strip_end < n_strips) the last local strip
+ * writes into out_* = the right neighbour's inbox. */
+struct NwbStripParams {
+    const uint8_t *top;  /* A bytes  */
+    const uint8_t *side; /* B bytes  */
+    int A, B;
+    int m, k, d;
+    int n_strips;     /* total strips of the table                         */
+    int strip_begin;  /* first strip of this launch                        */
+    int strip_end;    /* one past the last strip of this launch            */
+    uint8_t *arrows;  /* nibble table, B rows x pitch bytes                */
+    size_t pitch;
+    int32_t *scores;        /* interior scores, B rows x spitch (or NULL)  */
+    unsigned long long *cntmat; /* interior counts, B rows x spitch (NULL) */
+    size_t spitch;          /* elements per row of scores / cntmat         */
+    /* boundary streams of the local strips, [c - strip_begin][row j] */
+    int32_t *bnd_s;             /* general kernel: int32 score of (c_last, j) */
+    unsigned long long *bnd_c;  /* count of (c_last, j) (WANT_COUNT)          */
+    uint32_t *bnd_w;            /* packed kernel: stream word per row         */
+    size_t bpitch;              /* elements per strip in bnd_*                */
+    int *progress;              /* [strip_end - strip_begin] rows published   */
+    /* inbox (valid iff strip_begin > 0): written by the left-neighbour GPU */
+    const int32_t *in_bnd_s;
+    const unsigned long long *in_bnd_c;
+    const uint32_t *in_bnd_w;
+    const int *in_progress;
+    /* right neighbour's inbox (valid iff strip_end < n_strips) */
+    int32_t *out_bnd_s;
+    unsigned long long *out_bnd_c;
+    uint32_t *out_bnd_w;
+    int *out_progress;
+    NwbDevSummary *summary;
+};

@@ -1,0 +1,73 @@
+"""ctypes driver for the test-only SIMT emulator build of the kernels
+(tests/emu/libnwb_emu.so).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class _Out(C.Structure):
+    _fields_ = [("opt_score", C.c_int), ("branch_count", C.c_uint), ("greatest_abs", C.c_int),
+                ("pad", C.c_int), ("count", C.c_ulonglong), ("pitch", C.c_ulonglong),
+                ("spitch", C.c_ulonglong)]
+
+
+_lib = None
+
+
+def build() -> None:
+    subprocess.run(["make", "-s", "-C", HERE], check=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(os.path.join(HERE, "libnwb_emu.so"))
+        for name in ("emu_pitch_i32", "emu_spitch_i32"):
+            f = getattr(_lib, name)
+            f.restype = C.c_size_t
+            f.argtypes = [C.c_int, C.c_int]
+    return _lib
+
+
+def _b(s):
+    return s if isinstance(s, (bytes, bytearray)) else s.encode("latin-1")
+
+
+def fill_i32(top, side, m, k, d, *, flags=0, grid=2, split=0):
+    """Run nwb_fill_i32_kernel under the emulator.  Returns dict of outputs."""
+    top, side = _b(top), _b(side)
+    a, b = len(top), len(side)
+    L = lib()
+    pitch = L.emu_pitch_i32(a, b)
+    spitch = L.emu_spitch_i32(a, b)
+    arrows = np.full((b, pitch), 0xEE, np.uint8)
+    scores = np.zeros((b, spitch), np.int32) if flags & 1 else None
+    cntmat = np.zeros((b, spitch), np.uint64) if flags & 0x20 else None
+    out = _Out()
+    ptr = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    L.emu_fill_i32.restype = C.c_int
+    L.emu_fill_i32.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.POINTER(_Out)]
+    rc = L.emu_fill_i32(top, a, side, b, m, k, d, flags, grid, split, ptr(arrows), ptr(scores),
+                        ptr(cntmat), C.byref(out))
+    assert rc == 0
+    return dict(opt_score=out.opt_score, branch_count=out.branch_count, greatest_abs=out.greatest_abs,
+                count=out.count, arrows=arrows, scores=scores, cntmat=cntmat, pitch=pitch)
+
+
+def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:
+    """(B, pitch) nibble table -> (B, A) uint8 codes (DIAG|LEFT|UP)."""
+    lo = packed & 0xF
+    hi = packed >> 4
+    inter = np.empty((packed.shape[0], packed.shape[1] * 2), np.uint8)
+    inter[:, 0::2] = lo
+    inter[:, 1::2] = hi
+    return inter[:, :a]

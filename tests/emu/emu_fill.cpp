@@ -1,0 +1,108 @@
+/*
+ * emu_fill.cpp -- runs the REAL kernel sources (needleman-wunsch_b200/csrc/
+ * *.cuh) on the CPU under the SIMT emulator.  TEST INFRASTRUCTURE ONLY: built
+ * by tests/emu/Makefile into tests/emu/libnwb_emu.so, loaded only by tests.
+ */
+#define NWB_EMU 1
+#include "emu_cuda.h"
+#include "nwb_layout.h"
+#include "nwb_fill_i32.cuh"
+
+#include <vector>
+
+template <bool COUNT, bool SCORES, bool ABS, bool CNTMAT>
+static void run_i32(unsigned grid, const NwbStripParams &p)
+{
+    emu_launch(grid, 32 * NWB_I32_WARPS, NWB_I32_SMEM_BYTES,
+               [&]() { nwb_fill_i32_kernel<COUNT, SCORES, ABS, CNTMAT>(p); });
+}
+
+extern "C" {
+
+struct emu_out {
+    int opt_score;
+    unsigned branch_count;
+    int greatest_abs;
+    int pad;
+    unsigned long long count;
+    unsigned long long pitch;
+    unsigned long long spitch;
+};
+
+/* flags: 1 scores, 2 count, 8 abs, 0x20 cntmat (same bits as include/nwb.h).
+ * arrows: B*pitch bytes (pitch from emu_pitch_i32), scores/cntmat: B*spitch. */
+size_t emu_pitch_i32(int A, int B) { return nwb_make_layout(A, B, NWB_KIND_I32, 0, NWB_I32_STRIP_W).pitch; }
+size_t emu_spitch_i32(int A, int B) { return nwb_make_layout(A, B, NWB_KIND_I32, 0, NWB_I32_STRIP_W).spitch; }
+
+
+int emu_fill_i32(const char *top, int A, const char *side, int B, int m, int k, int d,
+                 unsigned flags, unsigned grid, int split, /* emulate a 2-GPU strip split at this strip (0 = none) */
+                 uint8_t *arrows, int32_t *scores, unsigned long long *cntmat, emu_out *out)
+{
+    NwbLayout L = nwb_make_layout(A, B, NWB_KIND_I32, 0, NWB_I32_STRIP_W);
+    std::vector<int32_t> bnd_s((size_t)L.n_strips * L.bpitch, 0x7f7f7f7f);
+    std::vector<unsigned long long> bnd_c((size_t)L.n_strips * L.bpitch, 0xdeadbeefULL);
+    std::vector<int> progress((size_t)L.n_strips, 0);
+    NwbDevSummary sum;
+    memset(&sum, 0, sizeof(sum));
+
+    NwbStripParams p;
+    memset(&p, 0, sizeof(p));
+    p.top = (const uint8_t *)top;
+    p.side = (const uint8_t *)side;
+    p.A = A; p.B = B; p.m = m; p.k = k; p.d = d;
+    p.n_strips = L.n_strips;
+    p.strip_begin = 0;
+    p.strip_end = L.n_strips;
+    p.arrows = arrows;
+    p.pitch = L.pitch;
+    p.scores = scores;
+    p.cntmat = cntmat;
+    p.spitch = L.spitch;
+    p.bnd_s = bnd_s.data();
+    p.bnd_c = bnd_c.data();
+    p.bpitch = L.bpitch;
+    p.progress = progress.data();
+    p.summary = &sum;
+
+    const bool C = flags & 2, S = flags & 1, AB = flags & 8, CM = flags & 0x20;
+    auto launch = [&](const NwbStripParams &q) {
+        if (C) {
+            if (S) { if (AB) { if (CM) run_i32<true, true, true, true>(grid, q); else run_i32<true, true, true, false>(grid, q); }
+                     else { if (CM) run_i32<true, true, false, true>(grid, q); else run_i32<true, true, false, false>(grid, q); } }
+            else { if (AB) { if (CM) run_i32<true, false, true, true>(grid, q); else run_i32<true, false, true, false>(grid, q); }
+                   else { if (CM) run_i32<true, false, false, true>(grid, q); else run_i32<true, false, false, false>(grid, q); } }
+        } else {
+            if (S) { if (AB) run_i32<false, true, true, false>(grid, q); else run_i32<false, true, false, false>(grid, q); }
+            else { if (AB) run_i32<false, false, true, false>(grid, q); else run_i32<false, false, false, false>(grid, q); }
+        }
+    };
+    if (split > 0 && split < L.n_strips) {
+        /* two "GPUs" run one after the other: the first publishes its last
+         * strip's boundary through the out_* pointers into the second's arrays */
+        NwbStripParams p0 = p, p1 = p;
+        std::vector<int32_t> inbox_s(L.bpitch, 0x7f7f7f7f);
+        std::vector<unsigned long long> inbox_c(L.bpitch, 0xdeadbeefULL);
+        int inbox_flag = 0;
+        p0.strip_end = split;
+        p0.out_bnd_s = inbox_s.data();
+        p0.out_bnd_c = inbox_c.data();
+        p0.out_progress = &inbox_flag;
+        p1.strip_begin = split;
+        p1.in_bnd_s = inbox_s.data();
+        p1.in_bnd_c = inbox_c.data();
+        p1.in_progress = &inbox_flag;
+        launch(p0);
+        launch(p1);
+    } else {
+        launch(p);
+    }
+    out->opt_score = sum.opt_score;
+    out->branch_count = sum.branch_count;
+    out->greatest_abs = sum.greatest_abs;
+    out->count = sum.count;
+    out->pitch = L.pitch;
+    out->spitch = L.spitch;
+    return 0;
+}
+}

@@ -1,0 +1,172 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI
+(libnwb.so via ctypes), against the CPU oracle and the committed goldens.
+Bit-exact: integer scores, arrow sets, counts mod 2^64, branch counts."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden(name):
+    with open(os.path.join(HERE, "golden", name)) as f:
+        return json.load(f)
+
+
+def case_strings(oracle, c):
+    if "seed" in c:
+        alpha = oracle.DNA if c["alphabet"] == "dna" else oracle.PROTEIN
+        return oracle.generate_pair(c["seed"], c["top_len"], c["side_len"], alpha)
+    return c["top"].encode(), c["side"].encode()
+
+
+def check_arrows(oracle, nwb, tab, t, s, m, k, d):
+    """Whole nibble table against the oracle's, byte for byte over the valid region."""
+    a, b = len(t), len(s)
+    if a == 0 or b == 0:
+        return
+    rows = tab.arrow_rows()
+    o = oracle.fill(t, s, m, k, d, want_packed=True, pitch=tab.pitch)
+    nb = (a + 1) // 2
+    got, exp = rows[:, :nb].copy(), o.packed[:, :nb].copy()
+    got &= 0x77
+    if a & 1:
+        got[:, nb - 1] &= 0x07
+    assert np.array_equal(got, exp)
+    return o
+
+
+def full_check(oracle, nwb, t, s, m, k, d, extra_flags=0, num_gpus=1):
+    flags = nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | extra_flags
+    tab = nwb.fill(t, s, m, k, d, flags, num_gpus=num_gpus)
+    o = oracle.fill(t, s, m, k, d)
+    assert tab.opt_score == o.final_score
+    assert tab.branch_count == o.branch_count
+    assert tab.count == o.count
+    if extra_flags & nwb.TRACK_ABS:
+        assert tab.greatest_abs == o.greatest_abs
+    check_arrows(oracle, nwb, tab, t, s, m, k, d)
+    return tab
+
+
+@pytest.mark.parametrize("force", [True, False], ids=["general", "auto"])
+def test_readme_example_every_cell(oracle, nwb, force):
+    """BASELINE config 1: GCATGCU/GATTACA 1 1 1 -s -t, every score, arrow set, count."""
+    ff = nwb.FORCE_GENERAL if force else 0
+    tab = nwb.fill(b"GCATGCU", b"GATTACA", 1, 1, 1,
+                   nwb.WANT_SCORES | nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | nwb.TRACK_ABS | nwb.WANT_COUNT_MATRIX | ff)
+    o = oracle.fill("GCATGCU", "GATTACA", 1, 1, 1, want_scores=True, want_codes=True, want_counts=True)
+    for j in range(8):
+        for i in range(8):
+            assert tab.score(i, j) == o.scores[j, i]
+            assert tab.arrows(i, j) == o.codes[j, i]
+            assert tab.count_at(i, j) == o.counts[j, i]
+    assert (tab.opt_score, tab.count, tab.branch_count, tab.greatest_abs) == (0, 3, 12, 5)
+    tab0 = nwb.fill(b"GCATGCU", b"GATTACA", 0, 0, 0, nwb.WANT_COUNT | ff)
+    assert tab0.count == 48639 and tab0.branch_count == 49
+
+
+@pytest.mark.parametrize("force", [True, False], ids=["general", "auto"])
+@pytest.mark.parametrize("case", golden("golden.json"), ids=lambda c: c["name"])
+def test_goldens(oracle, nwb, case, force):
+    t, s = case_strings(oracle, case)
+    ff = nwb.FORCE_GENERAL if force else 0
+    tab = full_check(oracle, nwb, t, s, case["m"], case["k"], case["d"], nwb.TRACK_ABS | ff)
+    assert tab.opt_score == case["final_score"]
+    assert tab.branch_count == case["branch_count"]
+    assert tab.greatest_abs == case["greatest_abs"]
+    assert tab.count == case["count_u64"]
+
+
+@pytest.mark.parametrize("force", [True, False], ids=["general", "auto"])
+def test_edge_shapes(oracle, nwb, force):
+    """Lengths around lane / strip / chunk edges, ragged, arbitrary bytes."""
+    ff = nwb.FORCE_GENERAL if force else 0
+    rng = random.Random(7)
+    sizes = [1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 191, 192, 193, 255, 256, 257, 511, 513, 769]
+    for _ in range(40):
+        a, b = rng.choice(sizes), rng.choice(sizes)
+        alpha = rng.choice([b"ACGT", b"AB", bytes(range(1, 256)), b"ARNDCQEGHILKMFPSTWYV"])
+        t = bytes(rng.choice(alpha) for _ in range(a))
+        s = bytes(rng.choice(alpha) for _ in range(b))
+        m, k, d = rng.choice([(1, 1, 1), (2, 1, 2), (0, 0, 0), (1, 2, 3), (5, 4, 3), (-1, 3, -2), (3, -1, 0), (1, 1, 0)])
+        full_check(oracle, nwb, t, s, m, k, d, ff)
+
+
+def test_scores_and_count_matrix(oracle, nwb):
+    """Every score cell and every intermediate count (SURVEY hard part 6: the
+    final count is 0 mod 2^64 on the big configs, so intermediates must match)."""
+    for seed, a, b, (m, k, d) in [(0x5EED0A00, 700, 900, (1, 1, 1)), (0x5EED0A02, 1300, 517, (2, 1, 2))]:
+        t, s = oracle.generate_pair(seed, a, b)
+        tab = nwb.fill(t, s, m, k, d, nwb.WANT_SCORES | nwb.WANT_COUNT_MATRIX | nwb.TRACK_ABS)
+        o = oracle.fill(t, s, m, k, d, want_scores=True, want_counts=True)
+        assert np.array_equal(tab.score_rows(), o.scores[1:, 1:])
+        assert np.array_equal(tab.count_rows(), o.counts[1:, 1:])
+        assert tab.greatest_abs == o.greatest_abs and tab.count == o.count
+
+
+def test_empty_top_string(oracle, nwb):
+    # leading-whitespace input gives an empty top string
+    tab = nwb.fill(b"", b"ACG", 1, 1, 1, nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | nwb.WANT_SCORES)
+    assert (tab.opt_score, tab.count, tab.branch_count) == (-3, 1, 0)
+    assert [tab.arrows(0, j) for j in range(4)] == [0, nwb.UP, nwb.UP, nwb.UP]
+    assert [tab.score(0, j) for j in range(4)] == [0, -1, -2, -3]
+
+
+@pytest.mark.parametrize("force", [True, False], ids=["general", "auto"])
+def test_config2_dna_10k(oracle, nwb, force):
+    """BASELINE config 2 (10k x 10k DNA, 1 1 1, -q -s) vs the reference's goldens."""
+    t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
+    ff = nwb.FORCE_GENERAL if force else 0
+    tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | ff)
+    assert (tab.opt_score, tab.branch_count, tab.count) == (1056, 34377799, 0)
+    check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
+
+
+def test_config5_protein_30k_summary(oracle, nwb):
+    """BASELINE config 5 (30k x 30k protein, 2 1 2, -q -s): summary vs golden_big.json."""
+    g = [c for c in golden("golden_big.json") if c["name"] == "config5_protein_30k"]
+    if not g:
+        pytest.skip("golden_big.json has no config 5 entry")
+    g = g[0]
+    t, s = oracle.generate_pair(0x5EED0005, 30000, 30000, oracle.PROTEIN)
+    tab = nwb.fill(t, s, 2, 1, 2, nwb.WANT_COUNT)
+    assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"])
+
+
+def test_config3_dna_100k_properties(oracle, nwb):
+    """BASELINE config 3 (100k x 100k DNA) at full size, by size-independent
+    properties: (1) the first R rows of the table equal the table of
+    (top, side[:R]) -- checked against the oracle for R = 1500, which crosses
+    every strip hand-off; (2) swapping the strings transposes the table, so
+    score, count and branch count are equal; (3) golden summary if recorded."""
+    t, s = oracle.generate_pair(0x5EED0030, 100000, 100000)
+    plan = nwb.Plan(100000, 100000, nwb.WANT_COUNT)
+    plan.upload(t, s)
+    plan.run(1, 1, 1)
+    sm = plan.summary()
+    R = 1500
+    rows = plan.download_arrows(0, R)
+    o = oracle.fill(t, s[:R], 1, 1, 1, want_packed=True, pitch=rows.shape[1])
+    assert np.array_equal(rows[:, :50000] & 0x77, o.packed[:, :50000])
+    plan.upload(s, t)
+    plan.run(1, 1, 1)
+    sm2 = plan.summary()
+    assert (sm.opt_score, sm.count, sm.branch_count) == (sm2.opt_score, sm2.count, sm2.branch_count)
+    g = [c for c in golden("golden_big.json") if c["name"] == "config3_dna_100k"]
+    if g:
+        assert (sm.opt_score, sm.branch_count, sm.count) == (g[0]["final_score"], g[0]["branch_count"], g[0]["count_u64"])
+    plan.close()
+
+
+def test_two_gpu_strips_match_one(oracle, nwb):
+    if nwb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    t, s = oracle.generate_pair(0x5EED0B00, 5000, 3000)
+    full_check(oracle, nwb, t, s, 1, 1, 1, num_gpus=2)
+    full_check(oracle, nwb, t, s, 2, 1, 2, nwb.FORCE_GENERAL, num_gpus=2)
