@@ -179,7 +179,11 @@ def run_ours(args) -> None:
         if rank + 1 < world:
             plan.ipc_attach_right(blobs[rank + 1])
     plan.upload(t, s)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: the C ABI treats a NULL stream as "the plan's own",
+    # and torch.cuda.Event only sees torch's current stream
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def step():
         if world > 1:
@@ -271,7 +275,7 @@ def run_ours(args) -> None:
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                              "note": "secondary: 0.5 B/cell arrow write-back + strings; not the binding roofline"},
-            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": A + B, "d2h_bytes_per_step": 24},
+            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": A + B, "d2h_bytes_per_step": 32},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "result": {"opt_score": summ.opt_score, "branch_count": summ.branch_count, "kernel_kind": summ.kernel_kind},

@@ -63,6 +63,10 @@ extern "C" {
 #define NWB_FORCE_GENERAL 0x10u
 /* Verification aid: materialise the full uint64 count matrix (small inputs). */
 #define NWB_WANT_COUNT_MATRIX 0x20u
+/* Do not produce the branch counter (walk_table_t.branch_count, which the
+ * reference only prints from debug builds, needleman-wunsch.c:624).  The packed
+ * kernel obtains it with a second pass over the arrow table; this skips it. */
+#define NWB_NO_BRANCH_COUNT 0x40u
 
 /* ---- error codes ---------------------------------------------------------- */
 #define NWB_OK 0
@@ -150,6 +154,10 @@ typedef struct nwb_summary {
     int32_t greatest_abs;
     int32_t kernel_kind;
     uint64_t count;
+    /* packed kernel only: this rank's share of sum_i u(i,B).  For a single-rank
+     * plan opt_score is already final; in a strip group the true score is
+     * sum over ranks of partial_r, minus d*(A+B). */
+    int64_t partial_r;
 } nwb_summary;
 
 /* Allocate device workspace for fills up to max_top x max_side on `device`.
@@ -163,7 +171,7 @@ int nwb_plan_upload(nwb_plan *p, const char *top, int top_len, const char *side,
 /* Launch the fill on `stream` (a cudaStream_t; NULL = the plan's own stream).
  * Asynchronous; inputs and outputs stay on the device. */
 int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream);
-/* Wait for the plan's work and fetch the 24-byte summary (device -> host). */
+/* Wait for the plan's work and fetch the 32-byte summary (device -> host). */
 int nwb_plan_summary(nwb_plan *p, nwb_summary *out);
 /* Device pointer / pitch of the arrow table (layout above). */
 void *nwb_plan_arrows_device(nwb_plan *p);

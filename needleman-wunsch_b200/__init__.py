@@ -33,6 +33,7 @@ WANT_ARROWS_HOST = 0x04
 TRACK_ABS = 0x08
 FORCE_GENERAL = 0x10
 WANT_COUNT_MATRIX = 0x20
+NO_BRANCH_COUNT = 0x40
 KIND_I32, KIND_PK = 0, 1
 
 
@@ -50,7 +51,7 @@ class NwbError(RuntimeError):
 
 class Summary(C.Structure):
     _fields_ = [("opt_score", C.c_int32), ("branch_count", C.c_uint32), ("greatest_abs", C.c_int32),
-                ("kernel_kind", C.c_int32), ("count", C.c_uint64)]
+                ("kernel_kind", C.c_int32), ("count", C.c_uint64), ("partial_r", C.c_int64)]
 
 
 _lib = None

@@ -131,6 +131,7 @@ struct nwb_plan {
     NwbDevSummary last = {};
     bool ran = false;
     cudaStream_t last_stream = nullptr;
+    int m = 0, k = 0, d = 0;
 };
 
 static void make_inbox_layout(Inbox &ib, size_t bpitch)
@@ -230,7 +231,8 @@ extern "C" int nwb_plan_upload(nwb_plan *p, const char *top, int top_len, const 
  * requested, the general int32 kernel runs. */
 static int choose_kind(unsigned flags, int m, int k, int d, NwbPkConsts *pc)
 {
-    if (flags & (NWB_FORCE_GENERAL | NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_WANT_COUNT_MATRIX)) return NWB_KIND_I32;
+    if (flags & (NWB_FORCE_GENERAL | NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_WANT_COUNT_MATRIX | NWB_WANT_COUNT))
+        return NWB_KIND_I32;
     if (!nwb_pk_supported(m, k, d, pc)) return NWB_KIND_I32;
     return NWB_KIND_PK;
 }
@@ -278,6 +280,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     CK(cudaSetDevice(p->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
     p->last_stream = st;
+    p->m = m; p->k = k; p->d = d;
     const int A = p->A, B = p->B;
     unsigned flags = p->flags;
     if (flags & NWB_WANT_COUNT_MATRIX) flags |= NWB_WANT_COUNT;
@@ -371,6 +374,15 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     CK(cudaEventRecord(p->ev1, st));
     p->timed = true;
     p->launches += 1;
+    if (p->kind == NWB_KIND_PK && !(flags & NWB_NO_BRANCH_COUNT)) {
+        /* get_branch_count() (walk-table.c:133): second, HBM-bound pass over this rank's columns */
+        long long cb = (long long)p->strip_begin * L.strip_w, ce = (long long)p->strip_end * L.strip_w;
+        if (ce > A) ce = A;
+        nwb_branch_count_kernel<<<p->sm_count * 8, 256, 0, st>>>(p->arrows.p, L.pitch, A, B, (int)cb, (int)ce,
+                                                                 &p->summary.p->branch_count);
+        CK(cudaGetLastError());
+        p->launches += 1;
+    }
     return NWB_OK;
 }
 
@@ -397,6 +409,13 @@ extern "C" int nwb_plan_summary(nwb_plan *p, nwb_summary *out)
     CK(cudaMemcpyAsync(&p->last, p->summary.p, sizeof(NwbDevSummary), cudaMemcpyDeviceToHost, p->last_stream));
     CK(cudaStreamSynchronize(p->last_stream));
     out->opt_score = p->last.opt_score;
+    out->partial_r = 0;
+    if (p->last.kernel_kind == NWB_KIND_PK && p->A > 0 && p->B > 0) {
+        /* packed kernel: score(A,B) = sum_i u(i,B) - d*(A+B); a strip group sums the ranks' shares */
+        out->partial_r = p->last.rsum;
+        out->opt_score = (int32_t)(uint32_t)((unsigned long long)p->last.rsum -
+                                             (unsigned long long)((long long)p->d * ((long long)p->A + p->B)));
+    }
     out->branch_count = p->last.branch_count;
     out->greatest_abs = p->last.greatest_abs;
     out->kernel_kind = p->last.kernel_kind;
@@ -561,9 +580,13 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
             t->sum.opt_score = s.opt_score;
             t->sum.count = s.count;
         }
+        t->sum.partial_r += s.partial_r;
         const float ms = nwb_plan_kernel_ms(p);
         if (ms > t->kernel_ms) t->kernel_ms = ms;
     }
+    if (rc == NWB_OK && top_len > 0 && side_len > 0 && t->sum.kernel_kind == NWB_KIND_PK)
+        t->sum.opt_score = (int32_t)(uint32_t)((unsigned long long)t->sum.partial_r -
+                                               (unsigned long long)((long long)d * ((long long)top_len + side_len)));
     if (rc == NWB_OK && top_len > 0 && side_len > 0) {
         const NwbLayout &L = t->plans[0]->L;
         t->pitch = L.pitch;

@@ -1,14 +1,322 @@
-/* nwb_fill_pk.cuh -- packed 16x2 difference kernel (placeholder until implemented). */
+/*
+ * nwb_fill_pk.cuh -- packed 16x2 "difference" fill: two cells per instruction.
+ *
+ * Same results as the general kernel (nwb_fill_i32.cuh) -- i.e. as the
+ * reference's score_cell() (needleman-wunsch.c:418-510) -- for scoring schemes
+ * whose per-cell differences are small (nwb_pk_supported()).  Selected
+ * automatically; everything else runs the int32 kernel.
+ *
+ * Formulation.  With r(i,j) = score(i,j) + d*(i+j) the gap penalty disappears:
+ *     r(i,j) = max( r(i-1,j-1) + a(i,j),  r(i,j-1),  r(i-1,j) ),
+ *     a = 2d + m on a match, 2d - k on a mismatch,  r = 0 on both borders.
+ * Only differences are carried:  u = r(i,j) - r(i-1,j),  v = r(i,j) - r(i,j-1),
+ *     z = max3(a, vL, uU)        (vL = v of the left cell, uU = u of the upper cell)
+ *     u = z - vL,   v = z - uU
+ * and the reference's tie rule "every candidate equal to the maximum gets an
+ * arrow" (needleman-wunsch.c:485-503) becomes three zero tests:
+ *     DIAG <=> z - a == 0,   LEFT <=> u == 0,   UP <=> v == 0.
+ * All values live in [0, 2d+m], so two cells are packed in the 16-bit halves of
+ * one register and processed by one DPX instruction each:
+ *     VIADDMNMX.S16x2 (a from the characters), VIMNMX3.S16x2 (z), VIMNMX.U16x2
+ *     (zero tests).  The optimal score is recovered as sum_i u(i,B) - d*(A+B).
+ *
+ * Mapping.  A strip is 64*K columns (K = 1, 2 or 4).  Lane l owns two column
+ * blocks of K columns: block 2l in the low halves, block 2l+1 in the high
+ * halves; the high half runs one row behind the low half and lane l+1 one row
+ * behind lane l's high half (64 virtual lanes on an anti-diagonal).  Per row
+ * step one __shfl_up_sync carries {v of my last column, side character} to the
+ * right neighbour.  Strips are chained exactly as in the general kernel:
+ * persistent warps, cyclic strip assignment, boundary stream + progress word
+ * (st.release / ld.acquire), optional peer-GPU inbox/outbox.
+ *
+ * Rows above the table (j <= 0) need no predication: a virtual row fed with
+ * vL = BIG keeps u = 0 and hands BIG on to the right, so lanes that have not
+ * reached row 1 yet just idle on harmless values.
+ */
 #pragma once
 #include "nwb_device.cuh"
+
 #define NWB_PK_WARPS 4
-struct NwbPkConsts { int a_match, a_mis, c; };
-static inline bool nwb_pk_supported(int, int, int, NwbPkConsts *) { return false; }
-static inline int nwb_pk_choose_k(int, int, int) { return 1; }
+#define NWB_PK_RING_ROWS 128
+#define NWB_PK_BIG 0x7FFFu
+
+struct NwbPkConsts {
+    int a_match, a_mis, c; /* a_match = 2d+m, a_mis = 2d-k, c = m+k            */
+    int shift;             /* characters are pre-shifted by this many bits     */
+    unsigned TT1;          /* (a_match + 1) in both halves                     */
+    unsigned AMIS;         /* a_mis in both halves                             */
+};
+
+/* The packed path needs 0 <= a_mis <= a_match (mismatch never beats match, the
+ * mismatch diagonal is not negative) and a match/mismatch gap c that fits the
+ * character trick: (top ^ side) << shift is 0 on a match and >= 2^shift >= c
+ * otherwise, and a_match - 255 * 2^shift must not wrap a signed 16-bit half. */
+static inline bool nwb_pk_supported(int m, int k, int d, NwbPkConsts *pc)
+{
+    const long long am = 2LL * d + m, ax = 2LL * d - k, c = (long long)m + k;
+    if (ax < 0 || am < ax || am > 4000 || c > 128) return false;
+    int sh = 0;
+    while ((1LL << sh) < c) sh++;
+    if (sh > 7) return false;
+    if (pc) {
+        pc->a_match = (int)am;
+        pc->a_mis = (int)ax;
+        pc->c = (int)c;
+        pc->shift = sh;
+        pc->TT1 = (unsigned)(am + 1) * 0x00010001u;
+        pc->AMIS = (unsigned)ax * 0x00010001u;
+    }
+    return true;
+}
+
+/* Columns per half-lane: the smallest K whose strip count fits the resident
+ * warps (one warp per SM sub-partition), else 4 with cyclic passes. */
+static inline int nwb_pk_choose_k(int A, int B, int total_warps)
+{
+    (void)B;
+    for (int K = 1; K <= 4; K *= 2)
+        if ((A + 64 * K - 1) / (64 * K) <= total_warps) return K;
+    return 4;
+}
+
+#define NWB_PK_SMEM_BYTES(K) (NWB_PK_WARPS * NWB_PK_RING_ROWS * 32 * (K))
+
+template <int K>
+struct NwbPkStage;
+template <>
+struct NwbPkStage<4> { typedef uint32_t T; };
+template <>
+struct NwbPkStage<2> { typedef uint16_t T; };
+template <>
+struct NwbPkStage<1> { typedef uint8_t T; };
+
+template <int K, bool COUNT>
+__device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
+                                              unsigned char *stage_bytes, const int lane, long long &rsum)
+{
+    typedef typename NwbPkStage<K>::T stage_t;
+    stage_t *stage = reinterpret_cast<stage_t *>(stage_bytes);
+    const int A = p.A, B = p.B;
+    const int W = 64 * K;
+    const int col_lo = c * W + (2 * lane) * K + 1; /* first column (1-based) of the low block */
+    const int col_hi = col_lo + K;                 /* ... of the high block                   */
+    const unsigned ONE = 0x00010001u;
+
+    /* pre-shifted top characters of my columns: low block in the low half */
+    unsigned tpw[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const unsigned lo = (col_lo + k <= A) ? (unsigned)p.top[col_lo + k - 1] : 0u;
+        const unsigned hi = (col_hi + k <= A) ? (unsigned)p.top[col_hi + k - 1] : 0u;
+        tpw[k] = ((lo << pc.shift) | ((hi << pc.shift) << 16));
+    }
+
+    const int lc = c - p.strip_begin;
+    const bool has_left = (c > 0);
+    const bool left_remote = has_left && (lc == 0);
+    const bool publish = (c + 1 < p.n_strips);
+    const bool out_remote = publish && (c == p.strip_end - 1);
+    uint32_t *out_w = out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch;
+    int *out_flag = out_remote ? p.out_progress : p.progress + lc;
+    const uint32_t *in_w = nullptr;
+    const int *in_flag = nullptr;
+    if (has_left) {
+        in_w = left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch;
+        in_flag = left_remote ? p.in_progress : p.progress + (lc - 1);
+    }
+
+    unsigned u[K]; /* u of my columns in the previous row (both halves) */
+#pragma unroll
+    for (int k = 0; k < K; k++) u[k] = 0u;
+    unsigned vlast = NWB_PK_BIG * ONE;    /* v of my last columns (virtual rows: BIG)   */
+    unsigned send = NWB_PK_BIG << 16;     /* {hi: v of my high block's last col, lo: side char of that row} */
+    unsigned sp = 0xFFFFFFFFu;            /* ~(side char << shift) of my two rows        */
+    unsigned acc_prev = 0u;               /* low-half nibbles of the previous step       */
+
+    const int nblocks = (B + 63 + 31) / 32;
+    for (int blk = 0; blk < nblocks; blk++) {
+        /* stream words for lane 0's low-half rows 32*blk+1 .. 32*blk+32 */
+        unsigned bq = 0u;
+        {
+            const int jj = 32 * blk + 1 + lane;
+            if (has_left) {
+                int need = 32 * blk + 32;
+                if (need > B) need = B;
+                nwb_wait_ge(in_flag, need, left_remote);
+                if (jj <= B) bq = in_w[jj];
+            } else if (jj <= B) {
+                /* column 0: v(0,j) = 0; the word also carries the row's side character */
+                bq = (~((unsigned)p.side[jj - 1] << pc.shift)) & 0xFFFFu;
+            }
+        }
+#pragma unroll 1
+        for (int t = 0; t < 32; t++) {
+            const int s = 32 * blk + t;
+            const int jl = s + 1 - 2 * lane; /* row of the low half  */
+            const int jh = jl - 1;           /* row of the high half */
+            unsigned recv = __shfl_up_sync(NWB_FULL_MASK, send, 1);
+            const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
+            if (lane == 0) recv = b;
+            /* left inputs: low half <- neighbour's high half, high half <- my low half */
+            unsigned vL = __byte_perm(recv, vlast, 0x5432);
+            sp = __byte_perm(recv, sp, 0x5410);
+            unsigned acc = 0u;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const unsigned nx = tpw[k] ^ sp;                            /* -x'-1 per half */
+                const unsigned a = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);    /* a_match or a_mis */
+                const unsigned z = __vimax3_s16x2(a, vL, u[k]);
+                const unsigned un = z - vL;
+                const unsigned vn = z - u[k];
+                const unsigned td = z - a;
+                const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
+                acc += fd << (4 * k);
+                acc += fl << (4 * k + 1);
+                acc += fu << (4 * k + 2);
+                u[k] = un;
+                vL = vn;
+            }
+            vlast = vL;
+            send = __byte_perm(sp, vlast, 0x7632);
+            /* arrow codes of row jh: low block from the previous step, high block from this one
+             * (stored inverted: a set bit = NO arrow; the flush flips them) */
+            if (jh >= 1 && jh <= B) {
+                stage_t w;
+                if (K == 4) w = (stage_t)__byte_perm(acc_prev, acc, 0x7610);
+                else if (K == 2) w = (stage_t)((acc_prev & 0xFFu) | ((acc >> 8) & 0xFF00u));
+                else w = (stage_t)((acc_prev & 0xFu) | ((acc >> 12) & 0xF0u));
+                stage[(jh & (NWB_PK_RING_ROWS - 1)) * 32 + lane] = w;
+                if (lane == 31 && publish) out_w[jh] = send;
+            }
+            acc_prev = acc;
+            /* bottom row: r(A,B) = sum of u(i,B) */
+            if (jl == B) {
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (col_lo + k <= A) rsum += (long long)(u[k] & 0xFFFFu);
+            }
+            if (jh == B) {
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (col_hi + k <= A) rsum += (long long)(u[k] >> 16);
+            }
+        }
+        __syncwarp();
+        /* rows <= 32*blk-31 are complete: flush the 32 newest complete rows, 16 B per lane */
+        {
+            const int jhi = 32 * blk - 31;
+            const int jlo = jhi - 31;
+            const int row_bytes = 32 * K;          /* bytes per strip row          */
+            const int lanes_per_row = row_bytes / 16;
+            const int rows_per_pass = 32 / lanes_per_row;
+            const int sub = lane % lanes_per_row;
+#pragma unroll
+            for (int r = 0; r < 32 / rows_per_pass; r++) {
+                const int j = jlo + r * rows_per_pass + lane / lanes_per_row;
+                if (j >= 1 && j <= B) {
+                    uint4 v = *reinterpret_cast<const uint4 *>(stage_bytes + (size_t)(j & (NWB_PK_RING_ROWS - 1)) * row_bytes + sub * 16);
+                    v.x = ~v.x & 0x77777777u; v.y = ~v.y & 0x77777777u;
+                    v.z = ~v.z & 0x77777777u; v.w = ~v.w & 0x77777777u;
+                    *reinterpret_cast<uint4 *>(p.arrows + (size_t)(j - 1) * p.pitch + (size_t)c * row_bytes + sub * 16) = v;
+                }
+            }
+        }
+        __syncwarp();
+        if (publish && lane == 31) {
+            int done = 32 * blk - 31;
+            if (done > B) done = B;
+            if (done >= 1) {
+                if (out_remote) {
+                    __threadfence_system();
+                    nwb_st_release_sys(out_flag, done);
+                } else {
+                    nwb_st_release_gpu(out_flag, done);
+                }
+            }
+        }
+    }
+}
+
+template <int K, bool COUNT>
+__global__ void __launch_bounds__(32 * NWB_PK_WARPS, 1) nwb_fill_pk_kernel(const NwbStripParams p, const NwbPkConsts pc)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nworkers = (int)gridDim.x * (int)(blockDim.x >> 5);
+    const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
+    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_RING_ROWS * 32 * K;
+
+    long long rsum = 0;
+    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
+        nwb_pk_strip<K, COUNT>(p, pc, c, stage, lane, rsum);
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+    if (lane == 0 && rsum) atomicAdd((unsigned long long *)&p.summary->rsum, (unsigned long long)rsum);
+}
+
+/* ---- branch counter over the finished nibble table -----------------------------
+ * get_branch_count() (walk-table.c:133-147): number of interior cells with two
+ * or more arrows.  The packed kernel does not count in its inner loop; this
+ * HBM-bound pass (0.5 B/cell) produces the counter when it is asked for. */
+__global__ void nwb_branch_count_kernel(const uint8_t *arrows, size_t pitch, int A, int B, int col_begin, int col_end,
+                                        unsigned *out)
+{
+    /* columns [col_begin, col_end) (0-based interior), whole 32-cell groups of 16 B */
+    const int g0 = col_begin / 32, g1 = (col_end + 31) / 32;
+    const long long groups = (long long)(g1 - g0) * B;
+    unsigned cnt = 0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < groups;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / (g1 - g0));
+        const int g = g0 + (int)(idx % (g1 - g0));
+        const uint4 v = *reinterpret_cast<const uint4 *>(arrows + (size_t)row * pitch + (size_t)g * 16);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int first = g * 32 + q * 8; /* 0-based column of nibble 0 */
+            unsigned x = w[q];
+            const unsigned b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u;
+            unsigned two = (b0 & b1) | (b0 & b2) | (b1 & b2);
+            /* keep columns in [col_begin, col_end) and < A */
+            int lo = col_begin - first, hi = (col_end < A ? col_end : A) - first;
+            if (lo < 0) lo = 0;
+            if (hi > 8) hi = 8;
+            unsigned mask = 0u;
+            if (hi > lo) mask = (hi >= 8 ? 0xFFFFFFFFu : ((1u << (4 * hi)) - 1u)) & ~((lo <= 0) ? 0u : ((1u << (4 * lo)) - 1u));
+            cnt += (unsigned)__popc(two & mask);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(NWB_FULL_MASK, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
 #ifndef NWB_EMU
 typedef int (*nwb_fail_fn)(cudaError_t, const char *);
-static inline int nwb_pk_launch(const NwbStripParams &, const NwbPkConsts &, int, bool, int, cudaStream_t, nwb_fail_fn)
+
+template <int K, bool COUNT>
+static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st, nwb_fail_fn fail)
 {
-    return -5;
+    auto kernel = nwb_fill_pk_kernel<K, COUNT>;
+    const size_t smem = NWB_PK_SMEM_BYTES(K);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    void *args[] = {(void *)&sp, (void *)&pc};
+    e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(32 * NWB_PK_WARPS), args, smem, st);
+    if (e != cudaSuccess) return fail(e, "cudaLaunchCooperativeKernel");
+    return 0;
+}
+
+static inline int nwb_pk_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int K, bool count, int grid,
+                                cudaStream_t st, nwb_fail_fn fail)
+{
+    if (count) return -5; /* the fused count lives in the general kernel for now */
+    switch (K) {
+    case 1: return nwb_pk_launch_k<1, false>(sp, pc, grid, st, fail);
+    case 2: return nwb_pk_launch_k<2, false>(sp, pc, grid, st, fail);
+    case 4: return nwb_pk_launch_k<4, false>(sp, pc, grid, st, fail);
+    default: return -1;
+    }
 }
 #endif

@@ -29,6 +29,8 @@ def lib() -> C.CDLL:
     if _lib is None:
         build()
         _lib = C.CDLL(os.path.join(HERE, "libnwb_emu.so"))
+        _lib.emu_pitch_pk.restype = C.c_size_t
+        _lib.emu_pitch_pk.argtypes = [C.c_int, C.c_int, C.c_int]
         for name in ("emu_pitch_i32", "emu_spitch_i32"):
             f = getattr(_lib, name)
             f.restype = C.c_size_t
@@ -61,6 +63,26 @@ def fill_i32(top, side, m, k, d, *, flags=0, grid=2, split=0):
     assert rc == 0
     return dict(opt_score=out.opt_score, branch_count=out.branch_count, greatest_abs=out.greatest_abs,
                 count=out.count, arrows=arrows, scores=scores, cntmat=cntmat, pitch=pitch)
+
+
+def pk_supported(m, k, d) -> bool:
+    return bool(lib().emu_pk_supported(m, k, d))
+
+
+def fill_pk(top, side, m, k, d, *, K=4, grid=2, split=0):
+    """Run nwb_fill_pk_kernel<K> (+ the branch-count pass) under the emulator."""
+    top, side = _b(top), _b(side)
+    a, b = len(top), len(side)
+    L = lib()
+    pitch = L.emu_pitch_pk(a, b, K)
+    arrows = np.full((b, pitch), 0xEE, np.uint8)
+    out = _Out()
+    L.emu_fill_pk.restype = C.c_int
+    L.emu_fill_pk.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_uint, C.c_int, C.c_void_p, C.POINTER(_Out)]
+    rc = L.emu_fill_pk(top, a, side, b, m, k, d, K, grid, split, arrows.ctypes.data_as(C.c_void_p), C.byref(out))
+    assert rc == 0, rc
+    return dict(opt_score=out.opt_score, branch_count=out.branch_count, arrows=arrows, pitch=pitch)
 
 
 def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:

@@ -189,6 +189,23 @@ static inline unsigned __vmaxu2(unsigned a, unsigned b)
 }
 static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
 static inline unsigned __vimax3_u16x2(unsigned a, unsigned b, unsigned c) { return __vmaxu2(__vmaxu2(a, b), c); }
+static inline int emu_s16(unsigned v) { return (int)(int16_t)(v & 0xffff); }
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c)
+{
+    /* per half: max((int16)(a + b), c), the add wraps in 16 bits */
+    const int lo = emu_s16((a & 0xffff) + (b & 0xffff)), hi = emu_s16((a >> 16) + (b >> 16));
+    const int clo = emu_s16(c), chi = emu_s16(c >> 16);
+    return EMU_PER_HALF((unsigned)(lo > clo ? lo : clo), (unsigned)(hi > chi ? hi : chi));
+}
+static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c)
+{
+    int lo = emu_s16(a), hi = emu_s16(a >> 16);
+    if (emu_s16(b) > lo) lo = emu_s16(b);
+    if (emu_s16(b >> 16) > hi) hi = emu_s16(b >> 16);
+    if (emu_s16(c) > lo) lo = emu_s16(c);
+    if (emu_s16(c >> 16) > hi) hi = emu_s16(c >> 16);
+    return EMU_PER_HALF((unsigned)lo, (unsigned)hi);
+}
 static inline unsigned __vadd2(unsigned a, unsigned b)
 {
     return EMU_PER_HALF((a & 0xffff) + (b & 0xffff), (a >> 16) + (b >> 16));

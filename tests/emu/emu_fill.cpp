@@ -7,6 +7,7 @@
 #include "emu_cuda.h"
 #include "nwb_layout.h"
 #include "nwb_fill_i32.cuh"
+#include "nwb_fill_pk.cuh"
 
 #include <vector>
 
@@ -15,6 +16,12 @@ static void run_i32(unsigned grid, const NwbStripParams &p)
 {
     emu_launch(grid, 32 * NWB_I32_WARPS, NWB_I32_SMEM_BYTES,
                [&]() { nwb_fill_i32_kernel<COUNT, SCORES, ABS, CNTMAT>(p); });
+}
+
+template <int K>
+static void run_pk_emu(unsigned grid, const NwbStripParams &p, const NwbPkConsts &pc)
+{
+    emu_launch(grid, 32 * NWB_PK_WARPS, NWB_PK_SMEM_BYTES(K), [&]() { nwb_fill_pk_kernel<K, false>(p, pc); });
 }
 
 extern "C" {
@@ -103,6 +110,68 @@ int emu_fill_i32(const char *top, int A, const char *side, int B, int m, int k, 
     out->count = sum.count;
     out->pitch = L.pitch;
     out->spitch = L.spitch;
+    return 0;
+}
+
+size_t emu_pitch_pk(int A, int B, int K) { return nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K).pitch; }
+int emu_pk_supported(int m, int k, int d) { return nwb_pk_supported(m, k, d, nullptr) ? 1 : 0; }
+
+int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K,
+                unsigned grid, int split, uint8_t *arrows, emu_out *out)
+{
+    NwbPkConsts pc;
+    if (!nwb_pk_supported(m, k, d, &pc)) return -5;
+    NwbLayout L = nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K);
+    std::vector<uint32_t> bnd_w((size_t)L.n_strips * L.bpitch, 0xdeadbeefu);
+    std::vector<int> progress((size_t)L.n_strips, 0);
+    NwbDevSummary sum;
+    memset(&sum, 0, sizeof(sum));
+    NwbStripParams p;
+    memset(&p, 0, sizeof(p));
+    p.top = (const uint8_t *)top;
+    p.side = (const uint8_t *)side;
+    p.A = A; p.B = B; p.m = m; p.k = k; p.d = d;
+    p.n_strips = L.n_strips;
+    p.strip_begin = 0;
+    p.strip_end = L.n_strips;
+    p.arrows = arrows;
+    p.pitch = L.pitch;
+    p.bnd_w = bnd_w.data();
+    p.bpitch = L.bpitch;
+    p.progress = progress.data();
+    p.summary = &sum;
+    auto launch = [&](const NwbStripParams &q) {
+        if (K == 1) run_pk_emu<1>(grid, q, pc);
+        else if (K == 2) run_pk_emu<2>(grid, q, pc);
+        else run_pk_emu<4>(grid, q, pc);
+    };
+    if (split > 0 && split < L.n_strips) {
+        NwbStripParams p0 = p, p1 = p;
+        std::vector<uint32_t> inbox_w(L.bpitch, 0xdeadbeefu);
+        int inbox_flag = 0;
+        std::vector<uint32_t> bnd1((size_t)L.n_strips * L.bpitch, 0xdeadbeefu);
+        std::vector<int> prog1((size_t)L.n_strips, 0);
+        p0.strip_end = split;
+        p0.out_bnd_w = inbox_w.data();
+        p0.out_progress = &inbox_flag;
+        p1.strip_begin = split;
+        p1.in_bnd_w = inbox_w.data();
+        p1.in_progress = &inbox_flag;
+        p1.bnd_w = bnd1.data();
+        p1.progress = prog1.data();
+        launch(p0);
+        launch(p1);
+    } else {
+        launch(p);
+    }
+    unsigned branches = 0;
+    emu_launch(3, 64, 0, [&]() { nwb_branch_count_kernel(arrows, L.pitch, A, B, 0, A, &branches); });
+    out->opt_score = (int)(sum.rsum - (long long)d * ((long long)A + B));
+    out->branch_count = branches;
+    out->greatest_abs = 0;
+    out->count = 0;
+    out->pitch = L.pitch;
+    out->spitch = 0;
     return 0;
 }
 }
