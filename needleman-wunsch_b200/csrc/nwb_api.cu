@@ -291,6 +291,10 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     int strip_w = NWB_I32_STRIP_W, pk_k = 0;
     if (p->kind == NWB_KIND_PK) {
         pk_k = nwb_pk_choose_k(A, B, p->sm_count * NWB_PK_WARPS * p->world);
+        if (const char *ek = getenv("NWB_PK_K")) { /* diagnostics */
+            const int v = atoi(ek);
+            if (v == 1 || v == 2 || v == 4) pk_k = v;
+        }
         strip_w = 64 * pk_k;
     }
     p->L = nwb_make_layout(A, B, p->kind, pk_k, strip_w);
@@ -349,6 +353,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     sp.bpitch = L.bpitch;
     sp.progress = p->progress.p;
     sp.summary = p->summary.p;
+    sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? 1 : 0;
     if (p->strip_begin > 0) {
         if (!p->inbox.base || L.bpitch > p->inbox.bpitch) return NWB_ERR_INVALID;
         sp.in_bnd_s = (const int32_t *)(p->inbox.base + p->inbox.off_s);

@@ -132,4 +132,5 @@ struct NwbStripParams {
     uint32_t *out_bnd_w;
     int *out_progress;
     NwbDevSummary *summary;
+    int debug_nowait; /* diagnostics: skip the inter-strip waits (results are wrong) */
 };

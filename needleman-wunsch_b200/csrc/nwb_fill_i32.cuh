@@ -80,7 +80,7 @@ __device__ __forceinline__ void nwb_i32_strip(const NwbStripParams &p, const int
         if (has_left) {
             int need = 32 * blk + 32;
             if (need > B) need = B;
-            nwb_wait_ge(in_flag, need, left_remote);
+            if (!p.debug_nowait) nwb_wait_ge(in_flag, need, left_remote);
             const int jj = 32 * blk + 1 + lane;
             if (jj <= B) {
                 bq_s = in_s[jj];

@@ -142,7 +142,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             if (has_left) {
                 int need = 32 * blk + 32;
                 if (need > B) need = B;
-                nwb_wait_ge(in_flag, need, left_remote);
+                if (!p.debug_nowait) nwb_wait_ge(in_flag, need, left_remote);
                 if (jj <= B) bq = in_w[jj];
             } else if (jj <= B) {
                 /* column 0: v(0,j) = 0; the word also carries the row's side character */
