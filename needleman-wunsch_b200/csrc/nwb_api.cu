@@ -272,7 +272,7 @@ static int run_i32(nwb_plan *p, const NwbStripParams &sp, int grid, cudaStream_t
 #undef L_
 }
 
-static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st);
+static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st);
 
 extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
 {
@@ -333,6 +333,8 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     }
     if (rc != NWB_OK) return rc;
     CK(cudaMemsetAsync(p->progress.p, 0, (size_t)nloc * sizeof(int), st));
+    /* the packed kernel's stream words validate themselves (bit 31): start from zero */
+    if (p->kind == NWB_KIND_PK) CK(cudaMemsetAsync(p->bnd_w.p, 0, (size_t)nloc * L.bpitch * sizeof(uint32_t), st));
 
     NwbStripParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -369,11 +371,15 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         sp.out_progress = (int *)(p->right_base + p->right.off_flag);
     }
 
-    const int warps = (p->kind == NWB_KIND_PK) ? NWB_PK_WARPS : NWB_I32_WARPS;
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
-    (void)warps;
+    /* one warp per SM sub-partition; a second one when there are more strips than that */
+    int pk_warps = (nloc > p->sm_count * NWB_PK_WARPS) ? NWB_PK_MAX_WARPS : NWB_PK_WARPS;
+    if (const char *ew = getenv("NWB_PK_WARPS")) { /* diagnostics */
+        const int v = atoi(ew);
+        if (v >= 1 && v <= NWB_PK_MAX_WARPS) pk_warps = v;
+    }
     CK(cudaEventRecord(p->ev0, st));
-    if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, st);
+    if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
     if (rc != NWB_OK) return rc;
     CK(cudaEventRecord(p->ev1, st));
@@ -391,9 +397,9 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     return NWB_OK;
 }
 
-static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st)
+static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st)
 {
-    return nwb_pk_launch(sp, pc, p->L.pk_k, (p->flags & NWB_WANT_COUNT) != 0, grid, st, cuda_fail);
+    return nwb_pk_launch(sp, pc, p->L.pk_k, (p->flags & NWB_WANT_COUNT) != 0, grid, warps, st, cuda_fail);
 }
 
 extern "C" int nwb_plan_reset_inbox(nwb_plan *p, void *stream)
@@ -402,7 +408,7 @@ extern "C" int nwb_plan_reset_inbox(nwb_plan *p, void *stream)
     if (!p->inbox.base) return NWB_OK;
     CK(cudaSetDevice(p->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-    CK(cudaMemsetAsync(p->inbox.base + p->inbox.off_flag, 0, 256, st));
+    CK(cudaMemsetAsync(p->inbox.base, 0, p->inbox.bytes, st));
     return NWB_OK;
 }
 

@@ -66,6 +66,30 @@ __device__ __forceinline__ void nwb_pause()
     __nanosleep(32);
 }
 
+/* relaxed (L2-coherent, L1-bypassing) 32-bit accesses for self-validating stream words */
+__device__ __forceinline__ unsigned nwb_ld_relaxed_u32(const uint32_t *p, bool sys)
+{
+#ifdef NWB_EMU
+    (void)sys;
+    return *(const volatile uint32_t *)p;
+#else
+    unsigned v;
+    if (sys) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void nwb_st_relaxed_u32(uint32_t *p, unsigned v, bool sys)
+{
+#ifdef NWB_EMU
+    (void)sys;
+    *(volatile uint32_t *)p = v;
+#else
+    if (sys) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
 /* Spin until *flag >= need.  `sys` selects system scope (peer memory). */
 __device__ __forceinline__ void nwb_wait_ge(const int *flag, int need, bool sys)
 {

@@ -36,7 +36,8 @@
 #pragma once
 #include "nwb_device.cuh"
 
-#define NWB_PK_WARPS 4
+#define NWB_PK_WARPS 4      /* default warps per block: one per SM sub-partition */
+#define NWB_PK_MAX_WARPS 8
 #define NWB_PK_RING_ROWS 128
 #define NWB_PK_BIG 0x7FFFu
 
@@ -79,7 +80,7 @@ static inline int nwb_pk_choose_k(int A, int B, int total_warps)
     return 4;
 }
 
-#define NWB_PK_SMEM_BYTES(K) (NWB_PK_WARPS * NWB_PK_RING_ROWS * 32 * (K))
+#define NWB_PK_SMEM_BYTES(K, WARPS) ((WARPS) * NWB_PK_RING_ROWS * 32 * (K))
 
 template <int K>
 struct NwbPkStage;
@@ -89,6 +90,85 @@ template <>
 struct NwbPkStage<2> { typedef uint16_t T; };
 template <>
 struct NwbPkStage<1> { typedef uint8_t T; };
+
+/* Boundary stream words validate themselves: bit 31 is set by the producer, the
+ * buffers are zeroed before every fill.  A consumer lane polls its own word with
+ * relaxed (L2) loads, so the hand-off needs neither a separate flag nor fences:
+ * every 32-bit word is written and read atomically and carries everything the
+ * consumer needs for that row ({v of the boundary column, side character}). */
+#define NWB_PK_VALID 0x80000000u
+
+template <int K>
+struct NwbPkState {
+    unsigned tpw[K]; /* pre-shifted top characters of my columns (low block | high block) */
+    unsigned u[K];   /* u of my columns in the previous row                                */
+    unsigned vlast;  /* v of my last columns (virtual rows: BIG)                           */
+    unsigned send;   /* {hi: v of my high block's last column, lo: side char of that row}  */
+    unsigned sp;     /* ~(side char << shift) of my two rows                               */
+    unsigned acc_prev; /* low-half arrow nibbles of the previous step                      */
+};
+
+/* One row step of one lane: 2*K cells.  CHECKED adds the row-range tests needed
+ * while some lanes are still above row 1 or already below row B. */
+template <int K, bool CHECKED>
+__device__ __forceinline__ void nwb_pk_step(NwbPkState<K> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
+                                             const int lane, const int jh, const int A, const int B,
+                                             const int col_lo, const int col_hi,
+                                             typename NwbPkStage<K>::T *stage, uint32_t *out_w, const bool pub31,
+                                             const bool out_remote, long long &rsum)
+{
+    typedef typename NwbPkStage<K>::T stage_t;
+    const unsigned ONE = 0x00010001u;
+    unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
+    const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
+    if (lane == 0) recv = b;
+    /* left inputs: low half <- neighbour's high half, high half <- my own low half */
+    unsigned vL = __byte_perm(recv, st.vlast, 0x5432);
+    st.sp = __byte_perm(recv, st.sp, 0x5410);
+    unsigned code[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const unsigned nx = st.tpw[k] ^ st.sp;                          /* -x'-1 per half     */
+        const unsigned a = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);      /* a_match or a_mis   */
+        const unsigned z = __vimax3_s16x2(a, vL, st.u[k]);
+        const unsigned un = z - vL;
+        const unsigned vn = z - st.u[k];
+        const unsigned td = z - a;
+        const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
+        code[k] = fd + fl * 2u + fu * 4u; /* inverted: a set bit = NO arrow */
+        st.u[k] = un;
+        vL = vn;
+    }
+    st.vlast = vL;
+    st.send = __byte_perm(st.sp, vL, 0x7632);
+    unsigned acc;
+    if (K == 4) acc = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
+    else if (K == 2) acc = code[0] + code[1] * 16u;
+    else acc = code[0];
+    /* arrow codes of row jh: low block from the previous step, high block from this one */
+    if (!CHECKED || (jh >= 1 && jh <= B)) {
+        stage_t w;
+        if (K == 4) w = (stage_t)__byte_perm(st.acc_prev, acc, 0x7610);
+        else if (K == 2) w = (stage_t)((st.acc_prev & 0xFFu) | ((acc >> 8) & 0xFF00u));
+        else w = (stage_t)((st.acc_prev & 0xFu) | ((acc >> 12) & 0xF0u));
+        stage[(jh & (NWB_PK_RING_ROWS - 1)) * 32 + lane] = w;
+        if (pub31) nwb_st_relaxed_u32(out_w + jh, st.send | NWB_PK_VALID, out_remote);
+    }
+    st.acc_prev = acc;
+    if (CHECKED) {
+        /* bottom row: r(A,B) = sum of u(i,B) */
+        if (jh + 1 == B) {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (col_lo + k <= A) rsum += (long long)(st.u[k] & 0xFFFFu);
+        }
+        if (jh == B) {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                if (col_hi + k <= A) rsum += (long long)(st.u[k] >> 16);
+        }
+    }
+}
 
 template <int K, bool COUNT>
 __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
@@ -102,14 +182,18 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     const int col_hi = col_lo + K;                 /* ... of the high block                   */
     const unsigned ONE = 0x00010001u;
 
-    /* pre-shifted top characters of my columns: low block in the low half */
-    unsigned tpw[K];
+    NwbPkState<K> st;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const unsigned lo = (col_lo + k <= A) ? (unsigned)p.top[col_lo + k - 1] : 0u;
         const unsigned hi = (col_hi + k <= A) ? (unsigned)p.top[col_hi + k - 1] : 0u;
-        tpw[k] = ((lo << pc.shift) | ((hi << pc.shift) << 16));
+        st.tpw[k] = ((lo << pc.shift) | ((hi << pc.shift) << 16));
+        st.u[k] = 0u;
     }
+    st.vlast = NWB_PK_BIG * ONE;
+    st.send = NWB_PK_BIG << 16;
+    st.sp = 0xFFFFFFFFu;
+    st.acc_prev = 0u;
 
     const int lc = c - p.strip_begin;
     const bool has_left = (c > 0);
@@ -117,89 +201,59 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     const bool publish = (c + 1 < p.n_strips);
     const bool out_remote = publish && (c == p.strip_end - 1);
     uint32_t *out_w = out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch;
-    int *out_flag = out_remote ? p.out_progress : p.progress + lc;
     const uint32_t *in_w = nullptr;
-    const int *in_flag = nullptr;
-    if (has_left) {
-        in_w = left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch;
-        in_flag = left_remote ? p.in_progress : p.progress + (lc - 1);
-    }
+    if (has_left) in_w = left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch;
+    const bool pub31 = publish && (lane == 31);
 
-    unsigned u[K]; /* u of my columns in the previous row (both halves) */
-#pragma unroll
-    for (int k = 0; k < K; k++) u[k] = 0u;
-    unsigned vlast = NWB_PK_BIG * ONE;    /* v of my last columns (virtual rows: BIG)   */
-    unsigned send = NWB_PK_BIG << 16;     /* {hi: v of my high block's last col, lo: side char of that row} */
-    unsigned sp = 0xFFFFFFFFu;            /* ~(side char << shift) of my two rows        */
-    unsigned acc_prev = 0u;               /* low-half nibbles of the previous step       */
+    /* stream word of row j for lane 0: from the left strip, or synthesised for column 0
+     * (v(0,j) = 0 plus the row's side character) */
+    unsigned bq_next = 0u;
+    {
+        const int jj = 1 + lane;
+        if (jj <= B) {
+            if (has_left) bq_next = nwb_ld_relaxed_u32(in_w + jj, left_remote);
+            else bq_next = ((~((unsigned)p.side[jj - 1] << pc.shift)) & 0xFFFFu) | NWB_PK_VALID;
+        }
+    }
 
     const int nblocks = (B + 63 + 31) / 32;
     for (int blk = 0; blk < nblocks; blk++) {
-        /* stream words for lane 0's low-half rows 32*blk+1 .. 32*blk+32 */
-        unsigned bq = 0u;
+        /* stream words for lane 0's low-half rows 32*blk+1 .. 32*blk+32 (prefetched one block ahead) */
+        unsigned bq;
         {
             const int jj = 32 * blk + 1 + lane;
-            if (has_left) {
-                int need = 32 * blk + 32;
-                if (need > B) need = B;
-                if (!p.debug_nowait) nwb_wait_ge(in_flag, need, left_remote);
-                if (jj <= B) bq = in_w[jj];
-            } else if (jj <= B) {
-                /* column 0: v(0,j) = 0; the word also carries the row's side character */
-                bq = (~((unsigned)p.side[jj - 1] << pc.shift)) & 0xFFFFu;
+            unsigned w = bq_next;
+            if (has_left && !p.debug_nowait) {
+                bool ok = (jj > B) || (w & NWB_PK_VALID);
+                while (!__all_sync(NWB_FULL_MASK, ok)) {
+                    if (!ok) {
+                        nwb_pause();
+                        w = nwb_ld_relaxed_u32(in_w + jj, left_remote);
+                        ok = (w & NWB_PK_VALID) != 0u;
+                    }
+                }
+            }
+            bq = w & ~NWB_PK_VALID;
+            const int jn = jj + 32;
+            bq_next = 0u;
+            if (jn <= B) {
+                if (has_left) bq_next = nwb_ld_relaxed_u32(in_w + jn, left_remote);
+                else bq_next = ((~((unsigned)p.side[jn - 1] << pc.shift)) & 0xFFFFu) | NWB_PK_VALID;
             }
         }
+        const int s0 = 32 * blk;
+        /* every lane inside rows 1..B for the whole block?  (lane 31's high half is the last
+         * to enter: row s-62; lane 0's low half the first to leave: row s+1) */
+        if (s0 >= 63 && s0 + 32 <= B) {
 #pragma unroll 1
-        for (int t = 0; t < 32; t++) {
-            const int s = 32 * blk + t;
-            const int jl = s + 1 - 2 * lane; /* row of the low half  */
-            const int jh = jl - 1;           /* row of the high half */
-            unsigned recv = __shfl_up_sync(NWB_FULL_MASK, send, 1);
-            const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
-            if (lane == 0) recv = b;
-            /* left inputs: low half <- neighbour's high half, high half <- my low half */
-            unsigned vL = __byte_perm(recv, vlast, 0x5432);
-            sp = __byte_perm(recv, sp, 0x5410);
-            unsigned acc = 0u;
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const unsigned nx = tpw[k] ^ sp;                            /* -x'-1 per half */
-                const unsigned a = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);    /* a_match or a_mis */
-                const unsigned z = __vimax3_s16x2(a, vL, u[k]);
-                const unsigned un = z - vL;
-                const unsigned vn = z - u[k];
-                const unsigned td = z - a;
-                const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
-                acc += fd << (4 * k);
-                acc += fl << (4 * k + 1);
-                acc += fu << (4 * k + 2);
-                u[k] = un;
-                vL = vn;
-            }
-            vlast = vL;
-            send = __byte_perm(sp, vlast, 0x7632);
-            /* arrow codes of row jh: low block from the previous step, high block from this one
-             * (stored inverted: a set bit = NO arrow; the flush flips them) */
-            if (jh >= 1 && jh <= B) {
-                stage_t w;
-                if (K == 4) w = (stage_t)__byte_perm(acc_prev, acc, 0x7610);
-                else if (K == 2) w = (stage_t)((acc_prev & 0xFFu) | ((acc >> 8) & 0xFF00u));
-                else w = (stage_t)((acc_prev & 0xFu) | ((acc >> 12) & 0xF0u));
-                stage[(jh & (NWB_PK_RING_ROWS - 1)) * 32 + lane] = w;
-                if (lane == 31 && publish) out_w[jh] = send;
-            }
-            acc_prev = acc;
-            /* bottom row: r(A,B) = sum of u(i,B) */
-            if (jl == B) {
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (col_lo + k <= A) rsum += (long long)(u[k] & 0xFFFFu);
-            }
-            if (jh == B) {
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (col_hi + k <= A) rsum += (long long)(u[k] >> 16);
-            }
+            for (int t = 0; t < 32; t++)
+                nwb_pk_step<K, false>(st, pc, bq, t, lane, s0 + t - 2 * lane, A, B, col_lo, col_hi, stage, out_w, pub31,
+                                      out_remote, rsum);
+        } else {
+#pragma unroll 1
+            for (int t = 0; t < 32; t++)
+                nwb_pk_step<K, true>(st, pc, bq, t, lane, s0 + t - 2 * lane, A, B, col_lo, col_hi, stage, out_w, pub31,
+                                     out_remote, rsum);
         }
         __syncwarp();
         /* rows <= 32*blk-31 are complete: flush the 32 newest complete rows, 16 B per lane */
@@ -222,23 +276,11 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             }
         }
         __syncwarp();
-        if (publish && lane == 31) {
-            int done = 32 * blk - 31;
-            if (done > B) done = B;
-            if (done >= 1) {
-                if (out_remote) {
-                    __threadfence_system();
-                    nwb_st_release_sys(out_flag, done);
-                } else {
-                    nwb_st_release_gpu(out_flag, done);
-                }
-            }
-        }
     }
 }
 
 template <int K, bool COUNT>
-__global__ void __launch_bounds__(32 * NWB_PK_WARPS, 1) nwb_fill_pk_kernel(const NwbStripParams p, const NwbPkConsts pc)
+__global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(const NwbStripParams p, const NwbPkConsts pc)
 {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -296,26 +338,27 @@ __global__ void nwb_branch_count_kernel(const uint8_t *arrows, size_t pitch, int
 typedef int (*nwb_fail_fn)(cudaError_t, const char *);
 
 template <int K, bool COUNT>
-static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st, nwb_fail_fn fail)
+static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st,
+                           nwb_fail_fn fail)
 {
     auto kernel = nwb_fill_pk_kernel<K, COUNT>;
-    const size_t smem = NWB_PK_SMEM_BYTES(K);
+    const size_t smem = NWB_PK_SMEM_BYTES(K, warps);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     void *args[] = {(void *)&sp, (void *)&pc};
-    e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(32 * NWB_PK_WARPS), args, smem, st);
+    e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(32 * warps), args, smem, st);
     if (e != cudaSuccess) return fail(e, "cudaLaunchCooperativeKernel");
     return 0;
 }
 
 static inline int nwb_pk_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int K, bool count, int grid,
-                                cudaStream_t st, nwb_fail_fn fail)
+                                int warps, cudaStream_t st, nwb_fail_fn fail)
 {
     if (count) return -5; /* the fused count lives in the general kernel for now */
     switch (K) {
-    case 1: return nwb_pk_launch_k<1, false>(sp, pc, grid, st, fail);
-    case 2: return nwb_pk_launch_k<2, false>(sp, pc, grid, st, fail);
-    case 4: return nwb_pk_launch_k<4, false>(sp, pc, grid, st, fail);
+    case 1: return nwb_pk_launch_k<1, false>(sp, pc, grid, warps, st, fail);
+    case 2: return nwb_pk_launch_k<2, false>(sp, pc, grid, warps, st, fail);
+    case 4: return nwb_pk_launch_k<4, false>(sp, pc, grid, warps, st, fail);
     default: return -1;
     }
 }

@@ -133,6 +133,16 @@ static inline T __shfl_xor_sync(unsigned m, T v, int mask, int = 32)
     return __shfl_sync(m, v, emu_cur->lane ^ mask);
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier(); }
+static inline int __all_sync(unsigned, int pred)
+{
+    emu_warp *w = emu_cur->warp;
+    w->slot[emu_cur->lane] = pred ? 1 : 0;
+    emu_warp_barrier();
+    int all = 1;
+    for (int i = 0; i < w->nlanes; i++) all &= (int)w->slot[i];
+    emu_warp_barrier();
+    return all;
+}
 static inline void __syncthreads(void)
 {
     emu_block *b = emu_cur->block;

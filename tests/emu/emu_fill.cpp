@@ -19,9 +19,9 @@ static void run_i32(unsigned grid, const NwbStripParams &p)
 }
 
 template <int K>
-static void run_pk_emu(unsigned grid, const NwbStripParams &p, const NwbPkConsts &pc)
+static void run_pk_emu(unsigned grid, int warps, const NwbStripParams &p, const NwbPkConsts &pc)
 {
-    emu_launch(grid, 32 * NWB_PK_WARPS, NWB_PK_SMEM_BYTES(K), [&]() { nwb_fill_pk_kernel<K, false>(p, pc); });
+    emu_launch(grid, 32 * warps, NWB_PK_SMEM_BYTES(K, warps), [&]() { nwb_fill_pk_kernel<K, false>(p, pc); });
 }
 
 extern "C" {
@@ -117,12 +117,12 @@ size_t emu_pitch_pk(int A, int B, int K) { return nwb_make_layout(A, B, NWB_KIND
 int emu_pk_supported(int m, int k, int d) { return nwb_pk_supported(m, k, d, nullptr) ? 1 : 0; }
 
 int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K,
-                unsigned grid, int split, uint8_t *arrows, emu_out *out)
+                unsigned grid, int warps, int split, uint8_t *arrows, emu_out *out)
 {
     NwbPkConsts pc;
     if (!nwb_pk_supported(m, k, d, &pc)) return -5;
     NwbLayout L = nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K);
-    std::vector<uint32_t> bnd_w((size_t)L.n_strips * L.bpitch, 0xdeadbeefu);
+    std::vector<uint32_t> bnd_w((size_t)L.n_strips * L.bpitch, 0u);
     std::vector<int> progress((size_t)L.n_strips, 0);
     NwbDevSummary sum;
     memset(&sum, 0, sizeof(sum));
@@ -141,15 +141,15 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.progress = progress.data();
     p.summary = &sum;
     auto launch = [&](const NwbStripParams &q) {
-        if (K == 1) run_pk_emu<1>(grid, q, pc);
-        else if (K == 2) run_pk_emu<2>(grid, q, pc);
-        else run_pk_emu<4>(grid, q, pc);
+        if (K == 1) run_pk_emu<1>(grid, warps, q, pc);
+        else if (K == 2) run_pk_emu<2>(grid, warps, q, pc);
+        else run_pk_emu<4>(grid, warps, q, pc);
     };
     if (split > 0 && split < L.n_strips) {
         NwbStripParams p0 = p, p1 = p;
-        std::vector<uint32_t> inbox_w(L.bpitch, 0xdeadbeefu);
+        std::vector<uint32_t> inbox_w(L.bpitch, 0u);
         int inbox_flag = 0;
-        std::vector<uint32_t> bnd1((size_t)L.n_strips * L.bpitch, 0xdeadbeefu);
+        std::vector<uint32_t> bnd1((size_t)L.n_strips * L.bpitch, 0u);
         std::vector<int> prog1((size_t)L.n_strips, 0);
         p0.strip_end = split;
         p0.out_bnd_w = inbox_w.data();

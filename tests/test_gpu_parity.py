@@ -41,16 +41,30 @@ def check_arrows(oracle, nwb, tab, t, s, m, k, d):
     return o
 
 
+def pk_supported(m, k, d):
+    """The packed 16x2 kernel's precondition (csrc/nwb_fill_pk.cuh nwb_pk_supported)."""
+    return 0 <= 2 * d - k <= 2 * d + m <= 4000 and m + k <= 128
+
+
 def full_check(oracle, nwb, t, s, m, k, d, extra_flags=0, num_gpus=1):
+    """Count-fused general kernel AND (without count) the automatically selected
+    kernel -- the packed 16x2 one whenever the scheme allows it."""
+    o = oracle.fill(t, s, m, k, d)
     flags = nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | extra_flags
     tab = nwb.fill(t, s, m, k, d, flags, num_gpus=num_gpus)
-    o = oracle.fill(t, s, m, k, d)
     assert tab.opt_score == o.final_score
     assert tab.branch_count == o.branch_count
     assert tab.count == o.count
     if extra_flags & nwb.TRACK_ABS:
         assert tab.greatest_abs == o.greatest_abs
     check_arrows(oracle, nwb, tab, t, s, m, k, d)
+    if not (extra_flags & (nwb.FORCE_GENERAL | nwb.TRACK_ABS)):
+        tab2 = nwb.fill(t, s, m, k, d, nwb.WANT_ARROWS_HOST, num_gpus=num_gpus)
+        if len(t) and len(s):
+            assert tab2.kernel_kind == (nwb.KIND_PK if pk_supported(m, k, d) else nwb.KIND_I32)
+        assert tab2.opt_score == o.final_score
+        assert tab2.branch_count == o.branch_count
+        check_arrows(oracle, nwb, tab2, t, s, m, k, d)
     return tab
 
 
@@ -76,6 +90,7 @@ def test_readme_example_every_cell(oracle, nwb, force):
 def test_goldens(oracle, nwb, case, force):
     t, s = case_strings(oracle, case)
     ff = nwb.FORCE_GENERAL if force else 0
+    tab = full_check(oracle, nwb, t, s, case["m"], case["k"], case["d"], ff)
     tab = full_check(oracle, nwb, t, s, case["m"], case["k"], case["d"], nwb.TRACK_ABS | ff)
     assert tab.opt_score == case["final_score"]
     assert tab.branch_count == case["branch_count"]
@@ -123,7 +138,8 @@ def test_config2_dna_10k(oracle, nwb, force):
     """BASELINE config 2 (10k x 10k DNA, 1 1 1, -q -s) vs the reference's goldens."""
     t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
     ff = nwb.FORCE_GENERAL if force else 0
-    tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | ff)
+    tab = nwb.fill(t, s, 1, 1, 1, (nwb.WANT_COUNT if force else 0) | nwb.WANT_ARROWS_HOST | ff)
+    assert tab.kernel_kind == (nwb.KIND_I32 if force else nwb.KIND_PK)
     assert (tab.opt_score, tab.branch_count, tab.count) == (1056, 34377799, 0)
     check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
 
@@ -137,6 +153,9 @@ def test_config5_protein_30k_summary(oracle, nwb):
     t, s = oracle.generate_pair(0x5EED0005, 30000, 30000, oracle.PROTEIN)
     tab = nwb.fill(t, s, 2, 1, 2, nwb.WANT_COUNT)
     assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"])
+    tab = nwb.fill(t, s, 2, 1, 2, 0)
+    assert tab.kernel_kind == nwb.KIND_PK
+    assert (tab.opt_score, tab.branch_count) == (g["final_score"], g["branch_count"])
 
 
 def test_config3_dna_100k_properties(oracle, nwb):
@@ -146,22 +165,28 @@ def test_config3_dna_100k_properties(oracle, nwb):
     every strip hand-off; (2) swapping the strings transposes the table, so
     score, count and branch count are equal; (3) golden summary if recorded."""
     t, s = oracle.generate_pair(0x5EED0030, 100000, 100000)
-    plan = nwb.Plan(100000, 100000, nwb.WANT_COUNT)
-    plan.upload(t, s)
-    plan.run(1, 1, 1)
-    sm = plan.summary()
-    R = 1500
-    rows = plan.download_arrows(0, R)
-    o = oracle.fill(t, s[:R], 1, 1, 1, want_packed=True, pitch=rows.shape[1])
-    assert np.array_equal(rows[:, :50000] & 0x77, o.packed[:, :50000])
-    plan.upload(s, t)
-    plan.run(1, 1, 1)
-    sm2 = plan.summary()
-    assert (sm.opt_score, sm.count, sm.branch_count) == (sm2.opt_score, sm2.count, sm2.branch_count)
     g = [c for c in golden("golden_big.json") if c["name"] == "config3_dna_100k"]
-    if g:
-        assert (sm.opt_score, sm.branch_count, sm.count) == (g[0]["final_score"], g[0]["branch_count"], g[0]["count_u64"])
-    plan.close()
+    R = 1500
+    o = None
+    for flags, kind in ((0, nwb.KIND_PK), (nwb.WANT_COUNT, nwb.KIND_I32)):
+        plan = nwb.Plan(100000, 100000, flags)
+        plan.upload(t, s)
+        plan.run(1, 1, 1)
+        sm = plan.summary()
+        assert sm.kernel_kind == kind
+        rows = plan.download_arrows(0, R)
+        if o is None or o.packed.shape[1] != rows.shape[1]:
+            o = oracle.fill(t, s[:R], 1, 1, 1, want_packed=True, pitch=rows.shape[1])
+        assert np.array_equal(rows[:, :50000] & 0x77, o.packed[:, :50000])
+        plan.upload(s, t)
+        plan.run(1, 1, 1)
+        sm2 = plan.summary()
+        assert (sm.opt_score, sm.count, sm.branch_count) == (sm2.opt_score, sm2.count, sm2.branch_count)
+        if g:
+            assert (sm.opt_score, sm.branch_count) == (g[0]["final_score"], g[0]["branch_count"])
+            if flags & nwb.WANT_COUNT:
+                assert sm.count == g[0]["count_u64"]
+        plan.close()
 
 
 def test_two_gpu_strips_match_one(oracle, nwb):
