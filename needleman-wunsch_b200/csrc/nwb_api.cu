@@ -117,6 +117,7 @@ struct nwb_plan {
     DevBuf<int32_t> scores, bnd_s;
     DevBuf<unsigned long long> cntmat, bnd_c;
     DevBuf<uint32_t> bnd_w;
+    DevBuf<uint16_t> side_pre;
     DevBuf<int> progress;
     DevBuf<NwbDevSummary> summary;
     Inbox inbox = {};
@@ -202,7 +203,7 @@ extern "C" void nwb_plan_destroy(nwb_plan *p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     p->top.release(); p->side.release(); p->arrows.release(); p->scores.release();
     p->bnd_s.release(); p->cntmat.release(); p->bnd_c.release(); p->bnd_w.release();
-    p->progress.release(); p->summary.release();
+    p->progress.release(); p->summary.release(); p->side_pre.release();
     if (p->inbox.base) cudaFree(p->inbox.base);
     if (p->right_base && p->right_is_ipc) cudaIpcCloseMemHandle(p->right_base);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -329,6 +330,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     }
     if (rc == NWB_OK && p->kind == NWB_KIND_PK) {
         rc = p->bnd_w.ensure((size_t)nloc * L.bpitch);
+        if (rc == NWB_OK) rc = p->side_pre.ensure(NWB_PK_SPRE_LEN(B));
         if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * L.bpitch);
     }
     if (rc != NWB_OK) return rc;
@@ -340,6 +342,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     memset(&sp, 0, sizeof(sp));
     sp.top = p->top.p;
     sp.side = p->side.p;
+    sp.side_pre = p->side_pre.p;
     sp.A = A; sp.B = B; sp.m = m; sp.k = k; sp.d = d;
     sp.n_strips = L.n_strips;
     sp.strip_begin = p->strip_begin;
@@ -379,6 +382,11 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         if (v >= 1 && v <= NWB_PK_MAX_WARPS) pk_warps = v;
     }
     CK(cudaEventRecord(p->ev0, st));
+    if (p->kind == NWB_KIND_PK) {
+        nwb_pk_prep_side_kernel<<<64, 256, 0, st>>>(p->side.p, B, pc.shift, p->side_pre.p);
+        CK(cudaGetLastError());
+        p->launches += 1;
+    }
     if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
     if (rc != NWB_OK) return rc;

@@ -66,6 +66,16 @@ __device__ __forceinline__ void nwb_pause()
     __nanosleep(32);
 }
 
+/* read-only (non-coherent) 16-bit load */
+__device__ __forceinline__ unsigned short nwb_ldg_u16(const uint16_t *p)
+{
+#ifdef NWB_EMU
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
+
 /* relaxed (L2-coherent, L1-bypassing) 32-bit accesses for self-validating stream words */
 __device__ __forceinline__ unsigned nwb_ld_relaxed_u32(const uint32_t *p, bool sys)
 {
@@ -129,6 +139,7 @@ struct NwbDevSummary {
 struct NwbStripParams {
     const uint8_t *top;  /* A bytes  */
     const uint8_t *side; /* B bytes  */
+    const uint16_t *side_pre; /* packed kernel: pre-shifted, complemented, padded side string */
     int A, B;
     int m, k, d;
     int n_strips;     /* total strips of the table                         */

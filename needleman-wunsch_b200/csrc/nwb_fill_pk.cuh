@@ -80,7 +80,7 @@ static inline int nwb_pk_choose_k(int A, int B, int total_warps)
     return 4;
 }
 
-#define NWB_PK_SMEM_BYTES(K, WARPS) ((WARPS) * NWB_PK_RING_ROWS * 32 * (K))
+#define NWB_PK_SMEM_BYTES(K, WARPS) ((WARPS) * NWB_PK_RING_ROWS * (32 * (K) + 4))
 
 template <int K>
 struct NwbPkStage;
@@ -91,40 +91,73 @@ struct NwbPkStage<2> { typedef uint16_t T; };
 template <>
 struct NwbPkStage<1> { typedef uint8_t T; };
 
-/* Boundary stream words validate themselves: bit 31 is set by the producer, the
- * buffers are zeroed before every fill.  A consumer lane polls its own word with
- * relaxed (L2) loads, so the hand-off needs neither a separate flag nor fences:
- * every 32-bit word is written and read atomically and carries everything the
- * consumer needs for that row ({v of the boundary column, side character}). */
+/* Boundary stream words validate themselves: {bit 31: valid, bits 16..30: v of the
+ * strip's last column in that row}.  The buffers are zeroed before every fill; a
+ * consumer lane polls its own word with relaxed (L2) loads, so the hand-off needs
+ * neither a separate flag nor fences: every 32-bit word is written and read
+ * atomically and is all the consumer needs from the left strip for that row. */
 #define NWB_PK_VALID 0x80000000u
+/* The side string is pre-shifted and complemented once per fill into a uint16
+ * array padded on both sides, so the row loop never range-checks its index:
+ * side_pre[j + NWB_PK_SPAD] = ~(side[j-1] << shift) & 0xFFFF for 1 <= j <= B. */
+#define NWB_PK_SPAD 64
+#define NWB_PK_SPRE_LEN(B) ((size_t)(B) + NWB_PK_SPAD + 160)
+
+__global__ void nwb_pk_prep_side_kernel(const uint8_t *side, int B, int shift, uint16_t *side_pre)
+{
+    const size_t n = NWB_PK_SPRE_LEN(B);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const long long j = (long long)i - NWB_PK_SPAD;
+        unsigned v = 0xFFFFu;
+        if (j >= 1 && j <= B) v = (~((unsigned)side[j - 1] << shift)) & 0xFFFFu;
+        side_pre[i] = (uint16_t)v;
+    }
+}
+
+/* staging ring: one slot per row STEP (not per row): at step s every lane writes
+ * slot s & 127, so the address is a block base plus an immediate; the flush
+ * un-skews (row j of lane l sits in slot (j + 2l) & 127).  One pad word per slot
+ * keeps the un-skewing reads free of bank conflicts. */
+#define NWB_PK_SLOT_BYTES(K) (32 * (K) + 4)
 
 template <int K>
 struct NwbPkState {
     unsigned tpw[K]; /* pre-shifted top characters of my columns (low block | high block) */
     unsigned u[K];   /* u of my columns in the previous row                                */
     unsigned vlast;  /* v of my last columns (virtual rows: BIG)                           */
-    unsigned send;   /* {hi: v of my high block's last column, lo: side char of that row}  */
     unsigned sp;     /* ~(side char << shift) of my two rows                               */
     unsigned acc_prev; /* low-half arrow nibbles of the previous step                      */
 };
+
+__device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v, bool pred)
+{
+#ifdef NWB_EMU
+    if (pred) *(volatile uint32_t *)p = v;
+#else
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.relaxed.sys.global.u32 [%0], %1;\n\t}"
+                 ::"l"(p), "r"(v), "r"((unsigned)pred)
+                 : "memory");
+#endif
+}
 
 /* One row step of one lane: 2*K cells.  CHECKED adds the row-range tests needed
  * while some lanes are still above row 1 or already below row B. */
 template <int K, bool CHECKED>
 __device__ __forceinline__ void nwb_pk_step(NwbPkState<K> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
                                              const int lane, const int jh, const int A, const int B,
-                                             const int col_lo, const int col_hi,
-                                             typename NwbPkStage<K>::T *stage, uint32_t *out_w, const bool pub31,
-                                             const bool out_remote, long long &rsum)
+                                             const int col_lo, const int col_hi, const unsigned scn,
+                                             typename NwbPkStage<K>::T *slot, uint32_t *out_w, const bool pub31,
+                                             long long &rsum)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
-    unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
+    unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.vlast, 1);
     const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
     if (lane == 0) recv = b;
     /* left inputs: low half <- neighbour's high half, high half <- my own low half */
     unsigned vL = __byte_perm(recv, st.vlast, 0x5432);
-    st.sp = __byte_perm(recv, st.sp, 0x5410);
+    /* side characters: low half <- this step's row, high half <- my previous low row */
+    st.sp = __byte_perm(scn, st.sp, 0x5410);
     unsigned code[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -140,7 +173,6 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K> &st, const NwbPkConsts
         vL = vn;
     }
     st.vlast = vL;
-    st.send = __byte_perm(st.sp, vL, 0x7632);
     unsigned acc;
     if (K == 4) acc = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
     else if (K == 2) acc = code[0] + code[1] * 16u;
@@ -151,8 +183,9 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K> &st, const NwbPkConsts
         if (K == 4) w = (stage_t)__byte_perm(st.acc_prev, acc, 0x7610);
         else if (K == 2) w = (stage_t)((st.acc_prev & 0xFFu) | ((acc >> 8) & 0xFF00u));
         else w = (stage_t)((st.acc_prev & 0xFu) | ((acc >> 12) & 0xF0u));
-        stage[(jh & (NWB_PK_RING_ROWS - 1)) * 32 + lane] = w;
-        if (pub31) nwb_st_relaxed_u32(out_w + jh, st.send | NWB_PK_VALID, out_remote);
+        slot[lane] = w;
+        /* lane 31: v of the strip's last column in row jh, self-validating */
+        nwb_st_relaxed_sys_pred(out_w + jh, vL | NWB_PK_VALID, pub31);
     }
     st.acc_prev = acc;
     if (CHECKED) {
@@ -175,12 +208,12 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                                               unsigned char *stage_bytes, const int lane, long long &rsum)
 {
     typedef typename NwbPkStage<K>::T stage_t;
-    stage_t *stage = reinterpret_cast<stage_t *>(stage_bytes);
     const int A = p.A, B = p.B;
     const int W = 64 * K;
     const int col_lo = c * W + (2 * lane) * K + 1; /* first column (1-based) of the low block */
     const int col_hi = col_lo + K;                 /* ... of the high block                   */
     const unsigned ONE = 0x00010001u;
+    const int SLOT = NWB_PK_SLOT_BYTES(K);
 
     NwbPkState<K> st;
 #pragma unroll
@@ -191,7 +224,6 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
         st.u[k] = 0u;
     }
     st.vlast = NWB_PK_BIG * ONE;
-    st.send = NWB_PK_BIG << 16;
     st.sp = 0xFFFFFFFFu;
     st.acc_prev = 0u;
 
@@ -204,16 +236,14 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     const uint32_t *in_w = nullptr;
     if (has_left) in_w = left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch;
     const bool pub31 = publish && (lane == 31);
+    /* my low-half row at step s is s + 1 - 2*lane */
+    const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * lane;
 
-    /* stream word of row j for lane 0: from the left strip, or synthesised for column 0
-     * (v(0,j) = 0 plus the row's side character) */
-    unsigned bq_next = 0u;
-    {
-        const int jj = 1 + lane;
-        if (jj <= B) {
-            if (has_left) bq_next = nwb_ld_relaxed_u32(in_w + jj, left_remote);
-            else bq_next = ((~((unsigned)p.side[jj - 1] << pc.shift)) & 0xFFFFu) | NWB_PK_VALID;
-        }
+    /* stream words of rows 1..32 for lane 0 (column 0 of the table: v(0,j) = 0) */
+    unsigned bq_next = NWB_PK_VALID;
+    if (has_left) {
+        bq_next = 0u;
+        if (1 + lane <= B) bq_next = nwb_ld_relaxed_u32(in_w + 1 + lane, left_remote);
     }
 
     const int nblocks = (B + 63 + 31) / 32;
@@ -234,29 +264,32 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 }
             }
             bq = w & ~NWB_PK_VALID;
-            const int jn = jj + 32;
-            bq_next = 0u;
-            if (jn <= B) {
-                if (has_left) bq_next = nwb_ld_relaxed_u32(in_w + jn, left_remote);
-                else bq_next = ((~((unsigned)p.side[jn - 1] << pc.shift)) & 0xFFFFu) | NWB_PK_VALID;
+            if (has_left) {
+                bq_next = 0u;
+                if (jj + 32 <= B) bq_next = nwb_ld_relaxed_u32(in_w + jj + 32, left_remote);
             }
         }
         const int s0 = 32 * blk;
-        /* every lane inside rows 1..B for the whole block?  (lane 31's high half is the last
-         * to enter: row s-62; lane 0's low half the first to leave: row s+1) */
-        if (s0 >= 63 && s0 + 32 <= B) {
-#pragma unroll 1
+        const uint16_t *spb = sp_lane + s0;
+        unsigned char *slot0 = stage_bytes + (size_t)(s0 & (NWB_PK_RING_ROWS - 1)) * SLOT;
+        uint32_t *outb = out_w + (s0 - 2 * lane);
+        /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high half is
+         * the last to enter: row s-62; lane 0's low half the first to reach row B: row s+1;
+         * row B itself needs the checked step, which captures the bottom-row sums) */
+        if (s0 >= 63 && s0 + 32 < B) {
+#pragma unroll 4
             for (int t = 0; t < 32; t++)
-                nwb_pk_step<K, false>(st, pc, bq, t, lane, s0 + t - 2 * lane, A, B, col_lo, col_hi, stage, out_w, pub31,
-                                      out_remote, rsum);
+                nwb_pk_step<K, false>(st, pc, bq, t, lane, t, A, B, col_lo, col_hi, (unsigned)nwb_ldg_u16(spb + t),
+                                      reinterpret_cast<stage_t *>(slot0 + t * SLOT), outb, pub31, rsum);
         } else {
 #pragma unroll 1
             for (int t = 0; t < 32; t++)
-                nwb_pk_step<K, true>(st, pc, bq, t, lane, s0 + t - 2 * lane, A, B, col_lo, col_hi, stage, out_w, pub31,
-                                     out_remote, rsum);
+                nwb_pk_step<K, true>(st, pc, bq, t, lane, s0 + t - 2 * lane, A, B, col_lo, col_hi, (unsigned)nwb_ldg_u16(spb + t),
+                                     reinterpret_cast<stage_t *>(slot0 + t * SLOT), out_w, pub31, rsum);
         }
         __syncwarp();
-        /* rows <= 32*blk-31 are complete: flush the 32 newest complete rows, 16 B per lane */
+        /* rows <= 32*blk-31 are complete: un-skew the 32 newest complete rows out of the ring and
+         * write them with 16-byte stores (flipping the inverted codes) */
         {
             const int jhi = 32 * blk - 31;
             const int jlo = jhi - 31;
@@ -264,13 +297,22 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             const int lanes_per_row = row_bytes / 16;
             const int rows_per_pass = 32 / lanes_per_row;
             const int sub = lane % lanes_per_row;
+            const int src_per_chunk = 16 / K;      /* source lanes per 16-byte chunk: 4, 8 or 16 */
 #pragma unroll
             for (int r = 0; r < 32 / rows_per_pass; r++) {
                 const int j = jlo + r * rows_per_pass + lane / lanes_per_row;
                 if (j >= 1 && j <= B) {
-                    uint4 v = *reinterpret_cast<const uint4 *>(stage_bytes + (size_t)(j & (NWB_PK_RING_ROWS - 1)) * row_bytes + sub * 16);
-                    v.x = ~v.x & 0x77777777u; v.y = ~v.y & 0x77777777u;
-                    v.z = ~v.z & 0x77777777u; v.w = ~v.w & 0x77777777u;
+                    unsigned wv[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int i = 0; i < src_per_chunk; i++) {
+                        const int l2 = sub * src_per_chunk + i; /* source lane */
+                        const stage_t e = *reinterpret_cast<const stage_t *>(
+                            stage_bytes + (size_t)((j + 2 * l2) & (NWB_PK_RING_ROWS - 1)) * SLOT + l2 * K);
+                        wv[(i * K) / 4] |= (unsigned)e << (8 * ((i * K) % 4));
+                    }
+                    uint4 v;
+                    v.x = ~wv[0] & 0x77777777u; v.y = ~wv[1] & 0x77777777u;
+                    v.z = ~wv[2] & 0x77777777u; v.w = ~wv[3] & 0x77777777u;
                     *reinterpret_cast<uint4 *>(p.arrows + (size_t)(j - 1) * p.pitch + (size_t)c * row_bytes + sub * 16) = v;
                 }
             }
@@ -286,7 +328,7 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
     const int warp = threadIdx.x >> 5;
     const int nworkers = (int)gridDim.x * (int)(blockDim.x >> 5);
     const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
-    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_RING_ROWS * 32 * K;
+    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_RING_ROWS * NWB_PK_SLOT_BYTES(K);
 
     long long rsum = 0;
     for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)

@@ -140,6 +140,9 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.bpitch = L.bpitch;
     p.progress = progress.data();
     p.summary = &sum;
+    std::vector<uint16_t> side_pre(NWB_PK_SPRE_LEN(B), 0x1234);
+    emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
+    p.side_pre = side_pre.data();
     auto launch = [&](const NwbStripParams &q) {
         if (K == 1) run_pk_emu<1>(grid, warps, q, pc);
         else if (K == 2) run_pk_emu<2>(grid, warps, q, pc);

@@ -37,7 +37,7 @@ def test_readme(oracle, K):
 
 
 @pytest.mark.parametrize("a,b", [(1, 1), (5, 40), (40, 5), (63, 33), (64, 64), (65, 65), (255, 33), (256, 64),
-                                 (257, 130), (513, 70), (600, 200)])
+                                 (257, 130), (513, 70), (600, 200), (200, 128), (130, 256), (70, 257)])
 def test_shapes(oracle, a, b):
     rng = random.Random(a * 7919 + b)
     for alpha in (b"ACGT", bytes(range(1, 256))):
