@@ -299,6 +299,14 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         strip_w = 64 * pk_k;
     }
     p->L = nwb_make_layout(A, B, p->kind, pk_k, strip_w);
+    if (p->kind == NWB_KIND_PK) {
+        /* two rows per step once the table is tall enough to amortise the doubled lane skew */
+        p->L.pk_r = (B >= 4096) ? 2 : 1;
+        if (const char *er = getenv("NWB_PK_R")) { /* diagnostics */
+            const int v = atoi(er);
+            if (v == 1 || v == 2) p->L.pk_r = v;
+        }
+    }
     const NwbLayout &L = p->L;
 
     /* this rank's strips */
@@ -381,6 +389,8 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         const int v = atoi(ew);
         if (v >= 1 && v <= NWB_PK_MAX_WARPS) pk_warps = v;
     }
+    if (p->kind == NWB_KIND_PK)
+        while (pk_warps > 1 && NWB_PK_SMEM_BYTES(L.pk_k, L.pk_r, pk_warps) > 200 * 1024) pk_warps--;
     CK(cudaEventRecord(p->ev0, st));
     if (p->kind == NWB_KIND_PK) {
         nwb_pk_prep_side_kernel<<<64, 256, 0, st>>>(p->side.p, B, pc.shift, p->side_pre.p);
@@ -407,7 +417,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
 
 static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st)
 {
-    return nwb_pk_launch(sp, pc, p->L.pk_k, (p->flags & NWB_WANT_COUNT) != 0, grid, warps, st, cuda_fail);
+    return nwb_pk_launch(sp, pc, p->L.pk_k, p->L.pk_r, (p->flags & NWB_WANT_COUNT) != 0, grid, warps, st, cuda_fail);
 }
 
 extern "C" int nwb_plan_reset_inbox(nwb_plan *p, void *stream)

@@ -76,6 +76,15 @@ __device__ __forceinline__ unsigned short nwb_ldg_u16(const uint16_t *p)
 #endif
 }
 
+__device__ __forceinline__ unsigned nwb_ldg_u32(const unsigned *p)
+{
+#ifdef NWB_EMU
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
+
 /* relaxed (L2-coherent, L1-bypassing) 32-bit accesses for self-validating stream words */
 __device__ __forceinline__ unsigned nwb_ld_relaxed_u32(const uint32_t *p, bool sys)
 {

@@ -80,7 +80,7 @@ static inline int nwb_pk_choose_k(int A, int B, int total_warps)
     return 4;
 }
 
-#define NWB_PK_SMEM_BYTES(K, WARPS) ((WARPS) * NWB_PK_RING_ROWS * (32 * (K) + 4))
+#define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * NWB_PK_RING_ROWS * (R) * (32 * (K) + 4))
 
 template <int K>
 struct NwbPkStage;
@@ -91,17 +91,22 @@ struct NwbPkStage<2> { typedef uint16_t T; };
 template <>
 struct NwbPkStage<1> { typedef uint8_t T; };
 
-/* Boundary stream words validate themselves: {bit 31: valid, bits 16..30: v of the
- * strip's last column in that row}.  The buffers are zeroed before every fill; a
- * consumer lane polls its own word with relaxed (L2) loads, so the hand-off needs
- * neither a separate flag nor fences: every 32-bit word is written and read
- * atomically and is all the consumer needs from the left strip for that row. */
+/* Boundary stream words validate themselves.  One 32-bit word per row GROUP (R
+ * rows): R = 1: {bit 31: valid, bits 16..30: v};  R = 2: {bit 31: valid,
+ * bits 16..30: v of the group's second row, bit 15: valid, bits 0..14: v of its
+ * first row}, v = the strip's last-column vertical difference in that row.  The
+ * buffers are zeroed before every fill; the consumer reads the words with relaxed
+ * (L2) loads a few steps ahead of use and re-polls only if a word is not valid
+ * yet, so the hand-off needs neither a separate flag nor fences: every word is
+ * written and read atomically and is all the consumer needs for that row group. */
 #define NWB_PK_VALID 0x80000000u
+#define NWB_PK_LOOKAHEAD 12 /* steps between the load of a stream word and its use */
 /* The side string is pre-shifted and complemented once per fill into a uint16
  * array padded on both sides, so the row loop never range-checks its index:
- * side_pre[j + NWB_PK_SPAD] = ~(side[j-1] << shift) & 0xFFFF for 1 <= j <= B. */
-#define NWB_PK_SPAD 64
-#define NWB_PK_SPRE_LEN(B) ((size_t)(B) + NWB_PK_SPAD + 160)
+ * side_pre[j + NWB_PK_SPAD] = ~(side[j-1] << shift) & 0xFFFF for 1 <= j <= B.
+ * NWB_PK_SPAD is odd so that row 1 + 2*n sits at an even (4-byte aligned) index. */
+#define NWB_PK_SPAD 257
+#define NWB_PK_SPRE_LEN(B) ((size_t)(B) + NWB_PK_SPAD + 512)
 
 __global__ void nwb_pk_prep_side_kernel(const uint8_t *side, int B, int shift, uint16_t *side_pre)
 {
@@ -115,18 +120,20 @@ __global__ void nwb_pk_prep_side_kernel(const uint8_t *side, int B, int shift, u
 }
 
 /* staging ring: one slot per row STEP (not per row): at step s every lane writes
- * slot s & 127, so the address is a block base plus an immediate; the flush
- * un-skews (row j of lane l sits in slot (j + 2l) & 127).  One pad word per slot
- * keeps the un-skewing reads free of bank conflicts. */
-#define NWB_PK_SLOT_BYTES(K) (32 * (K) + 4)
+ * slot s & 127 (R sub-rows), so the address is a block base plus an immediate;
+ * the flush un-skews.  One pad word per sub-row keeps the un-skewing reads free
+ * of bank conflicts. */
+#define NWB_PK_SUBROW_BYTES(K) (32 * (K) + 4)
+#define NWB_PK_SLOT_BYTES(K, R) ((R) * NWB_PK_SUBROW_BYTES(K))
 
-template <int K>
+template <int K, int R>
 struct NwbPkState {
-    unsigned tpw[K]; /* pre-shifted top characters of my columns (low block | high block) */
-    unsigned u[K];   /* u of my columns in the previous row                                */
-    unsigned vlast;  /* v of my last columns (virtual rows: BIG)                           */
-    unsigned sp;     /* ~(side char << shift) of my two rows                               */
-    unsigned acc_prev; /* low-half arrow nibbles of the previous step                      */
+    unsigned tpw[K];      /* pre-shifted top characters of my columns (low block | high block) */
+    unsigned u[K];        /* u of my columns in the row above                                   */
+    unsigned vlast[R];    /* v of my last columns per sub-row (virtual rows: BIG)               */
+    unsigned sp[R];       /* ~(side char << shift) per sub-row (low half row | high half row)   */
+    unsigned acc_prev[R]; /* low-half arrow nibbles of the previous step per sub-row            */
+    unsigned send;        /* v of my HIGH block's last column for the R rows just done          */
 };
 
 __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v, bool pred)
@@ -140,70 +147,107 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
 #endif
 }
 
-/* One row step of one lane: 2*K cells.  CHECKED adds the row-range tests needed
- * while some lanes are still above row 1 or already below row B. */
-template <int K, bool CHECKED>
-__device__ __forceinline__ void nwb_pk_step(NwbPkState<K> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
-                                             const int lane, const int jh, const int A, const int B,
-                                             const int col_lo, const int col_hi, const unsigned scn,
-                                             typename NwbPkStage<K>::T *slot, uint32_t *out_w, const bool pub31,
-                                             long long &rsum)
+/* One row step of one lane: R rows x 2*K cells.  At step s lane l's low block is
+ * on row group s - 2l, its high block on group s - 2l - 1 (= g_hi); group g holds
+ * rows R*g+1 .. R*g+R.  CHECKED adds the row-range tests needed while some lanes
+ * are still above row 1 or already at/below row B. */
+template <int K, int R, bool CHECKED>
+__device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, unsigned &bq, const int t,
+                                             const int s, const int lane, const int g_hi, const int A, const int B,
+                                             const int ngroups, const int col_lo, const int col_hi, const unsigned chars,
+                                             unsigned char *slot, uint32_t *out_w, const bool pub31,
+                                             const uint32_t *in_w, const bool has_left, const bool left_remote,
+                                             const bool nowait, long long &rsum)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
-    unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.vlast, 1);
-    const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
-    if (lane == 0) recv = b;
-    /* left inputs: low half <- neighbour's high half, high half <- my own low half */
-    unsigned vL = __byte_perm(recv, st.vlast, 0x5432);
-    /* side characters: low half <- this step's row, high half <- my previous low row */
-    st.sp = __byte_perm(scn, st.sp, 0x5410);
-    unsigned code[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const unsigned nx = st.tpw[k] ^ st.sp;                          /* -x'-1 per half     */
-        const unsigned a = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);      /* a_match or a_mis   */
-        const unsigned z = __vimax3_s16x2(a, vL, st.u[k]);
-        const unsigned un = z - vL;
-        const unsigned vn = z - st.u[k];
-        const unsigned td = z - a;
-        const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
-        code[k] = fd + fl * 2u + fu * 4u; /* inverted: a set bit = NO arrow */
-        st.u[k] = un;
-        vL = vn;
-    }
-    st.vlast = vL;
-    unsigned acc;
-    if (K == 4) acc = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
-    else if (K == 2) acc = code[0] + code[1] * 16u;
-    else acc = code[0];
-    /* arrow codes of row jh: low block from the previous step, high block from this one */
-    if (!CHECKED || (jh >= 1 && jh <= B)) {
-        stage_t w;
-        if (K == 4) w = (stage_t)__byte_perm(st.acc_prev, acc, 0x7610);
-        else if (K == 2) w = (stage_t)((st.acc_prev & 0xFFu) | ((acc >> 8) & 0xFF00u));
-        else w = (stage_t)((st.acc_prev & 0xFu) | ((acc >> 12) & 0xF0u));
-        slot[lane] = w;
-        /* lane 31: v of the strip's last column in row jh, self-validating */
-        nwb_st_relaxed_sys_pred(out_w + jh, vL | NWB_PK_VALID, pub31);
-    }
-    st.acc_prev = acc;
-    if (CHECKED) {
-        /* bottom row: r(A,B) = sum of u(i,B) */
-        if (jh + 1 == B) {
-#pragma unroll
-            for (int k = 0; k < K; k++)
-                if (col_lo + k <= A) rsum += (long long)(st.u[k] & 0xFFFFu);
+    const unsigned VMASK = (R == 2) ? 0x7FFF7FFFu : 0x7FFFFFFFu;
+    /* ---- left inputs: from my left neighbour lane; lane 0 from the stream word of group s */
+    unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
+    unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
+    if (has_left && !nowait) {
+        const bool wanted = !CHECKED || (s < ngroups);
+        while (wanted && !(b & NWB_PK_VALID)) { /* warp-uniform; rare: the word was loaded LOOKAHEAD steps ago */
+            nwb_pause();
+            if (lane == t) bq = nwb_ld_relaxed_u32(in_w + s, left_remote);
+            b = __shfl_sync(NWB_FULL_MASK, bq, t);
         }
-        if (jh == B) {
+    }
+    if (lane == 0) recv = b & VMASK;
+    unsigned vL[R];
+    if (R == 2) {
+        vL[0] = __byte_perm(recv, st.vlast[0], 0x5410); /* lo <- neighbour's row 0, hi <- my low block's row 0 */
+        vL[R - 1] = __byte_perm(recv, st.vlast[R - 1], 0x5432);
+        st.sp[0] = __byte_perm(chars, st.sp[0], 0x5410);
+        st.sp[R - 1] = __byte_perm(chars, st.sp[R - 1], 0x5432);
+    } else {
+        vL[0] = __byte_perm(recv, st.vlast[0], 0x5432);
+        st.sp[0] = __byte_perm(chars, st.sp[0], 0x5410);
+    }
+    /* ---- the cells: row by row, column by column (the scheduler finds the wavefront) */
+    unsigned acc[R];
 #pragma unroll
-            for (int k = 0; k < K; k++)
-                if (col_hi + k <= A) rsum += (long long)(st.u[k] >> 16);
+    for (int r = 0; r < R; r++) {
+        unsigned v = vL[r];
+        unsigned code[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const unsigned nx = st.tpw[k] ^ st.sp[r];                      /* -x'-1 per half   */
+            const unsigned a = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);     /* a_match or a_mis */
+            const unsigned z = __vimax3_s16x2(a, v, st.u[k]);
+            const unsigned un = z - v;
+            const unsigned vn = z - st.u[k];
+            const unsigned td = z - a;
+            const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
+            code[k] = fd + fl * 2u + fu * 4u; /* inverted: a set bit = NO arrow */
+            st.u[k] = un;
+            v = vn;
         }
+        st.vlast[r] = v;
+        if (K == 4) acc[r] = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
+        else if (K == 2) acc[r] = code[0] + code[1] * 16u;
+        else acc[r] = code[0];
+        if (CHECKED) {
+            /* bottom row: r(A,B) = sum of u(i,B) */
+            const int row_hi = R * g_hi + 1 + r, row_lo = row_hi + R;
+            if (row_lo == B) {
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (col_lo + k <= A) rsum += (long long)(st.u[k] & 0xFFFFu);
+            }
+            if (row_hi == B) {
+#pragma unroll
+                for (int k = 0; k < K; k++)
+                    if (col_hi + k <= A) rsum += (long long)(st.u[k] >> 16);
+            }
+        }
+    }
+    /* ---- outputs */
+    st.send = (R == 2) ? __byte_perm(st.vlast[0], st.vlast[R - 1], 0x7632) : st.vlast[0];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int row_hi = R * g_hi + 1 + r;
+        /* arrow codes of row row_hi: low block from the previous step, high block from this one */
+        if (!CHECKED || (row_hi >= 1 && row_hi <= B)) {
+            stage_t w;
+            if (K == 4) w = (stage_t)__byte_perm(st.acc_prev[r], acc[r], 0x7610);
+            else if (K == 2) w = (stage_t)((st.acc_prev[r] & 0xFFu) | ((acc[r] >> 8) & 0xFF00u));
+            else w = (stage_t)((st.acc_prev[r] & 0xFu) | ((acc[r] >> 12) & 0xF0u));
+            reinterpret_cast<stage_t *>(slot + r * NWB_PK_SUBROW_BYTES(K))[lane] = w;
+        }
+        st.acc_prev[r] = acc[r];
+    }
+    /* lane 31: the strip's last column for group g_hi, self-validating */
+    if (!CHECKED || (g_hi >= 0 && g_hi < ngroups))
+        nwb_st_relaxed_sys_pred(out_w + g_hi, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub31);
+    /* ---- stream word of group s + LOOKAHEAD: loaded by the lane that will serve it */
+    if (has_left) {
+        const int gl = s + NWB_PK_LOOKAHEAD;
+        if (lane == ((t + NWB_PK_LOOKAHEAD) & 31) && gl < ngroups) bq = nwb_ld_relaxed_u32(in_w + gl, left_remote);
     }
 }
 
-template <int K, bool COUNT>
+template <int K, int R, bool COUNT>
 __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
                                               unsigned char *stage_bytes, const int lane, long long &rsum)
 {
@@ -213,9 +257,10 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     const int col_lo = c * W + (2 * lane) * K + 1; /* first column (1-based) of the low block */
     const int col_hi = col_lo + K;                 /* ... of the high block                   */
     const unsigned ONE = 0x00010001u;
-    const int SLOT = NWB_PK_SLOT_BYTES(K);
+    const int SLOT = NWB_PK_SLOT_BYTES(K, R);
+    const int ngroups = (B + R - 1) / R;
 
-    NwbPkState<K> st;
+    NwbPkState<K, R> st;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const unsigned lo = (col_lo + k <= A) ? (unsigned)p.top[col_lo + k - 1] : 0u;
@@ -223,9 +268,13 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
         st.tpw[k] = ((lo << pc.shift) | ((hi << pc.shift) << 16));
         st.u[k] = 0u;
     }
-    st.vlast = NWB_PK_BIG * ONE;
-    st.sp = 0xFFFFFFFFu;
-    st.acc_prev = 0u;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        st.vlast[r] = NWB_PK_BIG * ONE;
+        st.sp[r] = 0xFFFFFFFFu;
+        st.acc_prev[r] = 0u;
+    }
+    st.send = NWB_PK_BIG * ONE;
 
     const int lc = c - p.strip_begin;
     const bool has_left = (c > 0);
@@ -236,78 +285,70 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     const uint32_t *in_w = nullptr;
     if (has_left) in_w = left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch;
     const bool pub31 = publish && (lane == 31);
-    /* my low-half row at step s is s + 1 - 2*lane */
-    const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * lane;
+    const bool nowait = p.debug_nowait != 0;
+    /* my low block's first row at step s is R*(s - 2*lane) + 1 */
+    const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
 
-    /* stream words of rows 1..32 for lane 0 (column 0 of the table: v(0,j) = 0) */
-    unsigned bq_next = NWB_PK_VALID;
+    /* stream words of the first LOOKAHEAD groups (column 0 of the table: v(0,j) = 0, always valid) */
+    unsigned bq = NWB_PK_VALID;
     if (has_left) {
-        bq_next = 0u;
-        if (1 + lane <= B) bq_next = nwb_ld_relaxed_u32(in_w + 1 + lane, left_remote);
+        bq = 0u;
+        if (lane < NWB_PK_LOOKAHEAD && lane < ngroups) bq = nwb_ld_relaxed_u32(in_w + lane, left_remote);
     }
 
-    const int nblocks = (B + 63 + 31) / 32;
+    const int nsteps = ngroups + 63;
+    const int nblocks = (nsteps + 31) / 32;
     for (int blk = 0; blk < nblocks; blk++) {
-        /* stream words for lane 0's low-half rows 32*blk+1 .. 32*blk+32 (prefetched one block ahead) */
-        unsigned bq;
-        {
-            const int jj = 32 * blk + 1 + lane;
-            unsigned w = bq_next;
-            if (has_left && !p.debug_nowait) {
-                bool ok = (jj > B) || (w & NWB_PK_VALID);
-                while (!__all_sync(NWB_FULL_MASK, ok)) {
-                    if (!ok) {
-                        nwb_pause();
-                        w = nwb_ld_relaxed_u32(in_w + jj, left_remote);
-                        ok = (w & NWB_PK_VALID) != 0u;
-                    }
-                }
-            }
-            bq = w & ~NWB_PK_VALID;
-            if (has_left) {
-                bq_next = 0u;
-                if (jj + 32 <= B) bq_next = nwb_ld_relaxed_u32(in_w + jj + 32, left_remote);
-            }
-        }
         const int s0 = 32 * blk;
-        const uint16_t *spb = sp_lane + s0;
+        const uint16_t *spb = sp_lane + R * s0;
         unsigned char *slot0 = stage_bytes + (size_t)(s0 & (NWB_PK_RING_ROWS - 1)) * SLOT;
-        uint32_t *outb = out_w + (s0 - 2 * lane);
-        /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high half is
-         * the last to enter: row s-62; lane 0's low half the first to reach row B: row s+1;
-         * row B itself needs the checked step, which captures the bottom-row sums) */
-        if (s0 >= 63 && s0 + 32 < B) {
+        /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is
+         * the last to enter: group s-63; lane 0's low block the first to reach row B; row B itself
+         * needs the checked step, which captures the bottom-row sums) */
+        if (s0 >= 63 && R * (s0 + 32) < B) {
+            uint32_t *outb = out_w + (s0 - 2 * lane - 1);
 #pragma unroll 4
-            for (int t = 0; t < 32; t++)
-                nwb_pk_step<K, false>(st, pc, bq, t, lane, t, A, B, col_lo, col_hi, (unsigned)nwb_ldg_u16(spb + t),
-                                      reinterpret_cast<stage_t *>(slot0 + t * SLOT), outb, pub31, rsum);
+            for (int t = 0; t < 32; t++) {
+                unsigned chars;
+                if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
+                else chars = (unsigned)nwb_ldg_u16(spb + t);
+                nwb_pk_step<K, R, false>(st, pc, bq, t, s0 + t, lane, t, A, B, ngroups, col_lo, col_hi, chars,
+                                         slot0 + t * SLOT, outb, pub31, in_w, has_left, left_remote, nowait, rsum);
+            }
         } else {
 #pragma unroll 1
-            for (int t = 0; t < 32; t++)
-                nwb_pk_step<K, true>(st, pc, bq, t, lane, s0 + t - 2 * lane, A, B, col_lo, col_hi, (unsigned)nwb_ldg_u16(spb + t),
-                                     reinterpret_cast<stage_t *>(slot0 + t * SLOT), out_w, pub31, rsum);
+            for (int t = 0; t < 32; t++) {
+                unsigned chars;
+                if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
+                else chars = (unsigned)nwb_ldg_u16(spb + t);
+                nwb_pk_step<K, R, true>(st, pc, bq, t, s0 + t, lane, s0 + t - 2 * lane - 1, A, B, ngroups, col_lo,
+                                        col_hi, chars, slot0 + t * SLOT, out_w, pub31, in_w, has_left, left_remote,
+                                        nowait, rsum);
+            }
         }
         __syncwarp();
-        /* rows <= 32*blk-31 are complete: un-skew the 32 newest complete rows out of the ring and
-         * write them with 16-byte stores (flipping the inverted codes) */
+        /* groups <= 32*blk-32 are complete in every lane: un-skew the 32*R newest complete rows out
+         * of the ring and write them with 16-byte stores (flipping the inverted codes) */
         {
-            const int jhi = 32 * blk - 31;
-            const int jlo = jhi - 31;
+            const int jhi = R * (32 * blk - 31);
+            const int jlo = jhi - 32 * R + 1;
             const int row_bytes = 32 * K;          /* bytes per strip row          */
             const int lanes_per_row = row_bytes / 16;
             const int rows_per_pass = 32 / lanes_per_row;
             const int sub = lane % lanes_per_row;
             const int src_per_chunk = 16 / K;      /* source lanes per 16-byte chunk: 4, 8 or 16 */
 #pragma unroll
-            for (int r = 0; r < 32 / rows_per_pass; r++) {
-                const int j = jlo + r * rows_per_pass + lane / lanes_per_row;
+            for (int q = 0; q < (32 * R) / rows_per_pass; q++) {
+                const int j = jlo + q * rows_per_pass + lane / lanes_per_row;
                 if (j >= 1 && j <= B) {
+                    const int g = (j - 1) / R, r = (j - 1) - g * R;
                     unsigned wv[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int i = 0; i < src_per_chunk; i++) {
-                        const int l2 = sub * src_per_chunk + i; /* source lane */
+                        const int l2 = sub * src_per_chunk + i; /* source lane; it stored group g at step g+2*l2+1 */
                         const stage_t e = *reinterpret_cast<const stage_t *>(
-                            stage_bytes + (size_t)((j + 2 * l2) & (NWB_PK_RING_ROWS - 1)) * SLOT + l2 * K);
+                            stage_bytes + (size_t)((g + 2 * l2 + 1) & (NWB_PK_RING_ROWS - 1)) * SLOT +
+                            r * NWB_PK_SUBROW_BYTES(K) + l2 * K);
                         wv[(i * K) / 4] |= (unsigned)e << (8 * ((i * K) % 4));
                     }
                     uint4 v;
@@ -321,18 +362,18 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     }
 }
 
-template <int K, bool COUNT>
+template <int K, int R, bool COUNT>
 __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(const NwbStripParams p, const NwbPkConsts pc)
 {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nworkers = (int)gridDim.x * (int)(blockDim.x >> 5);
     const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
-    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_RING_ROWS * NWB_PK_SLOT_BYTES(K);
+    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_RING_ROWS * NWB_PK_SLOT_BYTES(K, R);
 
     long long rsum = 0;
     for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
-        nwb_pk_strip<K, COUNT>(p, pc, c, stage, lane, rsum);
+        nwb_pk_strip<K, R, COUNT>(p, pc, c, stage, lane, rsum);
 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
@@ -379,12 +420,12 @@ __global__ void nwb_branch_count_kernel(const uint8_t *arrows, size_t pitch, int
 #ifndef NWB_EMU
 typedef int (*nwb_fail_fn)(cudaError_t, const char *);
 
-template <int K, bool COUNT>
+template <int K, int R, bool COUNT>
 static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st,
                            nwb_fail_fn fail)
 {
-    auto kernel = nwb_fill_pk_kernel<K, COUNT>;
-    const size_t smem = NWB_PK_SMEM_BYTES(K, warps);
+    auto kernel = nwb_fill_pk_kernel<K, R, COUNT>;
+    const size_t smem = NWB_PK_SMEM_BYTES(K, R, warps);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     void *args[] = {(void *)&sp, (void *)&pc};
@@ -393,14 +434,17 @@ static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int 
     return 0;
 }
 
-static inline int nwb_pk_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int K, bool count, int grid,
+static inline int nwb_pk_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int K, int R, bool count, int grid,
                                 int warps, cudaStream_t st, nwb_fail_fn fail)
 {
     if (count) return -5; /* the fused count lives in the general kernel for now */
-    switch (K) {
-    case 1: return nwb_pk_launch_k<1, false>(sp, pc, grid, warps, st, fail);
-    case 2: return nwb_pk_launch_k<2, false>(sp, pc, grid, warps, st, fail);
-    case 4: return nwb_pk_launch_k<4, false>(sp, pc, grid, warps, st, fail);
+    switch (K * 10 + R) {
+    case 11: return nwb_pk_launch_k<1, 1, false>(sp, pc, grid, warps, st, fail);
+    case 21: return nwb_pk_launch_k<2, 1, false>(sp, pc, grid, warps, st, fail);
+    case 41: return nwb_pk_launch_k<4, 1, false>(sp, pc, grid, warps, st, fail);
+    case 12: return nwb_pk_launch_k<1, 2, false>(sp, pc, grid, warps, st, fail);
+    case 22: return nwb_pk_launch_k<2, 2, false>(sp, pc, grid, warps, st, fail);
+    case 42: return nwb_pk_launch_k<4, 2, false>(sp, pc, grid, warps, st, fail);
     default: return -1;
     }
 }

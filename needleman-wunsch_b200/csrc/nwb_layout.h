@@ -14,6 +14,7 @@ struct NwbLayout {
     int A, B;
     int kind;        /* NWB_KIND_*                                   */
     int pk_k;        /* packed kernel: columns per half-lane (1..4)  */
+    int pk_r;        /* packed kernel: rows per step (1 or 2)        */
     int strip_w;     /* interior columns per strip                   */
     int n_strips;
     size_t pitch;    /* arrow row pitch in bytes (multiple of 16)    */
@@ -31,6 +32,7 @@ static inline NwbLayout nwb_make_layout(int A, int B, int kind, int pk_k, int st
     L.B = B;
     L.kind = kind;
     L.pk_k = pk_k;
+    L.pk_r = 1;
     L.strip_w = strip_w;
     L.n_strips = (A + strip_w - 1) / strip_w;
     if (L.n_strips < 1) L.n_strips = 1;

@@ -18,10 +18,10 @@ static void run_i32(unsigned grid, const NwbStripParams &p)
                [&]() { nwb_fill_i32_kernel<COUNT, SCORES, ABS, CNTMAT>(p); });
 }
 
-template <int K>
+template <int K, int R>
 static void run_pk_emu(unsigned grid, int warps, const NwbStripParams &p, const NwbPkConsts &pc)
 {
-    emu_launch(grid, 32 * warps, NWB_PK_SMEM_BYTES(K, warps), [&]() { nwb_fill_pk_kernel<K, false>(p, pc); });
+    emu_launch(grid, 32 * warps, NWB_PK_SMEM_BYTES(K, R, warps), [&]() { nwb_fill_pk_kernel<K, R, false>(p, pc); });
 }
 
 extern "C" {
@@ -116,7 +116,7 @@ int emu_fill_i32(const char *top, int A, const char *side, int B, int m, int k, 
 size_t emu_pitch_pk(int A, int B, int K) { return nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K).pitch; }
 int emu_pk_supported(int m, int k, int d) { return nwb_pk_supported(m, k, d, nullptr) ? 1 : 0; }
 
-int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K,
+int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K, int R,
                 unsigned grid, int warps, int split, uint8_t *arrows, emu_out *out)
 {
     NwbPkConsts pc;
@@ -144,9 +144,15 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
     p.side_pre = side_pre.data();
     auto launch = [&](const NwbStripParams &q) {
-        if (K == 1) run_pk_emu<1>(grid, warps, q, pc);
-        else if (K == 2) run_pk_emu<2>(grid, warps, q, pc);
-        else run_pk_emu<4>(grid, warps, q, pc);
+        if (R == 2) {
+            if (K == 1) run_pk_emu<1, 2>(grid, warps, q, pc);
+            else if (K == 2) run_pk_emu<2, 2>(grid, warps, q, pc);
+            else run_pk_emu<4, 2>(grid, warps, q, pc);
+        } else {
+            if (K == 1) run_pk_emu<1, 1>(grid, warps, q, pc);
+            else if (K == 2) run_pk_emu<2, 1>(grid, warps, q, pc);
+            else run_pk_emu<4, 1>(grid, warps, q, pc);
+        }
     };
     if (split > 0 && split < L.n_strips) {
         NwbStripParams p0 = p, p1 = p;

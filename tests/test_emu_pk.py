@@ -12,8 +12,12 @@ import emu
 SCHEMES = [(1, 1, 1), (2, 1, 2), (0, 0, 0), (1, 2, 3), (5, 4, 3), (1, 0, 0), (3, -1, 0)]
 
 
-def check(oracle, t, s, m, k, d, K, grid=2, split=0):
-    r = emu.fill_pk(t, s, m, k, d, K=K, grid=grid, split=split)
+def check(oracle, t, s, m, k, d, K, grid=2, split=0, R=None):
+    if R is None:
+        for rr in (1, 2):
+            check(oracle, t, s, m, k, d, K, grid, split, rr)
+        return
+    r = emu.fill_pk(t, s, m, k, d, K=K, R=R, grid=grid, split=split)
     o = oracle.fill(t, s, m, k, d, want_codes=True)
     assert np.array_equal(emu.unpack_arrows(r["arrows"], len(t)) & 7, o.codes[1:, 1:] & 7)
     assert r["opt_score"] == o.final_score
@@ -37,7 +41,7 @@ def test_readme(oracle, K):
 
 
 @pytest.mark.parametrize("a,b", [(1, 1), (5, 40), (40, 5), (63, 33), (64, 64), (65, 65), (255, 33), (256, 64),
-                                 (257, 130), (513, 70), (600, 200), (200, 128), (130, 256), (70, 257)])
+                                 (257, 130), (513, 70), (600, 200), (200, 128), (130, 256), (70, 257), (90, 700)])
 def test_shapes(oracle, a, b):
     rng = random.Random(a * 7919 + b)
     for alpha in (b"ACGT", bytes(range(1, 256))):
