@@ -100,7 +100,7 @@ struct NwbPkStage<1> { typedef uint8_t T; };
  * yet, so the hand-off needs neither a separate flag nor fences: every word is
  * written and read atomically and is all the consumer needs for that row group. */
 #define NWB_PK_VALID 0x80000000u
-#define NWB_PK_LOOKAHEAD 12 /* steps between the load of a stream word and its use */
+#define NWB_PK_SUB 8 /* stream words are fetched 8 row groups at a time, one sub-block ahead */
 /* The side string is pre-shifted and complemented once per fill into a uint16
  * array padded on both sides, so the row loop never range-checks its index:
  * side_pre[j + NWB_PK_SPAD] = ~(side[j-1] << shift) & 0xFFFF for 1 <= j <= B.
@@ -142,8 +142,7 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
     if (pred) *(volatile uint32_t *)p = v;
 #else
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.relaxed.sys.global.u32 [%0], %1;\n\t}"
-                 ::"l"(p), "r"(v), "r"((unsigned)pred)
-                 : "memory");
+                 ::"l"(p), "r"(v), "r"((unsigned)pred));
 #endif
 }
 
@@ -152,28 +151,17 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
  * rows R*g+1 .. R*g+R.  CHECKED adds the row-range tests needed while some lanes
  * are still above row 1 or already at/below row B. */
 template <int K, int R, bool CHECKED>
-__device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, unsigned &bq, const int t,
-                                             const int s, const int lane, const int g_hi, const int A, const int B,
+__device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
+                                             const int lane, const int g_hi, const int A, const int B,
                                              const int ngroups, const int col_lo, const int col_hi, const unsigned chars,
-                                             unsigned char *slot, uint32_t *out_w, const bool pub31,
-                                             const uint32_t *in_w, const bool has_left, const bool left_remote,
-                                             const bool nowait, long long &rsum)
+                                             unsigned char *slot, uint32_t *out_w, const bool pub31, long long &rsum)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
-    const unsigned VMASK = (R == 2) ? 0x7FFF7FFFu : 0x7FFFFFFFu;
-    /* ---- left inputs: from my left neighbour lane; lane 0 from the stream word of group s */
+    /* ---- left inputs: from my left neighbour lane; lane 0 from the (validated) stream word */
     unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
-    unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
-    if (has_left && !nowait) {
-        const bool wanted = !CHECKED || (s < ngroups);
-        while (wanted && !(b & NWB_PK_VALID)) { /* warp-uniform; rare: the word was loaded LOOKAHEAD steps ago */
-            nwb_pause();
-            if (lane == t) bq = nwb_ld_relaxed_u32(in_w + s, left_remote);
-            b = __shfl_sync(NWB_FULL_MASK, bq, t);
-        }
-    }
-    if (lane == 0) recv = b & VMASK;
+    const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
+    if (lane == 0) recv = b;
     unsigned vL[R];
     if (R == 2) {
         vL[0] = __byte_perm(recv, st.vlast[0], 0x5410); /* lo <- neighbour's row 0, hi <- my low block's row 0 */
@@ -240,11 +228,6 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     /* lane 31: the strip's last column for group g_hi, self-validating */
     if (!CHECKED || (g_hi >= 0 && g_hi < ngroups))
         nwb_st_relaxed_sys_pred(out_w + g_hi, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub31);
-    /* ---- stream word of group s + LOOKAHEAD: loaded by the lane that will serve it */
-    if (has_left) {
-        const int gl = s + NWB_PK_LOOKAHEAD;
-        if (lane == ((t + NWB_PK_LOOKAHEAD) & 31) && gl < ngroups) bq = nwb_ld_relaxed_u32(in_w + gl, left_remote);
-    }
 }
 
 template <int K, int R, bool COUNT>
@@ -289,41 +272,64 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     /* my low block's first row at step s is R*(s - 2*lane) + 1 */
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
 
-    /* stream words of the first LOOKAHEAD groups (column 0 of the table: v(0,j) = 0, always valid) */
-    unsigned bq = NWB_PK_VALID;
-    if (has_left) {
-        bq = 0u;
-        if (lane < NWB_PK_LOOKAHEAD && lane < ngroups) bq = nwb_ld_relaxed_u32(in_w + lane, left_remote);
-    }
+    /* stream words: lane i < 8 holds the word of row group 8*q + i of the current sub-block q;
+     * the next sub-block's words are loaded one sub-block (8 steps) ahead into bq_next.
+     * Column 0 of the table (no left strip): v(0,j) = 0. */
+    const unsigned VMASK = (R == 2) ? 0x7FFF7FFFu : 0x7FFFFFFFu;
+    unsigned bq = 0u, bq_next = 0u;
+    if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
 
     const int nsteps = ngroups + 63;
     const int nblocks = (nsteps + 31) / 32;
     for (int blk = 0; blk < nblocks; blk++) {
         const int s0 = 32 * blk;
-        const uint16_t *spb = sp_lane + R * s0;
-        unsigned char *slot0 = stage_bytes + (size_t)(s0 & (NWB_PK_RING_ROWS - 1)) * SLOT;
         /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is
          * the last to enter: group s-63; lane 0's low block the first to reach row B; row B itself
          * needs the checked step, which captures the bottom-row sums) */
-        if (s0 >= 63 && R * (s0 + 32) < B) {
-            uint32_t *outb = out_w + (s0 - 2 * lane - 1);
-#pragma unroll 4
-            for (int t = 0; t < 32; t++) {
-                unsigned chars;
-                if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
-                else chars = (unsigned)nwb_ldg_u16(spb + t);
-                nwb_pk_step<K, R, false>(st, pc, bq, t, s0 + t, lane, t, A, B, ngroups, col_lo, col_hi, chars,
-                                         slot0 + t * SLOT, outb, pub31, in_w, has_left, left_remote, nowait, rsum);
-            }
-        } else {
+        const bool lean = (s0 >= 63 && R * (s0 + 32) < B);
 #pragma unroll 1
-            for (int t = 0; t < 32; t++) {
-                unsigned chars;
-                if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
-                else chars = (unsigned)nwb_ldg_u16(spb + t);
-                nwb_pk_step<K, R, true>(st, pc, bq, t, s0 + t, lane, s0 + t - 2 * lane - 1, A, B, ngroups, col_lo,
-                                        col_hi, chars, slot0 + t * SLOT, out_w, pub31, in_w, has_left, left_remote,
-                                        nowait, rsum);
+        for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
+            const int ss = s0 + NWB_PK_SUB * sub;
+            if (has_left) {
+                /* commit the prefetched words of groups ss .. ss+7; re-poll the ones not valid yet */
+                const int gs = ss + lane;
+                unsigned w = bq_next;
+                if (!nowait) {
+                    bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID);
+                    while (!__all_sync(NWB_FULL_MASK, ok)) {
+                        if (!ok) {
+                            nwb_pause();
+                            w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
+                            ok = (w & NWB_PK_VALID) != 0u;
+                        }
+                    }
+                }
+                bq = w & VMASK;
+                bq_next = 0u;
+                if (lane < NWB_PK_SUB && gs + NWB_PK_SUB < ngroups)
+                    bq_next = nwb_ld_relaxed_u32(in_w + gs + NWB_PK_SUB, left_remote);
+            }
+            const uint16_t *spb = sp_lane + R * ss;
+            unsigned char *slot0 = stage_bytes + (size_t)(ss & (NWB_PK_RING_ROWS - 1)) * SLOT;
+            if (lean) {
+                uint32_t *outb = out_w + (ss - 2 * lane - 1);
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++) {
+                    unsigned chars;
+                    if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
+                    else chars = (unsigned)nwb_ldg_u16(spb + t);
+                    nwb_pk_step<K, R, false>(st, pc, bq, t, lane, t, A, B, ngroups, col_lo, col_hi, chars,
+                                             slot0 + t * SLOT, outb, pub31, rsum);
+                }
+            } else {
+#pragma unroll 1
+                for (int t = 0; t < NWB_PK_SUB; t++) {
+                    unsigned chars;
+                    if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
+                    else chars = (unsigned)nwb_ldg_u16(spb + t);
+                    nwb_pk_step<K, R, true>(st, pc, bq, t, lane, ss + t - 2 * lane - 1, A, B, ngroups, col_lo,
+                                            col_hi, chars, slot0 + t * SLOT, out_w, pub31, rsum);
+                }
             }
         }
         __syncwarp();
