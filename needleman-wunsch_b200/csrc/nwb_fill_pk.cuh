@@ -106,7 +106,7 @@ struct NwbPkStage<1> { typedef uint8_t T; };
  * side_pre[j + NWB_PK_SPAD] = ~(side[j-1] << shift) & 0xFFFF for 1 <= j <= B.
  * NWB_PK_SPAD is odd so that row 1 + 2*n sits at an even (4-byte aligned) index. */
 #define NWB_PK_SPAD 257
-#define NWB_PK_SPRE_LEN(B) ((size_t)(B) + NWB_PK_SPAD + 512)
+#define NWB_PK_SPRE_LEN(B) ((size_t)(B) + NWB_PK_SPAD + 640)
 
 __global__ void nwb_pk_prep_side_kernel(const uint8_t *side, int B, int shift, uint16_t *side_pre)
 {
@@ -148,14 +148,23 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
 
 /* One row step of one lane: R rows x 2*K cells.  At step s lane l's low block is
  * on row group s - 2l, its high block on group s - 2l - 1 (= g_hi); group g holds
- * rows R*g+1 .. R*g+R.  CHECKED adds the row-range tests needed while some lanes
- * are still above row 1 or already at/below row B. */
-template <int K, int R, bool CHECKED>
+ * rows R*g+1 .. R*g+R.  MODE selects the row-range tests:
+ *   NWB_PK_LEAN  every lane is strictly inside rows 1..B-1: no tests at all;
+ *   NWB_PK_HEAD  some lanes are still above row 1 (the first 63 steps of a strip,
+ *                which sit on the strip-to-strip critical path): only "g_hi >= 0";
+ *   NWB_PK_FULL  anything, including row B (captures the bottom-row sums).
+ * out_w + g_idx addresses the stream word of group g_hi (g_idx is a compile-time
+ * constant against a rebased pointer in the unrolled loops). */
+#define NWB_PK_LEAN 0
+#define NWB_PK_HEAD 1
+#define NWB_PK_FULL 2
+template <int K, int R, int MODE>
 __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
-                                             const int lane, const int g_hi, const int A, const int B,
+                                             const int lane, const int g_idx, const int g_hi, const int A, const int B,
                                              const int ngroups, const int col_lo, const int col_hi, const unsigned chars,
                                              unsigned char *slot, uint32_t *out_w, const bool pub31, long long &rsum)
 {
+    const bool CHECKED = (MODE == NWB_PK_FULL);
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
     /* ---- left inputs: from my left neighbour lane; lane 0 from the (validated) stream word */
@@ -216,7 +225,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     for (int r = 0; r < R; r++) {
         const int row_hi = R * g_hi + 1 + r;
         /* arrow codes of row row_hi: low block from the previous step, high block from this one */
-        if (!CHECKED || (row_hi >= 1 && row_hi <= B)) {
+        if (MODE == NWB_PK_LEAN || (MODE == NWB_PK_HEAD && g_hi >= 0) || (CHECKED && row_hi >= 1 && row_hi <= B)) {
             stage_t w;
             if (K == 4) w = (stage_t)__byte_perm(st.acc_prev[r], acc[r], 0x7610);
             else if (K == 2) w = (stage_t)((st.acc_prev[r] & 0xFFu) | ((acc[r] >> 8) & 0xFF00u));
@@ -226,8 +235,12 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
         st.acc_prev[r] = acc[r];
     }
     /* lane 31: the strip's last column for group g_hi, self-validating */
-    if (!CHECKED || (g_hi >= 0 && g_hi < ngroups))
-        nwb_st_relaxed_sys_pred(out_w + g_hi, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub31);
+    {
+        bool pub = pub31;
+        if (MODE == NWB_PK_HEAD) pub = pub && (g_hi >= 0);
+        if (CHECKED) pub = pub && (g_hi >= 0 && g_hi < ngroups);
+        nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub);
+    }
 }
 
 template <int K, int R, bool COUNT>
@@ -279,6 +292,13 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     unsigned bq = 0u, bq_next = 0u;
     if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
 
+    unsigned chars_next[NWB_PK_SUB];
+#pragma unroll
+    for (int t = 0; t < NWB_PK_SUB; t++) {
+        if (R == 2) chars_next[t] = nwb_ldg_u32(reinterpret_cast<const unsigned *>(sp_lane + 2 * t));
+        else chars_next[t] = (unsigned)nwb_ldg_u16(sp_lane + t);
+    }
+
     const int nsteps = ngroups + 63;
     const int nblocks = (nsteps + 31) / 32;
     for (int blk = 0; blk < nblocks; blk++) {
@@ -286,7 +306,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
         /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is
          * the last to enter: group s-63; lane 0's low block the first to reach row B; row B itself
          * needs the checked step, which captures the bottom-row sums) */
-        const bool lean = (s0 >= 63 && R * (s0 + 32) < B);
+        const int mode = (R * (s0 + 32) < B) ? (s0 >= 63 ? NWB_PK_LEAN : NWB_PK_HEAD) : NWB_PK_FULL;
 #pragma unroll 1
         for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
             const int ss = s0 + NWB_PK_SUB * sub;
@@ -309,27 +329,36 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 if (lane < NWB_PK_SUB && gs + NWB_PK_SUB < ngroups)
                     bq_next = nwb_ld_relaxed_u32(in_w + gs + NWB_PK_SUB, left_remote);
             }
-            const uint16_t *spb = sp_lane + R * ss;
-            unsigned char *slot0 = stage_bytes + (size_t)(ss & (NWB_PK_RING_ROWS - 1)) * SLOT;
-            if (lean) {
-                uint32_t *outb = out_w + (ss - 2 * lane - 1);
+            /* side characters of the NEXT sub-block's steps are loaded one sub-block ahead */
+            unsigned chars[NWB_PK_SUB];
+#pragma unroll
+            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = chars_next[t];
+            {
+                const uint16_t *spn = sp_lane + R * (ss + NWB_PK_SUB);
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++) {
-                    unsigned chars;
-                    if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
-                    else chars = (unsigned)nwb_ldg_u16(spb + t);
-                    nwb_pk_step<K, R, false>(st, pc, bq, t, lane, t, A, B, ngroups, col_lo, col_hi, chars,
-                                             slot0 + t * SLOT, outb, pub31, rsum);
+                    if (R == 2) chars_next[t] = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spn + 2 * t));
+                    else chars_next[t] = (unsigned)nwb_ldg_u16(spn + t);
                 }
+            }
+            unsigned char *slot0 = stage_bytes + (size_t)(ss & (NWB_PK_RING_ROWS - 1)) * SLOT;
+            uint32_t *outb = out_w + (ss - 2 * lane - 1);
+            const int gb = ss - 2 * lane - 1;
+            if (mode == NWB_PK_LEAN) {
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_pk_step<K, R, NWB_PK_LEAN>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
+                                                   slot0 + t * SLOT, outb, pub31, rsum);
+            } else if (mode == NWB_PK_HEAD) {
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_pk_step<K, R, NWB_PK_HEAD>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
+                                                   slot0 + t * SLOT, outb, pub31, rsum);
             } else {
 #pragma unroll 1
-                for (int t = 0; t < NWB_PK_SUB; t++) {
-                    unsigned chars;
-                    if (R == 2) chars = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spb + 2 * t));
-                    else chars = (unsigned)nwb_ldg_u16(spb + t);
-                    nwb_pk_step<K, R, true>(st, pc, bq, t, lane, ss + t - 2 * lane - 1, A, B, ngroups, col_lo,
-                                            col_hi, chars, slot0 + t * SLOT, out_w, pub31, rsum);
-                }
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_pk_step<K, R, NWB_PK_FULL>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
+                                                   slot0 + t * SLOT, outb, pub31, rsum);
             }
         }
         __syncwarp();
