@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "nwb_layout.h"
@@ -118,6 +119,8 @@ struct nwb_plan {
     DevBuf<unsigned long long> cntmat, bnd_c;
     DevBuf<uint32_t> bnd_w;
     DevBuf<uint16_t> side_pre;
+    DevBuf<unsigned long long> dbg_times, dbg_trace;
+    int dbg_trace_blocks = 0, dbg_trace_stride = 1;
     DevBuf<int> progress;
     DevBuf<NwbDevSummary> summary;
     Inbox inbox = {};
@@ -203,7 +206,7 @@ extern "C" void nwb_plan_destroy(nwb_plan *p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     p->top.release(); p->side.release(); p->arrows.release(); p->scores.release();
     p->bnd_s.release(); p->cntmat.release(); p->bnd_c.release(); p->bnd_w.release();
-    p->progress.release(); p->summary.release(); p->side_pre.release();
+    p->progress.release(); p->summary.release(); p->side_pre.release(); p->dbg_times.release(); p->dbg_trace.release();
     if (p->inbox.base) cudaFree(p->inbox.base);
     if (p->right_base && p->right_is_ipc) cudaIpcCloseMemHandle(p->right_base);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -367,6 +370,18 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     sp.progress = p->progress.p;
     sp.summary = p->summary.p;
     sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? 1 : 0;
+    if (getenv("NWB_DEBUG_TIMES") && p->kind == NWB_KIND_PK) { /* diagnostics: per-strip timestamps dumped to a file */
+        if (p->dbg_times.ensure((size_t)L.n_strips * 4) != NWB_OK) return NWB_ERR_NOMEM;
+        CK(cudaMemsetAsync(p->dbg_times.p, 0, (size_t)L.n_strips * 4 * sizeof(unsigned long long), st));
+        sp.debug_times = p->dbg_times.p;
+        p->dbg_trace_blocks = (B / L.pk_r + 63 + 31) / 32 + 1;
+        p->dbg_trace_stride = L.n_strips >= 8 ? (L.n_strips - 1) / 7 : 1;
+        if (p->dbg_trace.ensure((size_t)8 * p->dbg_trace_blocks * 2) != NWB_OK) return NWB_ERR_NOMEM;
+        CK(cudaMemsetAsync(p->dbg_trace.p, 0, (size_t)8 * p->dbg_trace_blocks * 2 * sizeof(unsigned long long), st));
+        sp.debug_trace = p->dbg_trace.p;
+        sp.debug_trace_stride = p->dbg_trace_stride;
+        sp.debug_trace_blocks = p->dbg_trace_blocks;
+    }
     if (p->strip_begin > 0) {
         if (!p->inbox.base || L.bpitch > p->inbox.bpitch) return NWB_ERR_INVALID;
         sp.in_bnd_s = (const int32_t *)(p->inbox.base + p->inbox.off_s);
@@ -444,6 +459,29 @@ extern "C" int nwb_plan_summary(nwb_plan *p, nwb_summary *out)
         out->partial_r = p->last.rsum;
         out->opt_score = (int32_t)(uint32_t)((unsigned long long)p->last.rsum -
                                              (unsigned long long)((long long)p->d * ((long long)p->A + p->B)));
+    }
+    if (const char *path = getenv("NWB_DEBUG_TIMES")) {
+        if (p->dbg_times.p && p->L.n_strips > 0) {
+            std::vector<unsigned long long> h((size_t)p->L.n_strips * 4);
+            cudaMemcpy(h.data(), p->dbg_times.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(path, "w")) {
+                for (int i = 0; i < p->L.n_strips; i++)
+                    fprintf(f, "%d %llu %llu %llu %llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                fclose(f);
+            }
+            if (p->dbg_trace.p) {
+                std::vector<unsigned long long> ht((size_t)8 * p->dbg_trace_blocks * 2);
+                cudaMemcpy(ht.data(), p->dbg_trace.p, ht.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                std::string tp = std::string(path) + ".trace";
+                if (FILE *f = fopen(tp.c_str(), "w")) {
+                    for (int sl = 0; sl < 8; sl++)
+                        for (int b = 0; b < p->dbg_trace_blocks; b++)
+                            fprintf(f, "%d %d %llu %llu\n", sl * p->dbg_trace_stride, b,
+                                    ht[((size_t)sl * p->dbg_trace_blocks + b) * 2], ht[((size_t)sl * p->dbg_trace_blocks + b) * 2 + 1]);
+                    fclose(f);
+                }
+            }
+        }
     }
     out->branch_count = p->last.branch_count;
     out->greatest_abs = p->last.greatest_abs;

@@ -66,6 +66,17 @@ __device__ __forceinline__ void nwb_pause()
     __nanosleep(32);
 }
 
+__device__ __forceinline__ unsigned long long nwb_globaltimer()
+{
+#ifdef NWB_EMU
+    return 0ull;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+#endif
+}
+
 /* read-only (non-coherent) 16-bit load */
 __device__ __forceinline__ unsigned short nwb_ldg_u16(const uint16_t *p)
 {
@@ -177,4 +188,8 @@ struct NwbStripParams {
     int *out_progress;
     NwbDevSummary *summary;
     int debug_nowait; /* diagnostics: skip the inter-strip waits (results are wrong) */
+    unsigned long long *debug_times; /* diagnostics: per strip {entry, first words valid, step 64, exit} in ns, or NULL */
+    unsigned long long *debug_trace; /* diagnostics: [8 traced strips][nblocks][2] = {ns at block start, polls so far} */
+    int debug_trace_stride;          /* strips c with c % stride == 0 are traced (slot c / stride, < 8) */
+    int debug_trace_blocks;
 };

@@ -80,7 +80,7 @@ static inline int nwb_pk_choose_k(int A, int B, int total_warps)
     return 4;
 }
 
-#define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * NWB_PK_RING_ROWS * (R) * (32 * (K) + 4))
+#define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * NWB_PK_RING_ROWS * (R) * (32 * (K)))
 
 template <int K>
 struct NwbPkStage;
@@ -119,11 +119,10 @@ __global__ void nwb_pk_prep_side_kernel(const uint8_t *side, int B, int shift, u
     }
 }
 
-/* staging ring: one slot per row STEP (not per row): at step s every lane writes
- * slot s & 127 (R sub-rows), so the address is a block base plus an immediate;
- * the flush un-skews.  One pad word per sub-row keeps the un-skewing reads free
- * of bank conflicts. */
-#define NWB_PK_SUBROW_BYTES(K) (32 * (K) + 4)
+/* staging ring: one slot per row GROUP (slot g & 127, R sub-rows of 32*K bytes);
+ * lane l drops its 2*K nibbles of a row at byte l*K of the sub-row, so a finished
+ * row is contiguous and the flush moves it with LDS.128 / STG.128. */
+#define NWB_PK_SUBROW_BYTES(K) (32 * (K))
 #define NWB_PK_SLOT_BYTES(K, R) ((R) * NWB_PK_SUBROW_BYTES(K))
 
 template <int K, int R>
@@ -152,12 +151,16 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
  *   NWB_PK_LEAN  every lane is strictly inside rows 1..B-1: no tests at all;
  *   NWB_PK_HEAD  some lanes are still above row 1 (the first 63 steps of a strip,
  *                which sit on the strip-to-strip critical path): only "g_hi >= 0";
- *   NWB_PK_FULL  anything, including row B (captures the bottom-row sums).
+ *   NWB_PK_TAIL  every lane has started, some are at/below row B (the last 63 steps,
+ *                also on the strip-to-strip critical path): "row <= B" tests and the
+ *                capture of the bottom-row sums;
+ *   NWB_PK_FULL  anything (tables too short for separate head and tail phases).
  * out_w + g_idx addresses the stream word of group g_hi (g_idx is a compile-time
  * constant against a rebased pointer in the unrolled loops). */
 #define NWB_PK_LEAN 0
 #define NWB_PK_HEAD 1
-#define NWB_PK_FULL 2
+#define NWB_PK_TAIL 2
+#define NWB_PK_FULL 3
 template <int K, int R, int MODE>
 __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
                                              const int lane, const int g_idx, const int g_hi, const int A, const int B,
@@ -165,6 +168,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
                                              unsigned char *slot, uint32_t *out_w, const bool pub31, long long &rsum)
 {
     const bool CHECKED = (MODE == NWB_PK_FULL);
+    const bool CAPTURE = (MODE == NWB_PK_FULL || MODE == NWB_PK_TAIL);
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
     /* ---- left inputs: from my left neighbour lane; lane 0 from the (validated) stream word */
@@ -204,7 +208,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
         if (K == 4) acc[r] = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
         else if (K == 2) acc[r] = code[0] + code[1] * 16u;
         else acc[r] = code[0];
-        if (CHECKED) {
+        if (CAPTURE) {
             /* bottom row: r(A,B) = sum of u(i,B) */
             const int row_hi = R * g_hi + 1 + r, row_lo = row_hi + R;
             if (row_lo == B) {
@@ -225,12 +229,13 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     for (int r = 0; r < R; r++) {
         const int row_hi = R * g_hi + 1 + r;
         /* arrow codes of row row_hi: low block from the previous step, high block from this one */
-        if (MODE == NWB_PK_LEAN || (MODE == NWB_PK_HEAD && g_hi >= 0) || (CHECKED && row_hi >= 1 && row_hi <= B)) {
+        if (MODE == NWB_PK_LEAN || (MODE == NWB_PK_HEAD && g_hi >= 0) || (MODE == NWB_PK_TAIL && row_hi <= B) ||
+            (CHECKED && row_hi >= 1 && row_hi <= B)) {
             stage_t w;
             if (K == 4) w = (stage_t)__byte_perm(st.acc_prev[r], acc[r], 0x7610);
             else if (K == 2) w = (stage_t)((st.acc_prev[r] & 0xFFu) | ((acc[r] >> 8) & 0xFF00u));
             else w = (stage_t)((st.acc_prev[r] & 0xFu) | ((acc[r] >> 12) & 0xF0u));
-            reinterpret_cast<stage_t *>(slot + r * NWB_PK_SUBROW_BYTES(K))[lane] = w;
+            *reinterpret_cast<stage_t *>(slot + r * NWB_PK_SUBROW_BYTES(K)) = w;
         }
         st.acc_prev[r] = acc[r];
     }
@@ -238,6 +243,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     {
         bool pub = pub31;
         if (MODE == NWB_PK_HEAD) pub = pub && (g_hi >= 0);
+        if (MODE == NWB_PK_TAIL) pub = pub && (g_hi < ngroups);
         if (CHECKED) pub = pub && (g_hi >= 0 && g_hi < ngroups);
         nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub);
     }
@@ -292,6 +298,8 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     unsigned bq = 0u, bq_next = 0u;
     if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
 
+    unsigned long long *dbg = p.debug_times ? p.debug_times + 4 * (size_t)c : nullptr;
+    if (dbg && lane == 0) dbg[0] = nwb_globaltimer();
     unsigned chars_next[NWB_PK_SUB];
 #pragma unroll
     for (int t = 0; t < NWB_PK_SUB; t++) {
@@ -301,12 +309,21 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
 
     const int nsteps = ngroups + 63;
     const int nblocks = (nsteps + 31) / 32;
+    unsigned long long *trace = nullptr;
+    unsigned long long npolls = 0;
+    if (p.debug_trace && (c % p.debug_trace_stride) == 0 && c / p.debug_trace_stride < 8)
+        trace = p.debug_trace + (size_t)(c / p.debug_trace_stride) * p.debug_trace_blocks * 2;
     for (int blk = 0; blk < nblocks; blk++) {
         const int s0 = 32 * blk;
+        if (trace && lane == 0 && blk < p.debug_trace_blocks) {
+            trace[2 * blk] = nwb_globaltimer();
+            trace[2 * blk + 1] = npolls;
+        }
         /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is
          * the last to enter: group s-63; lane 0's low block the first to reach row B; row B itself
          * needs the checked step, which captures the bottom-row sums) */
-        const int mode = (R * (s0 + 32) < B) ? (s0 >= 63 ? NWB_PK_LEAN : NWB_PK_HEAD) : NWB_PK_FULL;
+        const int mode = (R * (s0 + 32) < B) ? (s0 >= 63 ? NWB_PK_LEAN : NWB_PK_HEAD)
+                                             : (s0 >= 63 ? NWB_PK_TAIL : NWB_PK_FULL);
 #pragma unroll 1
         for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
             const int ss = s0 + NWB_PK_SUB * sub;
@@ -317,13 +334,15 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 if (!nowait) {
                     bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID);
                     while (!__all_sync(NWB_FULL_MASK, ok)) {
-                        if (!ok) {
-                            nwb_pause();
+                        npolls++;
+                        if (!ok) { /* plain spin: a sleep quantum here would sit on the strip-to-strip critical path */
                             w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
                             ok = (w & NWB_PK_VALID) != 0u;
                         }
                     }
                 }
+                if (dbg && lane == 0 && ss == 0) dbg[1] = nwb_globaltimer();
+                if (dbg && lane == 0 && ss == 64) dbg[2] = nwb_globaltimer();
                 bq = w & VMASK;
                 bq_next = 0u;
                 if (lane < NWB_PK_SUB && gs + NWB_PK_SUB < ngroups)
@@ -341,29 +360,35 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                     else chars_next[t] = (unsigned)nwb_ldg_u16(spn + t);
                 }
             }
-            unsigned char *slot0 = stage_bytes + (size_t)(ss & (NWB_PK_RING_ROWS - 1)) * SLOT;
             uint32_t *outb = out_w + (ss - 2 * lane - 1);
             const int gb = ss - 2 * lane - 1;
+            unsigned char *lane_stage = stage_bytes + lane * K;
+#define NWB_PK_SLOT_PTR(t) (lane_stage + (size_t)((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT)
             if (mode == NWB_PK_LEAN) {
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++)
                     nwb_pk_step<K, R, NWB_PK_LEAN>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   slot0 + t * SLOT, outb, pub31, rsum);
+                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
             } else if (mode == NWB_PK_HEAD) {
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++)
                     nwb_pk_step<K, R, NWB_PK_HEAD>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   slot0 + t * SLOT, outb, pub31, rsum);
+                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
+            } else if (mode == NWB_PK_TAIL) {
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_pk_step<K, R, NWB_PK_TAIL>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
+                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
             } else {
 #pragma unroll 1
                 for (int t = 0; t < NWB_PK_SUB; t++)
                     nwb_pk_step<K, R, NWB_PK_FULL>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   slot0 + t * SLOT, outb, pub31, rsum);
+                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
             }
         }
         __syncwarp();
-        /* groups <= 32*blk-32 are complete in every lane: un-skew the 32*R newest complete rows out
-         * of the ring and write them with 16-byte stores (flipping the inverted codes) */
+        /* groups <= 32*blk-32 are complete in every lane: move the 32*R newest complete rows from
+         * the ring to the arrow table with 16-byte loads/stores (flipping the inverted codes) */
         {
             const int jhi = R * (32 * blk - 31);
             const int jlo = jhi - 32 * R + 1;
@@ -371,30 +396,22 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             const int lanes_per_row = row_bytes / 16;
             const int rows_per_pass = 32 / lanes_per_row;
             const int sub = lane % lanes_per_row;
-            const int src_per_chunk = 16 / K;      /* source lanes per 16-byte chunk: 4, 8 or 16 */
 #pragma unroll
             for (int q = 0; q < (32 * R) / rows_per_pass; q++) {
                 const int j = jlo + q * rows_per_pass + lane / lanes_per_row;
                 if (j >= 1 && j <= B) {
                     const int g = (j - 1) / R, r = (j - 1) - g * R;
-                    unsigned wv[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int i = 0; i < src_per_chunk; i++) {
-                        const int l2 = sub * src_per_chunk + i; /* source lane; it stored group g at step g+2*l2+1 */
-                        const stage_t e = *reinterpret_cast<const stage_t *>(
-                            stage_bytes + (size_t)((g + 2 * l2 + 1) & (NWB_PK_RING_ROWS - 1)) * SLOT +
-                            r * NWB_PK_SUBROW_BYTES(K) + l2 * K);
-                        wv[(i * K) / 4] |= (unsigned)e << (8 * ((i * K) % 4));
-                    }
-                    uint4 v;
-                    v.x = ~wv[0] & 0x77777777u; v.y = ~wv[1] & 0x77777777u;
-                    v.z = ~wv[2] & 0x77777777u; v.w = ~wv[3] & 0x77777777u;
+                    uint4 v = *reinterpret_cast<const uint4 *>(stage_bytes + (size_t)(g & (NWB_PK_RING_ROWS - 1)) * SLOT +
+                                                               r * NWB_PK_SUBROW_BYTES(K) + sub * 16);
+                    v.x = ~v.x & 0x77777777u; v.y = ~v.y & 0x77777777u;
+                    v.z = ~v.z & 0x77777777u; v.w = ~v.w & 0x77777777u;
                     *reinterpret_cast<uint4 *>(p.arrows + (size_t)(j - 1) * p.pitch + (size_t)c * row_bytes + sub * 16) = v;
                 }
             }
         }
         __syncwarp();
     }
+    if (dbg && lane == 0) dbg[3] = nwb_globaltimer();
 }
 
 template <int K, int R, bool COUNT>
