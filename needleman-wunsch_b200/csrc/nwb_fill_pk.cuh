@@ -145,30 +145,41 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
 #endif
 }
 
+/* Bottom-row capture (once per lane and half, so kept out of line): r(A,B) = sum of u(i,B). */
+template <int K>
+__device__ __noinline__ long long nwb_pk_capture(const unsigned u0, const unsigned u1, const unsigned u2,
+                                                  const unsigned u3, const int col0, const int A, const int high)
+{
+    const unsigned u[4] = {u0, u1, u2, u3};
+    long long s = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (col0 + k <= A) s += (long long)(high ? (u[k] >> 16) : (u[k] & 0xFFFFu));
+    return s;
+}
+
+/* Per-strip constants of the row-range tests (one code body serves the head of a
+ * strip, its bulk and its tail: the first and last 63 steps sit on the
+ * strip-to-strip critical path and must not run through cold, separately
+ * unrolled code). */
+template <int R>
+struct NwbPkRange {
+    unsigned gcnt[R]; /* number of row groups whose sub-row r is inside the table (row <= B) */
+    int capg[R];      /* group in which sub-row r is row B, or -9 */
+    unsigned ngroups;
+};
+
 /* One row step of one lane: R rows x 2*K cells.  At step s lane l's low block is
  * on row group s - 2l, its high block on group s - 2l - 1 (= g_hi); group g holds
- * rows R*g+1 .. R*g+R.  MODE selects the row-range tests:
- *   NWB_PK_LEAN  every lane is strictly inside rows 1..B-1: no tests at all;
- *   NWB_PK_HEAD  some lanes are still above row 1 (the first 63 steps of a strip,
- *                which sit on the strip-to-strip critical path): only "g_hi >= 0";
- *   NWB_PK_TAIL  every lane has started, some are at/below row B (the last 63 steps,
- *                also on the strip-to-strip critical path): "row <= B" tests and the
- *                capture of the bottom-row sums;
- *   NWB_PK_FULL  anything (tables too short for separate head and tail phases).
- * out_w + g_idx addresses the stream word of group g_hi (g_idx is a compile-time
- * constant against a rebased pointer in the unrolled loops). */
-#define NWB_PK_LEAN 0
-#define NWB_PK_HEAD 1
-#define NWB_PK_TAIL 2
-#define NWB_PK_FULL 3
-template <int K, int R, int MODE>
-__device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const unsigned bq, const int t,
-                                             const int lane, const int g_idx, const int g_hi, const int A, const int B,
-                                             const int ngroups, const int col_lo, const int col_hi, const unsigned chars,
-                                             unsigned char *slot, uint32_t *out_w, const bool pub31, long long &rsum)
+ * rows R*g+1 .. R*g+R.  out_w + g_idx addresses the stream word of group g_hi
+ * (g_idx is a compile-time constant against a rebased pointer in the unrolled loop). */
+template <int K, int R>
+__device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const NwbPkRange<R> &rg,
+                                             const unsigned bq, const int t, const int lane, const int g_idx,
+                                             const int g_hi, const int A, const int col_lo, const int col_hi,
+                                             const unsigned chars, unsigned char *slot, uint32_t *out_w,
+                                             const bool pub31, long long &rsum)
 {
-    const bool CHECKED = (MODE == NWB_PK_FULL);
-    const bool CAPTURE = (MODE == NWB_PK_FULL || MODE == NWB_PK_TAIL);
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
     /* ---- left inputs: from my left neighbour lane; lane 0 from the (validated) stream word */
@@ -208,29 +219,19 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
         if (K == 4) acc[r] = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
         else if (K == 2) acc[r] = code[0] + code[1] * 16u;
         else acc[r] = code[0];
-        if (CAPTURE) {
-            /* bottom row: r(A,B) = sum of u(i,B) */
-            const int row_hi = R * g_hi + 1 + r, row_lo = row_hi + R;
-            if (row_lo == B) {
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (col_lo + k <= A) rsum += (long long)(st.u[k] & 0xFFFFu);
-            }
-            if (row_hi == B) {
-#pragma unroll
-                for (int k = 0; k < K; k++)
-                    if (col_hi + k <= A) rsum += (long long)(st.u[k] >> 16);
-            }
-        }
+        /* row B passes through this sub-row in exactly one step per half */
+        if (g_hi + 1 == rg.capg[r])
+            rsum += nwb_pk_capture<K>(st.u[0], st.u[K > 1 ? 1 : 0], st.u[K > 2 ? 2 : 0], st.u[K > 3 ? 3 : 0], col_lo, A, 0);
+        if (g_hi == rg.capg[r])
+            rsum += nwb_pk_capture<K>(st.u[0], st.u[K > 1 ? 1 : 0], st.u[K > 2 ? 2 : 0], st.u[K > 3 ? 3 : 0], col_hi, A, 1);
     }
     /* ---- outputs */
     st.send = (R == 2) ? __byte_perm(st.vlast[0], st.vlast[R - 1], 0x7632) : st.vlast[0];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const int row_hi = R * g_hi + 1 + r;
-        /* arrow codes of row row_hi: low block from the previous step, high block from this one */
-        if (MODE == NWB_PK_LEAN || (MODE == NWB_PK_HEAD && g_hi >= 0) || (MODE == NWB_PK_TAIL && row_hi <= B) ||
-            (CHECKED && row_hi >= 1 && row_hi <= B)) {
+        /* arrow codes of row R*g_hi+1+r: low block from the previous step, high block from this one;
+         * skipped while the lane is above row 1 (g_hi < 0) or below row B */
+        if ((unsigned)g_hi < rg.gcnt[r]) {
             stage_t w;
             if (K == 4) w = (stage_t)__byte_perm(st.acc_prev[r], acc[r], 0x7610);
             else if (K == 2) w = (stage_t)((st.acc_prev[r] & 0xFFu) | ((acc[r] >> 8) & 0xFF00u));
@@ -240,13 +241,8 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
         st.acc_prev[r] = acc[r];
     }
     /* lane 31: the strip's last column for group g_hi, self-validating */
-    {
-        bool pub = pub31;
-        if (MODE == NWB_PK_HEAD) pub = pub && (g_hi >= 0);
-        if (MODE == NWB_PK_TAIL) pub = pub && (g_hi < ngroups);
-        if (CHECKED) pub = pub && (g_hi >= 0 && g_hi < ngroups);
-        nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub);
-    }
+    nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u),
+                            pub31 && ((unsigned)g_hi < rg.ngroups));
 }
 
 template <int K, int R, bool COUNT>
@@ -298,6 +294,13 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     unsigned bq = 0u, bq_next = 0u;
     if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
 
+    NwbPkRange<R> rg;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        rg.gcnt[r] = (B - 1 - r >= 0) ? (unsigned)((B - 1 - r) / R + 1) : 0u;
+        rg.capg[r] = ((B - 1) % R == r) ? (B - 1) / R : -9;
+    }
+    rg.ngroups = (unsigned)ngroups;
     unsigned long long *dbg = p.debug_times ? p.debug_times + 4 * (size_t)c : nullptr;
     if (dbg && lane == 0) dbg[0] = nwb_globaltimer();
     unsigned chars_next[NWB_PK_SUB];
@@ -319,11 +322,6 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             trace[2 * blk] = nwb_globaltimer();
             trace[2 * blk + 1] = npolls;
         }
-        /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is
-         * the last to enter: group s-63; lane 0's low block the first to reach row B; row B itself
-         * needs the checked step, which captures the bottom-row sums) */
-        const int mode = (R * (s0 + 32) < B) ? (s0 >= 63 ? NWB_PK_LEAN : NWB_PK_HEAD)
-                                             : (s0 >= 63 ? NWB_PK_TAIL : NWB_PK_FULL);
 #pragma unroll 1
         for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
             const int ss = s0 + NWB_PK_SUB * sub;
@@ -364,27 +362,10 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             const int gb = ss - 2 * lane - 1;
             unsigned char *lane_stage = stage_bytes + lane * K;
 #define NWB_PK_SLOT_PTR(t) (lane_stage + (size_t)((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT)
-            if (mode == NWB_PK_LEAN) {
 #pragma unroll
-                for (int t = 0; t < NWB_PK_SUB; t++)
-                    nwb_pk_step<K, R, NWB_PK_LEAN>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
-            } else if (mode == NWB_PK_HEAD) {
-#pragma unroll
-                for (int t = 0; t < NWB_PK_SUB; t++)
-                    nwb_pk_step<K, R, NWB_PK_HEAD>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
-            } else if (mode == NWB_PK_TAIL) {
-#pragma unroll
-                for (int t = 0; t < NWB_PK_SUB; t++)
-                    nwb_pk_step<K, R, NWB_PK_TAIL>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
-            } else {
-#pragma unroll 1
-                for (int t = 0; t < NWB_PK_SUB; t++)
-                    nwb_pk_step<K, R, NWB_PK_FULL>(st, pc, bq, t, lane, t, gb + t, A, B, ngroups, col_lo, col_hi, chars[t],
-                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rsum);
-            }
+            for (int t = 0; t < NWB_PK_SUB; t++)
+                nwb_pk_step<K, R>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t], NWB_PK_SLOT_PTR(t),
+                                  outb, pub31, rsum);
         }
         __syncwarp();
         /* groups <= 32*blk-32 are complete in every lane: move the 32*R newest complete rows from

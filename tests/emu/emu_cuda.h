@@ -34,6 +34,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __restrict__
+#define __noinline__ __attribute__((noinline))
 
 struct emu_dim3 { unsigned x, y, z; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
