@@ -66,6 +66,35 @@ __device__ __forceinline__ void nwb_pause()
     __nanosleep(32);
 }
 
+/* shared-memory stores through an explicit shared-window address (keeps the
+ * address arithmetic 32-bit and out of the generic address space) */
+#ifdef NWB_EMU
+typedef unsigned char *nwb_smem_addr;
+__device__ __forceinline__ nwb_smem_addr nwb_smem_address(unsigned char *p) { return p; }
+template <typename T>
+__device__ __forceinline__ void nwb_sts(nwb_smem_addr a, int off, T v) { *reinterpret_cast<T *>(a + off) = v; }
+#else
+typedef unsigned nwb_smem_addr;
+__device__ __forceinline__ nwb_smem_addr nwb_smem_address(unsigned char *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <typename T>
+__device__ __forceinline__ void nwb_sts(nwb_smem_addr a, int off, T v);
+template <>
+__device__ __forceinline__ void nwb_sts<uint32_t>(nwb_smem_addr a, int off, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + (unsigned)off), "r"(v));
+}
+template <>
+__device__ __forceinline__ void nwb_sts<uint16_t>(nwb_smem_addr a, int off, uint16_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + (unsigned)off), "h"(v));
+}
+template <>
+__device__ __forceinline__ void nwb_sts<uint8_t>(nwb_smem_addr a, int off, uint8_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + (unsigned)off), "r"((unsigned)v));
+}
+#endif
+
 __device__ __forceinline__ unsigned long long nwb_globaltimer()
 {
 #ifdef NWB_EMU

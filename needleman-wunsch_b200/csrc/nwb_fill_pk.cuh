@@ -145,19 +145,6 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
 #endif
 }
 
-/* Bottom-row capture (once per lane and half, so kept out of line): r(A,B) = sum of u(i,B). */
-template <int K>
-__device__ __noinline__ long long nwb_pk_capture(const unsigned u0, const unsigned u1, const unsigned u2,
-                                                  const unsigned u3, const int col0, const int A, const int high)
-{
-    const unsigned u[4] = {u0, u1, u2, u3};
-    long long s = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++)
-        if (col0 + k <= A) s += (long long)(high ? (u[k] >> 16) : (u[k] & 0xFFFFu));
-    return s;
-}
-
 /* Per-strip constants of the row-range tests (one code body serves the head of a
  * strip, its bulk and its tail: the first and last 63 steps sit on the
  * strip-to-strip critical path and must not run through cold, separately
@@ -165,7 +152,8 @@ __device__ __noinline__ long long nwb_pk_capture(const unsigned u0, const unsign
 template <int R>
 struct NwbPkRange {
     unsigned gcnt[R]; /* number of row groups whose sub-row r is inside the table (row <= B) */
-    int capg[R];      /* group in which sub-row r is row B, or -9 */
+    int capg;         /* the row group that contains row B */
+    int rB;           /* ... and row B's sub-row in it      */
     unsigned ngroups;
 };
 
@@ -177,8 +165,8 @@ template <int K, int R>
 __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const NwbPkRange<R> &rg,
                                              const unsigned bq, const int t, const int lane, const int g_idx,
                                              const int g_hi, const int A, const int col_lo, const int col_hi,
-                                             const unsigned chars, unsigned char *slot, uint32_t *out_w,
-                                             const bool pub31, long long &rsum)
+                                             const unsigned chars, const nwb_smem_addr slot, uint32_t *out_w,
+                                             const bool pub31, unsigned &rs32)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
@@ -198,6 +186,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     }
     /* ---- the cells: row by row, column by column (the scheduler finds the wavefront) */
     unsigned acc[R];
+    unsigned uafter[R][K]; /* u right after sub-row r (only read by the rare bottom-row capture) */
 #pragma unroll
     for (int r = 0; r < R; r++) {
         unsigned v = vL[r];
@@ -213,17 +202,13 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
             const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
             code[k] = fd + fl * 2u + fu * 4u; /* inverted: a set bit = NO arrow */
             st.u[k] = un;
+            uafter[r][k] = un;
             v = vn;
         }
         st.vlast[r] = v;
         if (K == 4) acc[r] = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
         else if (K == 2) acc[r] = code[0] + code[1] * 16u;
         else acc[r] = code[0];
-        /* row B passes through this sub-row in exactly one step per half */
-        if (g_hi + 1 == rg.capg[r])
-            rsum += nwb_pk_capture<K>(st.u[0], st.u[K > 1 ? 1 : 0], st.u[K > 2 ? 2 : 0], st.u[K > 3 ? 3 : 0], col_lo, A, 0);
-        if (g_hi == rg.capg[r])
-            rsum += nwb_pk_capture<K>(st.u[0], st.u[K > 1 ? 1 : 0], st.u[K > 2 ? 2 : 0], st.u[K > 3 ? 3 : 0], col_hi, A, 1);
     }
     /* ---- outputs */
     st.send = (R == 2) ? __byte_perm(st.vlast[0], st.vlast[R - 1], 0x7632) : st.vlast[0];
@@ -236,9 +221,23 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
             if (K == 4) w = (stage_t)__byte_perm(st.acc_prev[r], acc[r], 0x7610);
             else if (K == 2) w = (stage_t)((st.acc_prev[r] & 0xFFu) | ((acc[r] >> 8) & 0xFF00u));
             else w = (stage_t)((st.acc_prev[r] & 0xFu) | ((acc[r] >> 12) & 0xF0u));
-            *reinterpret_cast<stage_t *>(slot + r * NWB_PK_SUBROW_BYTES(K)) = w;
+            nwb_sts<stage_t>(slot, r * NWB_PK_SUBROW_BYTES(K), w);
         }
         st.acc_prev[r] = acc[r];
+    }
+    /* row B passes through a lane's low block in one step and through its high block in the
+     * next: bottom row, r(A,B) = sum of u(i,B) */
+    if (__builtin_expect((unsigned)(rg.capg - g_hi) <= 1u, 0)) {
+        const unsigned half = (g_hi == rg.capg) ? 0xFFFF0000u : 0x0000FFFFu; /* which block is on row B now */
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            unsigned x = uafter[0][k];
+            if (R == 2 && rg.rB == 1) x = uafter[R - 1][k];
+            unsigned m = 0u;
+            if (col_lo + k <= A) m |= 0x0000FFFFu;
+            if (col_hi + k <= A) m |= 0xFFFF0000u;
+            rs32 += x & m & half; /* packed: each half sums at most K values below 2^13 */
+        }
     }
     /* lane 31: the strip's last column for group g_hi, self-validating */
     nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u),
@@ -294,12 +293,15 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     unsigned bq = 0u, bq_next = 0u;
     if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
 
+    const nwb_smem_addr lane_stage = nwb_smem_address(stage_bytes) + (unsigned)(lane * K);
+    unsigned rs32 = 0u; /* this lane's share of sum_i u(i,B), packed per half */
     NwbPkRange<R> rg;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         rg.gcnt[r] = (B - 1 - r >= 0) ? (unsigned)((B - 1 - r) / R + 1) : 0u;
-        rg.capg[r] = ((B - 1) % R == r) ? (B - 1) / R : -9;
     }
+    rg.capg = (B - 1) / R;
+    rg.rB = (B - 1) % R;
     rg.ngroups = (unsigned)ngroups;
     unsigned long long *dbg = p.debug_times ? p.debug_times + 4 * (size_t)c : nullptr;
     if (dbg && lane == 0) dbg[0] = nwb_globaltimer();
@@ -360,12 +362,11 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             }
             uint32_t *outb = out_w + (ss - 2 * lane - 1);
             const int gb = ss - 2 * lane - 1;
-            unsigned char *lane_stage = stage_bytes + lane * K;
-#define NWB_PK_SLOT_PTR(t) (lane_stage + (size_t)((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT)
+#define NWB_PK_SLOT_PTR(t) (lane_stage + (unsigned)(((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT))
 #pragma unroll
             for (int t = 0; t < NWB_PK_SUB; t++)
                 nwb_pk_step<K, R>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t], NWB_PK_SLOT_PTR(t),
-                                  outb, pub31, rsum);
+                                  outb, pub31, rs32);
         }
         __syncwarp();
         /* groups <= 32*blk-32 are complete in every lane: move the 32*R newest complete rows from
@@ -392,6 +393,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
         }
         __syncwarp();
     }
+    rsum += (long long)(rs32 & 0xFFFFu) + (long long)(rs32 >> 16);
     if (dbg && lane == 0) dbg[3] = nwb_globaltimer();
 }
 
