@@ -160,8 +160,13 @@ struct NwbPkRange {
 /* One row step of one lane: R rows x 2*K cells.  At step s lane l's low block is
  * on row group s - 2l, its high block on group s - 2l - 1 (= g_hi); group g holds
  * rows R*g+1 .. R*g+R.  out_w + g_idx addresses the stream word of group g_hi
- * (g_idx is a compile-time constant against a rebased pointer in the unrolled loop). */
-template <int K, int R>
+ * (g_idx is a compile-time constant against a rebased pointer in the unrolled loop).
+ * LEAN: every lane is strictly inside rows 1..B-1 for the whole block, so the
+ * row-range predicates and the bottom-row capture are compiled out (the bulk of a
+ * strip).  The checked variant serves the first and last 63 steps; it is kept
+ * small (4 steps unrolled) because it runs once per strip from a cold I-cache
+ * and sits on the strip-to-strip critical path. */
+template <int K, int R, bool LEAN>
 __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const NwbPkRange<R> &rg,
                                              const unsigned bq, const int t, const int lane, const int g_idx,
                                              const int g_hi, const int A, const int col_lo, const int col_hi,
@@ -216,7 +221,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     for (int r = 0; r < R; r++) {
         /* arrow codes of row R*g_hi+1+r: low block from the previous step, high block from this one;
          * skipped while the lane is above row 1 (g_hi < 0) or below row B */
-        if ((unsigned)g_hi < rg.gcnt[r]) {
+        if (LEAN || (unsigned)g_hi < rg.gcnt[r]) {
             stage_t w;
             if (K == 4) w = (stage_t)__byte_perm(st.acc_prev[r], acc[r], 0x7610);
             else if (K == 2) w = (stage_t)((st.acc_prev[r] & 0xFFu) | ((acc[r] >> 8) & 0xFF00u));
@@ -227,7 +232,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     }
     /* row B passes through a lane's low block in one step and through its high block in the
      * next: bottom row, r(A,B) = sum of u(i,B) */
-    if (__builtin_expect((unsigned)(rg.capg - g_hi) <= 1u, 0)) {
+    if (!LEAN && __builtin_expect((unsigned)(rg.capg - g_hi) <= 1u, 0)) {
         const unsigned half = (g_hi == rg.capg) ? 0xFFFF0000u : 0x0000FFFFu; /* which block is on row B now */
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -241,7 +246,7 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     }
     /* lane 31: the strip's last column for group g_hi, self-validating */
     nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u),
-                            pub31 && ((unsigned)g_hi < rg.ngroups));
+                            pub31 && (LEAN || (unsigned)g_hi < rg.ngroups));
 }
 
 template <int K, int R, bool COUNT>
@@ -324,6 +329,9 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             trace[2 * blk] = nwb_globaltimer();
             trace[2 * blk + 1] = npolls;
         }
+        /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is the
+         * last to enter: group s-63; lane 0's low block is the first to reach row B) */
+        const bool lean = (s0 >= 63 && R * (s0 + 32) < B);
 #pragma unroll 1
         for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
             const int ss = s0 + NWB_PK_SUB * sub;
@@ -363,10 +371,26 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             uint32_t *outb = out_w + (ss - 2 * lane - 1);
             const int gb = ss - 2 * lane - 1;
 #define NWB_PK_SLOT_PTR(t) (lane_stage + (unsigned)(((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT))
+            if (lean) {
 #pragma unroll
-            for (int t = 0; t < NWB_PK_SUB; t++)
-                nwb_pk_step<K, R>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t], NWB_PK_SLOT_PTR(t),
-                                  outb, pub31, rs32);
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_pk_step<K, R, true>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
+                                            NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
+            } else {
+                const uint16_t *spc = sp_lane + R * ss;
+#pragma unroll 1
+                for (int h = 0; h < NWB_PK_SUB; h += 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int t = h + i;
+                        unsigned ch; /* already prefetched one sub-block ago: an L1 hit */
+                        if (R == 2) ch = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spc + 2 * t));
+                        else ch = (unsigned)nwb_ldg_u16(spc + t);
+                        nwb_pk_step<K, R, false>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, ch,
+                                                 NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
+                    }
+                }
+            }
         }
         __syncwarp();
         /* groups <= 32*blk-32 are complete in every lane: move the 32*R newest complete rows from
