@@ -221,6 +221,7 @@ def run_ours(args) -> None:
         total_ms = float(tt.item())
     last_kernel_ms = plan.kernel_ms()
     summ = plan.summary()
+    launches_per_step = plan.launches() // (max(args.warmup, 3) + args.steps)
 
     # ---- end to end through the public plan API with host strings
     barrier()
@@ -239,6 +240,15 @@ def run_ours(args) -> None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     clocks = sampler.stop() if rank == 0 else None
+    opt_score = summ.opt_score
+    branch_total = summ.branch_count
+    if world > 1:
+        # a strip group's score is the sum of the ranks' bottom-row shares (include/nwb.h nwb_summary)
+        tt = torch.tensor([summ.partial_r, summ.branch_count], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        if summ.kernel_kind == 1:
+            opt_score = int(tt[0].item()) - D_ * (A + B)
+        branch_total = int(tt[1].item()) & 0xFFFFFFFF
 
     if rank == 0:
         cells = A * B
@@ -258,6 +268,14 @@ def run_ours(args) -> None:
         achieved_ops = cells * OPS_PER_CELL / (k_ms * 1e-3)
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = cells * 0.5 + A + B
+        # dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel from the committed ncu capture
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_fill_pk_ncu_summary.json")
+        if os.path.exists(tpath) and world == 1:
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_total")
+            except Exception:
+                traffic = None
         line = {
             "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -265,7 +283,7 @@ def run_ours(args) -> None:
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "int_issue", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tops/s (algorithmic INT ops, 10 per cell)", "frac": achieved_ops / peak_ops,
-                         "traffic": None,
+                         "traffic": traffic,
                          "peak_source": f"measured on this GPU: VIMNMX3 {r_per_clk:.1f} thread-results/clk/SM "
                                         f"(VIMNMX3.U16x2 {r16:.1f} instr/clk/SM, VIMNMX3+IMAD {rmix:.1f}) x "
                                         f"{props.multi_processor_count} SMs x {f_mhz:.0f} MHz "
@@ -273,12 +291,17 @@ def run_ours(args) -> None:
                          "kernel": "nwb_fill_pk_kernel" if summ.kernel_kind == 1 else "nwb_fill_i32_kernel",
                          "kernel_ms": k_ms},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+                             "algorithmic_bytes": alg_bytes,
                              "note": "secondary: 0.5 B/cell arrow write-back + strings; not the binding roofline"},
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": A + B, "d2h_bytes_per_step": 32},
-            "gpu_launches": args.steps * world,
+            "gpu_launches": args.steps * world * launches_per_step,
+            "launches_per_step": {"per_rank": launches_per_step,
+                                  "kernels": "nwb_pk_prep_side_kernel, nwb_fill_pk_kernel, nwb_branch_count_kernel"
+                                  if summ.kernel_kind == 1 else "nwb_fill_i32_kernel"},
             "clocks": clocks,
-            "result": {"opt_score": summ.opt_score, "branch_count": summ.branch_count, "kernel_kind": summ.kernel_kind},
+            "result": {"opt_score": opt_score, "branch_count": branch_total, "kernel_kind": summ.kernel_kind,
+                       "golden": "tests/golden/golden_big.json config3_dna_100k: score 11389, branches 3439940792"},
             "step_ms": [round(x, 3) for x in step_ms],
         }
         if world == 1:

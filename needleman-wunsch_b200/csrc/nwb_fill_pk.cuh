@@ -70,13 +70,16 @@ static inline bool nwb_pk_supported(int m, int k, int d, NwbPkConsts *pc)
     return true;
 }
 
-/* Columns per half-lane: the smallest K whose strip count fits the resident
- * warps (one warp per SM sub-partition), else 4 with cyclic passes. */
+/* Columns per half-lane.  Every strip boundary costs a pipeline hop of ~72 row
+ * steps (64 virtual lanes of skew plus the hand-off), every column per lane makes
+ * a step longer; measured on B200 the narrow strips only pay off while there are
+ * few of them, so take the smallest K that keeps the strip count moderate. */
 static inline int nwb_pk_choose_k(int A, int B, int total_warps)
 {
     (void)B;
+    (void)total_warps;
     for (int K = 1; K <= 4; K *= 2)
-        if ((A + 64 * K - 1) / (64 * K) <= total_warps) return K;
+        if ((A + 64 * K - 1) / (64 * K) <= 240) return K;
     return 4;
 }
 
