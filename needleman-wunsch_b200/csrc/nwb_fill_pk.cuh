@@ -71,15 +71,14 @@ static inline bool nwb_pk_supported(int m, int k, int d, NwbPkConsts *pc)
 }
 
 /* Columns per half-lane.  Every strip boundary costs a pipeline hop of ~72 row
- * steps (64 virtual lanes of skew plus the hand-off), every column per lane makes
- * a step longer; measured on B200 the narrow strips only pay off while there are
- * few of them, so take the smallest K that keeps the strip count moderate. */
+ * steps (64 virtual lanes of skew plus the hand-off) while every column per lane
+ * only lengthens a step; measured on B200 (10k, 30k, 100k squares) the widest
+ * strip, K = 4 (256 columns), wins at every size, so it is the default. */
 static inline int nwb_pk_choose_k(int A, int B, int total_warps)
 {
+    (void)A;
     (void)B;
     (void)total_warps;
-    for (int K = 1; K <= 4; K *= 2)
-        if ((A + 64 * K - 1) / (64 * K) <= 240) return K;
     return 4;
 }
 
