@@ -202,12 +202,25 @@ int nwb_plan_ipc_attach_right(nwb_plan *p, const void *blob);
  * ========================================================================== */
 typedef struct nwb_batch nwb_batch;
 
-/* Pair p has top = tops + top_off[p] .. top_off[p+1], side likewise.
- * Results per pair: opt score, branch count, count (if NWB_WANT_COUNT), and
- * with NWB_WANT_ARROWS_HOST each pair's arrow table. */
+/* Pair p has top = tops + top_off[p] .. top_off[p+1], side likewise (offset
+ * arrays hold n_pairs + 1 entries).  Results per pair: optimal score, branch
+ * count (unless NWB_NO_BRANCH_COUNT) and, with NWB_WANT_ARROWS_HOST, the pair's
+ * arrow table (layout of section 1 with pitch 128 * ceil(A/256) bytes).
+ * The batch path runs the packed 16x2 kernel only: schemes outside its range
+ * (see nwb_fill_pk.cuh) and NWB_WANT_COUNT / NWB_WANT_SCORES / NWB_TRACK_ABS
+ * return NWB_ERR_UNSUPPORTED -- use nwb_fill() per pair for those.
+ * nwb_fill_batch() = nwb_batch_create() + nwb_batch_run() + nwb_batch_fetch(). */
 int nwb_fill_batch(const char *tops, const int64_t *top_off,
                    const char *sides, const int64_t *side_off, int64_t n_pairs,
                    int m, int k, int d, unsigned flags, int device, nwb_batch **out);
+/* Upload the pairs and allocate the device-side tables (strings stay in HBM). */
+int nwb_batch_create(const char *tops, const int64_t *top_off,
+                     const char *sides, const int64_t *side_off, int64_t n_pairs,
+                     int m, int k, int d, unsigned flags, int device, nwb_batch **out);
+/* Launch the batch on `stream` (NULL = the batch's own); asynchronous. */
+int nwb_batch_run(nwb_batch *b, void *stream);
+/* Wait and copy the per-pair results (and arrows if requested) to the host. */
+int nwb_batch_fetch(nwb_batch *b);
 void nwb_batch_free(nwb_batch *b);
 int64_t nwb_batch_size(const nwb_batch *b);
 int32_t nwb_batch_opt_score(const nwb_batch *b, int64_t pair);
@@ -215,6 +228,8 @@ uint32_t nwb_batch_branch_count(const nwb_batch *b, int64_t pair);
 uint64_t nwb_batch_count_u64(const nwb_batch *b, int64_t pair);
 const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair, size_t *pitch);
 float nwb_batch_kernel_ms(const nwb_batch *b);
+int64_t nwb_batch_launches(const nwb_batch *b);
+void *nwb_batch_arrows_device(nwb_batch *b);
 
 /* ========================================================================== *
  * 4. Measurement aid (not on the fill path): INT/DPX issue rate of `device`,

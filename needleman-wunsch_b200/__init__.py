@@ -99,6 +99,12 @@ _SIGS = {
     "nwb_measure_int_issue": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nwb_fill_batch": (C.c_int, [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                  C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]),
+    "nwb_batch_create": (C.c_int, [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                   C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]),
+    "nwb_batch_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nwb_batch_fetch": (C.c_int, [C.c_void_p]),
+    "nwb_batch_launches": (C.c_int64, [C.c_void_p]),
+    "nwb_batch_arrows_device": (C.c_void_p, [C.c_void_p]),
     "nwb_batch_free": (None, [C.c_void_p]),
     "nwb_batch_size": (C.c_int64, [C.c_void_p]),
     "nwb_batch_opt_score": (C.c_int32, [C.c_void_p, C.c_int64]),
@@ -309,6 +315,76 @@ class Plan:
     def close(self) -> None:
         if self._h:
             load_library().nwb_plan_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """Batch of independent pairs (nwb_batch): one warp per pair on the GPU."""
+
+    def __init__(self, tops: list[bytes], sides: list[bytes], m: int, k: int, d: int, flags: int = 0,
+                 device: int = 0):
+        assert len(tops) == len(sides)
+        self.n = len(tops)
+        self.tops, self.sides = tops, sides
+        tcat, scat = b"".join(tops), b"".join(sides)
+        self._toff = np.zeros(self.n + 1, np.int64)
+        self._soff = np.zeros(self.n + 1, np.int64)
+        np.cumsum([len(t) for t in tops], out=self._toff[1:])
+        np.cumsum([len(s) for s in sides], out=self._soff[1:])
+        self._h = C.c_void_p()
+        _ck(load_library().nwb_batch_create(tcat, self._toff.ctypes.data_as(C.c_void_p), scat,
+                                            self._soff.ctypes.data_as(C.c_void_p), self.n, m, k, d, flags, device,
+                                            C.byref(self._h)), "nwb_batch_create")
+
+    @classmethod
+    def from_arrays(cls, tcat: bytes, toff: np.ndarray, scat: bytes, soff: np.ndarray, m, k, d, flags=0, device=0):
+        self = cls.__new__(cls)
+        self.n = len(toff) - 1
+        self.tops = self.sides = None
+        self._toff = np.ascontiguousarray(toff, np.int64)
+        self._soff = np.ascontiguousarray(soff, np.int64)
+        self._h = C.c_void_p()
+        _ck(load_library().nwb_batch_create(tcat, self._toff.ctypes.data_as(C.c_void_p), scat,
+                                            self._soff.ctypes.data_as(C.c_void_p), self.n, m, k, d, flags, device,
+                                            C.byref(self._h)), "nwb_batch_create")
+        return self
+
+    def run(self, stream: int | None = None) -> None:
+        _ck(load_library().nwb_batch_run(self._h, C.c_void_p(stream or 0)), "nwb_batch_run")
+
+    def fetch(self) -> None:
+        _ck(load_library().nwb_batch_fetch(self._h), "nwb_batch_fetch")
+
+    def kernel_ms(self) -> float:
+        return load_library().nwb_batch_kernel_ms(self._h)
+
+    def launches(self) -> int:
+        return load_library().nwb_batch_launches(self._h)
+
+    def opt_score(self, p: int) -> int:
+        return load_library().nwb_batch_opt_score(self._h, p)
+
+    def branch_count(self, p: int) -> int:
+        return load_library().nwb_batch_branch_count(self._h, p)
+
+    def arrow_rows(self, p: int) -> np.ndarray | None:
+        pitch = C.c_size_t()
+        ptr = load_library().nwb_batch_arrow_rows(self._h, p, C.byref(pitch))
+        b = int(self._soff[p + 1] - self._soff[p])
+        if not ptr or b == 0:
+            return None
+        buf = (C.c_uint8 * (pitch.value * b)).from_address(ptr)
+        return np.frombuffer(buf, np.uint8).reshape(b, pitch.value).copy()
+
+    def close(self) -> None:
+        if self._h:
+            load_library().nwb_batch_free(self._h)
             self._h = C.c_void_p(None)
 
     def __del__(self):

@@ -1,3 +1,143 @@
-/* nwb_batch.cuh -- batch kernel (placeholder until implemented). */
+/*
+ * nwb_batch.cuh -- batch of independent pairs: one warp per pair, no inter-block
+ * synchronisation (BASELINE config 4: 1M pairs of 256 x 256).  Replaces the
+ * reference looped per pair: alloc_computation + init_computation +
+ * compute_table_scores + free_computation (computation.c:51-214,
+ * needleman-wunsch.c:583) for every pair.
+ *
+ * A warp runs the packed 16x2 strip engine (nwb_fill_pk.cuh, K = 4 columns per
+ * half-lane, one row per step) over the 256-column strips of its pair, left to
+ * right; a pair of up to 256 columns is a single strip and needs no boundary
+ * stream at all.  The pair's side string is pre-shifted into the warp's shared
+ * memory once.  Pairs are handed out grid-stride.
+ */
 #pragma once
-#include "nwb_device.cuh"
+#include "nwb_fill_pk.cuh"
+
+#define NWB_BATCH_WARPS 8
+#define NWB_BATCH_K 4
+#define NWB_BATCH_R 1
+#define NWB_BATCH_SPADB 64   /* side_pre entries in front of row 1 (lane 31 starts 61 rows above the table) */
+#define NWB_BATCH_STAIL 192  /* ... and behind row B (skew + block rounding + prefetch) */
+
+struct NwbBatchParams {
+    const uint8_t *tops;
+    const long long *top_off;   /* n_pairs + 1 */
+    const uint8_t *sides;
+    const long long *side_off;  /* n_pairs + 1 */
+    long long n_pairs;
+    int m, k, d;
+    int max_B;                  /* longest side string: sizes the shared side_pre copy */
+    uint8_t *arrows;            /* all pairs' nibble tables */
+    const long long *arrow_off; /* byte offset of pair p's table; its pitch is 128 * ceil(A_p / 256) */
+    int *out_score;             /* [n_pairs] */
+    uint32_t *scratch;          /* boundary streams for pairs wider than one strip: per warp n_strips_max * bpitch */
+    size_t scratch_per_warp;    /* words */
+    size_t bpitch;              /* words per strip boundary */
+};
+
+#define NWB_BATCH_SIDE_ELEMS(maxB) ((size_t)(maxB) + NWB_BATCH_SPADB + NWB_BATCH_STAIL)
+#define NWB_BATCH_SMEM_PER_WARP(maxB) \
+    (NWB_PK_SMEM_BYTES(NWB_BATCH_K, NWB_BATCH_R, 1) + ((NWB_BATCH_SIDE_ELEMS(maxB) * 2 + 15) / 16) * 16)
+
+__global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(const NwbBatchParams bp, const NwbPkConsts pc)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const size_t per_warp = NWB_BATCH_SMEM_PER_WARP(bp.max_B);
+    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * per_warp;
+    uint16_t *side_sm = reinterpret_cast<uint16_t *>(stage + NWB_PK_SMEM_BYTES(NWB_BATCH_K, NWB_BATCH_R, 1));
+
+    for (long long pr = gwarp; pr < bp.n_pairs; pr += nwarps) {
+        const long long t0 = bp.top_off[pr], s0 = bp.side_off[pr];
+        const int A = (int)(bp.top_off[pr + 1] - t0), B = (int)(bp.side_off[pr + 1] - s0);
+        if (A == 0 || B == 0) {
+            if (lane == 0) bp.out_score[pr] = (A == 0) ? -B * bp.d : -A * bp.d; /* borders only */
+            continue;
+        }
+        /* side_pre of this pair: entry e is row e - SPADB */
+        const int nelem = B + NWB_BATCH_SPADB + NWB_BATCH_STAIL;
+        for (int e = lane; e < nelem; e += 32) {
+            const int j = e - NWB_BATCH_SPADB;
+            unsigned v = 0xFFFFu;
+            if (j >= 1 && j <= B) v = (~((unsigned)bp.sides[s0 + j - 1] << pc.shift)) & 0xFFFFu;
+            side_sm[e] = (uint16_t)v;
+        }
+        const int n_strips = (A + 64 * NWB_BATCH_K - 1) / (64 * NWB_BATCH_K);
+        uint32_t *scr = bp.scratch + (size_t)gwarp * bp.scratch_per_warp;
+        if (n_strips > 1) { /* boundary streams start invalid */
+            const size_t nw = (size_t)(n_strips - 1) * bp.bpitch;
+            for (size_t e = lane; e < nw; e += 32) scr[e] = 0u;
+        }
+        __syncwarp();
+
+        NwbStripParams sp;
+        sp.top = bp.tops + t0;
+        sp.side = bp.sides + s0;
+        sp.side_pre = side_sm - (NWB_PK_SPAD - NWB_BATCH_SPADB); /* the strip engine indexes from row -NWB_PK_SPAD */
+        sp.A = A; sp.B = B; sp.m = bp.m; sp.k = bp.k; sp.d = bp.d;
+        sp.n_strips = n_strips;
+        sp.strip_begin = 0;
+        sp.strip_end = n_strips;
+        sp.arrows = bp.arrows + bp.arrow_off[pr];
+        sp.pitch = (size_t)n_strips * 32 * NWB_BATCH_K;
+        sp.scores = nullptr; sp.cntmat = nullptr; sp.spitch = 0;
+        sp.bnd_s = nullptr; sp.bnd_c = nullptr;
+        sp.bnd_w = scr;
+        sp.bpitch = bp.bpitch;
+        sp.progress = nullptr;
+        sp.in_bnd_s = nullptr; sp.in_bnd_c = nullptr; sp.in_bnd_w = nullptr; sp.in_progress = nullptr;
+        sp.out_bnd_s = nullptr; sp.out_bnd_c = nullptr; sp.out_bnd_w = nullptr; sp.out_progress = nullptr;
+        sp.summary = nullptr;
+        sp.debug_nowait = 0;
+        sp.debug_times = nullptr; sp.debug_trace = nullptr; sp.debug_trace_stride = 1; sp.debug_trace_blocks = 0;
+
+        long long rsum = 0;
+        for (int c = 0; c < n_strips; c++) {
+            nwb_pk_strip<NWB_BATCH_K, NWB_BATCH_R, true>(sp, pc, c, stage, lane, rsum);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+        /* score(A,B) = sum_i u(i,B) - d*(A+B) */
+        if (lane == 0) bp.out_score[pr] = (int)(unsigned)((unsigned long long)rsum - (unsigned long long)((long long)bp.d * ((long long)A + B)));
+        __syncwarp();
+    }
+}
+
+/* per-pair branch counters (get_branch_count(), walk-table.c:133): one warp per pair over its finished table */
+__global__ void nwb_batch_branch_kernel(const NwbBatchParams bp, unsigned *out_branch)
+{
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long pr = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pr < bp.n_pairs; pr += nwarps) {
+        const int A = (int)(bp.top_off[pr + 1] - bp.top_off[pr]), B = (int)(bp.side_off[pr + 1] - bp.side_off[pr]);
+        unsigned cnt = 0;
+        if (A > 0 && B > 0) {
+            const int n_strips = (A + 64 * NWB_BATCH_K - 1) / (64 * NWB_BATCH_K);
+            const size_t pitch = (size_t)n_strips * 32 * NWB_BATCH_K;
+            const uint8_t *tab = bp.arrows + bp.arrow_off[pr];
+            const int groups_per_row = (A + 31) / 32;
+            const long long groups = (long long)groups_per_row * B;
+            for (long long idx = lane; idx < groups; idx += 32) {
+                const int row = (int)(idx / groups_per_row), g = (int)(idx % groups_per_row);
+                const uint4 v = *reinterpret_cast<const uint4 *>(tab + (size_t)row * pitch + (size_t)g * 16);
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned x = w[q];
+                    const unsigned b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u;
+                    unsigned two = (b0 & b1) | (b0 & b2) | (b1 & b2);
+                    int hi = A - (g * 32 + q * 8);
+                    if (hi < 8) two &= (hi <= 0) ? 0u : ((1u << (4 * hi)) - 1u);
+                    cnt += (unsigned)__popc(two);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(NWB_FULL_MASK, cnt, o);
+        if (lane == 0) out_branch[pr] = cnt;
+    }
+}

@@ -1,15 +1,202 @@
-/* nwb_batch_api.inl -- batch entry points (placeholder until implemented). */
-struct nwb_batch { int64_t n; };
-extern "C" int nwb_fill_batch(const char *, const int64_t *, const char *, const int64_t *, int64_t,
-                              int, int, int, unsigned, int, nwb_batch **out)
+/* nwb_batch_api.inl -- host side of the batch entry points (include/nwb.h section 3). */
+struct nwb_batch {
+    int device = 0;
+    unsigned flags = 0;
+    int64_t n = 0;
+    int m = 0, k = 0, d = 0;
+    int sm_count = 0;
+    int max_B = 0, max_strips = 1;
+    NwbPkConsts pc = {};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<uint8_t> tops, sides, arrows;
+    DevBuf<long long> top_off, side_off, arrow_off;
+    DevBuf<int> score;
+    DevBuf<unsigned> branch;
+    DevBuf<uint32_t> scratch;
+    std::vector<long long> h_top_off, h_side_off, h_arrow_off;
+    std::vector<int> h_score;
+    std::vector<unsigned> h_branch;
+    std::vector<uint8_t> h_arrows;
+    size_t arrows_bytes = 0;
+    bool ran = false, fetched = false;
+    int64_t launches = 0;
+};
+
+extern "C" void nwb_batch_free(nwb_batch *b)
 {
-    if (out) *out = nullptr;
-    return NWB_ERR_UNSUPPORTED;
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    b->tops.release(); b->sides.release(); b->arrows.release(); b->top_off.release(); b->side_off.release();
+    b->arrow_off.release(); b->score.release(); b->branch.release(); b->scratch.release();
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
 }
-extern "C" void nwb_batch_free(nwb_batch *b) { delete b; }
+
+extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const char *sides, const int64_t *side_off,
+                                int64_t n_pairs, int m, int k, int d, unsigned flags, int device, nwb_batch **out)
+{
+    if (!out) return NWB_ERR_INVALID;
+    *out = nullptr;
+    if (n_pairs < 0 || !top_off || !side_off) return NWB_ERR_INVALID;
+    if (flags & (NWB_WANT_SCORES | NWB_WANT_COUNT | NWB_WANT_COUNT_MATRIX | NWB_TRACK_ABS | NWB_FORCE_GENERAL))
+        return NWB_ERR_UNSUPPORTED; /* the batch path runs the packed kernel only */
+    const int ndev = nwb_device_count();
+    if (ndev <= 0) return NWB_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return NWB_ERR_INVALID;
+    NwbPkConsts pc;
+    if (!nwb_pk_supported(m, k, d, &pc)) return NWB_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(device));
+    nwb_batch *b = new (std::nothrow) nwb_batch();
+    if (!b) return NWB_ERR_NOMEM;
+    b->device = device; b->flags = flags; b->n = n_pairs; b->m = m; b->k = k; b->d = d; b->pc = pc;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e != cudaSuccess) { int rc = cuda_fail(e, "batch setup"); nwb_batch_free(b); return rc; }
+    b->sm_count = prop.multiProcessorCount;
+    b->h_top_off.assign(top_off, top_off + n_pairs + 1);
+    b->h_side_off.assign(side_off, side_off + n_pairs + 1);
+    b->h_arrow_off.resize((size_t)n_pairs + 1);
+    long long aoff = 0;
+    for (int64_t p = 0; p < n_pairs; p++) {
+        const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
+        if (A < 0 || B < 0 || A > INT_MAX / 2 || B > 60000) { nwb_batch_free(b); return NWB_ERR_INVALID; }
+        const int ns = (int)((A + 255) / 256);
+        if (ns > b->max_strips) b->max_strips = ns;
+        if ((int)B > b->max_B) b->max_B = (int)B;
+        b->h_arrow_off[(size_t)p] = aoff;
+        aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
+    }
+    b->h_arrow_off[(size_t)n_pairs] = aoff;
+    b->arrows_bytes = (size_t)aoff;
+    if (NWB_BATCH_SMEM_PER_WARP(b->max_B) * NWB_BATCH_WARPS > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
+    const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
+    int rc = b->tops.ensure(tbytes + 16);
+    if (rc == NWB_OK) rc = b->sides.ensure(sbytes + 16);
+    if (rc == NWB_OK) rc = b->top_off.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK) rc = b->side_off.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK) rc = b->arrow_off.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK) rc = b->arrows.ensure(b->arrows_bytes + 16);
+    if (rc == NWB_OK) rc = b->score.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK) rc = b->branch.ensure((size_t)n_pairs + 1);
+    if (rc != NWB_OK) { nwb_batch_free(b); return rc; }
+    e = cudaSuccess;
+    if (tbytes) e = cudaMemcpyAsync(b->tops.p, tops, tbytes, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(b->sides.p, sides, sbytes, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->top_off.p, b->h_top_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->side_off.p, b->h_side_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->arrow_off.p, b->h_arrow_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "batch upload"); nwb_batch_free(b); return rc; }
+    *out = b;
+    return NWB_OK;
+}
+
+extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
+{
+    if (!b) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    b->ran = true;
+    b->fetched = false;
+    if (b->n == 0) return NWB_OK;
+    NwbBatchParams bp;
+    memset(&bp, 0, sizeof(bp));
+    const int grid = b->sm_count;
+    const long long nwarps = (long long)grid * NWB_BATCH_WARPS;
+    bp.bpitch = nwb_round_up((size_t)b->max_B + 1 + 64, 32);
+    bp.scratch_per_warp = (b->max_strips > 1) ? (size_t)(b->max_strips - 1) * bp.bpitch : 0;
+    if (bp.scratch_per_warp) {
+        int rc = b->scratch.ensure((size_t)nwarps * bp.scratch_per_warp);
+        if (rc != NWB_OK) return rc;
+    }
+    bp.tops = b->tops.p; bp.top_off = b->top_off.p; bp.sides = b->sides.p; bp.side_off = b->side_off.p;
+    bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
+    bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p; bp.scratch = b->scratch.p;
+    const size_t smem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * NWB_BATCH_WARPS;
+    CK(cudaFuncSetAttribute(nwb_batch_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaEventRecord(b->ev0, st));
+    nwb_batch_pk_kernel<<<grid, 32 * NWB_BATCH_WARPS, smem, st>>>(bp, b->pc);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev1, st));
+    b->launches += 1;
+    if (!(b->flags & NWB_NO_BRANCH_COUNT)) {
+        nwb_batch_branch_kernel<<<b->sm_count * 8, 256, 0, st>>>(bp, b->branch.p);
+        CK(cudaGetLastError());
+        b->launches += 1;
+    }
+    return NWB_OK;
+}
+
+extern "C" int nwb_batch_fetch(nwb_batch *b)
+{
+    if (!b || !b->ran) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(b->device));
+    CK(cudaDeviceSynchronize());
+    b->h_score.resize((size_t)b->n);
+    b->h_branch.assign((size_t)b->n, 0u);
+    if (b->n) {
+        CK(cudaMemcpy(b->h_score.data(), b->score.p, (size_t)b->n * sizeof(int), cudaMemcpyDeviceToHost));
+        if (!(b->flags & NWB_NO_BRANCH_COUNT))
+            CK(cudaMemcpy(b->h_branch.data(), b->branch.p, (size_t)b->n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (b->flags & NWB_WANT_ARROWS_HOST) {
+            b->h_arrows.resize(b->arrows_bytes);
+            if (b->arrows_bytes) CK(cudaMemcpy(b->h_arrows.data(), b->arrows.p, b->arrows_bytes, cudaMemcpyDeviceToHost));
+        }
+    }
+    b->fetched = true;
+    return NWB_OK;
+}
+
+extern "C" int nwb_fill_batch(const char *tops, const int64_t *top_off, const char *sides, const int64_t *side_off,
+                              int64_t n_pairs, int m, int k, int d, unsigned flags, int device, nwb_batch **out)
+{
+    if (!out) return NWB_ERR_INVALID;
+    nwb_batch *b = nullptr;
+    int rc = nwb_batch_create(tops, top_off, sides, side_off, n_pairs, m, k, d, flags, device, &b);
+    if (rc == NWB_OK) rc = nwb_batch_run(b, nullptr);
+    if (rc == NWB_OK) rc = nwb_batch_fetch(b);
+    if (rc != NWB_OK) { nwb_batch_free(b); *out = nullptr; return rc; }
+    *out = b;
+    return NWB_OK;
+}
+
 extern "C" int64_t nwb_batch_size(const nwb_batch *b) { return b ? b->n : 0; }
-extern "C" int32_t nwb_batch_opt_score(const nwb_batch *, int64_t) { return 0; }
-extern "C" uint32_t nwb_batch_branch_count(const nwb_batch *, int64_t) { return 0; }
-extern "C" uint64_t nwb_batch_count_u64(const nwb_batch *, int64_t) { return 0; }
-extern "C" const uint8_t *nwb_batch_arrow_rows(const nwb_batch *, int64_t, size_t *) { return nullptr; }
-extern "C" float nwb_batch_kernel_ms(const nwb_batch *) { return 0.f; }
+extern "C" int32_t nwb_batch_opt_score(const nwb_batch *b, int64_t pair)
+{
+    return (b && b->fetched && pair >= 0 && pair < b->n) ? b->h_score[(size_t)pair] : 0;
+}
+extern "C" uint32_t nwb_batch_branch_count(const nwb_batch *b, int64_t pair)
+{
+    return (b && b->fetched && pair >= 0 && pair < b->n) ? b->h_branch[(size_t)pair] : 0u;
+}
+extern "C" uint64_t nwb_batch_count_u64(const nwb_batch *b, int64_t pair)
+{
+    (void)b; (void)pair;
+    return 0; /* NWB_WANT_COUNT is not available on the batch path yet */
+}
+extern "C" const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair, size_t *pitch)
+{
+    if (!b || pair < 0 || pair >= b->n) return nullptr;
+    const long long A = b->h_top_off[(size_t)pair + 1] - b->h_top_off[(size_t)pair];
+    if (pitch) *pitch = (size_t)((A + 255) / 256 > 0 ? (A + 255) / 256 : 1) * 128;
+    if (!b->fetched || b->h_arrows.empty()) return nullptr;
+    return b->h_arrows.data() + b->h_arrow_off[(size_t)pair];
+}
+extern "C" float nwb_batch_kernel_ms(const nwb_batch *b)
+{
+    if (!b || !b->ran || b->n == 0) return 0.f;
+    cudaSetDevice(b->device);
+    float ms = 0.f;
+    if (cudaEventSynchronize(b->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+extern "C" int64_t nwb_batch_launches(const nwb_batch *b) { return b ? b->launches : 0; }
+extern "C" void *nwb_batch_arrows_device(nwb_batch *b) { return b ? (void *)b->arrows.p : nullptr; }

@@ -251,7 +251,16 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
                             pub31 && (LEAN || (unsigned)g_hi < rg.ngroups));
 }
 
-template <int K, int R, bool COUNT>
+/* side characters of R consecutive rows: from the global side_pre array (read-only
+ * path) or, in the batch kernel, from the warp's shared-memory copy */
+template <int R, bool SMEMCH>
+__device__ __forceinline__ unsigned nwb_pk_chars(const uint16_t *q)
+{
+    if (R == 2) return SMEMCH ? *reinterpret_cast<const unsigned *>(q) : nwb_ldg_u32(reinterpret_cast<const unsigned *>(q));
+    return SMEMCH ? (unsigned)*q : (unsigned)nwb_ldg_u16(q);
+}
+
+template <int K, int R, bool SMEMCH>
 __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
                                               unsigned char *stage_bytes, const int lane, long long &rsum)
 {
@@ -315,8 +324,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     unsigned chars_next[NWB_PK_SUB];
 #pragma unroll
     for (int t = 0; t < NWB_PK_SUB; t++) {
-        if (R == 2) chars_next[t] = nwb_ldg_u32(reinterpret_cast<const unsigned *>(sp_lane + 2 * t));
-        else chars_next[t] = (unsigned)nwb_ldg_u16(sp_lane + t);
+        chars_next[t] = nwb_pk_chars<R, SMEMCH>(sp_lane + R * t);
     }
 
     const int nsteps = ngroups + 63;
@@ -366,8 +374,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 const uint16_t *spn = sp_lane + R * (ss + NWB_PK_SUB);
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++) {
-                    if (R == 2) chars_next[t] = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spn + 2 * t));
-                    else chars_next[t] = (unsigned)nwb_ldg_u16(spn + t);
+                    chars_next[t] = nwb_pk_chars<R, SMEMCH>(spn + R * t);
                 }
             }
             uint32_t *outb = out_w + (ss - 2 * lane - 1);
@@ -385,9 +392,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int t = h + i;
-                        unsigned ch; /* already prefetched one sub-block ago: an L1 hit */
-                        if (R == 2) ch = nwb_ldg_u32(reinterpret_cast<const unsigned *>(spc + 2 * t));
-                        else ch = (unsigned)nwb_ldg_u16(spc + t);
+                        const unsigned ch = nwb_pk_chars<R, SMEMCH>(spc + R * t); /* prefetched a sub-block ago: L1 hit */
                         nwb_pk_step<K, R, false>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, ch,
                                                  NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
                     }
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
 
     long long rsum = 0;
     for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
-        nwb_pk_strip<K, R, COUNT>(p, pc, c, stage, lane, rsum);
+        nwb_pk_strip<K, R, false>(p, pc, c, stage, lane, rsum);
 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);

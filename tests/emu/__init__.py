@@ -85,6 +85,33 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4):
     return dict(opt_score=out.opt_score, branch_count=out.branch_count, arrows=arrows, pitch=pitch)
 
 
+def fill_batch(tops, sides, m, k, d, *, grid=1):
+    """Run nwb_batch_pk_kernel + nwb_batch_branch_kernel under the emulator."""
+    n = len(tops)
+    toff = np.zeros(n + 1, np.int64)
+    soff = np.zeros(n + 1, np.int64)
+    np.cumsum([len(t) for t in tops], out=toff[1:])
+    np.cumsum([len(s) for s in sides], out=soff[1:])
+    total = sum(max(1, (len(t) + 255) // 256) * 128 * len(s) for t, s in zip(tops, sides))
+    arrows = np.full(total + 16, 0xEE, np.uint8)
+    aoff = np.zeros(n + 1, np.int64)
+    scores = np.zeros(n, np.int32)
+    branches = np.zeros(n, np.uint32)
+    L = lib()
+    L.emu_fill_batch.restype = C.c_int
+    L.emu_fill_batch.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                 C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    rc = L.emu_fill_batch(b"".join(tops), p(toff), b"".join(sides), p(soff), n, m, k, d, grid, p(arrows), p(aoff),
+                          p(scores), p(branches))
+    assert rc == 0, rc
+    tabs = []
+    for i in range(n):
+        pitch = max(1, (len(tops[i]) + 255) // 256) * 128
+        tabs.append(arrows[aoff[i]:aoff[i] + pitch * len(sides[i])].reshape(len(sides[i]), pitch))
+    return dict(scores=scores, branches=branches, tables=tabs)
+
+
 def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:
     """(B, pitch) nibble table -> (B, A) uint8 codes (DIAG|LEFT|UP)."""
     lo = packed & 0xF

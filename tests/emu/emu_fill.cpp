@@ -8,6 +8,7 @@
 #include "nwb_layout.h"
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
+#include "nwb_batch.cuh"
 
 #include <vector>
 
@@ -181,6 +182,39 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     out->count = 0;
     out->pitch = L.pitch;
     out->spitch = 0;
+    return 0;
+}
+
+/* batch kernel under the emulator: arrows = concatenated per-pair tables (offsets returned in arrow_off) */
+int emu_fill_batch(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
+                   long long n, int m, int k, int d, unsigned grid, uint8_t *arrows, long long *arrow_off,
+                   int *scores, unsigned *branches)
+{
+    NwbPkConsts pc;
+    if (!nwb_pk_supported(m, k, d, &pc)) return -5;
+    NwbBatchParams bp;
+    memset(&bp, 0, sizeof(bp));
+    int maxB = 0, maxS = 1;
+    long long aoff = 0;
+    for (long long p = 0; p < n; p++) {
+        const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
+        const int ns = (int)((A + 255) / 256);
+        if (ns > maxS) maxS = ns;
+        if (B > maxB) maxB = (int)B;
+        arrow_off[p] = aoff;
+        aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
+    }
+    arrow_off[n] = aoff;
+    const long long nwarps = (long long)grid * NWB_BATCH_WARPS;
+    bp.bpitch = nwb_round_up((size_t)maxB + 1 + 64, 32);
+    bp.scratch_per_warp = (maxS > 1) ? (size_t)(maxS - 1) * bp.bpitch : 0;
+    std::vector<uint32_t> scratch((size_t)nwarps * bp.scratch_per_warp + 1, 0xdeadbeefu);
+    bp.tops = (const uint8_t *)tops; bp.top_off = top_off; bp.sides = (const uint8_t *)sides; bp.side_off = side_off;
+    bp.n_pairs = n; bp.m = m; bp.k = k; bp.d = d; bp.max_B = maxB;
+    bp.arrows = arrows; bp.arrow_off = arrow_off; bp.out_score = scores; bp.scratch = scratch.data();
+    emu_launch(grid, 32 * NWB_BATCH_WARPS, NWB_BATCH_SMEM_PER_WARP(maxB) * NWB_BATCH_WARPS,
+               [&]() { nwb_batch_pk_kernel(bp, pc); });
+    emu_launch(2, 64, 0, [&]() { nwb_batch_branch_kernel(bp, branches); });
     return 0;
 }
 }

@@ -195,3 +195,51 @@ def test_two_gpu_strips_match_one(oracle, nwb):
     t, s = oracle.generate_pair(0x5EED0B00, 5000, 3000)
     full_check(oracle, nwb, t, s, 1, 1, 1, num_gpus=2)
     full_check(oracle, nwb, t, s, 2, 1, 2, nwb.FORCE_GENERAL, num_gpus=2)
+
+
+# ---- batch of independent pairs (BASELINE config 4) ---------------------------------
+def test_batch_ragged(oracle, nwb):
+    rng = random.Random(11)
+    lens = [(256, 256), (1, 1), (255, 257), (300, 40), (17, 130), (0, 5), (700, 90), (64, 64), (256, 1),
+            (33, 33), (257, 31), (100, 300), (5, 0), (1500, 700)] + \
+           [(rng.randint(1, 600), rng.randint(1, 500)) for _ in range(300)]
+    tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
+    sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
+    for m, k, d in ((1, 1, 1), (2, 1, 2)):
+        bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+        bt.run()
+        bt.fetch()
+        for i, (t, s) in enumerate(zip(tops, sides)):
+            o = oracle.fill(t, s, m, k, d, want_packed=True, pitch=max(1, (len(t) + 255) // 256) * 128)
+            assert bt.opt_score(i) == o.final_score, (i, len(t), len(s))
+            assert bt.branch_count(i) == o.branch_count, (i, len(t), len(s))
+            if len(t) and len(s):
+                nb = (len(t) + 1) // 2
+                got = bt.arrow_rows(i)[:, :nb] & 0x77
+                if len(t) & 1:
+                    got[:, nb - 1] &= 0x07
+                assert np.array_equal(got, o.packed[:, :nb]), i
+        bt.close()
+    # schemes outside the packed kernel's range are refused, not silently mis-scored
+    with pytest.raises(nwb.NwbError):
+        nwb.Batch(tops[:2], sides[:2], 1, 3, 1)
+
+
+def test_batch_config4_shard(oracle, nwb):
+    """One GPU's shard of config 4 at reduced count (20,000 pairs of 256 x 256, generator seeds
+    0x5EED4000 + 2p): the three SURVEY goldens and a random sample against the oracle."""
+    n = 20000
+    idx = list(range(n - 1)) + [999999]
+    tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
+    bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST)
+    bt.run()
+    bt.fetch()
+    assert (bt.opt_score(0), bt.branch_count(0)) == (19, 23713)
+    assert (bt.opt_score(1), bt.branch_count(1)) == (29, 22912)
+    assert (bt.opt_score(n - 1), bt.branch_count(n - 1)) == (19, 22090)
+    rng = random.Random(5)
+    for i in rng.sample(range(n), 60):
+        o = oracle.fill(tops[i], sides[i], 1, 1, 1, want_packed=True, pitch=128)
+        assert bt.opt_score(i) == o.final_score and bt.branch_count(i) == o.branch_count
+        assert np.array_equal(bt.arrow_rows(i) & 0x77, o.packed)
+    bt.close()

@@ -23,9 +23,31 @@ ap.add_argument("--k", type=int, default=1)
 ap.add_argument("--d", type=int, default=1)
 ap.add_argument("--flags", type=lambda x: int(x, 0), default=nwb.NO_BRANCH_COUNT)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--batch", type=int, default=0, help="run a batch of this many pairs (config 4 generator) instead")
 args = ap.parse_args()
 
 alpha = oracle.DNA if args.alphabet == "dna" else oracle.PROTEIN
+if args.batch:
+    import numpy as np
+    n = args.batch
+    a, b = min(args.a, 4096), min(args.b, 4096)
+    tcat = bytearray()
+    scat = bytearray()
+    for p in range(n):
+        tt, ss = oracle.generate_pair(0x5EED4000 + 2 * p, a, b, alpha)
+        tcat += tt
+        scat += ss
+    toff = np.arange(n + 1, dtype=np.int64) * a
+    soff = np.arange(n + 1, dtype=np.int64) * b
+    bt = nwb.Batch.from_arrays(bytes(tcat), toff, bytes(scat), soff, args.m, args.k, args.d, args.flags)
+    for r in range(args.reps):
+        bt.run()
+        bt.fetch()
+        ms = bt.kernel_ms()
+        print(f"rep {r}: batch {n} x {a}x{b} kernel_ms={ms:.3f} GCUPS={n * a * b / ms / 1e6:.1f} "
+              f"score0={bt.opt_score(0)} branches0={bt.branch_count(0)}", flush=True)
+    bt.close()
+    sys.exit(0)
 t, s = oracle.generate_pair(args.seed, args.a, args.b, alpha)
 plan = nwb.Plan(args.a, args.b, args.flags)
 plan.upload(t, s)
