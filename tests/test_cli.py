@@ -1,0 +1,105 @@
+"""The C99 host shell (needleman-wunsch_b200/host/needleman-wunsch) against the
+reference's own CLI (oracle/_ref/needleman-wunsch, the unmodified sources compiled
+by oracle/Makefile): stdout, stderr and exit code byte for byte.  Paths that end
+before the fill (usage, operand and input errors) run without a GPU; everything
+that computes is marked gpu."""
+import itertools
+import os
+import random
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "needleman-wunsch_b200", "host", "needleman-wunsch")
+
+
+def run(exe, args, stdin=b""):
+    # same argv[0] for both programs: getopt and the error messages print it
+    p = subprocess.run(["needleman-wunsch"] + list(args), executable=exe, input=stdin, capture_output=True)
+    return p.returncode, p.stdout, p.stderr
+
+
+@pytest.fixture(scope="module")
+def cli(oracle, nwb):
+    ref = oracle.reference_cli()
+    if ref is None:
+        pytest.skip("oracle/_ref/needleman-wunsch not built (no /root/reference here)")
+    if not os.path.exists(nwb.LIB_PATH):
+        nwb.build()
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "needleman-wunsch_b200", "host")], check=True)
+    return ref
+
+
+def same(ref, args, stdin=b""):
+    a = run(ref, args, stdin)
+    b = run(OURS, args, stdin)
+    assert a == b, (args, stdin, a, b)
+    return a
+
+
+def test_usage_and_operand_errors(cli, tmp_path):
+    for args in (["-h"], ["-x", "1", "1", "1"], [], ["1"], ["1", "1"], ["1", "1", "1", "1"], ["-q", "1", "1"],
+                 ["-p", "1", "1", "1", "1"], ["-p", "0", "1", "1", "1"], ["-p", "abc", "1", "1", "1"],
+                 ["-f"], ["-f", str(tmp_path / "missing.txt"), "1", "1", "1"]):
+        rc, out, err = same(cli, args, b"GT GA\n")
+        assert rc == 1 and out == b""
+
+
+def test_input_errors(cli, tmp_path):
+    for stdin in (b"", b"ACG", b"ACG ", b"ACG\n", b"   ", b"\n\n"):
+        rc, out, err = same(cli, ["1", "1", "1"], stdin)
+        assert rc == 1 and b"EOF too early" in err
+    f = tmp_path / "one.txt"
+    f.write_bytes(b"ACGT")
+    rc, _, err = same(cli, ["-f", str(f), "1", "1", "1"], b"GT GA\n")
+    assert rc == 1
+
+
+FLAG_SETS = [[]] + [list(c) for n in (1, 2, 3) for c in itertools.combinations(["-c", "-l", "-q", "-s", "-t", "-u"], n)] + \
+    [["-c", "-l", "-s", "-t", "-u"], ["-q", "-l", "-s", "-t"], ["-c", "-q", "-s", "-t", "-u"]]
+
+
+@pytest.mark.gpu
+def test_readme_examples(cli):
+    # README:117-173
+    same(cli, ["1", "1", "1"], b"GT GT\n")
+    same(cli, ["1", "1", "1"], b"GT GA\n")
+    rc, out, err = same(cli, ["-s", "-l", "1", "1", "1"], b"GAT GTA\n")
+    assert out.startswith(b"G-AT\nGTA-\n") and b"2 optimal alignments" in err
+    rc, out, err = same(cli, ["-q", "-s", "-t", "1", "1", "1"], b"GCATGCU GATTACA\n")
+    assert err == b"3 optimal alignments\nOptimal score is 0\n"
+    rc, out, err = same(cli, ["-q", "-s", "0", "0", "0"], b"GCATGCU GATTACA\n")
+    assert err.startswith(b"48639 optimal alignments")
+
+
+@pytest.mark.gpu
+def test_flag_combinations(cli, tmp_path):
+    rng = random.Random(2024)
+    inputs = [b"GCATGCU GATTACA\n", b" ACG", b"A A", b"ACGT\tTGCA  trailing text is ignored\n", b"AAAA AAAA"]
+    for _ in range(6):
+        a, b = rng.randint(1, 7), rng.randint(1, 7)
+        inputs.append(bytes(rng.choice(b"ACGT") for _ in range(a)) + b"\n" + bytes(rng.choice(b"ACGT") for _ in range(b)))
+    schemes = [("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0"), ("-1", "3", "-2"), ("5", "4", "3"), ("1", "3", "1")]
+    n = 0
+    for stdin in inputs:
+        for flags in rng.sample(FLAG_SETS, 12):
+            mkd = rng.choice(schemes)
+            same(cli, flags + list(mkd), stdin)
+            n += 1
+    # -f reads the file and ignores stdin; -p N (N > 1) is accepted
+    f = tmp_path / "pair.txt"
+    f.write_bytes(b"GATTACA\nGCATGCU\nmore\n")
+    same(cli, ["-f", str(f), "-s", "-t", "1", "1", "1"], b"GT GA\n")
+    same(cli, ["-p", "2", "-s", "1", "1", "1"], b"GCATGCU GATTACA\n")
+    assert n > 100
+
+
+@pytest.mark.gpu
+def test_summary_beyond_32_bits(cli, oracle):
+    """-q -s on a 256 x 256 pair: the count exceeds 2^32; the reference prints the low 32 bits with %d
+    (it would need to enumerate 3.9e17 alignments; ours reads the fused DP).  SURVEY.md 8c goldens."""
+    t, s = oracle.generate_pair(0x5EED4000, 256, 256)
+    rc, out, err = run(OURS, ["-q", "-s", "1", "1", "1"], t + b" " + s + b"\n")
+    assert (rc, out) == (0, b"")
+    assert err == b"-2087714816 optimal alignments\nOptimal score is 19\n"
