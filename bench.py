@@ -147,6 +147,77 @@ def cpu_baseline_leg() -> dict:
             "sample": f"{n}x{n} prefix of the workload, oracle/nw_oracle.c (scalar C)"}
 
 
+def run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) -> dict | None:
+    """Secondary measurements (not the headline): the other BASELINE configs.
+    config 4 runs on every rank (its own shard of 125,000 pairs = 1M / 8, no communication);
+    configs 2, 5 and config 3 with the fused count run on rank 0 only."""
+    out = {}
+    # ---- config 4: batch of 256 x 256 DNA pairs, pair p seeded 0x5EED4000 + 2p, sharded by rank
+    per = 125_000
+    first = rank * per
+    tcat, scat = bytearray(), bytearray()
+    for p in range(first, first + per):
+        tt, ss = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
+        tcat += tt
+        scat += ss
+    import numpy as np
+    off = np.arange(per + 1, dtype=np.int64) * 256
+    bt = nwb.Batch.from_arrays(bytes(tcat), off, bytes(scat), off, M_, K_, D_, 0, device=local)
+    for _ in range(2):
+        bt.run()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream().cuda_stream
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        bt.run(st)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    bt.fetch()
+    ok4 = True
+    if rank == 0:
+        ok4 = (bt.opt_score(0), bt.branch_count(0), bt.opt_score(1), bt.branch_count(1)) == (19, 23713, 29, 22912)
+    kms = bt.kernel_ms()
+    bt.close()
+    out["config4_batch"] = {"pairs_total": per * world, "pairs_per_gpu": per, "ms_per_pass": ms,
+                            "gcups_total": per * world * 65536 / (ms * 1e-3) / 1e9, "fill_kernel_ms": kms,
+                            "includes": "fill + per-pair branch-count pass, strings and 4.1 GB of arrow tables resident",
+                            "golden_pairs_ok": bool(ok4), "scaling": "weak (125,000 pairs per GPU; 8 GPUs = the 1M-pair config)"}
+    if rank != 0:
+        return None
+
+    def one(name, seed, n, alpha, mkd, flags, golden):
+        t, s = oracle.generate_pair(seed, n, n, alpha)
+        plan = nwb.Plan(n, n, flags, device=local)
+        plan.upload(t, s)
+        best = None
+        for _ in range(3):
+            plan.run(*mkd)
+            sm = plan.summary()
+            k = plan.kernel_ms()
+            best = k if best is None else min(best, k)
+        got = (sm.opt_score, sm.branch_count, sm.count)
+        out[name] = {"fill_kernel_ms": best, "gcups": n * n / (best * 1e-3) / 1e9, "kernel_kind": sm.kernel_kind,
+                     "result": {"opt_score": got[0], "branch_count": got[1], "count_u64": got[2]},
+                     "golden_ok": bool(got[:len(golden)] == golden)}
+        plan.close()
+
+    one("config2_dna_10k_fill", 0x5EED0002, 10000, oracle.DNA, (1, 1, 1), 0, (1056, 34377799))
+    one("config2_dna_10k_q_s_with_count", 0x5EED0002, 10000, oracle.DNA, (1, 1, 1), nwb.WANT_COUNT, (1056, 34377799, 0))
+    one("config5_protein_30k_fill", 0x5EED0005, 30000, oracle.PROTEIN, (2, 1, 2), 0, (-16401, 520440751))
+    one("config5_protein_30k_q_s_with_count", 0x5EED0005, 30000, oracle.PROTEIN, (2, 1, 2), nwb.WANT_COUNT,
+        (-16401, 520440751, 0))
+    one("config3_dna_100k_with_count", SEED, A, oracle.DNA, (1, 1, 1), nwb.WANT_COUNT, (11389, 3439940792, 0))
+    return out
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -250,6 +321,8 @@ def run_ours(args) -> None:
             opt_score = int(tt[0].item()) - D_ * (A + B)
         branch_total = int(tt[1].item()) & 0xFFFFFFFF
 
+    extras = run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) if not args.no_extras else None
+
     if rank == 0:
         cells = A * B
         ms_per_step = total_ms / args.steps
@@ -304,6 +377,8 @@ def run_ours(args) -> None:
                        "golden": "tests/golden/golden_big.json config3_dna_100k: score 11389, branches 3439940792"},
             "step_ms": [round(x, 3) for x in step_ms],
         }
+        if extras is not None:
+            line["extras"] = extras
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line))
@@ -319,6 +394,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (2, 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

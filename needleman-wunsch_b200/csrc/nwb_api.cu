@@ -294,7 +294,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     p->kind = choose_kind(flags, m, k, d, &pc);
     int strip_w = NWB_I32_STRIP_W, pk_k = 0;
     if (p->kind == NWB_KIND_PK) {
-        pk_k = nwb_pk_choose_k(A, B, p->sm_count * NWB_PK_WARPS * p->world);
+        pk_k = nwb_pk_choose_k(A, B, p->world);
         if (const char *ek = getenv("NWB_PK_K")) { /* diagnostics */
             const int v = atoi(ek);
             if (v == 1 || v == 2 || v == 4) pk_k = v;
@@ -422,7 +422,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         /* get_branch_count() (walk-table.c:133): second, HBM-bound pass over this rank's columns */
         long long cb = (long long)p->strip_begin * L.strip_w, ce = (long long)p->strip_end * L.strip_w;
         if (ce > A) ce = A;
-        nwb_branch_count_kernel<<<p->sm_count * 8, 256, 0, st>>>(p->arrows.p, L.pitch, A, B, (int)cb, (int)ce,
+        nwb_branch_count_kernel<<<p->sm_count * 16, 256, 0, st>>>(p->arrows.p, L.pitch, A, B, (int)cb, (int)ce,
                                                                  &p->summary.p->branch_count);
         CK(cudaGetLastError());
         p->launches += 1;

@@ -72,14 +72,19 @@ static inline bool nwb_pk_supported(int m, int k, int d, NwbPkConsts *pc)
 
 /* Columns per half-lane.  Every strip boundary costs a pipeline hop of ~72 row
  * steps (64 virtual lanes of skew plus the hand-off) while every column per lane
- * only lengthens a step; measured on B200 (10k, 30k, 100k squares) the widest
- * strip, K = 4 (256 columns), wins at every size, so it is the default. */
-static inline int nwb_pk_choose_k(int A, int B, int total_warps)
+ * only lengthens a step; measured on one B200 (10k, 30k, 100k squares) the widest
+ * strip, K = 4 (256 columns), wins at every size.  A strip group of G GPUs has G
+ * times the warps: narrower strips (K = 2 on two GPUs, K = 1 beyond) shorten the
+ * steps without putting two warps on one SM sub-partition, as long as every rank
+ * still gets at most one strip per sub-partition. */
+static inline int nwb_pk_choose_k(int A, int B, int world)
 {
-    (void)A;
     (void)B;
-    (void)total_warps;
-    return 4;
+    int K = 4;
+    if (world >= 4) K = 1;
+    else if (world >= 2) K = 2;
+    while (K < 4 && (A + 64 * K - 1) / (64 * K) > 592 * world) K *= 2;
+    return K;
 }
 
 #define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * NWB_PK_RING_ROWS * (R) * (32 * (K)))
@@ -386,17 +391,10 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                     nwb_pk_step<K, R, true>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
                                             NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
             } else {
-                const uint16_t *spc = sp_lane + R * ss;
-#pragma unroll 1
-                for (int h = 0; h < NWB_PK_SUB; h += 4) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int t = h + i;
-                        const unsigned ch = nwb_pk_chars<R, SMEMCH>(spc + R * t); /* prefetched a sub-block ago: L1 hit */
-                        nwb_pk_step<K, R, false>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, ch,
-                                                 NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
-                    }
-                }
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_pk_step<K, R, false>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
+                                             NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
             }
         }
         __syncwarp();
@@ -453,29 +451,33 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
 __global__ void nwb_branch_count_kernel(const uint8_t *arrows, size_t pitch, int A, int B, int col_begin, int col_end,
                                         unsigned *out)
 {
-    /* columns [col_begin, col_end) (0-based interior), whole 32-cell groups of 16 B */
+    /* columns [col_begin, col_end) (0-based interior), in whole 32-cell groups of 16 B; a block walks
+     * rows grid-stride, its threads walk the row's groups: coalesced 16-byte loads, no divisions */
     const int g0 = col_begin / 32, g1 = (col_end + 31) / 32;
-    const long long groups = (long long)(g1 - g0) * B;
+    const int cend = col_end < A ? col_end : A;
     unsigned cnt = 0;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < groups;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int row = (int)(idx / (g1 - g0));
-        const int g = g0 + (int)(idx % (g1 - g0));
-        const uint4 v = *reinterpret_cast<const uint4 *>(arrows + (size_t)row * pitch + (size_t)g * 16);
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    for (int row = blockIdx.x; row < B; row += gridDim.x) {
+        const uint8_t *rp = arrows + (size_t)row * pitch;
+        for (int g = g0 + (int)threadIdx.x; g < g1; g += (int)blockDim.x) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(rp + (size_t)g * 16);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            const int first = g * 32;
+            const bool edge = (first < col_begin) || (first + 32 > cend);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int first = g * 32 + q * 8; /* 0-based column of nibble 0 */
-            unsigned x = w[q];
-            const unsigned b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u;
-            unsigned two = (b0 & b1) | (b0 & b2) | (b1 & b2);
-            /* keep columns in [col_begin, col_end) and < A */
-            int lo = col_begin - first, hi = (col_end < A ? col_end : A) - first;
-            if (lo < 0) lo = 0;
-            if (hi > 8) hi = 8;
-            unsigned mask = 0u;
-            if (hi > lo) mask = (hi >= 8 ? 0xFFFFFFFFu : ((1u << (4 * hi)) - 1u)) & ~((lo <= 0) ? 0u : ((1u << (4 * lo)) - 1u));
-            cnt += (unsigned)__popc(two & mask);
+            for (int q = 0; q < 4; q++) {
+                const unsigned x = w[q];
+                const unsigned b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u;
+                unsigned two = (b0 & b1) | (b0 & b2) | (b1 & b2);
+                if (edge) { /* keep columns in [col_begin, cend) */
+                    int lo = col_begin - (first + q * 8), hi = cend - (first + q * 8);
+                    if (lo < 0) lo = 0;
+                    if (hi > 8) hi = 8;
+                    unsigned mask = 0u;
+                    if (hi > lo) mask = (hi >= 8 ? 0xFFFFFFFFu : ((1u << (4 * hi)) - 1u)) & ~((lo <= 0) ? 0u : ((1u << (4 * lo)) - 1u));
+                    two &= mask;
+                }
+                cnt += (unsigned)__popc(two);
+            }
         }
     }
 #pragma unroll
