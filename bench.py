@@ -219,6 +219,9 @@ def run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) -> dict | 
 
 
 def run_ours(args) -> None:
+    # keep stdout clean for the ONE JSON line: libraries (NCCL prints its version there) go to stderr
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import nw_b200 as nwb
@@ -381,7 +384,8 @@ def run_ours(args) -> None:
             line["extras"] = extras
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_leg()
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     plan.close()
     if world > 1:
         dist.barrier()

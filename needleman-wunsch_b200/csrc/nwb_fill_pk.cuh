@@ -407,16 +407,43 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             const int lanes_per_row = row_bytes / 16;
             const int rows_per_pass = 32 / lanes_per_row;
             const int sub = lane % lanes_per_row;
+            const int npass = (32 * R) / rows_per_pass;
+            /* row j sits at ring offset ((j-1) mod (128*R)) * row_bytes: slots are consecutive row groups */
+            const int j0 = jlo + lane / lanes_per_row;
+            uint8_t *dst = p.arrows + (size_t)c * row_bytes + sub * 16;
+            if (jlo >= 1 && jhi <= B) {
+                /* the common case, all rows inside the table: all loads first, then all stores */
 #pragma unroll
-            for (int q = 0; q < (32 * R) / rows_per_pass; q++) {
-                const int j = jlo + q * rows_per_pass + lane / lanes_per_row;
-                if (j >= 1 && j <= B) {
-                    const int g = (j - 1) / R, r = (j - 1) - g * R;
-                    uint4 v = *reinterpret_cast<const uint4 *>(stage_bytes + (size_t)(g & (NWB_PK_RING_ROWS - 1)) * SLOT +
-                                                               r * NWB_PK_SUBROW_BYTES(K) + sub * 16);
-                    v.x = ~v.x & 0x77777777u; v.y = ~v.y & 0x77777777u;
-                    v.z = ~v.z & 0x77777777u; v.w = ~v.w & 0x77777777u;
-                    *reinterpret_cast<uint4 *>(p.arrows + (size_t)(j - 1) * p.pitch + (size_t)c * row_bytes + sub * 16) = v;
+                for (int half = 0; half < npass; half += 8) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (half + q < npass) {
+                            const int j = j0 + (half + q) * rows_per_pass;
+                            v[q] = *reinterpret_cast<const uint4 *>(stage_bytes + (size_t)((j - 1) & (NWB_PK_RING_ROWS * R - 1)) * row_bytes + sub * 16);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (half + q < npass) {
+                            const int j = j0 + (half + q) * rows_per_pass;
+                            uint4 w = v[q];
+                            w.x = ~w.x & 0x77777777u; w.y = ~w.y & 0x77777777u;
+                            w.z = ~w.z & 0x77777777u; w.w = ~w.w & 0x77777777u;
+                            *reinterpret_cast<uint4 *>(dst + (size_t)(j - 1) * p.pitch) = w;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < npass; q++) {
+                    const int j = j0 + q * rows_per_pass;
+                    if (j >= 1 && j <= B) {
+                        uint4 w = *reinterpret_cast<const uint4 *>(stage_bytes + (size_t)((j - 1) & (NWB_PK_RING_ROWS * R - 1)) * row_bytes + sub * 16);
+                        w.x = ~w.x & 0x77777777u; w.y = ~w.y & 0x77777777u;
+                        w.z = ~w.z & 0x77777777u; w.w = ~w.w & 0x77777777u;
+                        *reinterpret_cast<uint4 *>(dst + (size_t)(j - 1) * p.pitch) = w;
+                    }
                 }
             }
         }
