@@ -185,7 +185,7 @@ extern "C" int nwb_plan_create(int max_top, int max_side, unsigned flags, int de
     if (rc == NWB_OK && strip_world > 1) {
         /* inbox sized for the longest side string; allocated once so that it
          * can be exported through CUDA IPC before any fill */
-        make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64, 32));
+        make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64 + 256, 32));
         e = cudaMalloc((void **)&p->inbox.base, p->inbox.bytes);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(inbox)");
         else e = cudaMemset(p->inbox.base, 0, p->inbox.bytes);
@@ -418,6 +418,15 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     CK(cudaEventRecord(p->ev1, st));
     p->timed = true;
     p->launches += 1;
+    if (p->kind == NWB_KIND_PK && L.n_strips >= 2 && p->strip_end == L.n_strips) {
+        /* this rank owns the last strip: add the score share carried by the stream it consumed */
+        const uint32_t *stream = (p->strip_begin == L.n_strips - 1)
+                                     ? sp.in_bnd_w
+                                     : p->bnd_w.p + (size_t)(L.n_strips - 2 - p->strip_begin) * L.bpitch;
+        nwb_pk_stream_sum_kernel<<<32, 256, 0, st>>>(stream, B, L.pk_r, &p->summary.p->rsum);
+        CK(cudaGetLastError());
+        p->launches += 1;
+    }
     if (p->kind == NWB_KIND_PK && !(flags & NWB_NO_BRANCH_COUNT)) {
         /* get_branch_count() (walk-table.c:133): second, HBM-bound pass over this rank's columns */
         long long cb = (long long)p->strip_begin * L.strip_w, ce = (long long)p->strip_end * L.strip_w;

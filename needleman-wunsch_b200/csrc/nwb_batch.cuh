@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
             nwb_pk_strip<NWB_BATCH_K, NWB_BATCH_R, true>(sp, pc, c, stage, lane, rsum);
             __syncwarp();
         }
+        if (n_strips > 1) {
+            /* the share of r(A,B) left of the last strip: sum of v down the boundary it consumed */
+            const uint32_t *w = scr + (size_t)(n_strips - 2) * bp.bpitch + NWB_PK_BPAD;
+            for (int g = lane; g < B; g += 32) rsum += (long long)((nwb_ld_relaxed_u32(w + g, false) >> 16) & 0x7FFFu);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
         /* score(A,B) = sum_i u(i,B) - d*(A+B) */

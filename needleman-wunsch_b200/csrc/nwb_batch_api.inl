@@ -110,7 +110,7 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
     const long long nwarps = (long long)grid * NWB_BATCH_WARPS;
-    bp.bpitch = nwb_round_up((size_t)b->max_B + 1 + 64, 32);
+    bp.bpitch = nwb_round_up((size_t)b->max_B + 1 + 64 + 256, 32);
     bp.scratch_per_warp = (b->max_strips > 1) ? (size_t)(b->max_strips - 1) * bp.bpitch : 0;
     if (bp.scratch_per_warp) {
         int rc = b->scratch.ensure((size_t)nwarps * bp.scratch_per_warp);

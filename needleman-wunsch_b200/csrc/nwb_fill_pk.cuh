@@ -108,6 +108,9 @@ struct NwbPkStage<1> { typedef uint8_t T; };
  * written and read atomically and is all the consumer needs for that row group. */
 #define NWB_PK_VALID 0x80000000u
 #define NWB_PK_SUB 8 /* stream words are fetched 8 row groups at a time, one sub-block ahead */
+/* words in front of group 0 of every boundary stream: lane 31 publishes from step 0 on, 63 row
+ * groups before its own group 0, without a range test (the words land in this padding) */
+#define NWB_PK_BPAD 64
 /* The side string is pre-shifted and complemented once per fill into a uint16
  * array padded on both sides, so the row loop never range-checks its index:
  * side_pre[j + NWB_PK_SPAD] = ~(side[j-1] << shift) & 0xFFFF for 1 <= j <= B.
@@ -299,10 +302,11 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     const bool left_remote = has_left && (lc == 0);
     const bool publish = (c + 1 < p.n_strips);
     const bool out_remote = publish && (c == p.strip_end - 1);
-    uint32_t *out_w = out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch;
+    uint32_t *out_w = (out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch) + NWB_PK_BPAD;
     const uint32_t *in_w = nullptr;
-    if (has_left) in_w = left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch;
+    if (has_left) in_w = (left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch) + NWB_PK_BPAD;
     const bool pub31 = publish && (lane == 31);
+    const bool is_last = (c == p.n_strips - 1);
     const bool nowait = p.debug_nowait != 0;
     /* my low block's first row at step s is R*(s - 2*lane) + 1 */
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
@@ -344,9 +348,12 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             trace[2 * blk] = nwb_globaltimer();
             trace[2 * blk + 1] = npolls;
         }
-        /* every lane strictly inside rows 1..B-1 for the whole block?  (lane 31's high block is the
-         * last to enter: group s-63; lane 0's low block is the first to reach row B) */
-        const bool lean = (s0 >= 63 && R * (s0 + 32) < B);
+        /* The unchecked step is safe everywhere except where the bottom-row sums are captured:
+         * rows above the table are virtual (BIG), rows below it compute garbage that is never
+         * flushed, and the stream words of row groups outside [0, ngroups) land in the padding of
+         * the boundary buffers.  Only the LAST strip captures (the others' share of r(A,B) is read
+         * off the boundary stream afterwards), and only once its first lane reaches row B. */
+        const bool lean = !(is_last && R * (s0 + 32) >= B);
 #pragma unroll 1
         for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
             const int ss = s0 + NWB_PK_SUB * sub;
@@ -469,6 +476,28 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
     if (lane == 0 && rsum) atomicAdd((unsigned long long *)&p.summary->rsum, (unsigned long long)rsum);
+}
+
+/* r(A,B) = [sum over the rows 1..B of v in the column left of the last strip] + [sum of u(i,B) over
+ * the last strip's columns].  The second term is captured by the last strip; this adds the first
+ * one from the boundary stream that strip consumed (strip n-2's words, all valid by now). */
+__global__ void nwb_pk_stream_sum_kernel(const uint32_t *stream, int B, int R, long long *rsum)
+{
+    const uint32_t *w = stream + NWB_PK_BPAD;
+    const int ngroups = (B + R - 1) / R;
+    long long s = 0;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        const unsigned x = w[g];
+        if (R == 1) {
+            s += (x >> 16) & 0x7FFFu;
+        } else {
+            s += x & 0x7FFFu;
+            if (2 * g + 2 <= B) s += (x >> 16) & 0x7FFFu;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(NWB_FULL_MASK, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd((unsigned long long *)rsum, (unsigned long long)s);
 }
 
 /* ---- branch counter over the finished nibble table -----------------------------

@@ -144,6 +144,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     std::vector<uint16_t> side_pre(NWB_PK_SPRE_LEN(B), 0x1234);
     emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
     p.side_pre = side_pre.data();
+    const uint32_t *last_stream = nullptr; /* the stream consumed by the last strip, when it is not in bnd_w */
     auto launch = [&](const NwbStripParams &q) {
         if (R == 2) {
             if (K == 1) run_pk_emu<1, 2>(grid, warps, q, pc);
@@ -171,8 +172,14 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         p1.progress = prog1.data();
         launch(p0);
         launch(p1);
+        last_stream = (split == L.n_strips - 1) ? inbox_w.data() : bnd1.data() + (size_t)(L.n_strips - 2 - split) * L.bpitch;
+        emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
     } else {
         launch(p);
+        if (L.n_strips >= 2) {
+            last_stream = bnd_w.data() + (size_t)(L.n_strips - 2) * L.bpitch;
+            emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
+        }
     }
     unsigned branches = 0;
     emu_launch(3, 64, 0, [&]() { nwb_branch_count_kernel(arrows, L.pitch, A, B, 0, A, &branches); });
@@ -206,7 +213,7 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
     }
     arrow_off[n] = aoff;
     const long long nwarps = (long long)grid * NWB_BATCH_WARPS;
-    bp.bpitch = nwb_round_up((size_t)maxB + 1 + 64, 32);
+    bp.bpitch = nwb_round_up((size_t)maxB + 1 + 64 + 256, 32);
     bp.scratch_per_warp = (maxS > 1) ? (size_t)(maxS - 1) * bp.bpitch : 0;
     std::vector<uint32_t> scratch((size_t)nwarps * bp.scratch_per_warp + 1, 0xdeadbeefu);
     bp.tops = (const uint8_t *)tops; bp.top_off = top_off; bp.sides = (const uint8_t *)sides; bp.side_off = side_off;
