@@ -149,14 +149,27 @@ __device__ __forceinline__ void nwb_st_relaxed_u32(uint32_t *p, unsigned v, bool
 #endif
 }
 
-/* Spin until *flag >= need.  `sys` selects system scope (peer memory). */
+/* Spin until *flag >= need, then order the following data reads after it.  The
+ * poll itself is a relaxed (L2) load: an ld.acquire inside the loop costs an L1
+ * invalidation (CCTL.IVALL) per iteration.  `sys` selects system scope (peer memory). */
 __device__ __forceinline__ void nwb_wait_ge(const int *flag, int need, bool sys)
 {
+#ifdef NWB_EMU
+    while (*(const volatile int *)flag < need) nwb_pause();
+#else
+    int v;
     if (sys) {
-        while (nwb_ld_acquire_sys(flag) < need) nwb_pause();
+        do {
+            asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
+        } while (v < need);
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
     } else {
-        while (nwb_ld_acquire_gpu(flag) < need) nwb_pause();
+        do {
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
+        } while (v < need);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
+#endif
 }
 
 /* ---- 16x2 helpers (DPX / video SIMD; VIMNMX.U16x2, VIMNMX3.U16x2, VIADD.16x2) */

@@ -72,19 +72,15 @@ static inline bool nwb_pk_supported(int m, int k, int d, NwbPkConsts *pc)
 
 /* Columns per half-lane.  Every strip boundary costs a pipeline hop of ~72 row
  * steps (64 virtual lanes of skew plus the hand-off) while every column per lane
- * only lengthens a step; measured on one B200 (10k, 30k, 100k squares) the widest
- * strip, K = 4 (256 columns), wins at every size.  A strip group of G GPUs has G
- * times the warps: narrower strips (K = 2 on two GPUs, K = 1 beyond) shorten the
- * steps without putting two warps on one SM sub-partition, as long as every rank
- * still gets at most one strip per sub-partition. */
+ * only lengthens a step; measured on B200 (10k, 30k, 100k squares; 1 and 2 GPUs)
+ * the widest strip, K = 4 (256 columns), wins everywhere: on 2 GPUs K = 4 / 2 / 1
+ * gave 972 / 940 / 677 GCUPS at 100k x 100k. */
 static inline int nwb_pk_choose_k(int A, int B, int world)
 {
+    (void)A;
     (void)B;
-    int K = 4;
-    if (world >= 4) K = 1;
-    else if (world >= 2) K = 2;
-    while (K < 4 && (A + 64 * K - 1) / (64 * K) > 592 * world) K *= 2;
-    return K;
+    (void)world;
+    return 4;
 }
 
 #define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * NWB_PK_RING_ROWS * (R) * (32 * (K)))
