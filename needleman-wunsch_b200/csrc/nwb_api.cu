@@ -143,7 +143,7 @@ static void make_inbox_layout(Inbox &ib, size_t bpitch)
     ib.bpitch = bpitch;
     ib.off_s = 0;
     ib.off_c = nwb_round_up(ib.off_s + bpitch * sizeof(int32_t), 256);
-    ib.off_w = nwb_round_up(ib.off_c + bpitch * sizeof(unsigned long long), 256);
+    ib.off_w = nwb_round_up(ib.off_c + 2 * bpitch * sizeof(unsigned long long), 256);
     ib.off_flag = nwb_round_up(ib.off_w + bpitch * sizeof(uint32_t), 256);
     ib.bytes = ib.off_flag + 256;
 }
@@ -185,7 +185,7 @@ extern "C" int nwb_plan_create(int max_top, int max_side, unsigned flags, int de
     if (rc == NWB_OK && strip_world > 1) {
         /* inbox sized for the longest side string; allocated once so that it
          * can be exported through CUDA IPC before any fill */
-        make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64 + 256, 32));
+        make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64 + 512, 32));
         e = cudaMalloc((void **)&p->inbox.base, p->inbox.bytes);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(inbox)");
         else e = cudaMemset(p->inbox.base, 0, p->inbox.bytes);
@@ -235,8 +235,7 @@ extern "C" int nwb_plan_upload(nwb_plan *p, const char *top, int top_len, const 
  * requested, the general int32 kernel runs. */
 static int choose_kind(unsigned flags, int m, int k, int d, NwbPkConsts *pc)
 {
-    if (flags & (NWB_FORCE_GENERAL | NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_WANT_COUNT_MATRIX | NWB_WANT_COUNT))
-        return NWB_KIND_I32;
+    if (flags & (NWB_FORCE_GENERAL | NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_WANT_COUNT_MATRIX)) return NWB_KIND_I32;
     if (!nwb_pk_supported(m, k, d, pc)) return NWB_KIND_I32;
     return NWB_KIND_PK;
 }
@@ -337,17 +336,21 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     if (rc == NWB_OK) rc = p->progress.ensure((size_t)nloc);
     if (rc == NWB_OK && p->kind == NWB_KIND_I32) {
         rc = p->bnd_s.ensure((size_t)nloc * L.bpitch);
-        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * L.bpitch);
+        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
     }
     if (rc == NWB_OK && p->kind == NWB_KIND_PK) {
         rc = p->bnd_w.ensure((size_t)nloc * L.bpitch);
         if (rc == NWB_OK) rc = p->side_pre.ensure(NWB_PK_SPRE_LEN(B));
-        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * L.bpitch);
+        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
     }
     if (rc != NWB_OK) return rc;
     CK(cudaMemsetAsync(p->progress.p, 0, (size_t)nloc * sizeof(int), st));
     /* the packed kernel's stream words validate themselves (bit 31): start from zero */
-    if (p->kind == NWB_KIND_PK) CK(cudaMemsetAsync(p->bnd_w.p, 0, (size_t)nloc * L.bpitch * sizeof(uint32_t), st));
+    if (p->kind == NWB_KIND_PK) {
+        CK(cudaMemsetAsync(p->bnd_w.p, 0, (size_t)nloc * L.bpitch * sizeof(uint32_t), st));
+        if (flags & NWB_WANT_COUNT)
+            CK(cudaMemsetAsync(p->bnd_c.p, 0, (size_t)nloc * 2 * L.bpitch * sizeof(unsigned long long), st));
+    }
 
     NwbStripParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -406,6 +409,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     }
     if (p->kind == NWB_KIND_PK)
         while (pk_warps > 1 && NWB_PK_SMEM_BYTES(L.pk_k, L.pk_r, pk_warps) > 200 * 1024) pk_warps--;
+    if (p->kind == NWB_KIND_PK && (flags & NWB_WANT_COUNT) && pk_warps > NWB_PK_WARPS) pk_warps = NWB_PK_WARPS;
     CK(cudaEventRecord(p->ev0, st));
     if (p->kind == NWB_KIND_PK) {
         nwb_pk_prep_side_kernel<<<64, 256, 0, st>>>(p->side.p, B, pc.shift, p->side_pre.p);

@@ -38,7 +38,7 @@ struct NwbBatchParams {
 
 #define NWB_BATCH_SIDE_ELEMS(maxB) ((size_t)(maxB) + NWB_BATCH_SPADB + NWB_BATCH_STAIL)
 #define NWB_BATCH_SMEM_PER_WARP(maxB) \
-    (NWB_PK_SMEM_BYTES(NWB_BATCH_K, NWB_BATCH_R, 1) + ((NWB_BATCH_SIDE_ELEMS(maxB) * 2 + 15) / 16) * 16)
+    (NWB_PK_WARP_SMEM(NWB_BATCH_K, NWB_BATCH_R, false) + ((NWB_BATCH_SIDE_ELEMS(maxB) * 2 + 15) / 16) * 16)
 
 __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(const NwbBatchParams bp, const NwbPkConsts pc)
 {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
     const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const size_t per_warp = NWB_BATCH_SMEM_PER_WARP(bp.max_B);
     unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * per_warp;
-    uint16_t *side_sm = reinterpret_cast<uint16_t *>(stage + NWB_PK_SMEM_BYTES(NWB_BATCH_K, NWB_BATCH_R, 1));
+    uint16_t *side_sm = reinterpret_cast<uint16_t *>(stage + NWB_PK_WARP_SMEM(NWB_BATCH_K, NWB_BATCH_R, false));
 
     for (long long pr = gwarp; pr < bp.n_pairs; pr += nwarps) {
         const long long t0 = bp.top_off[pr], s0 = bp.side_off[pr];
@@ -95,8 +95,9 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
         sp.debug_times = nullptr; sp.debug_trace = nullptr; sp.debug_trace_stride = 1; sp.debug_trace_blocks = 0;
 
         long long rsum = 0;
+        unsigned long long cfinal_unused = 0ull;
         for (int c = 0; c < n_strips; c++) {
-            nwb_pk_strip<NWB_BATCH_K, NWB_BATCH_R, true>(sp, pc, c, stage, lane, rsum);
+            nwb_pk_strip<NWB_BATCH_K, NWB_BATCH_R, true, false>(sp, pc, c, stage, lane, rsum, nullptr, cfinal_unused);
             __syncwarp();
         }
         if (n_strips > 1) {

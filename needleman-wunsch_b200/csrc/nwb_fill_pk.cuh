@@ -83,7 +83,7 @@ static inline int nwb_pk_choose_k(int A, int B, int world)
     return 4;
 }
 
-#define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * NWB_PK_RING_ROWS * (R) * (32 * (K)))
+#define NWB_PK_SMEM_BYTES(K, R, WARPS) ((size_t)(WARPS) * (NWB_PK_RING_ROWS * (R) * (32 * (K)) + 256))
 
 template <int K>
 struct NwbPkStage;
@@ -151,6 +151,44 @@ __device__ __forceinline__ void nwb_st_relaxed_sys_pred(uint32_t *p, unsigned v,
 #endif
 }
 
+/* ---- fused 64-bit path count (NWB_WANT_COUNT; replaces the enumeration behind
+ * get_solution_count(), computation.c:249, by cnt = [diag]cnt_diag + [left]cnt_left + [up]cnt_up
+ * in uint64 wrap-around arithmetic).  Counts cannot share a register, so each half keeps its
+ * own uint64 per column; the three tie tests come as predicate pairs straight out of
+ * VIMNMX.U16x2 (x <= 0 per half), the adds are predicated IADD3/IADD3.X pairs. */
+template <int K, int R>
+struct NwbPkCnt {
+    unsigned long long cnt[K][2];   /* counts of my columns in the row above, [low block, high block] */
+    unsigned long long clast[R][2]; /* counts of my blocks' last columns, per sub-row of the last step */
+    unsigned long long cdiag[2];    /* count left of my block in the last row of the previous step     */
+};
+
+/* count stream words: 2 x 64 bit per row, each self-validating (bit 63):
+ * word 0 = count bits 0..62, word 1 = count bit 63 */
+#define NWB_PK_CVALID 0x8000000000000000ull
+
+__device__ __forceinline__ void nwb_st_relaxed_sys_pred_u64(unsigned long long *p, unsigned long long v, bool pred)
+{
+#ifdef NWB_EMU
+    if (pred) *(volatile unsigned long long *)p = v;
+#else
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.relaxed.sys.global.u64 [%0], %1;\n\t}"
+                 ::"l"(p), "l"(v), "r"((unsigned)pred));
+#endif
+}
+__device__ __forceinline__ unsigned long long nwb_ld_relaxed_u64(const unsigned long long *p, bool sys)
+{
+#ifdef NWB_EMU
+    (void)sys;
+    return *(const volatile unsigned long long *)p;
+#else
+    unsigned long long v;
+    if (sys) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#endif
+}
+
 /* Per-strip constants of the row-range tests (one code body serves the head of a
  * strip, its bulk and its tail: the first and last 63 steps sit on the
  * strip-to-strip critical path and must not run through cold, separately
@@ -172,12 +210,14 @@ struct NwbPkRange {
  * strip).  The checked variant serves the first and last 63 steps; it is kept
  * small (4 steps unrolled) because it runs once per strip from a cold I-cache
  * and sits on the strip-to-strip critical path. */
-template <int K, int R, bool LEAN>
+template <int K, int R, bool LEAN, bool COUNT>
 __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkConsts &pc, const NwbPkRange<R> &rg,
                                              const unsigned bq, const int t, const int lane, const int g_idx,
                                              const int g_hi, const int A, const int col_lo, const int col_hi,
                                              const unsigned chars, const nwb_smem_addr slot, uint32_t *out_w,
-                                             const bool pub31, unsigned &rs32)
+                                             const bool pub31, unsigned &rs32, NwbPkCnt<K, R> &cc,
+                                             const unsigned long long *cstage, unsigned long long *out_c,
+                                             unsigned long long &cfinal)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const unsigned ONE = 0x00010001u;
@@ -195,6 +235,18 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
         vL[0] = __byte_perm(recv, st.vlast[0], 0x5432);
         st.sp[0] = __byte_perm(chars, st.sp[0], 0x5410);
     }
+    /* counts entering my blocks from the left, per sub-row: low block <- neighbour's high block
+     * (lane 0: the staged stream counts), high block <- my own low block of the previous step */
+    unsigned long long cL0[R][2];
+    if (COUNT) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            unsigned long long rc = __shfl_up_sync(NWB_FULL_MASK, cc.clast[r][1], 1);
+            if (lane == 0) rc = cstage[t * R + r];
+            cL0[r][0] = rc;
+            cL0[r][1] = cc.clast[r][0];
+        }
+    }
     /* ---- the cells: row by row, column by column (the scheduler finds the wavefront) */
     unsigned acc[R];
     unsigned uafter[R][K]; /* u right after sub-row r (only read by the rare bottom-row capture) */
@@ -202,6 +254,12 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     for (int r = 0; r < R; r++) {
         unsigned v = vL[r];
         unsigned code[K];
+        unsigned long long cl[2] = {0ull, 0ull}, cd[2] = {0ull, 0ull};
+        if (COUNT) {
+            cl[0] = cL0[r][0]; cl[1] = cL0[r][1];
+            cd[0] = (r == 0) ? cc.cdiag[0] : cL0[r > 0 ? r - 1 : 0][0];
+            cd[1] = (r == 0) ? cc.cdiag[1] : cL0[r > 0 ? r - 1 : 0][1];
+        }
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const unsigned nx = st.tpw[k] ^ st.sp[r];                      /* -x'-1 per half   */
@@ -212,14 +270,49 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
             const unsigned td = z - a;
             const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
             code[k] = fd + fl * 2u + fu * 4u; /* inverted: a set bit = NO arrow */
+            if (COUNT) {
+                bool pd[2], pl[2], pu[2]; /* [low half, high half]: x <= 0, i.e. the arrow is present */
+                (void)__vibmin_u16x2(td, 0u, &pd[1], &pd[0]);
+                (void)__vibmin_u16x2(un, 0u, &pl[1], &pl[0]);
+                (void)__vibmin_u16x2(vn, 0u, &pu[1], &pu[0]);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    unsigned long long n = pd[h] ? cd[h] : 0ull;
+                    if (pl[h]) n += cl[h];
+                    if (pu[h]) n += cc.cnt[k][h];
+                    cd[h] = cc.cnt[k][h];
+                    cc.cnt[k][h] = n;
+                    cl[h] = n;
+                }
+            }
             st.u[k] = un;
             uafter[r][k] = un;
             v = vn;
         }
         st.vlast[r] = v;
+        if (COUNT) {
+            cc.clast[r][0] = cl[0];
+            cc.clast[r][1] = cl[1];
+            if (!LEAN && r == rg.rB) { /* cells[M-1][N-1]: the block that owns column A, when it is on row B */
+                if (g_hi + 1 == rg.capg) {
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        if (col_lo + k == A) cfinal = cc.cnt[k][0];
+                }
+                if (g_hi == rg.capg) {
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        if (col_hi + k == A) cfinal = cc.cnt[k][1];
+                }
+            }
+        }
         if (K == 4) acc[r] = (code[0] + code[1] * 16u) + (code[2] + code[3] * 16u) * 256u;
         else if (K == 2) acc[r] = code[0] + code[1] * 16u;
         else acc[r] = code[0];
+    }
+    if (COUNT) {
+        cc.cdiag[0] = cL0[R - 1][0];
+        cc.cdiag[1] = cL0[R - 1][1];
     }
     /* ---- outputs */
     st.send = (R == 2) ? __byte_perm(st.vlast[0], st.vlast[R - 1], 0x7632) : st.vlast[0];
@@ -251,8 +344,16 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
         }
     }
     /* lane 31: the strip's last column for group g_hi, self-validating */
-    nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u),
-                            pub31 && (LEAN || (unsigned)g_hi < rg.ngroups));
+    const bool pub = pub31 && (LEAN || (unsigned)g_hi < rg.ngroups);
+    nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | ((R == 2) ? 0x80008000u : 0x80000000u), pub);
+    if (COUNT) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const unsigned long long cv = cc.clast[r][1];
+            nwb_st_relaxed_sys_pred_u64(out_c + (g_idx * R + r) * 2, cv | NWB_PK_CVALID, pub);
+            nwb_st_relaxed_sys_pred_u64(out_c + (g_idx * R + r) * 2 + 1, (cv >> 63) | NWB_PK_CVALID, pub);
+        }
+    }
 }
 
 /* side characters of R consecutive rows: from the global side_pre array (read-only
@@ -264,9 +365,10 @@ __device__ __forceinline__ unsigned nwb_pk_chars(const uint16_t *q)
     return SMEMCH ? (unsigned)*q : (unsigned)nwb_ldg_u16(q);
 }
 
-template <int K, int R, bool SMEMCH>
+template <int K, int R, bool SMEMCH, bool COUNT>
 __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
-                                              unsigned char *stage_bytes, const int lane, long long &rsum)
+                                              unsigned char *stage_bytes, const int lane, long long &rsum,
+                                              unsigned long long *cstage, unsigned long long &cfinal)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const int A = p.A, B = p.B;
@@ -292,6 +394,14 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
         st.acc_prev[r] = 0u;
     }
     st.send = NWB_PK_BIG * ONE;
+    /* counts: the border row/column and every virtual cell above the table count 1 path
+     * (a virtual cell has only its LEFT arrow, so it copies the 1 handed in from the left) */
+    NwbPkCnt<K, R> cc;
+#pragma unroll
+    for (int k = 0; k < K; k++) cc.cnt[k][0] = cc.cnt[k][1] = 1ull;
+#pragma unroll
+    for (int r = 0; r < R; r++) cc.clast[r][0] = cc.clast[r][1] = 1ull;
+    cc.cdiag[0] = cc.cdiag[1] = 1ull;
 
     const int lc = c - p.strip_begin;
     const bool has_left = (c > 0);
@@ -303,6 +413,15 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     if (has_left) in_w = (left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch) + NWB_PK_BPAD;
     const bool pub31 = publish && (lane == 31);
     const bool is_last = (c == p.n_strips - 1);
+    /* count streams: 2 x uint64 per row, (BPAD + group) * R + sub-row */
+    unsigned long long *out_c = nullptr;
+    const unsigned long long *in_c = nullptr;
+    if (COUNT) {
+        out_c = (out_remote ? p.out_bnd_c : p.bnd_c + (size_t)lc * 2 * p.bpitch) + (size_t)NWB_PK_BPAD * R * 2;
+        if (has_left) in_c = (left_remote ? p.in_bnd_c : p.bnd_c + (size_t)(lc - 1) * 2 * p.bpitch) + (size_t)NWB_PK_BPAD * R * 2;
+        if (!has_left && lane < NWB_PK_SUB * R) cstage[lane] = 1ull; /* column 0 of the table */
+        __syncwarp();
+    }
     const bool nowait = p.debug_nowait != 0;
     /* my low block's first row at step s is R*(s - 2*lane) + 1 */
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
@@ -373,6 +492,28 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 bq_next = 0u;
                 if (lane < NWB_PK_SUB && gs + NWB_PK_SUB < ngroups)
                     bq_next = nwb_ld_relaxed_u32(in_w + gs + NWB_PK_SUB, left_remote);
+                if (COUNT) {
+                    /* stage the counts of rows R*ss+1 .. R*(ss+SUB): lane i polls word i of the
+                     * sub-block (2 words per row), even lanes assemble and store the count */
+                    const int nw = NWB_PK_SUB * R * 2;
+                    const int row0 = lane >> 1;                 /* row within the sub-block */
+                    const bool need = (lane < nw) && (ss + row0 / R < ngroups);
+                    unsigned long long cw = 0ull;
+                    if (need) cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
+                    if (!nowait) {
+                        bool okc = !need || (cw & NWB_PK_CVALID);
+                        while (!__all_sync(NWB_FULL_MASK, okc)) {
+                            if (!okc) {
+                                cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
+                                okc = (cw & NWB_PK_CVALID) != 0ull;
+                            }
+                        }
+                    }
+                    const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
+                    __syncwarp(); /* the previous sub-block's reads of cstage are done */
+                    if (lane < nw && !(lane & 1)) cstage[row0] = (cw & ~NWB_PK_CVALID) | (hi << 63);
+                    __syncwarp();
+                }
             }
             /* side characters of the NEXT sub-block's steps are loaded one sub-block ahead */
             unsigned chars[NWB_PK_SUB];
@@ -386,18 +527,19 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 }
             }
             uint32_t *outb = out_w + (ss - 2 * lane - 1);
+            unsigned long long *outcb = COUNT ? out_c + (ptrdiff_t)(ss - 2 * lane - 1) * R * 2 : nullptr;
             const int gb = ss - 2 * lane - 1;
 #define NWB_PK_SLOT_PTR(t) (lane_stage + (unsigned)(((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT))
             if (lean) {
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++)
-                    nwb_pk_step<K, R, true>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
-                                            NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
+                    nwb_pk_step<K, R, true, COUNT>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
+                                                   NWB_PK_SLOT_PTR(t), outb, pub31, rs32, cc, cstage, outcb, cfinal);
             } else {
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++)
-                    nwb_pk_step<K, R, false>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
-                                             NWB_PK_SLOT_PTR(t), outb, pub31, rs32);
+                    nwb_pk_step<K, R, false, COUNT>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
+                                                    NWB_PK_SLOT_PTR(t), outb, pub31, rs32, cc, cstage, outcb, cfinal);
             }
         }
         __syncwarp();
@@ -456,6 +598,10 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     if (dbg && lane == 0) dbg[3] = nwb_globaltimer();
 }
 
+/* per-warp shared memory: the arrow ring, then (count kernel) the staged stream counts */
+#define NWB_PK_CSTAGE_BYTES (NWB_PK_SUB * 2 * 8)
+#define NWB_PK_WARP_SMEM(K, R, COUNT) ((size_t)NWB_PK_RING_ROWS * NWB_PK_SLOT_BYTES(K, R) + ((COUNT) ? NWB_PK_CSTAGE_BYTES : 0))
+
 template <int K, int R, bool COUNT>
 __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(const NwbStripParams p, const NwbPkConsts pc)
 {
@@ -463,11 +609,21 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
     const int warp = threadIdx.x >> 5;
     const int nworkers = (int)gridDim.x * (int)(blockDim.x >> 5);
     const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
-    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_RING_ROWS * NWB_PK_SLOT_BYTES(K, R);
+    unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * NWB_PK_WARP_SMEM(K, R, COUNT);
+    unsigned long long *cstage = reinterpret_cast<unsigned long long *>(stage + (size_t)NWB_PK_RING_ROWS * NWB_PK_SLOT_BYTES(K, R));
 
     long long rsum = 0;
-    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
-        nwb_pk_strip<K, R, false>(p, pc, c, stage, lane, rsum);
+    unsigned long long cfinal = 0ull;
+    bool owns_final = false;
+    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) {
+        nwb_pk_strip<K, R, false, COUNT>(p, pc, c, stage, lane, rsum, cstage, cfinal);
+        if (COUNT && c == p.n_strips - 1) {
+            /* the block that owns column A wrote cfinal when it passed row B */
+            const int W = 64 * K, col_lo = c * W + (2 * lane) * K + 1;
+            owns_final = (p.A >= col_lo && p.A < col_lo + 2 * K);
+        }
+    }
+    if (COUNT && owns_final) p.summary->count = cfinal;
 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
@@ -545,7 +701,7 @@ static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int 
                            nwb_fail_fn fail)
 {
     auto kernel = nwb_fill_pk_kernel<K, R, COUNT>;
-    const size_t smem = NWB_PK_SMEM_BYTES(K, R, warps);
+    const size_t smem = (size_t)warps * NWB_PK_WARP_SMEM(K, R, COUNT);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     void *args[] = {(void *)&sp, (void *)&pc};
@@ -557,7 +713,11 @@ static int nwb_pk_launch_k(const NwbStripParams &sp, const NwbPkConsts &pc, int 
 static inline int nwb_pk_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int K, int R, bool count, int grid,
                                 int warps, cudaStream_t st, nwb_fail_fn fail)
 {
-    if (count) return -5; /* the fused count lives in the general kernel for now */
+    if (count) {
+        if (K != 4) return -1;
+        return R == 2 ? nwb_pk_launch_k<4, 2, true>(sp, pc, grid, warps, st, fail)
+                      : nwb_pk_launch_k<4, 1, true>(sp, pc, grid, warps, st, fail);
+    }
     switch (K * 10 + R) {
     case 11: return nwb_pk_launch_k<1, 1, false>(sp, pc, grid, warps, st, fail);
     case 21: return nwb_pk_launch_k<2, 1, false>(sp, pc, grid, warps, st, fail);

@@ -38,6 +38,6 @@ static inline NwbLayout nwb_make_layout(int A, int B, int kind, int pk_k, int st
     if (L.n_strips < 1) L.n_strips = 1;
     L.pitch = nwb_round_up((size_t)L.n_strips * (size_t)strip_w / 2, 16);
     L.spitch = (size_t)L.n_strips * (size_t)strip_w;
-    L.bpitch = nwb_round_up((size_t)B + 1 + 64 + 256, 32); /* + front/back padding of the packed kernel's streams */
+    L.bpitch = nwb_round_up((size_t)B + 1 + 64 + 512, 32); /* + front/back padding of the packed kernel's streams */
     return L;
 }

@@ -217,6 +217,12 @@ static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c)
     if (emu_s16(c >> 16) > hi) hi = emu_s16(c >> 16);
     return EMU_PER_HALF((unsigned)lo, (unsigned)hi);
 }
+static inline unsigned __vibmin_u16x2(unsigned a, unsigned b, bool *pred_hi, bool *pred_lo)
+{
+    *pred_hi = (a >> 16) <= (b >> 16);
+    *pred_lo = (a & 0xffff) <= (b & 0xffff);
+    return __vminu2(a, b);
+}
 static inline unsigned __vadd2(unsigned a, unsigned b)
 {
     return EMU_PER_HALF((a & 0xffff) + (b & 0xffff), (a >> 16) + (b >> 16));

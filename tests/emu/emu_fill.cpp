@@ -19,10 +19,11 @@ static void run_i32(unsigned grid, const NwbStripParams &p)
                [&]() { nwb_fill_i32_kernel<COUNT, SCORES, ABS, CNTMAT>(p); });
 }
 
-template <int K, int R>
+template <int K, int R, bool COUNT>
 static void run_pk_emu(unsigned grid, int warps, const NwbStripParams &p, const NwbPkConsts &pc)
 {
-    emu_launch(grid, 32 * warps, NWB_PK_SMEM_BYTES(K, R, warps), [&]() { nwb_fill_pk_kernel<K, R, false>(p, pc); });
+    emu_launch(grid, 32 * warps, (size_t)warps * NWB_PK_WARP_SMEM(K, R, COUNT),
+               [&]() { nwb_fill_pk_kernel<K, R, COUNT>(p, pc); });
 }
 
 extern "C" {
@@ -117,7 +118,7 @@ int emu_fill_i32(const char *top, int A, const char *side, int B, int m, int k, 
 size_t emu_pitch_pk(int A, int B, int K) { return nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K).pitch; }
 int emu_pk_supported(int m, int k, int d) { return nwb_pk_supported(m, k, d, nullptr) ? 1 : 0; }
 
-int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K, int R,
+int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K, int R, int count,
                 unsigned grid, int warps, int split, uint8_t *arrows, emu_out *out)
 {
     NwbPkConsts pc;
@@ -138,6 +139,8 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.arrows = arrows;
     p.pitch = L.pitch;
     p.bnd_w = bnd_w.data();
+    std::vector<unsigned long long> bnd_cc((size_t)L.n_strips * 2 * L.bpitch, 0ull);
+    p.bnd_c = bnd_cc.data();
     p.bpitch = L.bpitch;
     p.progress = progress.data();
     p.summary = &sum;
@@ -146,27 +149,34 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.side_pre = side_pre.data();
     const uint32_t *last_stream = nullptr; /* the stream consumed by the last strip, when it is not in bnd_w */
     auto launch = [&](const NwbStripParams &q) {
-        if (R == 2) {
-            if (K == 1) run_pk_emu<1, 2>(grid, warps, q, pc);
-            else if (K == 2) run_pk_emu<2, 2>(grid, warps, q, pc);
-            else run_pk_emu<4, 2>(grid, warps, q, pc);
+        if (count) {
+            if (R == 2) run_pk_emu<4, 2, true>(grid, warps, q, pc);
+            else run_pk_emu<4, 1, true>(grid, warps, q, pc);
+        } else if (R == 2) {
+            if (K == 1) run_pk_emu<1, 2, false>(grid, warps, q, pc);
+            else if (K == 2) run_pk_emu<2, 2, false>(grid, warps, q, pc);
+            else run_pk_emu<4, 2, false>(grid, warps, q, pc);
         } else {
-            if (K == 1) run_pk_emu<1, 1>(grid, warps, q, pc);
-            else if (K == 2) run_pk_emu<2, 1>(grid, warps, q, pc);
-            else run_pk_emu<4, 1>(grid, warps, q, pc);
+            if (K == 1) run_pk_emu<1, 1, false>(grid, warps, q, pc);
+            else if (K == 2) run_pk_emu<2, 1, false>(grid, warps, q, pc);
+            else run_pk_emu<4, 1, false>(grid, warps, q, pc);
         }
     };
     if (split > 0 && split < L.n_strips) {
         NwbStripParams p0 = p, p1 = p;
         std::vector<uint32_t> inbox_w(L.bpitch, 0u);
+        std::vector<unsigned long long> inbox_cc(2 * L.bpitch, 0ull), bnd1c((size_t)L.n_strips * 2 * L.bpitch, 0ull);
         int inbox_flag = 0;
         std::vector<uint32_t> bnd1((size_t)L.n_strips * L.bpitch, 0u);
         std::vector<int> prog1((size_t)L.n_strips, 0);
         p0.strip_end = split;
         p0.out_bnd_w = inbox_w.data();
+        p0.out_bnd_c = inbox_cc.data();
         p0.out_progress = &inbox_flag;
         p1.strip_begin = split;
         p1.in_bnd_w = inbox_w.data();
+        p1.in_bnd_c = inbox_cc.data();
+        p1.bnd_c = bnd1c.data();
         p1.in_progress = &inbox_flag;
         p1.bnd_w = bnd1.data();
         p1.progress = prog1.data();
@@ -186,7 +196,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     out->opt_score = (int)(sum.rsum - (long long)d * ((long long)A + B));
     out->branch_count = branches;
     out->greatest_abs = 0;
-    out->count = 0;
+    out->count = sum.count;
     out->pitch = L.pitch;
     out->spitch = 0;
     return 0;

@@ -57,3 +57,27 @@ def test_two_gpu_split(oracle):
     check(oracle, t, s, 1, 1, 1, 4, grid=2, split=1)
     check(oracle, t, s, 1, 1, 1, 2, grid=1, split=2)
     check(oracle, t, s, 2, 1, 2, 1, grid=2, split=5)
+
+
+def test_fused_count(oracle):
+    """NWB_WANT_COUNT in the packed kernel: the final uint64 count (mod 2^64) against the oracle on
+    shapes with one and several strips, both row-group sizes, and across the 2-GPU split."""
+    rng = random.Random(9)
+
+    def chk(t, s, m, k, d, R, grid=2, split=0):
+        r = emu.fill_pk(t, s, m, k, d, K=4, R=R, grid=grid, split=split, count=True)
+        o = oracle.fill(t, s, m, k, d, want_codes=True)
+        assert np.array_equal(emu.unpack_arrows(r["arrows"], len(t)) & 7, o.codes[1:, 1:] & 7)
+        assert (r["opt_score"], r["branch_count"], r["count"]) == (o.final_score, o.branch_count, o.count)
+
+    chk(b"GCATGCU", b"GATTACA", 1, 1, 1, 1)
+    chk(b"GCATGCU", b"GATTACA", 0, 0, 0, 2)
+    for a, b in [(1, 1), (5, 40), (63, 33), (256, 64), (257, 130), (513, 70), (600, 200), (130, 256), (256, 256)]:
+        t = bytes(rng.choice(b"ACGT") for _ in range(a))
+        s = bytes(rng.choice(b"ACGT") for _ in range(b))
+        for m, k, d in [(1, 1, 1), (2, 1, 2)]:
+            for R in (1, 2):
+                chk(t, s, m, k, d, R, grid=rng.choice([1, 2, 3]))
+    t, s = oracle.generate_pair(0x5EED0910, 700, 210)
+    chk(t, s, 1, 1, 1, 2, grid=2, split=1)
+    chk(t, s, 1, 1, 1, 1, grid=1, split=2)

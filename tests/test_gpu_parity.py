@@ -57,6 +57,8 @@ def full_check(oracle, nwb, t, s, m, k, d, extra_flags=0, num_gpus=1):
     assert tab.count == o.count
     if extra_flags & nwb.TRACK_ABS:
         assert tab.greatest_abs == o.greatest_abs
+    if len(t) and len(s) and not (extra_flags & (nwb.FORCE_GENERAL | nwb.TRACK_ABS)):
+        assert tab.kernel_kind == (nwb.KIND_PK if pk_supported(m, k, d) else nwb.KIND_I32)
     check_arrows(oracle, nwb, tab, t, s, m, k, d)
     if not (extra_flags & (nwb.FORCE_GENERAL | nwb.TRACK_ABS)):
         tab2 = nwb.fill(t, s, m, k, d, nwb.WANT_ARROWS_HOST, num_gpus=num_gpus)
@@ -138,7 +140,7 @@ def test_config2_dna_10k(oracle, nwb, force):
     """BASELINE config 2 (10k x 10k DNA, 1 1 1, -q -s) vs the reference's goldens."""
     t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
     ff = nwb.FORCE_GENERAL if force else 0
-    tab = nwb.fill(t, s, 1, 1, 1, (nwb.WANT_COUNT if force else 0) | nwb.WANT_ARROWS_HOST | ff)
+    tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_COUNT | nwb.WANT_ARROWS_HOST | ff)
     assert tab.kernel_kind == (nwb.KIND_I32 if force else nwb.KIND_PK)
     assert (tab.opt_score, tab.branch_count, tab.count) == (1056, 34377799, 0)
     check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
@@ -153,9 +155,10 @@ def test_config5_protein_30k_summary(oracle, nwb):
     t, s = oracle.generate_pair(0x5EED0005, 30000, 30000, oracle.PROTEIN)
     tab = nwb.fill(t, s, 2, 1, 2, nwb.WANT_COUNT)
     assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"])
-    tab = nwb.fill(t, s, 2, 1, 2, 0)
     assert tab.kernel_kind == nwb.KIND_PK
-    assert (tab.opt_score, tab.branch_count) == (g["final_score"], g["branch_count"])
+    tab = nwb.fill(t, s, 2, 1, 2, nwb.WANT_COUNT | nwb.FORCE_GENERAL)
+    assert tab.kernel_kind == nwb.KIND_I32
+    assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"])
 
 
 def test_config3_dna_100k_properties(oracle, nwb):
@@ -168,7 +171,7 @@ def test_config3_dna_100k_properties(oracle, nwb):
     g = [c for c in golden("golden_big.json") if c["name"] == "config3_dna_100k"]
     R = 1500
     o = None
-    for flags, kind in ((0, nwb.KIND_PK), (nwb.WANT_COUNT, nwb.KIND_I32)):
+    for flags, kind in ((0, nwb.KIND_PK), (nwb.WANT_COUNT, nwb.KIND_PK), (nwb.WANT_COUNT | nwb.FORCE_GENERAL, nwb.KIND_I32)):
         plan = nwb.Plan(100000, 100000, flags)
         plan.upload(t, s)
         plan.run(1, 1, 1)
