@@ -163,6 +163,23 @@ struct NwbPkCnt {
     unsigned long long cdiag[2];    /* count left of my block in the last row of the previous step     */
 };
 
+/* n += c when the masked flag word is zero (flag = 1 means "no arrow"): one predicate-producing
+ * AND plus a predicated add-with-carry pair */
+__device__ __forceinline__ void nwb_add_if_arrow(unsigned long long &n, const unsigned long long c, const unsigned noarrow)
+{
+#ifdef NWB_EMU
+    if (noarrow == 0u) n += c;
+#else
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 al, ah, bl, bh;\n\t"
+        "setp.eq.u32 p, %2, 0;\n\t"
+        "mov.b64 {al, ah}, %0;\n\tmov.b64 {bl, bh}, %1;\n\t"
+        "@p add.cc.u32 al, al, bl;\n\t@p addc.u32 ah, ah, bh;\n\t"
+        "mov.b64 %0, {al, ah};\n\t}"
+        : "+l"(n)
+        : "l"(c), "r"(noarrow));
+#endif
+}
+
 /* count stream words: 2 x 64 bit per row, each self-validating (bit 63):
  * word 0 = count bits 0..62, word 1 = count bit 63 */
 #define NWB_PK_CVALID 0x8000000000000000ull
@@ -271,15 +288,16 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
             const unsigned fd = __vminu2(td, ONE), fl = __vminu2(un, ONE), fu = __vminu2(vn, ONE);
             code[k] = fd + fl * 2u + fu * 4u; /* inverted: a set bit = NO arrow */
             if (COUNT) {
-                bool pd[2], pl[2], pu[2]; /* [low half, high half]: x <= 0, i.e. the arrow is present */
-                (void)__vibmin_u16x2(td, 0u, &pd[1], &pd[0]);
-                (void)__vibmin_u16x2(un, 0u, &pl[1], &pl[0]);
-                (void)__vibmin_u16x2(vn, 0u, &pu[1], &pu[0]);
+                /* arrow present = 1 per half; the conditional 64-bit adds become 32x64-bit
+                 * multiply-adds on the FMA pipe (IMAD.WIDE.U32 + IMAD), no predicates, no selects */
+                const unsigned ad = fd ^ ONE, al = fl ^ ONE, au = fu ^ ONE;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    unsigned long long n = pd[h] ? cd[h] : 0ull;
-                    if (pl[h]) n += cl[h];
-                    if (pu[h]) n += cc.cnt[k][h];
+                    const unsigned xd = h ? (ad >> 16) : (ad & 0xFFFFu);
+                    const unsigned xl = h ? (al >> 16) : (al & 0xFFFFu);
+                    const unsigned xu = h ? (au >> 16) : (au & 0xFFFFu);
+                    const unsigned long long n = (unsigned long long)xd * cd[h] + (unsigned long long)xl * cl[h] +
+                                                 (unsigned long long)xu * cc.cnt[k][h];
                     cd[h] = cc.cnt[k][h];
                     cc.cnt[k][h] = n;
                     cl[h] = n;
@@ -530,7 +548,24 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
             unsigned long long *outcb = COUNT ? out_c + (ptrdiff_t)(ss - 2 * lane - 1) * R * 2 : nullptr;
             const int gb = ss - 2 * lane - 1;
 #define NWB_PK_SLOT_PTR(t) (lane_stage + (unsigned)(((gb + (t)) & (NWB_PK_RING_ROWS - 1)) * SLOT))
-            if (lean) {
+            if (COUNT) {
+                /* the count step is ~4x the code of the plain one: keep it rolled so that the loop
+                 * body stays inside the instruction cache (side characters come straight from L1) */
+                const uint16_t *spc = sp_lane + R * ss;
+                if (lean) {
+#pragma unroll 1
+                    for (int t = 0; t < NWB_PK_SUB; t++)
+                        nwb_pk_step<K, R, true, COUNT>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi,
+                                                       nwb_pk_chars<R, SMEMCH>(spc + R * t), NWB_PK_SLOT_PTR(t), outb,
+                                                       pub31, rs32, cc, cstage, outcb, cfinal);
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < NWB_PK_SUB; t++)
+                        nwb_pk_step<K, R, false, COUNT>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi,
+                                                        nwb_pk_chars<R, SMEMCH>(spc + R * t), NWB_PK_SLOT_PTR(t), outb,
+                                                        pub31, rs32, cc, cstage, outcb, cfinal);
+                }
+            } else if (lean) {
 #pragma unroll
                 for (int t = 0; t < NWB_PK_SUB; t++)
                     nwb_pk_step<K, R, true, COUNT>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
