@@ -246,3 +246,21 @@ def test_batch_config4_shard(oracle, nwb):
         assert bt.opt_score(i) == o.final_score and bt.branch_count(i) == o.branch_count
         assert np.array_equal(bt.arrow_rows(i) & 0x77, o.packed)
     bt.close()
+
+
+def test_count_prefix_property(oracle, nwb):
+    """Intermediate counts of the packed count kernel through the public ABI: the count of cell
+    (i, j) equals the final count of the sub-problem (top[:i], side[:j]).  The final count of the
+    big configs is 0 mod 2^64 (SURVEY hard part 6), so the check samples cells whose counts are not."""
+    t, s = oracle.generate_pair(0x5EED0D00, 900, 700)
+    o = oracle.fill(t, s, 1, 1, 1, want_counts=True)
+    rng = random.Random(17)
+    cells = [(900, 700), (256, 256), (257, 300), (512, 64), (513, 699)] + \
+            [(rng.randint(1, 900), rng.randint(1, 700)) for _ in range(20)]
+    nonzero = 0
+    for i, j in cells:
+        tab = nwb.fill(t[:i], s[:j], 1, 1, 1, nwb.WANT_COUNT)
+        assert tab.kernel_kind == nwb.KIND_PK
+        assert tab.count == int(o.counts[j, i]), (i, j)
+        nonzero += int(o.counts[j, i]) != 0
+    assert nonzero >= 10
