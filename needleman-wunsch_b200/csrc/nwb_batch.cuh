@@ -14,7 +14,7 @@
 #pragma once
 #include "nwb_fill_pk.cuh"
 
-#define NWB_BATCH_WARPS 8
+#define NWB_BATCH_WARPS 12
 #define NWB_BATCH_K 4
 #define NWB_BATCH_R 1
 #define NWB_BATCH_SPADB 64   /* side_pre entries in front of row 1 (lane 31 starts 61 rows above the table) */

@@ -75,7 +75,7 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     }
     b->h_arrow_off[(size_t)n_pairs] = aoff;
     b->arrows_bytes = (size_t)aoff;
-    if (NWB_BATCH_SMEM_PER_WARP(b->max_B) * NWB_BATCH_WARPS > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
+    if (NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
     int rc = b->tops.ensure(tbytes + 16);
     if (rc == NWB_OK) rc = b->sides.ensure(sbytes + 16);
@@ -109,7 +109,11 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     NwbBatchParams bp;
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
-    const long long nwarps = (long long)grid * NWB_BATCH_WARPS;
+    /* as many warps per SM as the per-warp shared memory (arrow ring + side string) allows, at most 12 */
+    int warps = (int)((220 * 1024) / NWB_BATCH_SMEM_PER_WARP(b->max_B));
+    if (warps > NWB_BATCH_WARPS) warps = NWB_BATCH_WARPS;
+    if (warps < 1) return NWB_ERR_UNSUPPORTED;
+    const long long nwarps = (long long)grid * warps;
     bp.bpitch = nwb_round_up((size_t)b->max_B + 1 + 64 + 256, 32);
     bp.scratch_per_warp = (b->max_strips > 1) ? (size_t)(b->max_strips - 1) * bp.bpitch : 0;
     if (bp.scratch_per_warp) {
@@ -119,10 +123,10 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     bp.tops = b->tops.p; bp.top_off = b->top_off.p; bp.sides = b->sides.p; bp.side_off = b->side_off.p;
     bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
     bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p; bp.scratch = b->scratch.p;
-    const size_t smem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * NWB_BATCH_WARPS;
+    const size_t smem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * (size_t)warps;
     CK(cudaFuncSetAttribute(nwb_batch_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(b->ev0, st));
-    nwb_batch_pk_kernel<<<grid, 32 * NWB_BATCH_WARPS, smem, st>>>(bp, b->pc);
+    nwb_batch_pk_kernel<<<grid, 32 * warps, smem, st>>>(bp, b->pc);
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->ev1, st));
     b->launches += 1;
