@@ -264,3 +264,20 @@ def test_count_prefix_property(oracle, nwb):
         assert tab.count == int(o.counts[j, i]), (i, j)
         nonzero += int(o.counts[j, i]) != 0
     assert nonzero >= 10
+
+
+def test_extreme_aspect_ratios_and_multi_pass(oracle, nwb):
+    """Wide-and-short / tall-and-narrow tables, and a table with more strips than persistent warps
+    (160,000 columns = 625 strips > 592 warps: the cyclic second pass of the strip assignment)."""
+    for seed, a, b, mkd in [(0x5EED0E00, 20000, 7, (1, 1, 1)), (0x5EED0E02, 5, 20000, (1, 1, 1)),
+                            (0x5EED0E04, 70000, 300, (2, 1, 2)), (0x5EED0E06, 160000, 200, (1, 1, 1)),
+                            (0x5EED0E08, 300, 70000, (1, 1, 1))]:
+        t, s = oracle.generate_pair(seed, a, b)
+        o = oracle.fill(t, s, *mkd)
+        for flags in (nwb.WANT_ARROWS_HOST, nwb.WANT_ARROWS_HOST | nwb.WANT_COUNT,
+                      nwb.WANT_ARROWS_HOST | nwb.WANT_COUNT | nwb.FORCE_GENERAL):
+            tab = nwb.fill(t, s, *mkd, flags)
+            assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, flags)
+            if flags & nwb.WANT_COUNT:
+                assert tab.count == o.count, (a, b, flags)
+            check_arrows(oracle, nwb, tab, t, s, *mkd)
