@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""A small set of fills through the C ABI for `compute-sanitizer --tool memcheck|racecheck`:
+both kernels, with and without the fused count, several strips, the batch kernel."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nw_b200 as nwb  # noqa: E402
+import oracle  # noqa: E402
+
+for a, b in ((7, 7), (300, 100), (700, 260), (1500, 64)):
+    t, s = oracle.generate_pair(0x5EED0F00 + a, a, b)
+    o = oracle.fill(t, s, 1, 1, 1)
+    for flags in (0, nwb.WANT_COUNT, nwb.WANT_COUNT | nwb.FORCE_GENERAL | nwb.TRACK_ABS | nwb.WANT_SCORES):
+        tab = nwb.fill(t, s, 1, 1, 1, flags | nwb.WANT_ARROWS_HOST)
+        assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, flags)
+        if flags & nwb.WANT_COUNT:
+            assert tab.count == o.count
+        tab.close()
+tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256 if p % 3 else 300, 256 if p % 2 else 100) for p in range(40)))
+bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST)
+bt.run()
+bt.fetch()
+for p in range(40):
+    o = oracle.fill(tops[p], sides[p], 1, 1, 1)
+    assert (bt.opt_score(p), bt.branch_count(p)) == (o.final_score, o.branch_count), p
+bt.close()
+print("sanitize_run ok")
