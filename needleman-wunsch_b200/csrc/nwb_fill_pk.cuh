@@ -163,23 +163,6 @@ struct NwbPkCnt {
     unsigned long long cdiag[2];    /* count left of my block in the last row of the previous step     */
 };
 
-/* n += c when the masked flag word is zero (flag = 1 means "no arrow"): one predicate-producing
- * AND plus a predicated add-with-carry pair */
-__device__ __forceinline__ void nwb_add_if_arrow(unsigned long long &n, const unsigned long long c, const unsigned noarrow)
-{
-#ifdef NWB_EMU
-    if (noarrow == 0u) n += c;
-#else
-    asm("{\n\t.reg .pred p;\n\t.reg .u32 al, ah, bl, bh;\n\t"
-        "setp.eq.u32 p, %2, 0;\n\t"
-        "mov.b64 {al, ah}, %0;\n\tmov.b64 {bl, bh}, %1;\n\t"
-        "@p add.cc.u32 al, al, bl;\n\t@p addc.u32 ah, ah, bh;\n\t"
-        "mov.b64 %0, {al, ah};\n\t}"
-        : "+l"(n)
-        : "l"(c), "r"(noarrow));
-#endif
-}
-
 /* count stream words: 2 x 64 bit per row, each self-validating (bit 63):
  * word 0 = count bits 0..62, word 1 = count bit 63 */
 #define NWB_PK_CVALID 0x8000000000000000ull
