@@ -372,6 +372,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     sp.bpitch = L.bpitch;
     sp.progress = p->progress.p;
     sp.summary = p->summary.p;
+    sp.count_branches = (flags & NWB_NO_BRANCH_COUNT) ? 0 : 1;
     sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? 1 : 0;
     if (getenv("NWB_DEBUG_TIMES") && p->kind == NWB_KIND_PK) { /* diagnostics: per-strip timestamps dumped to a file */
         if (p->dbg_times.ensure((size_t)L.n_strips * 4) != NWB_OK) return NWB_ERR_NOMEM;
@@ -428,15 +429,6 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
                                      ? sp.in_bnd_w
                                      : p->bnd_w.p + (size_t)(L.n_strips - 2 - p->strip_begin) * L.bpitch;
         nwb_pk_stream_sum_kernel<<<32, 256, 0, st>>>(stream, B, L.pk_r, &p->summary.p->rsum);
-        CK(cudaGetLastError());
-        p->launches += 1;
-    }
-    if (p->kind == NWB_KIND_PK && !(flags & NWB_NO_BRANCH_COUNT)) {
-        /* get_branch_count() (walk-table.c:133): second, HBM-bound pass over this rank's columns */
-        long long cb = (long long)p->strip_begin * L.strip_w, ce = (long long)p->strip_end * L.strip_w;
-        if (ce > A) ce = A;
-        nwb_branch_count_kernel<<<p->sm_count * 16, 256, 0, st>>>(p->arrows.p, L.pitch, A, B, (int)cb, (int)ce,
-                                                                 &p->summary.p->branch_count);
         CK(cudaGetLastError());
         p->launches += 1;
     }

@@ -31,6 +31,7 @@ struct NwbBatchParams {
     uint8_t *arrows;            /* all pairs' nibble tables */
     const long long *arrow_off; /* byte offset of pair p's table; its pitch is 128 * ceil(A_p / 256) */
     int *out_score;             /* [n_pairs] */
+    unsigned *out_branch;       /* [n_pairs] branch counters, or NULL */
     uint32_t *scratch;          /* boundary streams for pairs wider than one strip: per warp n_strips_max * bpitch */
     size_t scratch_per_warp;    /* words */
     size_t bpitch;              /* words per strip boundary */
@@ -54,7 +55,10 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
         const long long t0 = bp.top_off[pr], s0 = bp.side_off[pr];
         const int A = (int)(bp.top_off[pr + 1] - t0), B = (int)(bp.side_off[pr + 1] - s0);
         if (A == 0 || B == 0) {
-            if (lane == 0) bp.out_score[pr] = (A == 0) ? -B * bp.d : -A * bp.d; /* borders only */
+            if (lane == 0) {
+                bp.out_score[pr] = (A == 0) ? -B * bp.d : -A * bp.d; /* borders only */
+                if (bp.out_branch) bp.out_branch[pr] = 0u;
+            }
             continue;
         }
         /* side_pre of this pair: entry e is row e - SPADB */
@@ -91,13 +95,16 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
         sp.in_bnd_s = nullptr; sp.in_bnd_c = nullptr; sp.in_bnd_w = nullptr; sp.in_progress = nullptr;
         sp.out_bnd_s = nullptr; sp.out_bnd_c = nullptr; sp.out_bnd_w = nullptr; sp.out_progress = nullptr;
         sp.summary = nullptr;
+        sp.count_branches = 0;
         sp.debug_nowait = 0;
         sp.debug_times = nullptr; sp.debug_trace = nullptr; sp.debug_trace_stride = 1; sp.debug_trace_blocks = 0;
 
         long long rsum = 0;
         unsigned long long cfinal_unused = 0ull;
+        unsigned branches = 0;
         for (int c = 0; c < n_strips; c++) {
-            nwb_pk_strip<NWB_BATCH_K, NWB_BATCH_R, true, false>(sp, pc, c, stage, lane, rsum, nullptr, cfinal_unused);
+            nwb_pk_strip<NWB_BATCH_K, NWB_BATCH_R, true, false>(sp, pc, c, stage, lane, rsum, nullptr, cfinal_unused,
+                                                                bp.out_branch != nullptr, branches);
             __syncwarp();
         }
         if (n_strips > 1) {
@@ -106,44 +113,13 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
             for (int g = lane; g < B; g += 32) rsum += (long long)((nwb_ld_relaxed_u32(w + g, false) >> 16) & 0x7FFFu);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+            branches += __shfl_xor_sync(NWB_FULL_MASK, branches, o);
+        }
+        if (lane == 0 && bp.out_branch) bp.out_branch[pr] = branches;
         /* score(A,B) = sum_i u(i,B) - d*(A+B) */
         if (lane == 0) bp.out_score[pr] = (int)(unsigned)((unsigned long long)rsum - (unsigned long long)((long long)bp.d * ((long long)A + B)));
         __syncwarp();
-    }
-}
-
-/* per-pair branch counters (get_branch_count(), walk-table.c:133): one warp per pair over its finished table */
-__global__ void nwb_batch_branch_kernel(const NwbBatchParams bp, unsigned *out_branch)
-{
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long pr = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pr < bp.n_pairs; pr += nwarps) {
-        const int A = (int)(bp.top_off[pr + 1] - bp.top_off[pr]), B = (int)(bp.side_off[pr + 1] - bp.side_off[pr]);
-        unsigned cnt = 0;
-        if (A > 0 && B > 0) {
-            const int n_strips = (A + 64 * NWB_BATCH_K - 1) / (64 * NWB_BATCH_K);
-            const size_t pitch = (size_t)n_strips * 32 * NWB_BATCH_K;
-            const uint8_t *tab = bp.arrows + bp.arrow_off[pr];
-            const int groups_per_row = (A + 31) / 32;
-            const long long groups = (long long)groups_per_row * B;
-            for (long long idx = lane; idx < groups; idx += 32) {
-                const int row = (int)(idx / groups_per_row), g = (int)(idx % groups_per_row);
-                const uint4 v = *reinterpret_cast<const uint4 *>(tab + (size_t)row * pitch + (size_t)g * 16);
-                const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const unsigned x = w[q];
-                    const unsigned b0 = x & 0x11111111u, b1 = (x >> 1) & 0x11111111u, b2 = (x >> 2) & 0x11111111u;
-                    unsigned two = (b0 & b1) | (b0 & b2) | (b1 & b2);
-                    int hi = A - (g * 32 + q * 8);
-                    if (hi < 8) two &= (hi <= 0) ? 0u : ((1u << (4 * hi)) - 1u);
-                    cnt += (unsigned)__popc(two);
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(NWB_FULL_MASK, cnt, o);
-        if (lane == 0) out_branch[pr] = cnt;
     }
 }

@@ -123,6 +123,7 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     bp.tops = b->tops.p; bp.top_off = b->top_off.p; bp.sides = b->sides.p; bp.side_off = b->side_off.p;
     bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
     bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p; bp.scratch = b->scratch.p;
+    bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
     const size_t smem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * (size_t)warps;
     CK(cudaFuncSetAttribute(nwb_batch_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(b->ev0, st));
@@ -130,11 +131,6 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->ev1, st));
     b->launches += 1;
-    if (!(b->flags & NWB_NO_BRANCH_COUNT)) {
-        nwb_batch_branch_kernel<<<b->sm_count * 8, 256, 0, st>>>(bp, b->branch.p);
-        CK(cudaGetLastError());
-        b->launches += 1;
-    }
     return NWB_OK;
 }
 

@@ -357,6 +357,22 @@ __device__ __forceinline__ void nwb_pk_step(NwbPkState<K, R> &st, const NwbPkCon
     }
 }
 
+/* branch counter (get_branch_count(), walk-table.c:133-147) of 32 flushed cells: a cell branches
+ * when it has two or more arrows, i.e. at most one of its three inverted flags is set */
+__device__ __forceinline__ unsigned nwb_pk_branches(const uint4 arrows, const uint4 colmask)
+{
+    const unsigned w[4] = {arrows.x, arrows.y, arrows.z, arrows.w};
+    const unsigned m[4] = {colmask.x, colmask.y, colmask.z, colmask.w};
+    unsigned n = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const unsigned x = w[q], x1 = x >> 1, x2 = x >> 2;
+        const unsigned two = (x & x1) | (x & x2) | (x1 & x2); /* bit 0 of each nibble: >= 2 arrows */
+        n += (unsigned)__popc(two & m[q]);
+    }
+    return n;
+}
+
 /* side characters of R consecutive rows: from the global side_pre array (read-only
  * path) or, in the batch kernel, from the warp's shared-memory copy */
 template <int R, bool SMEMCH>
@@ -369,7 +385,8 @@ __device__ __forceinline__ unsigned nwb_pk_chars(const uint16_t *q)
 template <int K, int R, bool SMEMCH, bool COUNT>
 __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
                                               unsigned char *stage_bytes, const int lane, long long &rsum,
-                                              unsigned long long *cstage, unsigned long long &cfinal)
+                                              unsigned long long *cstage, unsigned long long &cfinal,
+                                              const bool count_branches, unsigned &branches)
 {
     typedef typename NwbPkStage<K>::T stage_t;
     const int A = p.A, B = p.B;
@@ -444,6 +461,19 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     rg.capg = (B - 1) / R;
     rg.rB = (B - 1) % R;
     rg.ngroups = (unsigned)ngroups;
+    /* columns of my 16-byte flush chunk that are inside the table (bit 0 of each nibble) */
+    uint4 colmask;
+    {
+        const int sub_ = lane % ((32 * K) / 16);
+        unsigned mm[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int hi = A - (c * W + sub_ * 32 + q * 8); /* valid nibbles of this word */
+            hi = hi < 0 ? 0 : (hi > 8 ? 8 : hi);
+            mm[q] = (hi >= 8) ? 0x11111111u : (0x11111111u & ((1u << (4 * hi)) - 1u));
+        }
+        colmask.x = mm[0]; colmask.y = mm[1]; colmask.z = mm[2]; colmask.w = mm[3];
+    }
     unsigned long long *dbg = p.debug_times ? p.debug_times + 4 * (size_t)c : nullptr;
     if (dbg && lane == 0) dbg[0] = nwb_globaltimer();
     unsigned chars_next[NWB_PK_SUB];
@@ -594,6 +624,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                             w.x = ~w.x & 0x77777777u; w.y = ~w.y & 0x77777777u;
                             w.z = ~w.z & 0x77777777u; w.w = ~w.w & 0x77777777u;
                             *reinterpret_cast<uint4 *>(dst + (size_t)(j - 1) * p.pitch) = w;
+                            if (count_branches) branches += nwb_pk_branches(w, colmask);
                         }
                     }
                 }
@@ -606,6 +637,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                         w.x = ~w.x & 0x77777777u; w.y = ~w.y & 0x77777777u;
                         w.z = ~w.z & 0x77777777u; w.w = ~w.w & 0x77777777u;
                         *reinterpret_cast<uint4 *>(dst + (size_t)(j - 1) * p.pitch) = w;
+                        if (count_branches) branches += nwb_pk_branches(w, colmask);
                     }
                 }
             }
@@ -633,8 +665,9 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
     long long rsum = 0;
     unsigned long long cfinal = 0ull;
     bool owns_final = false;
+    unsigned branches = 0;
     for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) {
-        nwb_pk_strip<K, R, false, COUNT>(p, pc, c, stage, lane, rsum, cstage, cfinal);
+        nwb_pk_strip<K, R, false, COUNT>(p, pc, c, stage, lane, rsum, cstage, cfinal, p.count_branches != 0, branches);
         if (COUNT && c == p.n_strips - 1) {
             /* the block that owns column A wrote cfinal when it passed row B */
             const int W = 64 * K, col_lo = c * W + (2 * lane) * K + 1;
@@ -644,8 +677,12 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
     if (COUNT && owns_final) p.summary->count = cfinal;
 
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+        branches += __shfl_xor_sync(NWB_FULL_MASK, branches, o);
+    }
     if (lane == 0 && rsum) atomicAdd((unsigned long long *)&p.summary->rsum, (unsigned long long)rsum);
+    if (lane == 0 && branches) atomicAdd(&p.summary->branch_count, branches);
 }
 
 /* r(A,B) = [sum over the rows 1..B of v in the column left of the last strip] + [sum of u(i,B) over

@@ -144,6 +144,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.bpitch = L.bpitch;
     p.progress = progress.data();
     p.summary = &sum;
+    p.count_branches = 1;
     std::vector<uint16_t> side_pre(NWB_PK_SPRE_LEN(B), 0x1234);
     emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
     p.side_pre = side_pre.data();
@@ -191,10 +192,12 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
             emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
         }
     }
+    /* the fused counter (flush) and the stand-alone pass over the finished table must agree */
     unsigned branches = 0;
     emu_launch(3, 64, 0, [&]() { nwb_branch_count_kernel(arrows, L.pitch, A, B, 0, A, &branches); });
+    if (branches != sum.branch_count) return -77;
     out->opt_score = (int)(sum.rsum - (long long)d * ((long long)A + B));
-    out->branch_count = branches;
+    out->branch_count = sum.branch_count;
     out->greatest_abs = 0;
     out->count = sum.count;
     out->pitch = L.pitch;
@@ -229,9 +232,9 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
     bp.tops = (const uint8_t *)tops; bp.top_off = top_off; bp.sides = (const uint8_t *)sides; bp.side_off = side_off;
     bp.n_pairs = n; bp.m = m; bp.k = k; bp.d = d; bp.max_B = maxB;
     bp.arrows = arrows; bp.arrow_off = arrow_off; bp.out_score = scores; bp.scratch = scratch.data();
+    bp.out_branch = branches;
     emu_launch(grid, 32 * NWB_BATCH_WARPS, NWB_BATCH_SMEM_PER_WARP(maxB) * NWB_BATCH_WARPS,
                [&]() { nwb_batch_pk_kernel(bp, pc); });
-    emu_launch(2, 64, 0, [&]() { nwb_batch_branch_kernel(bp, branches); });
     return 0;
 }
 }
