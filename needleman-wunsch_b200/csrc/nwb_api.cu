@@ -20,6 +20,7 @@
 #include "nwb_layout.h"
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
+#include "nwb_fill_hx.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_peak.cuh"
 
@@ -136,6 +137,7 @@ struct nwb_plan {
     bool ran = false;
     cudaStream_t last_stream = nullptr;
     int m = 0, k = 0, d = 0;
+    bool pk_hx = false; /* packed kernel variant with flush warps (nwb_fill_hx.cuh) */
 };
 
 static void make_inbox_layout(Inbox &ib, size_t bpitch)
@@ -291,24 +293,31 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     NwbPkConsts pc;
     memset(&pc, 0, sizeof(pc));
     p->kind = choose_kind(flags, m, k, d, &pc);
-    int strip_w = NWB_I32_STRIP_W, pk_k = 0;
+    int strip_w = NWB_I32_STRIP_W, pk_k = 0, pk_r = 1;
+    p->pk_hx = false;
     if (p->kind == NWB_KIND_PK) {
         pk_k = nwb_pk_choose_k(A, B, p->world);
+        /* two rows per step once the table is tall enough to amortise the doubled lane skew */
+        pk_r = (B >= 4096) ? 2 : 1;
         if (const char *ek = getenv("NWB_PK_K")) { /* diagnostics */
             const int v = atoi(ek);
             if (v == 1 || v == 2 || v == 4) pk_k = v;
         }
+        if (const char *er = getenv("NWB_PK_R")) { /* diagnostics */
+            const int v = atoi(er);
+            if (v == 1 || v == 2) pk_r = v;
+        }
+        /* sweeping + flush warps (nwb_fill_hx.cuh) when every difference fits a nibble */
+        const bool hx_ok = !(flags & NWB_WANT_COUNT) && nwb_hx_supported(pc);
+        p->pk_hx = hx_ok && pk_k == 4 && pk_r == 2;
+        if (const char *eh = getenv("NWB_PK_HX")) { /* diagnostics: 0 = never, 1 = whenever the scheme allows */
+            p->pk_hx = hx_ok && atoi(eh) != 0;
+            if (p->pk_hx) { pk_k = 4; pk_r = 2; }
+        }
         strip_w = 64 * pk_k;
     }
     p->L = nwb_make_layout(A, B, p->kind, pk_k, strip_w);
-    if (p->kind == NWB_KIND_PK) {
-        /* two rows per step once the table is tall enough to amortise the doubled lane skew */
-        p->L.pk_r = (B >= 4096) ? 2 : 1;
-        if (const char *er = getenv("NWB_PK_R")) { /* diagnostics */
-            const int v = atoi(er);
-            if (v == 1 || v == 2) p->L.pk_r = v;
-        }
-    }
+    p->L.pk_r = pk_r;
     const NwbLayout &L = p->L;
 
     /* this rank's strips */
@@ -373,7 +382,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     sp.progress = p->progress.p;
     sp.summary = p->summary.p;
     sp.count_branches = (flags & NWB_NO_BRANCH_COUNT) ? 0 : 1;
-    sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? 1 : 0;
+    sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? atoi(getenv("NWB_DEBUG_NOWAIT")) : 0;
     if (getenv("NWB_DEBUG_TIMES") && p->kind == NWB_KIND_PK) { /* diagnostics: per-strip timestamps dumped to a file */
         if (p->dbg_times.ensure((size_t)L.n_strips * 4) != NWB_OK) return NWB_ERR_NOMEM;
         CK(cudaMemsetAsync(p->dbg_times.p, 0, (size_t)L.n_strips * 4 * sizeof(unsigned long long), st));
@@ -402,6 +411,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     }
 
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
+    const bool hx = (p->kind == NWB_KIND_PK) && p->pk_hx;
     /* one warp per SM sub-partition; a second one when there are more strips than that */
     int pk_warps = (nloc > p->sm_count * NWB_PK_WARPS) ? NWB_PK_MAX_WARPS : NWB_PK_WARPS;
     if (const char *ew = getenv("NWB_PK_WARPS")) { /* diagnostics */
@@ -417,7 +427,8 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         CK(cudaGetLastError());
         p->launches += 1;
     }
-    if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, pk_warps, st);
+    if (hx) rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
+    else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
     if (rc != NWB_OK) return rc;
     CK(cudaEventRecord(p->ev1, st));

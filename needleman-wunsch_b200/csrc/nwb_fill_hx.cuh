@@ -1,0 +1,390 @@
+/*
+ * nwb_fill_hx.cuh -- packed 16x2 difference fill with flush warps ("hx").
+ *
+ * Same recurrence, strip pipeline and boundary streams as nwb_fill_pk.cuh (and
+ * therefore the same results as the reference's score_cell(),
+ * needleman-wunsch.c:418-510), for K = 4 columns per half-lane and R = 2 rows per
+ * step, when every per-cell difference fits a nibble (2d + m <= 7).
+ *
+ * Why.  A strip is swept by ONE warp, and one warp issues at most one
+ * instruction every ~2 cycles (measured on B200: tools/ubench/tput.cu), so the
+ * strip-to-strip critical path is the sweeping warp's instruction count.  In
+ * nwb_fill_pk.cuh a step of 16 cells per lane is ~134 instructions, 60 of them
+ * spent on turning differences into arrow nibbles and on the write-back.  Here the
+ * sweeping ("critical") warp only computes the recurrence and keeps the three
+ * differences of a row's cells as nibbles of two words (SWAR, integer
+ * multiply-adds):
+ *     P1 = un | 8*[DIAG],   P2 = vn        (un, vn: the cell's u and v, 0..7)
+ * DIAG <=> z - a == 0 comes out of  A4 - Z4 + 0x8888 (bit 3 of each nibble set iff the
+ * nibble difference is zero), Z4, A4, NU = the row's z, a, u packed by Horner's rule.
+ * Each critical warp streams {P1, P2} through a shared-memory ring to a FLUSH warp
+ * on the fourth SM sub-partition, which extracts the zero tests
+ *     LEFT <=> un == 0,  UP <=> vn == 0     (bit 3 of 0x8888... - x)
+ * builds the reference's arrow sets (needleman-wunsch.c:485-503) as 4-bit codes,
+ * counts the branch cells (walk-table.c:108-120) and writes the table, one whole
+ * 128-byte strip row per store instruction.
+ *
+ * Block = 12 warps: warps 0..2 sweep strips (sub-partitions 0..2), warps 3, 7, 11
+ * (all on sub-partition 3) flush for warps 0, 1, 2; the other warps exit at once.
+ */
+#pragma once
+#include "nwb_fill_pk.cuh"
+
+#define NWB_HX_CRIT 3
+#define NWB_HX_WARPS 12
+#define NWB_HX_RING_STEPS 128 /* ring slots, one per step of the sweeping warp */
+#define NWB_HX_SLOT_BYTES 512 /* 32 lanes x {P1, P2 of sub-row 0, P1, P2 of sub-row 1} */
+#define NWB_HX_RING_BYTES (NWB_HX_RING_STEPS * NWB_HX_SLOT_BYTES)
+#define NWB_HX_SMEM_BYTES ((size_t)NWB_HX_CRIT * NWB_HX_RING_BYTES + 64)
+#define NWB_HX_B8 0x88888888u
+#define NWB_HX_B7 0x77777777u
+
+static inline bool nwb_hx_supported(const NwbPkConsts &pc) { return pc.a_match <= 7; }
+
+struct NwbHxState {
+    unsigned tpw[4];   /* pre-shifted top characters of my columns (low block | high block) */
+    unsigned u[4];     /* u of my columns in the row above                                   */
+    unsigned vlast[2]; /* v of my last columns per sub-row                                   */
+    unsigned sp[2];    /* ~(side char << shift) per sub-row (low half row | high half row)   */
+    unsigned send;     /* v of my HIGH block's last column for the 2 rows just done          */
+    unsigned nu;       /* u of my columns in the row above, one nibble per column            */
+};
+
+__device__ __forceinline__ void nwb_sts128(nwb_smem_addr a, unsigned x, unsigned y, unsigned z, unsigned w)
+{
+#ifdef NWB_EMU
+    unsigned *q = reinterpret_cast<unsigned *>(a);
+    q[0] = x; q[1] = y; q[2] = z; q[3] = w;
+#else
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w));
+#endif
+}
+
+/* block-scope flags in shared memory between a sweeping warp and its flush warp */
+__device__ __forceinline__ int nwb_flag_load(const volatile int *p) { return *p; }
+__device__ __forceinline__ void nwb_flag_store(volatile int *p, int v)
+{
+#ifndef NWB_EMU
+    __threadfence_block();
+#endif
+    *p = v;
+}
+__device__ __forceinline__ void nwb_spin_pause(bool sleep)
+{
+#ifdef NWB_EMU
+    (void)sleep;
+    nwb_pause();
+#else
+    if (sleep) __nanosleep(64);
+#endif
+}
+
+/* One row step of one lane of a sweeping warp: 2 rows x 8 cells (see nwb_pk_step for the
+ * lane/half geometry).  slot = this lane's 16 bytes of the step's ring slot. */
+template <bool LEAN>
+__device__ __forceinline__ void nwb_hx_step(NwbHxState &st, const NwbPkConsts &pc, const NwbPkRange<2> &rg,
+                                             const unsigned bq, const int t, const int lane, const int g_idx,
+                                             const int g_hi, const int A, const int col_lo, const int col_hi,
+                                             const unsigned chars, const nwb_smem_addr slot, uint32_t *out_w,
+                                             const bool pub31, unsigned &rs32)
+{
+    unsigned recv = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
+    const unsigned b = __shfl_sync(NWB_FULL_MASK, bq, t);
+    if (lane == 0) recv = b;
+    unsigned vL[2];
+    vL[0] = __byte_perm(recv, st.vlast[0], 0x5410); /* lo <- neighbour's row 0, hi <- my low block's row 0 */
+    vL[1] = __byte_perm(recv, st.vlast[1], 0x5432);
+    st.sp[0] = __byte_perm(chars, st.sp[0], 0x5410);
+    st.sp[1] = __byte_perm(chars, st.sp[1], 0x5432);
+    unsigned uafter[2][4];
+    unsigned p1[2], p2[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        unsigned v = vL[r];
+        unsigned z[4], a[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned nx = st.tpw[k] ^ st.sp[r];                  /* -x'-1 per half   */
+            a[k] = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);             /* a_match or a_mis */
+            z[k] = __vimax3_s16x2(a[k], v, st.u[k]);
+            const unsigned un = z[k] - v;
+            const unsigned vn = z[k] - st.u[k];
+            st.u[k] = un;
+            uafter[r][k] = un;
+            v = vn;
+        }
+        st.vlast[r] = v;
+        /* the row's z, a and u as one nibble per column (per half: 4 columns) */
+        const unsigned Z4 = ((z[3] * 16u + z[2]) * 16u + z[1]) * 16u + z[0];
+        const unsigned A4 = ((a[3] * 16u + a[2]) * 16u + a[1]) * 16u + a[0];
+        const unsigned NU = ((st.u[3] * 16u + st.u[2]) * 16u + st.u[1]) * 16u + st.u[0];
+        const unsigned ZT = A4 - Z4 + NWB_HX_B8; /* bit 3 of a nibble: z == a (DIAG)            */
+        const unsigned NV = Z4 - st.nu;          /* vn = z - u(row above), nibble by nibble     */
+        st.nu = NU;
+        p1[r] = (ZT & NWB_HX_B8) | NU;
+        p2[r] = NV;
+    }
+    nwb_sts128(slot, p1[0], p2[0], p1[1], p2[1]);
+    st.send = __byte_perm(st.vlast[0], st.vlast[1], 0x7632);
+    /* bottom row, r(A,B) = sum of u(i,B): row B passes through a lane's low block in one step and
+     * through its high block in the next (see nwb_pk_step) */
+    if (!LEAN && __builtin_expect((unsigned)(rg.capg - g_hi) <= 1u, 0)) {
+        const unsigned half = (g_hi == rg.capg) ? 0xFFFF0000u : 0x0000FFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned x = uafter[0][k];
+            if (rg.rB == 1) x = uafter[1][k];
+            unsigned m = 0u;
+            if (col_lo + k <= A) m |= 0x0000FFFFu;
+            if (col_hi + k <= A) m |= 0xFFFF0000u;
+            rs32 += x & m & half;
+        }
+    }
+    /* lane 31: the strip's last column for group g_hi, self-validating (nwb_fill_pk.cuh) */
+    const bool pub = pub31 && (LEAN || (unsigned)g_hi < rg.ngroups);
+    nwb_st_relaxed_sys_pred(out_w + g_idx, st.send | 0x80008000u, pub);
+}
+
+/* A sweeping warp's strip: nwb_pk_strip<4, 2> without the write-back.  seq counts this warp's
+ * 32-step blocks over all its strips; ring slot of a step = (32 * seq + step in block) mod 128. */
+__device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
+                                              unsigned char *ring, volatile int *ready, volatile int *done,
+                                              int &seq, const int lane, long long &rsum)
+{
+    const int K = 4, R = 2;
+    const int A = p.A, B = p.B;
+    const int W = 64 * K;
+    const int col_lo = c * W + (2 * lane) * K + 1;
+    const int col_hi = col_lo + K;
+    const unsigned ONE = 0x00010001u;
+    const int ngroups = (B + R - 1) / R;
+
+    NwbHxState st;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const unsigned lo = (col_lo + k <= A) ? (unsigned)p.top[col_lo + k - 1] : 0u;
+        const unsigned hi = (col_hi + k <= A) ? (unsigned)p.top[col_hi + k - 1] : 0u;
+        st.tpw[k] = ((lo << pc.shift) | ((hi << pc.shift) << 16));
+        st.u[k] = 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        st.vlast[r] = NWB_PK_BIG * ONE;
+        st.sp[r] = 0xFFFFFFFFu;
+    }
+    st.send = NWB_PK_BIG * ONE;
+    st.nu = 0u;
+
+    const int lc = c - p.strip_begin;
+    const bool has_left = (c > 0);
+    const bool left_remote = has_left && (lc == 0);
+    const bool publish = (c + 1 < p.n_strips);
+    const bool out_remote = publish && (c == p.strip_end - 1);
+    uint32_t *out_w = (out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch) + NWB_PK_BPAD;
+    const uint32_t *in_w = nullptr;
+    if (has_left) in_w = (left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch) + NWB_PK_BPAD;
+    const bool pub31 = publish && (lane == 31);
+    const bool is_last = (c == p.n_strips - 1);
+    const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
+
+    const unsigned VMASK = 0x7FFF7FFFu;
+    unsigned bq = 0u, bq_next = 0u;
+    if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
+
+    const nwb_smem_addr lane_ring = nwb_smem_address(ring) + (unsigned)(lane * 16);
+    unsigned rs32 = 0u;
+    NwbPkRange<R> rg;
+#pragma unroll
+    for (int r = 0; r < R; r++) rg.gcnt[r] = (B - 1 - r >= 0) ? (unsigned)((B - 1 - r) / R + 1) : 0u;
+    rg.capg = (B - 1) / R;
+    rg.rB = (B - 1) % R;
+    rg.ngroups = (unsigned)ngroups;
+
+    unsigned chars_next[NWB_PK_SUB];
+#pragma unroll
+    for (int t = 0; t < NWB_PK_SUB; t++) chars_next[t] = nwb_pk_chars<R, false>(sp_lane + R * t);
+
+    const int nsteps = ngroups + 63;
+    const int nblocks = (nsteps + 31) / 32;
+    for (int blk = 0; blk < nblocks; blk++) {
+        const int s0 = 32 * blk;
+        /* ring back-pressure: this block overwrites the slots of block seq-4; the rows the flush
+         * warp takes after block seq-2 still read them */
+        if (seq >= 2) {
+            while (nwb_flag_load(done) < seq - 1) nwb_spin_pause(false);
+        }
+        const bool lean = !(is_last && R * (s0 + 32) >= B);
+#pragma unroll 1
+        for (int sub = 0; sub < 32 / NWB_PK_SUB; sub++) {
+            const int ss = s0 + NWB_PK_SUB * sub;
+            if (has_left) {
+                /* commit the prefetched words of groups ss .. ss+7; re-poll the ones not valid yet */
+                const int gs = ss + lane;
+                unsigned w = bq_next;
+                bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID);
+                while (!__all_sync(NWB_FULL_MASK, ok)) {
+                    if (!ok) {
+                        w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
+                        ok = (w & NWB_PK_VALID) != 0u;
+                    }
+#ifdef NWB_EMU
+                    nwb_pause();
+#endif
+                }
+                bq = w & VMASK;
+                bq_next = 0u;
+                if (lane < NWB_PK_SUB && gs + NWB_PK_SUB < ngroups)
+                    bq_next = nwb_ld_relaxed_u32(in_w + gs + NWB_PK_SUB, left_remote);
+            }
+            unsigned chars[NWB_PK_SUB];
+#pragma unroll
+            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = chars_next[t];
+            {
+                const uint16_t *spn = sp_lane + R * (ss + NWB_PK_SUB);
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++) chars_next[t] = nwb_pk_chars<R, false>(spn + R * t);
+            }
+            uint32_t *outb = out_w + (ss - 2 * lane - 1);
+            const int gb = ss - 2 * lane - 1;
+            const nwb_smem_addr slot0 =
+                lane_ring + (unsigned)(((32 * seq + NWB_PK_SUB * sub) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+            if (lean) {
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_hx_step<true>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
+                                      slot0 + (unsigned)(t * NWB_HX_SLOT_BYTES), outb, pub31, rs32);
+            } else {
+#pragma unroll
+                for (int t = 0; t < NWB_PK_SUB; t++)
+                    nwb_hx_step<false>(st, pc, rg, bq, t, lane, t, gb + t, A, col_lo, col_hi, chars[t],
+                                       slot0 + (unsigned)(t * NWB_HX_SLOT_BYTES), outb, pub31, rs32);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) nwb_flag_store(ready, seq + 1);
+        seq++;
+    }
+    rsum += (long long)(rs32 & 0xFFFFu) + (long long)(rs32 >> 16);
+}
+
+/* The flush warp of sweeping warp `wslot`.  Flush lane h owns the 8 cells per row that sweeping
+ * lane h computes (4 bytes of every arrow row of the strip; the warp's 32 lanes store one whole
+ * 128-byte strip row per instruction).  Sweeping lane h left, at step s, the words of {low half:
+ * its low block in group s - 2h, high half: its high block in group s - 2h - 1}; both halves of
+ * group g are therefore in the slots of steps g + 2h and g + 2h + 1, and walking the groups in
+ * order reads every slot once.  After block blk of a strip the groups 32*blk-63 .. 32*blk-32 are
+ * complete in every lane. */
+__device__ __forceinline__ unsigned nwb_hx_code(const unsigned p1, const unsigned p2, const unsigned colmask,
+                                                const bool count_branches, unsigned &branches)
+{
+    const unsigned zu = NWB_HX_B8 - (p1 & NWB_HX_B7); /* bit 3: un == 0 (LEFT) */
+    const unsigned zv = NWB_HX_B8 - p2;               /* bit 3: vn == 0 (UP)   */
+    if (count_branches) {
+        const unsigned two = (p1 & zu) | (p1 & zv) | (zu & zv); /* bit 3: two or more arrows */
+        branches += (unsigned)__popc(two & colmask);
+    }
+    return ((p1 >> 3) & 0x11111111u) | ((zu >> 2) & 0x22222222u) | ((zv >> 1) & 0x44444444u);
+}
+
+__device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int wslot, const unsigned char *ring,
+                                              volatile int *ready, volatile int *done, const int lane,
+                                              unsigned &branches)
+{
+    const int B = p.B, A = p.A;
+    const int nworkers = (int)gridDim.x * NWB_HX_CRIT;
+    const int worker = wslot * (int)gridDim.x + (int)blockIdx.x;
+    const int ngroups = (B + 1) / 2;
+    const int nblocks = (ngroups + 63 + 31) / 32;
+    const bool count_branches = p.count_branches != 0;
+    const unsigned char *lane_ring = ring + lane * 16;
+    int seq = 0;
+    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) {
+        /* bit 3 of the nibbles of my word whose column is inside the table */
+        int hi = A - (c * 256 + lane * 8);
+        hi = hi < 0 ? 0 : (hi > 8 ? 8 : hi);
+        const unsigned colmask = (hi >= 8) ? NWB_HX_B8 : (NWB_HX_B8 & ((1u << (4 * hi)) - 1u));
+        uint8_t *dst = p.arrows + (size_t)c * 128 + (size_t)lane * 4;
+        for (int blk = 0; blk < nblocks; blk++) {
+            while (nwb_flag_load(ready) < seq + 1) nwb_spin_pause(true);
+#ifndef NWB_EMU
+            __threadfence_block();
+#endif
+            if (!(p.debug_nowait & 2)) {
+                const int sbase = 32 * (seq - blk) + 2 * lane; /* ring step index of (group 0, my low half) */
+                int g = 32 * blk - 63;
+                int gend = g + 32;
+                if (g < 0) g = 0;
+                if (gend > ngroups) gend = ngroups;
+                if (g < gend) {
+                    uint4 lo = *reinterpret_cast<const uint4 *>(lane_ring + ((sbase + g) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+                    uint8_t *out = dst + (size_t)(2 * g) * p.pitch;
+#pragma unroll 4
+                    for (; g < gend; g++) {
+                        const uint4 hw = *reinterpret_cast<const uint4 *>(
+                            lane_ring + ((sbase + g + 1) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+                        const unsigned c0 = nwb_hx_code(__byte_perm(lo.x, hw.x, 0x7610), __byte_perm(lo.y, hw.y, 0x7610),
+                                                        colmask, count_branches, branches);
+                        *reinterpret_cast<unsigned *>(out) = c0;
+                        if (2 * g + 2 <= B) {
+                            const unsigned c1 = nwb_hx_code(__byte_perm(lo.z, hw.z, 0x7610), __byte_perm(lo.w, hw.w, 0x7610),
+                                                            colmask, count_branches, branches);
+                            *reinterpret_cast<unsigned *>(out + p.pitch) = c1;
+                        }
+                        out += 2 * p.pitch;
+                        lo = hw;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) nwb_flag_store(done, seq + 1);
+            seq++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const NwbStripParams p, const NwbPkConsts pc)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char *smem = NWB_SMEM_BASE();
+    volatile int *flags = reinterpret_cast<volatile int *>(smem + (size_t)NWB_HX_CRIT * NWB_HX_RING_BYTES);
+    if (threadIdx.x < 2 * NWB_HX_CRIT) flags[threadIdx.x] = 0;
+    __syncthreads();
+    if (warp < NWB_HX_CRIT) {
+        /* sweeping warp */
+        const int nworkers = (int)gridDim.x * NWB_HX_CRIT;
+        const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
+        unsigned char *ring = smem + (size_t)warp * NWB_HX_RING_BYTES;
+        long long rsum = 0;
+        int seq = 0;
+        for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
+            nwb_hx_strip(p, pc, c, ring, flags + warp, flags + NWB_HX_CRIT + warp, seq, lane, rsum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
+        if (lane == 0 && rsum) atomicAdd((unsigned long long *)&p.summary->rsum, (unsigned long long)rsum);
+    } else if ((warp & 3) == 3 && (warp >> 2) < NWB_HX_CRIT) {
+        /* flush warp of sweeping warp (warp >> 2) */
+        const int wslot = warp >> 2;
+        unsigned branches = 0;
+        nwb_hx_flush(p, wslot, smem + (size_t)wslot * NWB_HX_RING_BYTES, flags + wslot, flags + NWB_HX_CRIT + wslot,
+                     lane, branches);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) branches += __shfl_xor_sync(NWB_FULL_MASK, branches, o);
+        if (lane == 0 && branches) atomicAdd(&p.summary->branch_count, branches);
+    }
+}
+
+#ifndef NWB_EMU
+static inline int nwb_hx_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st,
+                                nwb_fail_fn fail)
+{
+    cudaError_t e = cudaFuncSetAttribute(nwb_fill_hx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)NWB_HX_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    void *args[] = {(void *)&sp, (void *)&pc};
+    e = cudaLaunchCooperativeKernel((const void *)nwb_fill_hx_kernel, dim3(grid), dim3(32 * NWB_HX_WARPS), args,
+                                    NWB_HX_SMEM_BYTES, st);
+    if (e != cudaSuccess) return fail(e, "cudaLaunchCooperativeKernel");
+    return 0;
+}
+#endif

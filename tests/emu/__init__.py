@@ -69,7 +69,11 @@ def pk_supported(m, k, d) -> bool:
     return bool(lib().emu_pk_supported(m, k, d))
 
 
-def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=False):
+def hx_supported(m, k, d) -> bool:
+    return bool(lib().emu_hx_supported(m, k, d))
+
+
+def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=False, hx=False):
     """Run nwb_fill_pk_kernel<K> (+ the branch-count pass) under the emulator."""
     top, side = _b(top), _b(side)
     a, b = len(top), len(side)
@@ -79,8 +83,9 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=Fal
     out = _Out()
     L.emu_fill_pk.restype = C.c_int
     L.emu_fill_pk.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                              C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.POINTER(_Out)]
-    rc = L.emu_fill_pk(top, a, side, b, m, k, d, K, R, int(count), grid, warps, split, arrows.ctypes.data_as(C.c_void_p), C.byref(out))
+                              C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_Out)]
+    rc = L.emu_fill_pk(top, a, side, b, m, k, d, K, R, int(count), grid, warps, split, int(hx),
+                       arrows.ctypes.data_as(C.c_void_p), C.byref(out))
     assert rc == 0, rc
     return dict(opt_score=out.opt_score, branch_count=out.branch_count, arrows=arrows, pitch=pitch, count=out.count)
 

@@ -8,6 +8,7 @@
 #include "nwb_layout.h"
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
+#include "nwb_fill_hx.cuh"
 #include "nwb_batch.cuh"
 
 #include <vector>
@@ -118,11 +119,19 @@ int emu_fill_i32(const char *top, int A, const char *side, int B, int m, int k, 
 size_t emu_pitch_pk(int A, int B, int K) { return nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K).pitch; }
 int emu_pk_supported(int m, int k, int d) { return nwb_pk_supported(m, k, d, nullptr) ? 1 : 0; }
 
+int emu_hx_supported(int m, int k, int d)
+{
+    NwbPkConsts pc;
+    return (nwb_pk_supported(m, k, d, &pc) && nwb_hx_supported(pc)) ? 1 : 0;
+}
+
+/* hx != 0: the sweeping + flush warp variant (nwb_fill_hx.cuh; K = 4, R = 2, no count) */
 int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K, int R, int count,
-                unsigned grid, int warps, int split, uint8_t *arrows, emu_out *out)
+                unsigned grid, int warps, int split, int hx, uint8_t *arrows, emu_out *out)
 {
     NwbPkConsts pc;
     if (!nwb_pk_supported(m, k, d, &pc)) return -5;
+    if (hx && (!nwb_hx_supported(pc) || K != 4 || R != 2 || count)) return -6;
     NwbLayout L = nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K);
     std::vector<uint32_t> bnd_w((size_t)L.n_strips * L.bpitch, 0u);
     std::vector<int> progress((size_t)L.n_strips, 0);
@@ -150,7 +159,9 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.side_pre = side_pre.data();
     const uint32_t *last_stream = nullptr; /* the stream consumed by the last strip, when it is not in bnd_w */
     auto launch = [&](const NwbStripParams &q) {
-        if (count) {
+        if (hx) {
+            emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel(q, pc); });
+        } else if (count) {
             if (R == 2) run_pk_emu<4, 2, true>(grid, warps, q, pc);
             else run_pk_emu<4, 1, true>(grid, warps, q, pc);
         } else if (R == 2) {
