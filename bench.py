@@ -204,7 +204,7 @@ def run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) -> dict | 
             k = plan.kernel_ms()
             best = k if best is None else min(best, k)
         got = (sm.opt_score, sm.branch_count, sm.count)
-        out[name] = {"fill_kernel_ms": best, "gcups": n * n / (best * 1e-3) / 1e9, "kernel_kind": sm.kernel_kind,
+        out[name] = {"fill_kernel_ms": best, "gcups": n * n / (best * 1e-3) / 1e9, "kernel": plan.kernel_name(),
                      "result": {"opt_score": got[0], "branch_count": got[1], "count_u64": got[2]},
                      "golden_ok": bool(got[:len(golden)] == golden)}
         plan.close()
@@ -294,6 +294,7 @@ def run_ours(args) -> None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     last_kernel_ms = plan.kernel_ms()
+    kernel_name = plan.kernel_name()
     summ = plan.summary()
     launches_per_step = plan.launches() // (max(args.warmup, 3) + args.steps)
 
@@ -346,7 +347,8 @@ def run_ours(args) -> None:
         alg_bytes = cells * 0.5 + A + B
         # dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel from the committed ncu capture
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_fill_pk_ncu_summary.json")
+        tpath = os.path.join(ROOT, "profiles", "r01_fill_hx_ncu_summary.json" if kernel_name == "nwb_fill_hx_kernel"
+                             else "r01_fill_pk_ncu_summary.json")
         if os.path.exists(tpath) and world == 1:
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_total")
@@ -364,7 +366,7 @@ def run_ours(args) -> None:
                                         f"(VIMNMX3.U16x2 {r16:.1f} instr/clk/SM, VIMNMX3+IMAD {rmix:.1f}) x "
                                         f"{props.multi_processor_count} SMs x {f_mhz:.0f} MHz "
                                         f"({'MEASURED_PEAKS.json' if peaks else 'fallback'} sm_max_mhz)",
-                         "kernel": "nwb_fill_pk_kernel" if summ.kernel_kind == 1 else "nwb_fill_i32_kernel",
+                         "kernel": kernel_name,
                          "kernel_ms": k_ms},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
@@ -373,8 +375,8 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": A + B, "d2h_bytes_per_step": 32},
             "gpu_launches": args.steps * world * launches_per_step,
             "launches_per_step": {"per_rank": launches_per_step,
-                                  "kernels": "nwb_pk_prep_side_kernel, nwb_fill_pk_kernel, nwb_branch_count_kernel"
-                                  if summ.kernel_kind == 1 else "nwb_fill_i32_kernel"},
+                                  "kernels": ("nwb_pk_prep_side_kernel, " + kernel_name + ", nwb_pk_stream_sum_kernel")
+                                  if summ.kernel_kind == 1 else kernel_name},
             "clocks": clocks,
             "result": {"opt_score": opt_score, "branch_count": branch_total, "kernel_kind": summ.kernel_kind,
                        "golden": "tests/golden/golden_big.json config3_dna_100k: score 11389, branches 3439940792"},

@@ -182,6 +182,9 @@ int nwb_plan_download_arrows(nwb_plan *p, uint8_t *dst, size_t dst_pitch, int ro
 int64_t nwb_plan_launches(const nwb_plan *p);
 /* Device time (ms, CUDA events on the launching stream) of the last run. */
 float nwb_plan_kernel_ms(nwb_plan *p);
+/* Name of the fill kernel the last run launched ("nwb_fill_hx_kernel", "nwb_fill_pk_kernel",
+ * "nwb_fill_i32_kernel"; "" before the first run): for logs and profiles. */
+const char *nwb_plan_kernel_name(const nwb_plan *p);
 /* Interior columns [begin,end) (0-based, i-1) this plan's strips cover. */
 int nwb_plan_strip_range(const nwb_plan *p, int *begin_col, int *end_col);
 /* Re-arm the inbound boundary flag before the next run of a strip group

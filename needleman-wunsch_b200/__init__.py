@@ -90,6 +90,7 @@ _SIGS = {
     "nwb_plan_arrow_pitch": (C.c_size_t, [C.c_void_p]),
     "nwb_plan_download_arrows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "nwb_plan_launches": (C.c_int64, [C.c_void_p]),
+    "nwb_plan_kernel_name": (C.c_char_p, [C.c_void_p]),
     "nwb_plan_kernel_ms": (C.c_float, [C.c_void_p]),
     "nwb_plan_strip_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nwb_plan_reset_inbox": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -279,6 +280,9 @@ class Plan:
 
     def launches(self) -> int:
         return load_library().nwb_plan_launches(self._h)
+
+    def kernel_name(self) -> str:
+        return load_library().nwb_plan_kernel_name(self._h).decode()
 
     def arrow_pitch(self) -> int:
         return load_library().nwb_plan_arrow_pitch(self._h)

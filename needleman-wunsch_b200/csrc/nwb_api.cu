@@ -519,6 +519,12 @@ extern "C" float nwb_plan_kernel_ms(nwb_plan *p)
 extern "C" void *nwb_plan_arrows_device(nwb_plan *p) { return p ? (void *)p->arrows.p : nullptr; }
 extern "C" size_t nwb_plan_arrow_pitch(const nwb_plan *p) { return p ? p->L.pitch : 0; }
 extern "C" int64_t nwb_plan_launches(const nwb_plan *p) { return p ? p->launches : 0; }
+extern "C" const char *nwb_plan_kernel_name(const nwb_plan *p)
+{
+    if (!p || !p->ran) return "";
+    if (p->kind == NWB_KIND_I32) return "nwb_fill_i32_kernel";
+    return p->pk_hx ? "nwb_fill_hx_kernel" : "nwb_fill_pk_kernel";
+}
 extern "C" int nwb_plan_strip_range(const nwb_plan *p, int *begin_col, int *end_col)
 {
     if (!p) return NWB_ERR_INVALID;

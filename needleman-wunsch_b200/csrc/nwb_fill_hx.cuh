@@ -14,12 +14,12 @@
  * sweeping ("critical") warp only computes the recurrence and keeps the three
  * differences of a row's cells as nibbles of two words (SWAR, integer
  * multiply-adds):
- *     P1 = un | 8*[DIAG],   P2 = vn        (un, vn: the cell's u and v, 0..7)
+ *     P1 = un | 8*[DIAG],   P2 = 8 - vn    (un, vn: the cell's u and v, 0..7)
  * DIAG <=> z - a == 0 comes out of  A4 - Z4 + 0x8888 (bit 3 of each nibble set iff the
  * nibble difference is zero), Z4, A4, NU = the row's z, a, u packed by Horner's rule.
  * Each critical warp streams {P1, P2} through a shared-memory ring to a FLUSH warp
  * on the fourth SM sub-partition, which extracts the zero tests
- *     LEFT <=> un == 0,  UP <=> vn == 0     (bit 3 of 0x8888... - x)
+ *     LEFT <=> un == 0,  UP <=> vn == 0     (bit 3 of 8 - x)
  * builds the reference's arrow sets (needleman-wunsch.c:485-503) as 4-bit codes,
  * counts the branch cells (walk-table.c:108-120) and writes the table, one whole
  * 128-byte strip row per store instruction.
@@ -119,10 +119,10 @@ __device__ __forceinline__ void nwb_hx_step(NwbHxState &st, const NwbPkConsts &p
         const unsigned A4 = ((a[3] * 16u + a[2]) * 16u + a[1]) * 16u + a[0];
         const unsigned NU = ((st.u[3] * 16u + st.u[2]) * 16u + st.u[1]) * 16u + st.u[0];
         const unsigned ZT = A4 - Z4 + NWB_HX_B8; /* bit 3 of a nibble: z == a (DIAG)            */
-        const unsigned NV = Z4 - st.nu;          /* vn = z - u(row above), nibble by nibble     */
+        const unsigned ZV = st.nu - Z4 + NWB_HX_B8; /* vn = z - u(row above); bit 3: vn == 0 (UP) */
         st.nu = NU;
         p1[r] = (ZT & NWB_HX_B8) | NU;
-        p2[r] = NV;
+        p2[r] = ZV;
     }
     nwb_sts128(slot, p1[0], p2[0], p1[1], p2[1]);
     st.send = __byte_perm(st.vlast[0], st.vlast[1], 0x7632);
@@ -183,7 +183,7 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
     uint32_t *out_w = (out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch) + NWB_PK_BPAD;
     const uint32_t *in_w = nullptr;
     if (has_left) in_w = (left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch) + NWB_PK_BPAD;
-    const bool pub31 = publish && (lane == 31);
+    const bool pub31 = publish && (lane == 31) && !(p.debug_nowait & 4);
     const bool is_last = (c == p.n_strips - 1);
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
 
@@ -221,7 +221,7 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
                 /* commit the prefetched words of groups ss .. ss+7; re-poll the ones not valid yet */
                 const int gs = ss + lane;
                 unsigned w = bq_next;
-                bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID);
+                bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID) || (p.debug_nowait & 1);
                 while (!__all_sync(NWB_FULL_MASK, ok)) {
                     if (!ok) {
                         w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
@@ -274,16 +274,38 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
  * group g are therefore in the slots of steps g + 2h and g + 2h + 1, and walking the groups in
  * order reads every slot once.  After block blk of a strip the groups 32*blk-63 .. 32*blk-32 are
  * complete in every lane. */
-__device__ __forceinline__ unsigned nwb_hx_code(const unsigned p1, const unsigned p2, const unsigned colmask,
-                                                const bool count_branches, unsigned &branches)
+/* Arrow codes of the 8 cells of one ring word pair {p1, p2} (both halves; the caller knows which
+ * half belongs to which row group).  zv = 0x8888.. - vn was formed by the sweeping warp. */
+__device__ __forceinline__ unsigned nwb_hx_code(const unsigned p1, const unsigned zv, unsigned &two)
 {
-    const unsigned zu = NWB_HX_B8 - (p1 & NWB_HX_B7); /* bit 3: un == 0 (LEFT) */
-    const unsigned zv = NWB_HX_B8 - p2;               /* bit 3: vn == 0 (UP)   */
-    if (count_branches) {
-        const unsigned two = (p1 & zu) | (p1 & zv) | (zu & zv); /* bit 3: two or more arrows */
-        branches += (unsigned)__popc(two & colmask);
+    const unsigned zu = NWB_HX_B8 - (p1 & NWB_HX_B7);                             /* bit 3: un == 0 (LEFT) */
+    two = (p1 & zu) | (p1 & zv) | (zu & zv);                                      /* bit 3: two or more arrows */
+    const unsigned q = (((zu >> 1) & 0x44444444u) | (zv & NWB_HX_B8)) >> 1;       /* LEFT at bit 1, UP at bit 2 */
+    return ((p1 >> 3) & 0x11111111u) | (q & 0x66666666u);
+}
+
+/* One ring slot of my lane: codes of {low half: group gl, high half: group gl - 1}, both sub-rows.
+ * Rows of group g are complete once the slots of steps g + 2h and g + 2h + 1 are both seen: the
+ * low half comes from the previous slot's codes (pc0/pc1), the high half from this one. */
+template <bool COUNT, bool EDGE>
+__device__ __forceinline__ void nwb_hx_flush_slot(const uint4 w, unsigned &pc0, unsigned &pc1, uint8_t *out,
+                                                  const size_t pitch, const bool row1, const unsigned colmask,
+                                                  const unsigned halfmask, unsigned &branches)
+{
+    unsigned t0, t1;
+    const unsigned c0 = nwb_hx_code(w.x, w.y, t0);
+    const unsigned c1 = nwb_hx_code(w.z, w.w, t1);
+    if (COUNT) {
+        /* both halves of a slot are cells of the table (different row groups); EDGE: first / last
+         * slots of a strip, where one half lies above row 1 or below row B */
+        const unsigned m0 = EDGE ? (colmask & halfmask) : colmask;
+        branches += (unsigned)__popc(t0 & m0);
+        if (!EDGE || row1) branches += (unsigned)__popc(t1 & m0);
     }
-    return ((p1 >> 3) & 0x11111111u) | ((zu >> 2) & 0x22222222u) | ((zv >> 1) & 0x44444444u);
+    *reinterpret_cast<unsigned *>(out) = __byte_perm(pc0, c0, 0x7610);
+    if (!EDGE || row1) *reinterpret_cast<unsigned *>(out + pitch) = __byte_perm(pc1, c1, 0x7610);
+    pc0 = c0;
+    pc1 = c1;
 }
 
 __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int wslot, const unsigned char *ring,
@@ -294,6 +316,7 @@ __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int 
     const int nworkers = (int)gridDim.x * NWB_HX_CRIT;
     const int worker = wslot * (int)gridDim.x + (int)blockIdx.x;
     const int ngroups = (B + 1) / 2;
+    const int nfull = B / 2; /* groups with both rows inside the table */
     const int nblocks = (ngroups + 63 + 31) / 32;
     const bool count_branches = p.count_branches != 0;
     const unsigned char *lane_ring = ring + lane * 16;
@@ -304,34 +327,61 @@ __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int 
         hi = hi < 0 ? 0 : (hi > 8 ? 8 : hi);
         const unsigned colmask = (hi >= 8) ? NWB_HX_B8 : (NWB_HX_B8 & ((1u << (4 * hi)) - 1u));
         uint8_t *dst = p.arrows + (size_t)c * 128 + (size_t)lane * 4;
+        unsigned pc0 = 0u, pc1 = 0u;
         for (int blk = 0; blk < nblocks; blk++) {
             while (nwb_flag_load(ready) < seq + 1) nwb_spin_pause(true);
 #ifndef NWB_EMU
             __threadfence_block();
 #endif
             if (!(p.debug_nowait & 2)) {
-                const int sbase = 32 * (seq - blk) + 2 * lane; /* ring step index of (group 0, my low half) */
+                /* slot of step s holds {low: group s - 2*lane, high: group s - 2*lane - 1}; walk the slots
+                 * whose HIGH half is one of this block's groups 32*blk-63 .. 32*blk-32 (clipped to the
+                 * table); the slot before the first one only primes pc0/pc1 */
+                const int sbase = 32 * (seq - blk) + 2 * lane + 1; /* ring step of the slot whose high half is group 0 */
                 int g = 32 * blk - 63;
                 int gend = g + 32;
                 if (g < 0) g = 0;
                 if (gend > ngroups) gend = ngroups;
                 if (g < gend) {
-                    uint4 lo = *reinterpret_cast<const uint4 *>(lane_ring + ((sbase + g) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+                    const unsigned char *q = lane_ring;
+                    if (g == 0) { /* the strip's first group: its low halves sit in the slot before */
+                        const uint4 w = *reinterpret_cast<const uint4 *>(q + ((sbase - 1) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+                        unsigned t;
+                        pc0 = nwb_hx_code(w.x, w.y, t);
+                        if (count_branches) branches += (unsigned)__popc(t & colmask & 0x0000FFFFu);
+                        pc1 = nwb_hx_code(w.z, w.w, t);
+                        if (count_branches && B >= 2) branches += (unsigned)__popc(t & colmask & 0x0000FFFFu);
+                    }
                     uint8_t *out = dst + (size_t)(2 * g) * p.pitch;
+                    const int gfull = gend < nfull ? gend : nfull;
+                    /* a slot's low half belongs to group g + 1: not a table cell for the last group,
+                     * and only its first sub-row when B is odd and g + 1 is the last group */
+                    const int gbulk = gfull < ngroups - 2 ? gfull : (ngroups - 2 < g ? g : ngroups - 2);
 #pragma unroll 4
-                    for (; g < gend; g++) {
-                        const uint4 hw = *reinterpret_cast<const uint4 *>(
-                            lane_ring + ((sbase + g + 1) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
-                        const unsigned c0 = nwb_hx_code(__byte_perm(lo.x, hw.x, 0x7610), __byte_perm(lo.y, hw.y, 0x7610),
-                                                        colmask, count_branches, branches);
-                        *reinterpret_cast<unsigned *>(out) = c0;
-                        if (2 * g + 2 <= B) {
-                            const unsigned c1 = nwb_hx_code(__byte_perm(lo.z, hw.z, 0x7610), __byte_perm(lo.w, hw.w, 0x7610),
-                                                            colmask, count_branches, branches);
-                            *reinterpret_cast<unsigned *>(out + p.pitch) = c1;
-                        }
+                    for (; g < gbulk; g++) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(q + ((sbase + g) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+                        if (count_branches) nwb_hx_flush_slot<true, false>(w, pc0, pc1, out, p.pitch, true, colmask, 0u, branches);
+                        else nwb_hx_flush_slot<false, false>(w, pc0, pc1, out, p.pitch, true, colmask, 0u, branches);
                         out += 2 * p.pitch;
-                        lo = hw;
+                    }
+                    for (; g < gend; g++) { /* the last two groups of the strip: per-half, per-row validity */
+                        const uint4 w = *reinterpret_cast<const uint4 *>(q + ((sbase + g) & (NWB_HX_RING_STEPS - 1)) * NWB_HX_SLOT_BYTES);
+                        const bool row1 = 2 * g + 2 <= B;
+                        unsigned t0, t1;
+                        const unsigned c0 = nwb_hx_code(w.x, w.y, t0);
+                        const unsigned c1 = nwb_hx_code(w.z, w.w, t1);
+                        if (count_branches) {
+                            /* high half: group g (rows 2g+1, 2g+2); low half: group g+1 (rows 2g+3, 2g+4) */
+                            unsigned m0 = colmask & 0xFFFF0000u, m1 = row1 ? (colmask & 0xFFFF0000u) : 0u;
+                            if (2 * g + 3 <= B) m0 |= colmask & 0x0000FFFFu;
+                            if (2 * g + 4 <= B) m1 |= colmask & 0x0000FFFFu;
+                            branches += (unsigned)__popc(t0 & m0) + (unsigned)__popc(t1 & m1);
+                        }
+                        *reinterpret_cast<unsigned *>(out) = __byte_perm(pc0, c0, 0x7610);
+                        if (row1) *reinterpret_cast<unsigned *>(out + p.pitch) = __byte_perm(pc1, c1, 0x7610);
+                        pc0 = c0;
+                        pc1 = c1;
+                        out += 2 * p.pitch;
                     }
                 }
             }
@@ -350,21 +400,23 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
     volatile int *flags = reinterpret_cast<volatile int *>(smem + (size_t)NWB_HX_CRIT * NWB_HX_RING_BYTES);
     if (threadIdx.x < 2 * NWB_HX_CRIT) flags[threadIdx.x] = 0;
     __syncthreads();
-    if (warp < NWB_HX_CRIT) {
+    const int crit_slot = (warp < NWB_HX_CRIT) ? warp : -1;
+    const int flush_slot = ((warp & 3) == 3 && (warp >> 2) < NWB_HX_CRIT) ? (warp >> 2) : -1;
+    if (crit_slot >= 0) {
         /* sweeping warp */
         const int nworkers = (int)gridDim.x * NWB_HX_CRIT;
-        const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
-        unsigned char *ring = smem + (size_t)warp * NWB_HX_RING_BYTES;
+        const int worker = crit_slot * (int)gridDim.x + (int)blockIdx.x;
+        unsigned char *ring = smem + (size_t)crit_slot * NWB_HX_RING_BYTES;
         long long rsum = 0;
         int seq = 0;
         for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
-            nwb_hx_strip(p, pc, c, ring, flags + warp, flags + NWB_HX_CRIT + warp, seq, lane, rsum);
+            nwb_hx_strip(p, pc, c, ring, flags + crit_slot, flags + NWB_HX_CRIT + crit_slot, seq, lane, rsum);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
         if (lane == 0 && rsum) atomicAdd((unsigned long long *)&p.summary->rsum, (unsigned long long)rsum);
-    } else if ((warp & 3) == 3 && (warp >> 2) < NWB_HX_CRIT) {
-        /* flush warp of sweeping warp (warp >> 2) */
-        const int wslot = warp >> 2;
+    } else if (flush_slot >= 0) {
+        /* flush warp of sweeping warp flush_slot */
+        const int wslot = flush_slot;
         unsigned branches = 0;
         nwb_hx_flush(p, wslot, smem + (size_t)wslot * NWB_HX_RING_BYTES, flags + wslot, flags + NWB_HX_CRIT + wslot,
                      lane, branches);

@@ -281,3 +281,68 @@ def test_extreme_aspect_ratios_and_multi_pass(oracle, nwb):
             if flags & nwb.WANT_COUNT:
                 assert tab.count == o.count, (a, b, flags)
             check_arrows(oracle, nwb, tab, t, s, *mkd)
+
+
+@pytest.fixture
+def force_hx():
+    """NWB_PK_HX=1: the sweeping + flush warp variant (csrc/nwb_fill_hx.cuh) at every size the
+    scheme allows, not only for tall tables (diagnostic knob read by libnwb.so at every fill)."""
+    old = os.environ.get("NWB_PK_HX")
+    os.environ["NWB_PK_HX"] = "1"
+    yield
+    if old is None:
+        del os.environ["NWB_PK_HX"]
+    else:
+        os.environ["NWB_PK_HX"] = old
+
+
+def test_hx_variant_edge_shapes(oracle, nwb, force_hx):
+    rng = random.Random(23)
+    sizes = [1, 2, 31, 33, 64, 65, 127, 129, 255, 256, 257, 511, 513, 769, 1025, 2049]
+    for _ in range(40):
+        a, b = rng.choice(sizes), rng.choice(sizes)
+        alpha = rng.choice([b"ACGT", b"AB", bytes(range(1, 256)), b"ARNDCQEGHILKMFPSTWYV"])
+        t = bytes(rng.choice(alpha) for _ in range(a))
+        s = bytes(rng.choice(alpha) for _ in range(b))
+        m, k, d = rng.choice([(1, 1, 1), (2, 1, 2), (0, 0, 0), (1, 2, 3), (3, -1, 0), (1, 1, 0), (1, 1, 3), (3, 1, 2)])
+        tab = nwb.fill(t, s, m, k, d, nwb.WANT_ARROWS_HOST)
+        o = check_arrows(oracle, nwb, tab, t, s, m, k, d)
+        assert tab.kernel_kind == (nwb.KIND_PK if pk_supported(m, k, d) else nwb.KIND_I32)
+        assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, m, k, d)
+
+
+def test_hx_variant_big_and_multi_pass(oracle, nwb, force_hx):
+    """Whole tables at 10k x 10k (config 2) and 3k x 3k protein, extreme aspect ratios, and more strips
+    than sweeping warps (160,000 columns = 625 strips > 444: several strips per warp, ring across strips)."""
+    t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
+    tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_ARROWS_HOST)
+    assert (tab.opt_score, tab.branch_count) == (1056, 34377799)
+    check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
+    for seed, a, b, mkd, alpha in [(0x5EED0005, 3000, 3000, (2, 1, 2), "protein"), (0x5EED0E00, 20000, 7, (1, 1, 1), "dna"),
+                                   (0x5EED0E02, 5, 20000, (1, 1, 1), "dna"), (0x5EED0E06, 160000, 200, (1, 1, 1), "dna"),
+                                   (0x5EED0E08, 300, 70001, (1, 1, 1), "dna")]:
+        t, s = oracle.generate_pair(seed, a, b, oracle.PROTEIN if alpha == "protein" else oracle.DNA)
+        tab = nwb.fill(t, s, *mkd, nwb.WANT_ARROWS_HOST)
+        o = check_arrows(oracle, nwb, tab, t, s, *mkd)
+        assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b)
+
+
+def test_plain_packed_kernel_without_hx(oracle, nwb):
+    """NWB_PK_HX=0 keeps the one-warp-per-strip packed kernel (the path for 2d + m > 7) covered at 10k x 10k."""
+    old = os.environ.get("NWB_PK_HX")
+    os.environ["NWB_PK_HX"] = "0"
+    try:
+        t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
+        tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_ARROWS_HOST)
+        assert (tab.opt_score, tab.branch_count) == (1056, 34377799)
+        check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
+    finally:
+        if old is None:
+            del os.environ["NWB_PK_HX"]
+        else:
+            os.environ["NWB_PK_HX"] = old
+    # a scheme whose differences do not fit a nibble (2d + m = 11) at a size where hx would otherwise run
+    t, s = oracle.generate_pair(0x5EED0F00, 3000, 5000)
+    tab = nwb.fill(t, s, 5, 4, 3, nwb.WANT_ARROWS_HOST)
+    o = check_arrows(oracle, nwb, tab, t, s, 5, 4, 3)
+    assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count)
