@@ -21,6 +21,7 @@
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
 #include "nwb_fill_hx.cuh"
+#include "nwb_count.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_peak.cuh"
 
@@ -138,6 +139,7 @@ struct nwb_plan {
     cudaStream_t last_stream = nullptr;
     int m = 0, k = 0, d = 0;
     bool pk_hx = false; /* packed kernel variant with flush warps (nwb_fill_hx.cuh) */
+    bool count_pass = false; /* the count runs as a second sweep over the arrow codes (nwb_count.cuh) */
 };
 
 static void make_inbox_layout(Inbox &ib, size_t bpitch)
@@ -277,7 +279,8 @@ static int run_i32(nwb_plan *p, const NwbStripParams &sp, int grid, cudaStream_t
 #undef L_
 }
 
-static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st);
+static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, bool count, int grid, int warps,
+                  cudaStream_t st);
 
 extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
 {
@@ -293,6 +296,10 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     NwbPkConsts pc;
     memset(&pc, 0, sizeof(pc));
     p->kind = choose_kind(flags, m, k, d, &pc);
+    /* packed kernels: the count behind -s is a second sweep over the finished arrow codes (nwb_count.cuh);
+     * NWB_COUNT_FUSED=1 (diagnostics) keeps it inside the fill (nwb_fill_pk.cuh, COUNT) */
+    p->count_pass = (p->kind == NWB_KIND_PK) && (flags & NWB_WANT_COUNT) && !getenv("NWB_COUNT_FUSED");
+    const bool fused_count = (flags & NWB_WANT_COUNT) && !p->count_pass;
     int strip_w = NWB_I32_STRIP_W, pk_k = 0, pk_r = 1;
     p->pk_hx = false;
     if (p->kind == NWB_KIND_PK) {
@@ -303,12 +310,13 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
             const int v = atoi(ek);
             if (v == 1 || v == 2 || v == 4) pk_k = v;
         }
+        if (p->count_pass) pk_k = 4; /* the count sweep walks 256-column strips */
         if (const char *er = getenv("NWB_PK_R")) { /* diagnostics */
             const int v = atoi(er);
             if (v == 1 || v == 2) pk_r = v;
         }
         /* sweeping + flush warps (nwb_fill_hx.cuh) when every difference fits a nibble */
-        const bool hx_ok = !(flags & NWB_WANT_COUNT) && nwb_hx_supported(pc);
+        const bool hx_ok = !fused_count && nwb_hx_supported(pc);
         p->pk_hx = hx_ok && pk_k == 4 && pk_r == 2;
         if (const char *eh = getenv("NWB_PK_HX")) { /* diagnostics: 0 = never, 1 = whenever the scheme allows */
             p->pk_hx = hx_ok && atoi(eh) != 0;
@@ -350,15 +358,35 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     if (rc == NWB_OK && p->kind == NWB_KIND_PK) {
         rc = p->bnd_w.ensure((size_t)nloc * L.bpitch);
         if (rc == NWB_OK) rc = p->side_pre.ensure(NWB_PK_SPRE_LEN(B));
-        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
+        if (rc == NWB_OK && fused_count) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
+    }
+    /* the count sweep's own strips: 32 * cpl columns wide, aligned with this rank's 256-column fill strips */
+    NwbCountParams cp;
+    memset(&cp, 0, sizeof(cp));
+    int cnt_cpl = 8;
+    if (rc == NWB_OK && p->count_pass) {
+        long long cols = (long long)nloc * 256;
+        if (cols > A) cols = A;
+        cnt_cpl = nwb_count_choose_cpl(cols, p->sm_count);
+        if (const char *ec = getenv("NWB_CNT_CPL")) { /* diagnostics */
+            const int v = atoi(ec);
+            if (v == 2 || v == 4 || v == 8) cnt_cpl = v;
+        }
+        const int wc = 32 * cnt_cpl, ratio = 256 / wc;
+        cp.n_strips = (A + wc - 1) / wc;
+        cp.strip_begin = p->strip_begin * ratio < cp.n_strips ? p->strip_begin * ratio : cp.n_strips;
+        cp.strip_end = p->strip_end * ratio < cp.n_strips ? p->strip_end * ratio : cp.n_strips;
+        rc = p->bnd_c.ensure((size_t)(cp.strip_end - cp.strip_begin) * 2 * L.bpitch);
     }
     if (rc != NWB_OK) return rc;
     CK(cudaMemsetAsync(p->progress.p, 0, (size_t)nloc * sizeof(int), st));
     /* the packed kernel's stream words validate themselves (bit 31): start from zero */
     if (p->kind == NWB_KIND_PK) {
         CK(cudaMemsetAsync(p->bnd_w.p, 0, (size_t)nloc * L.bpitch * sizeof(uint32_t), st));
-        if (flags & NWB_WANT_COUNT)
+        if (fused_count)
             CK(cudaMemsetAsync(p->bnd_c.p, 0, (size_t)nloc * 2 * L.bpitch * sizeof(unsigned long long), st));
+        if (p->count_pass)
+            CK(cudaMemsetAsync(p->bnd_c.p, 0, (size_t)(cp.strip_end - cp.strip_begin) * 2 * L.bpitch * sizeof(unsigned long long), st));
     }
 
     NwbStripParams sp;
@@ -420,7 +448,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     }
     if (p->kind == NWB_KIND_PK)
         while (pk_warps > 1 && NWB_PK_SMEM_BYTES(L.pk_k, L.pk_r, pk_warps) > 200 * 1024) pk_warps--;
-    if (p->kind == NWB_KIND_PK && (flags & NWB_WANT_COUNT) && pk_warps > NWB_PK_WARPS) pk_warps = NWB_PK_WARPS;
+    if (p->kind == NWB_KIND_PK && fused_count && pk_warps > NWB_PK_WARPS) pk_warps = NWB_PK_WARPS;
     CK(cudaEventRecord(p->ev0, st));
     if (p->kind == NWB_KIND_PK) {
         nwb_pk_prep_side_kernel<<<64, 256, 0, st>>>(p->side.p, B, pc.shift, p->side_pre.p);
@@ -428,9 +456,24 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         p->launches += 1;
     }
     if (hx) rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
-    else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, grid, pk_warps, st);
+    else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
     if (rc != NWB_OK) return rc;
+    if (p->count_pass && cp.strip_end > cp.strip_begin) {
+        cp.arrows = p->arrows.p;
+        cp.pitch = L.pitch;
+        cp.A = A; cp.B = B;
+        cp.bnd_c = p->bnd_c.p;
+        cp.bpitch = L.bpitch;
+        cp.in_bnd_c = sp.in_bnd_c;
+        cp.out_bnd_c = sp.out_bnd_c;
+        cp.summary = p->summary.p;
+        cp.debug_nowait = sp.debug_nowait;
+        const int nlocc = cp.strip_end - cp.strip_begin;
+        rc = nwb_count_launch(cp, cnt_cpl, nlocc < p->sm_count ? nlocc : p->sm_count, st, cuda_fail);
+        if (rc != NWB_OK) return rc;
+        p->launches += 1;
+    }
     CK(cudaEventRecord(p->ev1, st));
     p->timed = true;
     p->launches += 1;
@@ -446,9 +489,10 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     return NWB_OK;
 }
 
-static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, int grid, int warps, cudaStream_t st)
+static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, bool count, int grid, int warps,
+                  cudaStream_t st)
 {
-    return nwb_pk_launch(sp, pc, p->L.pk_k, p->L.pk_r, (p->flags & NWB_WANT_COUNT) != 0, grid, warps, st, cuda_fail);
+    return nwb_pk_launch(sp, pc, p->L.pk_k, p->L.pk_r, count, grid, warps, st, cuda_fail);
 }
 
 extern "C" int nwb_plan_reset_inbox(nwb_plan *p, void *stream)

@@ -84,6 +84,8 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=Fal
     L.emu_fill_pk.restype = C.c_int
     L.emu_fill_pk.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_Out)]
+    # count: False / True (fused into the fill) / 2, 4, 8 (second sweep over the arrow codes with that many
+    # cells per lane, csrc/nwb_count.cuh)
     rc = L.emu_fill_pk(top, a, side, b, m, k, d, K, R, int(count), grid, warps, split, int(hx),
                        arrows.ctypes.data_as(C.c_void_p), C.byref(out))
     assert rc == 0, rc

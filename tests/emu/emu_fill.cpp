@@ -9,6 +9,7 @@
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
 #include "nwb_fill_hx.cuh"
+#include "nwb_count.cuh"
 #include "nwb_batch.cuh"
 
 #include <vector>
@@ -125,13 +126,16 @@ int emu_hx_supported(int m, int k, int d)
     return (nwb_pk_supported(m, k, d, &pc) && nwb_hx_supported(pc)) ? 1 : 0;
 }
 
-/* hx != 0: the sweeping + flush warp variant (nwb_fill_hx.cuh; K = 4, R = 2, no count) */
+/* hx != 0: the sweeping + flush warp variant (nwb_fill_hx.cuh; K = 4, R = 2, no fused count).
+ * count: 0 none, 1 fused into nwb_fill_pk_kernel, 2 / 4 / 8 second sweep over the arrow codes with that
+ * many cells per lane (nwb_count.cuh). */
 int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, int d, int K, int R, int count,
                 unsigned grid, int warps, int split, int hx, uint8_t *arrows, emu_out *out)
 {
     NwbPkConsts pc;
     if (!nwb_pk_supported(m, k, d, &pc)) return -5;
-    if (hx && (!nwb_hx_supported(pc) || K != 4 || R != 2 || count)) return -6;
+    if (hx && (!nwb_hx_supported(pc) || K != 4 || R != 2 || count == 1)) return -6;
+    if (count >= 2 && (K != 4 || (count != 2 && count != 4 && count != 8))) return -6;
     NwbLayout L = nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K);
     std::vector<uint32_t> bnd_w((size_t)L.n_strips * L.bpitch, 0u);
     std::vector<int> progress((size_t)L.n_strips, 0);
@@ -161,7 +165,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     auto launch = [&](const NwbStripParams &q) {
         if (hx) {
             emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel(q, pc); });
-        } else if (count) {
+        } else if (count == 1) {
             if (R == 2) run_pk_emu<4, 2, true>(grid, warps, q, pc);
             else run_pk_emu<4, 1, true>(grid, warps, q, pc);
         } else if (R == 2) {
@@ -172,6 +176,37 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
             if (K == 1) run_pk_emu<1, 1, false>(grid, warps, q, pc);
             else if (K == 2) run_pk_emu<2, 1, false>(grid, warps, q, pc);
             else run_pk_emu<4, 1, false>(grid, warps, q, pc);
+        }
+    };
+    /* count >= 2: second sweep over the arrow codes with count cells per lane (8, 4 or 2); split_strip in
+     * 256-column fill strips, two launches chained through the inbox like two GPUs */
+    std::vector<unsigned long long> cnt_bnd;
+    auto run_count = [&](int cpl, int split_strip, unsigned long long *outbox, const unsigned long long *inbox) {
+        const int wc = 32 * cpl, ratio = 256 / wc;
+        NwbCountParams cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.arrows = arrows; cp.pitch = L.pitch; cp.A = A; cp.B = B;
+        cp.n_strips = (A + wc - 1) / wc;
+        cp.bpitch = L.bpitch;
+        cp.summary = &sum;
+        cnt_bnd.assign((size_t)cp.n_strips * 2 * L.bpitch, 0ull);
+        auto go = [&](const NwbCountParams &q) {
+            if (cpl == 2) emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<2>(q); });
+            else if (cpl == 4) emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<4>(q); });
+            else emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<8>(q); });
+        };
+        if (split_strip > 0) {
+            int sb = split_strip * ratio;
+            if (sb > cp.n_strips) sb = cp.n_strips;
+            NwbCountParams c0 = cp, c1 = cp;
+            c0.strip_begin = 0; c0.strip_end = sb; c0.bnd_c = cnt_bnd.data(); c0.out_bnd_c = outbox;
+            c1.strip_begin = sb; c1.strip_end = cp.n_strips; c1.bnd_c = cnt_bnd.data() + (size_t)sb * 2 * L.bpitch;
+            c1.in_bnd_c = inbox;
+            if (c0.strip_end > c0.strip_begin) go(c0);
+            if (c1.strip_end > c1.strip_begin) go(c1);
+        } else {
+            cp.strip_begin = 0; cp.strip_end = cp.n_strips; cp.bnd_c = cnt_bnd.data();
+            go(cp);
         }
     };
     if (split > 0 && split < L.n_strips) {
@@ -194,10 +229,12 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         p1.progress = prog1.data();
         launch(p0);
         launch(p1);
+        if (count >= 2) run_count(count, split, p0.out_bnd_c, p1.in_bnd_c);
         last_stream = (split == L.n_strips - 1) ? inbox_w.data() : bnd1.data() + (size_t)(L.n_strips - 2 - split) * L.bpitch;
         emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
     } else {
         launch(p);
+        if (count >= 2) run_count(count, 0, nullptr, nullptr);
         if (L.n_strips >= 2) {
             last_stream = bnd_w.data() + (size_t)(L.n_strips - 2) * L.bpitch;
             emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
