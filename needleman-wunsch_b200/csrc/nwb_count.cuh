@@ -27,7 +27,8 @@
 
 #define NWB_CNT_WARPS 4   /* one per SM sub-partition */
 #define NWB_CNT_SUB 8     /* rows per sub-block: arrow words and stream words are fetched one sub-block ahead */
-#define NWB_CNT_SMEM_PER_WARP (NWB_CNT_SUB * 8)
+#define NWB_CNT_RING 64   /* arrow-word ring slots per warp (>= 31 steps of lane skew + 3 sub-blocks) */
+#define NWB_CNT_SMEM_PER_WARP (NWB_CNT_SUB * 8 + NWB_CNT_RING * 32 * 4)
 #define NWB_CNT_SMEM_BYTES (NWB_CNT_WARPS * NWB_CNT_SMEM_PER_WARP)
 
 struct NwbCountParams {
@@ -64,6 +65,17 @@ __device__ __forceinline__ unsigned nwb_cnt_load(const T *p)
 #endif
 }
 
+__device__ __forceinline__ uint4 nwb_ldg_u128(const uint8_t *p)
+{
+#ifdef NWB_EMU
+    uint4 v;
+    memcpy(&v, p, 16);
+    return v;
+#else
+    return __ldcg(reinterpret_cast<const uint4 *>(p)); /* streamed once: L2 only */
+#endif
+}
+
 /* One row of one lane: CPL cells.  x = the lane's CPL arrow nibbles of the row. */
 template <int CPL>
 __device__ __forceinline__ void nwb_count_row(const unsigned x, unsigned long long (&cnt)[CPL], unsigned long long &left_above,
@@ -85,7 +97,8 @@ __device__ __forceinline__ void nwb_count_row(const unsigned x, unsigned long lo
 
 /* One strip: columns c*32*CPL+1 .. (c+1)*32*CPL, all rows. */
 template <int CPL>
-__device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const int c, unsigned long long *cstage, const int lane)
+__device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const int c, unsigned long long *cstage,
+                                                 unsigned *ring, const int lane)
 {
     typedef typename NwbCntWord<CPL>::T word_t;
     const int A = p.A, B = p.B;
@@ -115,15 +128,50 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
     if (!has_left && lane < NWB_CNT_SUB) cstage[lane] = 1ull; /* column 0 of the table */
     __syncwarp();
 
-    /* arrow words of my rows of the next sub-block, stream words of lane 0's rows of the next sub-block */
-    unsigned wnext[NWB_CNT_SUB];
+    /* CPL == 8: the arrow rows go through a shared-memory ring.  The warp loads 8 rows x 128 bytes per
+     * sub-block with two 16-byte loads per lane (coalesced, two sub-blocks ahead of use) and scatters the
+     * words so that lane l's word of row r sits in slot (r + l - 1) mod 64: at step s every lane reads
+     * slot s mod 64, an immediate offset inside an unrolled sub-block.  (Loading each lane's own word
+     * straight from the table touches 32 different rows per instruction.) */
+    const bool staged = (CPL == 8);
+    uint4 stage0 = make_uint4(0u, 0u, 0u, 0u), stage1 = stage0;
+    const int srow = lane >> 3, schunk = lane & 7; /* my row (0..3, +4) and 16-byte chunk of a staged block */
+    auto stage_load = [&](const int rbase) { /* rows rbase .. rbase+7 into stage0/1 */
+        const uint8_t *q = p.arrows + (size_t)c * (W / 2) + (size_t)schunk * 16;
+        const int r0 = rbase + srow, r1 = r0 + 4;
+        stage0 = (r0 >= 1 && r0 <= B) ? nwb_ldg_u128(q + (size_t)(r0 - 1) * p.pitch) : make_uint4(0u, 0u, 0u, 0u);
+        stage1 = (r1 >= 1 && r1 <= B) ? nwb_ldg_u128(q + (size_t)(r1 - 1) * p.pitch) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    auto stage_store = [&](const int rbase) {
+        const int r0 = rbase + srow, r1 = r0 + 4, w0 = 4 * schunk;
+        const unsigned v0[4] = {stage0.x, stage0.y, stage0.z, stage0.w}, v1[4] = {stage1.x, stage1.y, stage1.z, stage1.w};
 #pragma unroll
-    for (int t = 0; t < NWB_CNT_SUB; t++) {
-        const int j = t - lane + 1;
-        wnext[t] = (j >= 1 && j <= B) ? nwb_cnt_load(wp + (size_t)(j - 1) * wpitch) : 0u;
+        for (int i = 0; i < 4; i++) {
+            ring[((r0 + w0 + i - 1) & (NWB_CNT_RING - 1)) * 32 + w0 + i] = v0[i];
+            ring[((r1 + w0 + i - 1) & (NWB_CNT_RING - 1)) * 32 + w0 + i] = v1[i];
+        }
+    };
+    /* arrow words of my rows of the next sub-block (direct path), stream words of lane 0's rows of the next
+     * two sub-blocks */
+    unsigned wnext[NWB_CNT_SUB];
+    if (staged) {
+        __syncwarp(); /* the previous strip's reads of the ring are done */
+        stage_load(1);
+        stage_store(1);
+        __syncwarp();
+        stage_load(1 + NWB_CNT_SUB);
+    } else {
+#pragma unroll
+        for (int t = 0; t < NWB_CNT_SUB; t++) {
+            const int j = t - lane + 1;
+            wnext[t] = (j >= 1 && j <= B) ? nwb_cnt_load(wp + (size_t)(j - 1) * wpitch) : 0u;
+        }
     }
-    unsigned long long cw_next = 0ull;
-    if (has_left && lane < 2 * NWB_CNT_SUB && (lane >> 1) < B) cw_next = nwb_ld_relaxed_u64(in_c + lane, left_remote);
+    unsigned long long cw_next = 0ull, cw_next2 = 0ull;
+    if (has_left && lane < 2 * NWB_CNT_SUB) {
+        if ((lane >> 1) < B) cw_next = nwb_ld_relaxed_u64(in_c + lane, left_remote);
+        if ((lane >> 1) + NWB_CNT_SUB < B) cw_next2 = nwb_ld_relaxed_u64(in_c + 2 * NWB_CNT_SUB + lane, left_remote);
+    }
 
     const int nsteps = B + 31;
     for (int ss = 0; ss < nsteps; ss += NWB_CNT_SUB) {
@@ -142,23 +190,36 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 nwb_pause();
 #endif
             }
-            cw_next = 0ull;
-            if (lane < 2 * NWB_CNT_SUB && row + NWB_CNT_SUB <= B)
-                cw_next = nwb_ld_relaxed_u64(in_c + (size_t)(ss + NWB_CNT_SUB) * 2 + lane, left_remote);
+            cw_next = cw_next2; /* words are fetched two sub-blocks ahead: a word that is not valid yet costs an L2 round trip */
+            cw_next2 = 0ull;
+            if (lane < 2 * NWB_CNT_SUB && row + 2 * NWB_CNT_SUB <= B)
+                cw_next2 = nwb_ld_relaxed_u64(in_c + (size_t)(ss + 2 * NWB_CNT_SUB) * 2 + lane, left_remote);
             const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
             __syncwarp(); /* the previous sub-block's reads of cstage are done */
             if (lane < 2 * NWB_CNT_SUB && !(lane & 1)) cstage[lane >> 1] = (cw & ~NWB_PK_CVALID) | (hi << 63);
             __syncwarp();
         }
         unsigned w[NWB_CNT_SUB];
+        if (staged) {
+            /* rows ss+9 .. ss+16 (loaded during the previous sub-block) into the ring; rows ss+17 .. ss+24 on their way */
+            stage_store(ss + 1 + NWB_CNT_SUB);
+            stage_load(ss + 1 + 2 * NWB_CNT_SUB);
+            const unsigned *rq = ring + (ss & (NWB_CNT_RING - 1)) * 32 + lane;
 #pragma unroll
-        for (int t = 0; t < NWB_CNT_SUB; t++) w[t] = wnext[t];
+            for (int t = 0; t < NWB_CNT_SUB; t++) w[t] = rq[t * 32];
+            __syncwarp(); /* this sub-block's ring reads are issued before the next sub-block's stores */
+        } else {
+#pragma unroll
+            for (int t = 0; t < NWB_CNT_SUB; t++) w[t] = wnext[t];
+        }
         /* every lane strictly inside rows 1 .. B-1 for this sub-block and the next one's loads inside the table */
         const bool lean = (ss >= 31) && (ss + 2 * NWB_CNT_SUB < B);
         if (lean) {
-            const word_t *wq = wp + (size_t)(ss + NWB_CNT_SUB - lane) * wpitch;
+            if (!staged) {
+                const word_t *wq = wp + (size_t)(ss + NWB_CNT_SUB - lane) * wpitch;
 #pragma unroll
-            for (int t = 0; t < NWB_CNT_SUB; t++) wnext[t] = nwb_cnt_load(wq + (size_t)t * wpitch);
+                for (int t = 0; t < NWB_CNT_SUB; t++) wnext[t] = nwb_cnt_load(wq + (size_t)t * wpitch);
+            }
             unsigned long long *oc = out_c + (size_t)(ss - lane) * 2;
 #pragma unroll
             for (int t = 0; t < NWB_CNT_SUB; t++) {
@@ -169,10 +230,12 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 nwb_st_relaxed_sys_pred_u64(oc + 2 * t + 1, (send >> 63) | NWB_PK_CVALID, pub31);
             }
         } else {
+            if (!staged) {
 #pragma unroll
-            for (int t = 0; t < NWB_CNT_SUB; t++) {
-                const int j = ss + NWB_CNT_SUB + t - lane + 1;
-                wnext[t] = (j >= 1 && j <= B) ? nwb_cnt_load(wp + (size_t)(j - 1) * wpitch) : 0u;
+                for (int t = 0; t < NWB_CNT_SUB; t++) {
+                    const int j = ss + NWB_CNT_SUB + t - lane + 1;
+                    wnext[t] = (j >= 1 && j <= B) ? nwb_cnt_load(wp + (size_t)(j - 1) * wpitch) : 0u;
+                }
             }
 #pragma unroll 1
             for (int t = 0; t < NWB_CNT_SUB; t++) {
@@ -206,7 +269,8 @@ __global__ void __launch_bounds__(32 * NWB_CNT_WARPS, 1) nwb_count_kernel(const 
     const int nworkers = (int)gridDim.x * NWB_CNT_WARPS;
     const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
     unsigned long long *cstage = reinterpret_cast<unsigned long long *>(NWB_SMEM_BASE() + (size_t)warp * NWB_CNT_SMEM_PER_WARP);
-    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) nwb_count_strip<CPL>(p, c, cstage, lane);
+    unsigned *ring = reinterpret_cast<unsigned *>(cstage + NWB_CNT_SUB);
+    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) nwb_count_strip<CPL>(p, c, cstage, ring, lane);
 }
 
 /* Cells per lane and row.  Narrower strips shorten a row step but add a pipeline hop of ~45 steps per

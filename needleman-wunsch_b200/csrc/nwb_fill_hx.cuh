@@ -75,7 +75,7 @@ __device__ __forceinline__ void nwb_spin_pause(bool sleep)
     (void)sleep;
     nwb_pause();
 #else
-    if (sleep) __nanosleep(64);
+    if (sleep) __nanosleep(400);
 #endif
 }
 

@@ -346,3 +346,24 @@ def test_plain_packed_kernel_without_hx(oracle, nwb):
     tab = nwb.fill(t, s, 5, 4, 3, nwb.WANT_ARROWS_HOST)
     o = check_arrows(oracle, nwb, tab, t, s, 5, 4, 3)
     assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count)
+
+
+def test_fused_count_kernel_still_matches(oracle, nwb):
+    """NWB_COUNT_FUSED=1: the count fused into nwb_fill_pk_kernel (the default is the count sweep over the
+    arrow codes, csrc/nwb_count.cuh): final counts of sub-problems whose count is not 0 mod 2^64, and config 2."""
+    old = os.environ.get("NWB_COUNT_FUSED")
+    os.environ["NWB_COUNT_FUSED"] = "1"
+    try:
+        t, s = oracle.generate_pair(0x5EED0D00, 900, 700)
+        o = oracle.fill(t, s, 1, 1, 1, want_counts=True)
+        for i, j in [(900, 700), (256, 256), (257, 300), (513, 699), (100, 650)]:
+            tab = nwb.fill(t[:i], s[:j], 1, 1, 1, nwb.WANT_COUNT)
+            assert tab.count == int(o.counts[j, i]), (i, j)
+        t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
+        tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_COUNT)
+        assert (tab.opt_score, tab.branch_count, tab.count) == (1056, 34377799, 0)
+    finally:
+        if old is None:
+            del os.environ["NWB_COUNT_FUSED"]
+        else:
+            os.environ["NWB_COUNT_FUSED"] = old
