@@ -22,6 +22,13 @@ for (a,b) in [(7,7),(300,100),(513,70),(600,260),(90,700)]:
     r=emu.fill_i32(t,s,1,1,1,flags=1|2|8|0x20,grid=2)
     assert r['opt_score']==o.final_score
     r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=2,split=1,count=True) if a>256 else None
+    # sweeping + flush warp kernel (ring, flags) and the count sweep over its arrow codes (staged ring for 8 cells per lane)
+    for cpl in (0,2,4,8):
+        r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=2,count=cpl,hx=True)
+        assert r['opt_score']==o.final_score and (cpl==0 or r['count']==o.count)
+    if a>256:
+        r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=1,split=1,count=8,hx=True)
+        assert r['count']==o.count
 tops=[bytes(random.choice(b"ACGT") for _ in range(n)) for n in (256,300,17,700)]
 sides=[bytes(random.choice(b"ACGT") for _ in range(n)) for n in (256,40,130,90)]
 r=emu.fill_batch(tops,sides,1,1,1,grid=1)
