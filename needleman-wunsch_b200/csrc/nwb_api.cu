@@ -409,7 +409,12 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     sp.bpitch = L.bpitch;
     sp.progress = p->progress.p;
     sp.summary = p->summary.p;
-    sp.count_branches = (flags & NWB_NO_BRANCH_COUNT) ? 0 : 1;
+    /* branch counter (walk-table.c:108-120): the hx kernel's flush warps count for free; the one-warp-per-strip
+     * packed kernel counts in its ring flush only on short tables -- on tall ones the extra instructions sit on
+     * the strip-to-strip critical path (+1.6 ms at 100k x 100k) and a stand-alone HBM-bound pass (0.86 ms) is cheaper */
+    const bool want_branches = !(flags & NWB_NO_BRANCH_COUNT);
+    const bool branch_pass = want_branches && p->kind == NWB_KIND_PK && !p->pk_hx && B >= 4096;
+    sp.count_branches = (want_branches && !branch_pass) ? 1 : 0;
     sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? atoi(getenv("NWB_DEBUG_NOWAIT")) : 0;
     if (getenv("NWB_DEBUG_TIMES") && p->kind == NWB_KIND_PK) { /* diagnostics: per-strip timestamps dumped to a file */
         if (p->dbg_times.ensure((size_t)L.n_strips * 4) != NWB_OK) return NWB_ERR_NOMEM;
@@ -459,6 +464,14 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
     if (rc != NWB_OK) return rc;
+    if (branch_pass) {
+        long long cb = (long long)p->strip_begin * L.strip_w, ce = (long long)p->strip_end * L.strip_w;
+        if (ce > A) ce = A;
+        nwb_branch_count_kernel<<<p->sm_count * 16, 256, 0, st>>>(p->arrows.p, L.pitch, A, B, (int)cb, (int)ce,
+                                                                 &p->summary.p->branch_count);
+        CK(cudaGetLastError());
+        p->launches += 1;
+    }
     if (p->count_pass && cp.strip_end > cp.strip_begin) {
         cp.arrows = p->arrows.p;
         cp.pitch = L.pitch;
