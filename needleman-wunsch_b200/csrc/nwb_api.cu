@@ -114,6 +114,8 @@ struct nwb_plan {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream2 = nullptr;           /* the count sweep, when it trails the fill */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool timed = false;
     int A = 0, B = 0;
     DevBuf<uint8_t> top, side, arrows;
@@ -175,6 +177,9 @@ extern "C" int nwb_plan_create(int max_top, int max_side, unsigned flags, int de
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
     if (e != cudaSuccess) {
@@ -213,6 +218,9 @@ extern "C" void nwb_plan_destroy(nwb_plan *p)
     p->progress.release(); p->summary.release(); p->side_pre.release(); p->dbg_times.release(); p->dbg_trace.release();
     if (p->inbox.base) cudaFree(p->inbox.base);
     if (p->right_base && p->right_is_ipc) cudaIpcCloseMemHandle(p->right_base);
+    if (p->stream2) { cudaStreamSynchronize(p->stream2); cudaStreamDestroy(p->stream2); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -460,6 +468,15 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         CK(cudaGetLastError());
         p->launches += 1;
     }
+    /* The count sweep trails the hx fill on a second stream: the flush warps publish how many rows of each
+     * strip are in memory, the sweep waits for the rows it is about to read.  It needs SMs the fill does not
+     * occupy (a fill block holds nearly all registers and shared memory of its SM): tables of up to ~118 strips
+     * (30k columns); otherwise, and with NWB_COUNT_SERIAL=1 (diagnostics), it runs after the fill. */
+    const int cnt_grid_wanted = (cp.strip_end - cp.strip_begin + NWB_CNT_WARPS - 1) / NWB_CNT_WARPS;
+    const bool overlap = hx && p->count_pass && cnt_cpl == 8 && cp.strip_end > cp.strip_begin &&
+                         grid + cnt_grid_wanted <= p->sm_count && !getenv("NWB_COUNT_SERIAL");
+    sp.publish_rows = overlap ? 1 : 0;
+    if (overlap) CK(cudaEventRecord(p->ev_fork, st)); /* buffers are zeroed, strings uploaded */
     if (hx) rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
     else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
@@ -482,10 +499,23 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         cp.out_bnd_c = sp.out_bnd_c;
         cp.summary = p->summary.p;
         cp.debug_nowait = sp.debug_nowait;
+        cp.fill_progress = overlap ? p->progress.p : nullptr;
         const int nlocc = cp.strip_end - cp.strip_begin;
-        rc = nwb_count_launch(cp, cnt_cpl, nlocc < p->sm_count ? nlocc : p->sm_count, st, cuda_fail);
+        /* one warp per SM sub-partition on as few SMs as that takes */
+        int cgrid = (nlocc + NWB_CNT_WARPS - 1) / NWB_CNT_WARPS;
+        if (cgrid > p->sm_count) cgrid = p->sm_count;
+        cudaStream_t cst = st;
+        if (overlap) {
+            cst = p->stream2;
+            CK(cudaStreamWaitEvent(cst, p->ev_fork, 0));
+        }
+        rc = nwb_count_launch(cp, cnt_cpl, cgrid, cst, cuda_fail);
         if (rc != NWB_OK) return rc;
         p->launches += 1;
+        if (overlap) {
+            CK(cudaEventRecord(p->ev_join, cst));
+            CK(cudaStreamWaitEvent(st, p->ev_join, 0));
+        }
     }
     CK(cudaEventRecord(p->ev1, st));
     p->timed = true;

@@ -43,6 +43,8 @@ struct NwbCountParams {
     const unsigned long long *in_bnd_c; /* inbox written by the left-neighbour GPU (strip_begin > 0)   */
     unsigned long long *out_bnd_c;      /* right neighbour's inbox (strip_end < n_strips)              */
     NwbDevSummary *summary;
+    const int *fill_progress; /* CPL == 8 only: [strip - strip_begin] arrow rows of the strip the fill has written so
+                               * far, when the sweep runs concurrently with nwb_fill_hx_kernel; NULL = table is finished */
     int debug_nowait; /* diagnostics: 1 = do not wait for the left strip's stream (results are wrong) */
 };
 
@@ -154,8 +156,26 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
     /* arrow words of my rows of the next sub-block (direct path), stream words of lane 0's rows of the next
      * two sub-blocks */
     unsigned wnext[NWB_CNT_SUB];
+    const int *fillp = (staged && p.fill_progress) ? p.fill_progress + lc : nullptr;
+    int rows_seen = 0; /* the fill publishes 64 rows at a time: poll (and fence) only when the cached value is short */
+    auto wait_rows = [&](const int need) {
+        if (rows_seen >= need) return;
+        do {
+            rows_seen = (int)nwb_ld_relaxed_u32(reinterpret_cast<const uint32_t *>(fillp), false);
+#ifdef NWB_EMU
+            if (rows_seen < need) nwb_pause();
+#endif
+        } while (rows_seen < need);
+#ifndef NWB_EMU
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+    };
     if (staged) {
         __syncwarp(); /* the previous strip's reads of the ring are done */
+        if (fillp) {
+            rows_seen = 0;
+            wait_rows(B < 2 * NWB_CNT_SUB ? B : 2 * NWB_CNT_SUB);
+        }
         stage_load(1);
         stage_store(1);
         __syncwarp();
@@ -203,6 +223,10 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
         if (staged) {
             /* rows ss+9 .. ss+16 (loaded during the previous sub-block) into the ring; rows ss+17 .. ss+24 on their way */
             stage_store(ss + 1 + NWB_CNT_SUB);
+            if (fillp) { /* rows up to ss + 24 are about to be read from the table */
+                const int need = ss + 3 * NWB_CNT_SUB;
+                wait_rows(need < B ? need : B);
+            }
             stage_load(ss + 1 + 2 * NWB_CNT_SUB);
             const unsigned *rq = ring + (ss & (NWB_CNT_RING - 1)) * 32 + lane;
 #pragma unroll

@@ -230,6 +230,8 @@ struct NwbStripParams {
     int *out_progress;
     NwbDevSummary *summary;
     int count_branches; /* packed kernel: count cells with >= 2 arrows while flushing rows */
+    int publish_rows;   /* hx kernel: publish in progress[] how many arrow rows of each strip are in memory
+                         * (the count sweep of nwb_count.cuh trails the fill on a second stream) */
     int debug_nowait; /* diagnostics: skip the inter-strip waits (results are wrong) */
     unsigned long long *debug_times; /* diagnostics: per strip {entry, first words valid, step 64, exit} in ns, or NULL */
     unsigned long long *debug_trace; /* diagnostics: [8 traced strips][nblocks][2] = {ns at block start, polls so far} */

@@ -308,6 +308,7 @@ __device__ __forceinline__ void nwb_hx_flush_slot(const uint4 w, unsigned &pc0, 
     pc1 = c1;
 }
 
+template <bool PUBLISH>
 __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int wslot, const unsigned char *ring,
                                               volatile int *ready, volatile int *done, const int lane,
                                               unsigned &branches)
@@ -387,11 +388,26 @@ __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int 
             }
             __syncwarp();
             if (lane == 0) nwb_flag_store(done, seq + 1);
+            if (PUBLISH) {
+                /* rows 1 .. 2 * (last group of this block) of the strip are written: tell the count sweep */
+                int gdone = 32 * blk - 31;
+                gdone = gdone < 0 ? 0 : (gdone > ngroups ? ngroups : gdone);
+                const int rows = 2 * gdone < B ? 2 * gdone : B;
+#ifndef NWB_EMU
+                __threadfence(); /* my stores before the flag */
+#endif
+                __syncwarp();
+                if (lane == 0 && rows > 0) nwb_st_relaxed_u32(reinterpret_cast<uint32_t *>(p.progress + (c - p.strip_begin)), (unsigned)rows, false);
+            }
             seq++;
         }
     }
 }
 
+/* PUBLISH: the flush warps also publish in p.progress[] how many arrow rows of each strip are in memory, for a
+ * count sweep (nwb_count.cuh) that trails the fill on another stream.  A separate instantiation: the sweeping
+ * warps' instruction schedule is sensitive to any code added to the kernel. */
+template <bool PUBLISH>
 __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const NwbStripParams p, const NwbPkConsts pc)
 {
     const int lane = threadIdx.x & 31;
@@ -418,8 +434,8 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
         /* flush warp of sweeping warp flush_slot */
         const int wslot = flush_slot;
         unsigned branches = 0;
-        nwb_hx_flush(p, wslot, smem + (size_t)wslot * NWB_HX_RING_BYTES, flags + wslot, flags + NWB_HX_CRIT + wslot,
-                     lane, branches);
+        nwb_hx_flush<PUBLISH>(p, wslot, smem + (size_t)wslot * NWB_HX_RING_BYTES, flags + wslot,
+                              flags + NWB_HX_CRIT + wslot, lane, branches);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) branches += __shfl_xor_sync(NWB_FULL_MASK, branches, o);
         if (lane == 0 && branches) atomicAdd(&p.summary->branch_count, branches);
@@ -427,16 +443,19 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
 }
 
 #ifndef NWB_EMU
-static inline int nwb_hx_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st,
-                                nwb_fail_fn fail)
+template <bool PUBLISH>
+static int nwb_hx_launch_t(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st, nwb_fail_fn fail)
 {
-    cudaError_t e = cudaFuncSetAttribute(nwb_fill_hx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)NWB_HX_SMEM_BYTES);
+    auto kernel = nwb_fill_hx_kernel<PUBLISH>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NWB_HX_SMEM_BYTES);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
     void *args[] = {(void *)&sp, (void *)&pc};
-    e = cudaLaunchCooperativeKernel((const void *)nwb_fill_hx_kernel, dim3(grid), dim3(32 * NWB_HX_WARPS), args,
-                                    NWB_HX_SMEM_BYTES, st);
+    e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(32 * NWB_HX_WARPS), args, NWB_HX_SMEM_BYTES, st);
     if (e != cudaSuccess) return fail(e, "cudaLaunchCooperativeKernel");
     return 0;
+}
+static inline int nwb_hx_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st, nwb_fail_fn fail)
+{
+    return sp.publish_rows ? nwb_hx_launch_t<true>(sp, pc, grid, st, fail) : nwb_hx_launch_t<false>(sp, pc, grid, st, fail);
 }
 #endif

@@ -164,7 +164,8 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     const uint32_t *last_stream = nullptr; /* the stream consumed by the last strip, when it is not in bnd_w */
     auto launch = [&](const NwbStripParams &q) {
         if (hx) {
-            emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel(q, pc); });
+            if (q.publish_rows) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<true>(q, pc); });
+            else emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false>(q, pc); });
         } else if (count == 1) {
             if (R == 2) run_pk_emu<4, 2, true>(grid, warps, q, pc);
             else run_pk_emu<4, 1, true>(grid, warps, q, pc);
@@ -181,6 +182,9 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     /* count >= 2: second sweep over the arrow codes with count cells per lane (8, 4 or 2); split_strip in
      * 256-column fill strips, two launches chained through the inbox like two GPUs */
     std::vector<unsigned long long> cnt_bnd;
+    /* cpl == 8 after the hx kernel: the sweep also waits on the rows the flush warps published (it trails the
+     * fill on a second stream on the GPU; here the fill has finished, so every wait must already be satisfied) */
+    const int *prog0 = nullptr, *prog1 = nullptr;
     auto run_count = [&](int cpl, int split_strip, unsigned long long *outbox, const unsigned long long *inbox) {
         const int wc = 32 * cpl, ratio = 256 / wc;
         NwbCountParams cp;
@@ -202,10 +206,12 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
             c0.strip_begin = 0; c0.strip_end = sb; c0.bnd_c = cnt_bnd.data(); c0.out_bnd_c = outbox;
             c1.strip_begin = sb; c1.strip_end = cp.n_strips; c1.bnd_c = cnt_bnd.data() + (size_t)sb * 2 * L.bpitch;
             c1.in_bnd_c = inbox;
+            if (cpl == 8) { c0.fill_progress = prog0; c1.fill_progress = prog1; }
             if (c0.strip_end > c0.strip_begin) go(c0);
             if (c1.strip_end > c1.strip_begin) go(c1);
         } else {
             cp.strip_begin = 0; cp.strip_end = cp.n_strips; cp.bnd_c = cnt_bnd.data();
+            if (cpl == 8) cp.fill_progress = prog0;
             go(cp);
         }
     };
@@ -215,7 +221,8 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         std::vector<unsigned long long> inbox_cc(2 * L.bpitch, 0ull), bnd1c((size_t)L.n_strips * 2 * L.bpitch, 0ull);
         int inbox_flag = 0;
         std::vector<uint32_t> bnd1((size_t)L.n_strips * L.bpitch, 0u);
-        std::vector<int> prog1((size_t)L.n_strips, 0);
+        std::vector<int> prog1v((size_t)L.n_strips, 0);
+        if (hx && count >= 2) { p0.publish_rows = 1; p1.publish_rows = 1; prog0 = progress.data(); prog1 = prog1v.data(); }
         p0.strip_end = split;
         p0.out_bnd_w = inbox_w.data();
         p0.out_bnd_c = inbox_cc.data();
@@ -226,13 +233,14 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         p1.bnd_c = bnd1c.data();
         p1.in_progress = &inbox_flag;
         p1.bnd_w = bnd1.data();
-        p1.progress = prog1.data();
+        p1.progress = prog1v.data();
         launch(p0);
         launch(p1);
         if (count >= 2) run_count(count, split, p0.out_bnd_c, p1.in_bnd_c);
         last_stream = (split == L.n_strips - 1) ? inbox_w.data() : bnd1.data() + (size_t)(L.n_strips - 2 - split) * L.bpitch;
         emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
     } else {
+        if (hx && count >= 2) { p.publish_rows = 1; prog0 = progress.data(); }
         launch(p);
         if (count >= 2) run_count(count, 0, nullptr, nullptr);
         if (L.n_strips >= 2) {

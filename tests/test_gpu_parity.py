@@ -309,6 +309,9 @@ def test_hx_variant_edge_shapes(oracle, nwb, force_hx):
         o = check_arrows(oracle, nwb, tab, t, s, m, k, d)
         assert tab.kernel_kind == (nwb.KIND_PK if pk_supported(m, k, d) else nwb.KIND_I32)
         assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, m, k, d)
+        # -s: the count sweep trails the hx fill on a second stream (rows published by the flush warps)
+        tabc = nwb.fill(t, s, m, k, d, nwb.WANT_COUNT)
+        assert (tabc.opt_score, tabc.branch_count, tabc.count) == (o.final_score, o.branch_count, o.count), (a, b, m, k, d)
 
 
 def test_hx_variant_big_and_multi_pass(oracle, nwb, force_hx):
@@ -367,3 +370,21 @@ def test_fused_count_kernel_still_matches(oracle, nwb):
             del os.environ["NWB_COUNT_FUSED"]
         else:
             os.environ["NWB_COUNT_FUSED"] = old
+
+
+def test_count_sweep_after_the_fill(oracle, nwb):
+    """NWB_COUNT_SERIAL=1: the count sweep launched after the hx fill instead of trailing it (the order used
+    anyway when the fill occupies every SM): same counts."""
+    old = os.environ.get("NWB_COUNT_SERIAL")
+    os.environ["NWB_COUNT_SERIAL"] = "1"
+    try:
+        t, s = oracle.generate_pair(0x5EED0D10, 900, 4500)
+        o = oracle.fill(t, s, 1, 1, 1, want_counts=True)
+        for i, j in [(900, 4500), (256, 4100), (513, 4499)]:
+            tab = nwb.fill(t[:i], s[:j], 1, 1, 1, nwb.WANT_COUNT)
+            assert tab.count == int(o.counts[j, i]), (i, j)
+    finally:
+        if old is None:
+            del os.environ["NWB_COUNT_SERIAL"]
+        else:
+            os.environ["NWB_COUNT_SERIAL"] = old
