@@ -154,7 +154,8 @@ def run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) -> dict | 
     out = {}
     # ---- config 4: batch of 256 x 256 DNA pairs, pair p seeded 0x5EED4000 + 2p, sharded by rank
     per = 125_000
-    first = rank * per
+    first, cnt = nwb.batch_partition(per * world, rank, world)   # include/nwb.h: contiguous pair ranges, no communication
+    assert cnt == per
     tcat, scat = bytearray(), bytearray()
     for p in range(first, first + per):
         tt, ss = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
@@ -322,7 +323,7 @@ def run_ours(args) -> None:
         tt = torch.tensor([summ.partial_r, summ.branch_count], device="cuda", dtype=torch.int64)
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         if summ.kernel_kind == 1:
-            opt_score = int(tt[0].item()) - D_ * (A + B)
+            opt_score = nwb.strip_group_score(int(tt[0].item()), A, B, D_)
         branch_total = int(tt[1].item()) & 0xFFFFFFFF
 
     extras = run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) if not args.no_extras else None

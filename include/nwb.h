@@ -187,6 +187,15 @@ float nwb_plan_kernel_ms(nwb_plan *p);
 const char *nwb_plan_kernel_name(const nwb_plan *p);
 /* Interior columns [begin,end) (0-based, i-1) this plan's strips cover. */
 int nwb_plan_strip_range(const nwb_plan *p, int *begin_col, int *end_col);
+/* Host-only helpers for a launcher with one process per GPU (no device needed).
+ * nwb_strip_partition: the interior columns [begin,end) rank `rank` of `world` owns when the table is
+ * cut into strips of `strip_width` columns (256 for the packed kernels) -- the contiguous analogue of the
+ * reference's per-thread column sets (needleman-wunsch.c:568-571); the same rule nwb_plan_create() uses.
+ * nwb_batch_partition: the contiguous pair range of a rank when a batch is sharded with no communication.
+ * nwb_strip_group_score: the optimal score of a strip group from the sum of the ranks' partial_r. */
+int nwb_strip_partition(int top_len, int strip_width, int rank, int world, int *begin_col, int *end_col);
+int nwb_batch_partition(int64_t n_pairs, int rank, int world, int64_t *first_pair, int64_t *pair_count);
+int32_t nwb_strip_group_score(int64_t partial_r_sum, int top_len, int side_len, int d);
 /* Re-arm the inbound boundary flag before the next run of a strip group
  * (all ranks must do this, then synchronise, before any rank runs again). */
 int nwb_plan_reset_inbox(nwb_plan *p, void *stream);

@@ -113,6 +113,9 @@ _SIGS = {
     "nwb_batch_count_u64": (C.c_uint64, [C.c_void_p, C.c_int64]),
     "nwb_batch_arrow_rows": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
     "nwb_batch_kernel_ms": (C.c_float, [C.c_void_p]),
+    "nwb_strip_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nwb_batch_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nwb_strip_group_score": (C.c_int32, [C.c_int64, C.c_int, C.c_int, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -155,6 +158,26 @@ def measure_int_issue(mode: int = 1, device: int = 0) -> tuple[float, float]:
     if rc != 0:
         raise NwbError(rc, "nwb_measure_int_issue")
     return a.value, b.value
+
+
+def strip_partition(top_len: int, rank: int, world: int, strip_width: int = 256) -> tuple[int, int]:
+    """Interior columns [begin, end) of rank `rank` in a column-strip group (host-only, include/nwb.h)."""
+    b, e = C.c_int(), C.c_int()
+    _ck(load_library().nwb_strip_partition(top_len, strip_width, rank, world, C.byref(b), C.byref(e)),
+        "nwb_strip_partition")
+    return b.value, e.value
+
+
+def batch_partition(n_pairs: int, rank: int, world: int) -> tuple[int, int]:
+    """(first pair, pair count) of rank `rank` when a batch is sharded across `world` GPUs (host-only)."""
+    f, c = C.c_int64(), C.c_int64()
+    _ck(load_library().nwb_batch_partition(n_pairs, rank, world, C.byref(f), C.byref(c)), "nwb_batch_partition")
+    return f.value, c.value
+
+
+def strip_group_score(partial_r_sum: int, top_len: int, side_len: int, d: int) -> int:
+    """Optimal score of a strip group from the sum over ranks of Summary.partial_r (host-only)."""
+    return int(load_library().nwb_strip_group_score(partial_r_sum, top_len, side_len, d))
 
 
 def _b(s) -> bytes:

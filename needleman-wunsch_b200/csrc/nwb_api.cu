@@ -337,9 +337,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     const NwbLayout &L = p->L;
 
     /* this rank's strips */
-    const int per = (L.n_strips + p->world - 1) / p->world;
-    p->strip_begin = p->rank * per < L.n_strips ? p->rank * per : L.n_strips;
-    p->strip_end = (p->rank + 1) * per < L.n_strips ? (p->rank + 1) * per : L.n_strips;
+    nwb_rank_strip_range(L.n_strips, p->rank, p->world, &p->strip_begin, &p->strip_end);
     const int nloc = p->strip_end - p->strip_begin;
 
     NwbDevSummary init;
@@ -612,6 +610,37 @@ extern "C" const char *nwb_plan_kernel_name(const nwb_plan *p)
     if (p->kind == NWB_KIND_I32) return "nwb_fill_i32_kernel";
     return p->pk_hx ? "nwb_fill_hx_kernel" : "nwb_fill_pk_kernel";
 }
+/* Host-only partition helpers (no device needed): what a launcher with one process per GPU uses to
+ * shard the work the same way nwb_plan_create() / nwb_fill_on() do. */
+extern "C" int nwb_strip_partition(int top_len, int strip_width, int rank, int world, int *begin_col, int *end_col)
+{
+    if (top_len < 0 || strip_width < 1 || world < 1 || rank < 0 || rank >= world) return NWB_ERR_INVALID;
+    int n = (top_len + strip_width - 1) / strip_width;
+    if (n < 1) n = 1;
+    int sb, se;
+    nwb_rank_strip_range(n, rank, world, &sb, &se);
+    long long b = (long long)sb * strip_width, e = (long long)se * strip_width;
+    if (b > top_len) b = top_len;
+    if (e > top_len) e = top_len;
+    if (begin_col) *begin_col = (int)b;
+    if (end_col) *end_col = (int)e;
+    return NWB_OK;
+}
+extern "C" int nwb_batch_partition(int64_t n_pairs, int rank, int world, int64_t *first_pair, int64_t *pair_count)
+{
+    if (n_pairs < 0 || world < 1 || rank < 0 || rank >= world) return NWB_ERR_INVALID;
+    long long f, c;
+    nwb_rank_pair_range(n_pairs, rank, world, &f, &c);
+    if (first_pair) *first_pair = f;
+    if (pair_count) *pair_count = c;
+    return NWB_OK;
+}
+extern "C" int32_t nwb_strip_group_score(int64_t partial_r_sum, int top_len, int side_len, int d)
+{
+    return (int32_t)(uint32_t)((unsigned long long)partial_r_sum -
+                               (unsigned long long)((long long)d * ((long long)top_len + side_len)));
+}
+
 extern "C" int nwb_plan_strip_range(const nwb_plan *p, int *begin_col, int *end_col)
 {
     if (!p) return NWB_ERR_INVALID;
@@ -761,8 +790,7 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
         if (ms > t->kernel_ms) t->kernel_ms = ms;
     }
     if (rc == NWB_OK && top_len > 0 && side_len > 0 && t->sum.kernel_kind == NWB_KIND_PK)
-        t->sum.opt_score = (int32_t)(uint32_t)((unsigned long long)t->sum.partial_r -
-                                               (unsigned long long)((long long)d * ((long long)top_len + side_len)));
+        t->sum.opt_score = nwb_strip_group_score(t->sum.partial_r, top_len, side_len, d);
     if (rc == NWB_OK && top_len > 0 && side_len > 0) {
         const NwbLayout &L = t->plans[0]->L;
         t->pitch = L.pitch;

@@ -41,3 +41,22 @@ static inline NwbLayout nwb_make_layout(int A, int B, int kind, int pk_k, int st
     L.bpitch = nwb_round_up((size_t)B + 1 + 64 + 512, 32); /* + front/back padding of the packed kernel's streams */
     return L;
 }
+
+/* Strip group: rank r of `world` owns strips [begin, end) = r * ceil(n / world) ... (clamped to n).  The
+ * reference's cyclic column sets (needleman-wunsch.c:568-571) interleave columns between threads; across
+ * GPUs the strips are contiguous so that one boundary column per rank crosses NVLink. */
+static inline void nwb_rank_strip_range(int n_strips, int rank, int world, int *begin, int *end)
+{
+    const int per = (n_strips + world - 1) / world;
+    *begin = rank * per < n_strips ? rank * per : n_strips;
+    *end = (rank + 1) * per < n_strips ? (rank + 1) * per : n_strips;
+}
+
+/* Batch of pairs: rank r takes the contiguous range [first, first + count); the first n % world ranks
+ * take one pair more. */
+static inline void nwb_rank_pair_range(long long n_pairs, int rank, int world, long long *first, long long *count)
+{
+    const long long q = n_pairs / world, r = n_pairs % world;
+    *first = rank * q + (rank < r ? rank : r);
+    *count = q + (rank < r ? 1 : 0);
+}

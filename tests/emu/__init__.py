@@ -92,6 +92,43 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=Fal
     return dict(opt_score=out.opt_score, branch_count=out.branch_count, arrows=arrows, pitch=pitch, count=out.count)
 
 
+def bpitch_pk(a: int, b: int) -> int:
+    L = lib()
+    L.emu_bpitch_pk.restype = C.c_size_t
+    L.emu_bpitch_pk.argtypes = [C.c_int, C.c_int]
+    return int(L.emu_bpitch_pk(a, b))
+
+
+def fill_pk_rank(top, side, m, k, d, *, rank, world, inbox=None, hx=True, grid=2):
+    """One rank of a column-strip group (K = 4, R = 2) under the emulator.  inbox: uint32[bpitch] written by
+    rank - 1 (None for rank 0).  Returns the rank's arrow table (only its own columns are written), its
+    outbox for rank + 1, partial_r, branch count and strip range."""
+    top, side = _b(top), _b(side)
+    a, b = len(top), len(side)
+    L = lib()
+    pitch = L.emu_pitch_pk(a, b, 4)
+    bp = bpitch_pk(a, b)
+    arrows = np.zeros((b, pitch), np.uint8)
+    outbox = np.zeros(bp, np.uint32)
+    if inbox is not None:
+        inbox = np.ascontiguousarray(inbox, np.uint32)
+        assert inbox.shape == (bp,)
+    pr = C.c_longlong()
+    br = C.c_uint()
+    info = (C.c_int * 4)()
+    L.emu_fill_pk_rank.restype = C.c_int
+    L.emu_fill_pk_rank.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong),
+                                   C.POINTER(C.c_uint), C.POINTER(C.c_int)]
+    rc = L.emu_fill_pk_rank(top, a, side, b, m, k, d, grid, int(hx), rank, world,
+                            None if inbox is None else inbox.ctypes.data_as(C.c_void_p),
+                            outbox.ctypes.data_as(C.c_void_p), arrows.ctypes.data_as(C.c_void_p),
+                            C.byref(pr), C.byref(br), info)
+    assert rc == 0, rc
+    return dict(arrows=arrows, outbox=outbox, partial_r=pr.value, branch_count=br.value,
+                strip_begin=info[0], strip_end=info[1], n_strips=info[2], pitch=pitch)
+
+
 def fill_batch(tops, sides, m, k, d, *, grid=1):
     """Run nwb_batch_pk_kernel + nwb_batch_branch_kernel under the emulator."""
     n = len(tops)

@@ -261,6 +261,71 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     return 0;
 }
 
+/* ONE rank of a column-strip group under the emulator (tests/test_dist_gloo.py: one process per rank, the
+ * boundary stream travels between the processes the way it crosses NVLink between GPUs).  The rank sweeps
+ * strips [begin, end) given by nwb_rank_strip_range(); `inbox` = the bpitch words its first strip consumes
+ * (written by rank - 1, NULL for rank 0); `outbox` = the words its last strip publishes for rank + 1 (NULL
+ * for the last rank).  hx != 0: nwb_fill_hx_kernel, else nwb_fill_pk_kernel<4, 2>.  info = {strip_begin,
+ * strip_end, n_strips, bpitch}; partial_r = this rank's share of sum_i u(i,B) as in nwb_plan_summary(). */
+size_t emu_bpitch_pk(int A, int B) { return nwb_make_layout(A, B, NWB_KIND_PK, 4, 256).bpitch; }
+
+int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int k, int d, unsigned grid, int hx,
+                     int rank, int world, uint32_t *inbox, uint32_t *outbox, uint8_t *arrows,
+                     long long *partial_r, unsigned *branches, int *info)
+{
+    const int K = 4, R = 2;
+    NwbPkConsts pc;
+    if (!nwb_pk_supported(m, k, d, &pc)) return -5;
+    if (hx && !nwb_hx_supported(pc)) return -6;
+    NwbLayout L = nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K);
+    int sb, se;
+    nwb_rank_strip_range(L.n_strips, rank, world, &sb, &se);
+    info[0] = sb; info[1] = se; info[2] = L.n_strips; info[3] = (int)L.bpitch;
+    *partial_r = 0;
+    *branches = 0;
+    if (se <= sb) return 0;
+    if ((sb > 0 && !inbox) || (se < L.n_strips && !outbox)) return -1;
+    std::vector<uint32_t> bnd_w((size_t)(se - sb) * L.bpitch, 0u);
+    std::vector<int> progress((size_t)(se - sb), 0);
+    NwbDevSummary sum;
+    memset(&sum, 0, sizeof(sum));
+    NwbStripParams p;
+    memset(&p, 0, sizeof(p));
+    p.top = (const uint8_t *)top;
+    p.side = (const uint8_t *)side;
+    p.A = A; p.B = B; p.m = m; p.k = k; p.d = d;
+    p.n_strips = L.n_strips;
+    p.strip_begin = sb;
+    p.strip_end = se;
+    p.arrows = arrows;
+    p.pitch = L.pitch;
+    p.bnd_w = bnd_w.data();
+    p.bpitch = L.bpitch;
+    p.progress = progress.data();
+    p.summary = &sum;
+    p.count_branches = 1;
+    p.in_bnd_w = inbox;
+    p.out_bnd_w = outbox;
+    std::vector<uint16_t> side_pre(NWB_PK_SPRE_LEN(B), 0x1234);
+    emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
+    p.side_pre = side_pre.data();
+    if (hx) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false>(p, pc); });
+    else run_pk_emu<4, 2, false>(grid, 4, p, pc);
+    { /* the counter fused into the flush and the stand-alone pass over this rank's columns must agree */
+        unsigned bc = 0;
+        const int c0 = sb * 64 * K, c1 = (se * 64 * K < A) ? se * 64 * K : A;
+        emu_launch(3, 64, 0, [&]() { nwb_branch_count_kernel(arrows, L.pitch, A, B, c0, c1, &bc); });
+        if (bc != sum.branch_count) return -77;
+    }
+    if (L.n_strips >= 2 && se == L.n_strips) {
+        const uint32_t *stream = (sb == L.n_strips - 1) ? inbox : bnd_w.data() + (size_t)(L.n_strips - 2 - sb) * L.bpitch;
+        emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(stream, B, R, &sum.rsum); });
+    }
+    *partial_r = sum.rsum;
+    *branches = sum.branch_count;
+    return 0;
+}
+
 /* batch kernel under the emulator: arrows = concatenated per-pair tables (offsets returned in arrow_off) */
 int emu_fill_batch(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
                    long long n, int m, int k, int d, unsigned grid, uint8_t *arrows, long long *arrow_off,
