@@ -105,6 +105,7 @@ _SIGS = {
     "nwb_batch_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nwb_batch_fetch": (C.c_int, [C.c_void_p]),
     "nwb_batch_launches": (C.c_int64, [C.c_void_p]),
+    "nwb_batch_kernel_name": (C.c_char_p, [C.c_void_p]),
     "nwb_batch_arrows_device": (C.c_void_p, [C.c_void_p]),
     "nwb_batch_free": (None, [C.c_void_p]),
     "nwb_batch_size": (C.c_int64, [C.c_void_p]),
@@ -390,6 +391,9 @@ class Batch:
 
     def kernel_ms(self) -> float:
         return load_library().nwb_batch_kernel_ms(self._h)
+
+    def kernel_name(self) -> str:
+        return (load_library().nwb_batch_kernel_name(self._h) or b"").decode()
 
     def launches(self) -> int:
         return load_library().nwb_batch_launches(self._h)

@@ -23,6 +23,7 @@
 #include "nwb_fill_hx.cuh"
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
+#include "nwb_batch_bx.cuh"
 #include "nwb_peak.cuh"
 
 #define NWB_ABI_VERSION 1

@@ -6,6 +6,8 @@ struct nwb_batch {
     int m = 0, k = 0, d = 0;
     int sm_count = 0;
     int max_B = 0, max_strips = 1;
+    long long max_A = 0;
+    bool use_bx = false; /* two pairs per warp (nwb_batch_bx.cuh) */
     NwbPkConsts pc = {};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -70,12 +72,19 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
         const int ns = (int)((A + 255) / 256);
         if (ns > b->max_strips) b->max_strips = ns;
         if ((int)B > b->max_B) b->max_B = (int)B;
+        if (A > b->max_A) b->max_A = A;
         b->h_arrow_off[(size_t)p] = aoff;
         aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
     }
     b->h_arrow_off[(size_t)n_pairs] = aoff;
     b->arrows_bytes = (size_t)aoff;
-    if (NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
+    {
+        /* short top strings and nibble-sized differences: two pairs per warp; NWB_BATCH_BX=0 keeps the
+         * one-pair-per-warp kernel (diagnostics) */
+        const char *e = getenv("NWB_BATCH_BX");
+        b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && !(e && atoi(e) == 0);
+    }
+    if (!b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
     int rc = b->tops.ensure(tbytes + 16);
     if (rc == NWB_OK) rc = b->sides.ensure(sbytes + 16);
@@ -109,6 +118,23 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     NwbBatchParams bp;
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
+    if (b->use_bx) {
+        int warps = (int)((220 * 1024) / NWB_BX_SMEM_PER_WARP(b->max_B));
+        if (warps > NWB_BX_WARPS) warps = NWB_BX_WARPS;
+        if (warps < 1) return NWB_ERR_UNSUPPORTED;
+        bp.tops = b->tops.p; bp.top_off = b->top_off.p; bp.sides = b->sides.p; bp.side_off = b->side_off.p;
+        bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
+        bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p;
+        bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
+        const size_t smem = NWB_BX_SMEM_PER_WARP(b->max_B) * (size_t)warps;
+        CK(cudaFuncSetAttribute(nwb_batch_bx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaEventRecord(b->ev0, st));
+        nwb_batch_bx_kernel<<<grid, 32 * warps, smem, st>>>(bp, b->pc);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b->ev1, st));
+        b->launches += 1;
+        return NWB_OK;
+    }
     /* as many warps per SM as the per-warp shared memory (arrow ring + side string) allows, at most 12 */
     int warps = (int)((220 * 1024) / NWB_BATCH_SMEM_PER_WARP(b->max_B));
     if (warps > NWB_BATCH_WARPS) warps = NWB_BATCH_WARPS;
@@ -197,6 +223,11 @@ extern "C" float nwb_batch_kernel_ms(const nwb_batch *b)
     if (cudaEventSynchronize(b->ev1) != cudaSuccess) return -1.f;
     if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) return -1.f;
     return ms;
+}
+extern "C" const char *nwb_batch_kernel_name(const nwb_batch *b)
+{
+    if (!b) return "";
+    return b->use_bx ? "nwb_batch_bx_kernel" : "nwb_batch_pk_kernel";
 }
 extern "C" int64_t nwb_batch_launches(const nwb_batch *b) { return b ? b->launches : 0; }
 extern "C" void *nwb_batch_arrows_device(nwb_batch *b) { return b ? (void *)b->arrows.p : nullptr; }

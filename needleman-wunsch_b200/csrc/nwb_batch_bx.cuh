@@ -1,0 +1,260 @@
+/*
+ * nwb_batch_bx.cuh -- batch of independent pairs, TWO pairs per warp ("bx").
+ *
+ * Same job as nwb_batch.cuh (the reference looped per pair: alloc_computation +
+ * init_computation + compute_table_scores + free_computation, computation.c:51-214,
+ * needleman-wunsch.c:583) and the same results, for batches whose top strings are at
+ * most 256 characters and whose per-cell differences fit a nibble (2d + m <= 7,
+ * nwb_hx_supported).
+ *
+ * nwb_batch.cuh packs two COLUMN BLOCKS of one pair into the 16-bit halves of a
+ * register (64 virtual lanes on an anti-diagonal: 63 steps of skew for a table of
+ * 256 rows) and turns differences into arrow codes with compare instructions.  A
+ * batch has a better source of pairs of cells: two DIFFERENT PAIRS.  Here the low
+ * halves of every register belong to pair 2q, the high halves to pair 2q + 1; lane l
+ * owns columns 8l+1 .. 8l+8 of both pairs and works on row t - l + 1 at step t (31
+ * steps of skew), one __shfl_up_sync per step carries the neighbour's v of both pairs.
+ * The differences of a row are packed as nibbles with integer multiply-adds and the
+ * three zero tests (DIAG <=> z == a, LEFT <=> u == 0, UP <=> v == 0: every tie keeps
+ * its arrow, needleman-wunsch.c:485-503) are done on 8 cells per instruction exactly as
+ * in nwb_fill_hx.cuh.  No boundary streams, no inter-warp synchronisation.
+ *
+ * Arrow rows are de-skewed through a per-warp shared-memory ring (slot = row mod 64,
+ * one ring per pair) and leave with LDS.128 / STG.128, four whole 128-byte rows per
+ * instruction.  Steps whose lanes are all strictly inside both tables run an
+ * unchecked body; the first 31 steps (lanes still above row 1) and the steps around
+ * and below the last rows run a checked one (row masks for the branch counter,
+ * walk-table.c:108-120, and the capture of sum_i u(i,B) = r(A,B)).
+ */
+#pragma once
+#include "nwb_fill_hx.cuh"
+#include "nwb_batch.cuh"
+
+#define NWB_BX_WARPS 12
+#define NWB_BX_MAX_A 256
+#define NWB_BX_RING_ROWS 64
+#define NWB_BX_RING_WORDS (NWB_BX_RING_ROWS * 32) /* per pair: 64 rows x 128 bytes */
+#define NWB_BX_SPADF 32  /* side words in front of row 1: lane 31 starts 30 rows above the table */
+#define NWB_BX_STAIL 72  /* ... and behind the longer side string: 31 steps of skew + 31 of block rounding + prefetch */
+#define NWB_BX_SIDE_WORDS(maxB) ((size_t)(maxB) + NWB_BX_SPADF + NWB_BX_STAIL)
+#define NWB_BX_SMEM_PER_WARP(maxB) (2 * NWB_BX_RING_WORDS * 4 + ((NWB_BX_SIDE_WORDS(maxB) * 4 + 15) / 16) * 16)
+
+/* whether a batch runs this kernel (host and emulator harness share the rule) */
+static inline bool nwb_bx_usable(const NwbPkConsts &pc, long long max_A, int max_B)
+{
+    return nwb_hx_supported(pc) && max_A <= NWB_BX_MAX_A && NWB_BX_SMEM_PER_WARP(max_B) <= 220 * 1024;
+}
+
+struct NwbBxState {
+    unsigned tpw[8]; /* pre-shifted top characters of my 8 columns (pair 2q | pair 2q+1)       */
+    unsigned u[8];   /* u of my columns in the row above                                        */
+    unsigned send;   /* v of my last column in the row I just finished (rows above row 1: BIG) */
+    unsigned nu_a;   /* u of columns 0..3 / 4..7 in the row above, one nibble per column       */
+    unsigned nu_b;
+};
+
+/* One step of one lane: row j = t - lane + 1 of both pairs, 8 cells each.  sp = ~(side char << shift) of
+ * row j (pair 2q | pair 2q+1).  roff = word offset of row j's slot in the rings.  EDGE: j may lie outside
+ * either table. */
+template <bool EDGE>
+__device__ __forceinline__ void nwb_bx_step(NwbBxState &st, const NwbPkConsts &pc, const int lane, const unsigned sp,
+                                             unsigned *ring_l, unsigned &roff, const unsigned cm_a, const unsigned cm_b,
+                                             const int j, const int B0, const int B1, const int na0, const int na1,
+                                             unsigned &br0, unsigned &br1, unsigned &rs0, unsigned &rs1)
+{
+    unsigned v = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
+    if (lane == 0) v = 0u; /* column 0: r(0,j) = 0 */
+    unsigned z[8], a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned nx = st.tpw[k] ^ sp;                 /* -1 per half on a match  */
+        a[k] = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);       /* a_match or a_mis        */
+        z[k] = __vimax3_s16x2(a[k], v, st.u[k]);
+        const unsigned un = z[k] - v;
+        const unsigned vn = z[k] - st.u[k];
+        st.u[k] = un;
+        v = vn;
+    }
+    st.send = v;
+    /* the row's z, a and u as one nibble per column (word a: columns 0..3, word b: columns 4..7) */
+    const unsigned Z4a = ((z[3] * 16u + z[2]) * 16u + z[1]) * 16u + z[0];
+    const unsigned Z4b = ((z[7] * 16u + z[6]) * 16u + z[5]) * 16u + z[4];
+    const unsigned A4a = ((a[3] * 16u + a[2]) * 16u + a[1]) * 16u + a[0];
+    const unsigned A4b = ((a[7] * 16u + a[6]) * 16u + a[5]) * 16u + a[4];
+    const unsigned NUa = ((st.u[3] * 16u + st.u[2]) * 16u + st.u[1]) * 16u + st.u[0];
+    const unsigned NUb = ((st.u[7] * 16u + st.u[6]) * 16u + st.u[5]) * 16u + st.u[4];
+    const unsigned p1a = ((A4a - Z4a + NWB_HX_B8) & NWB_HX_B8) | NUa; /* bit 3: z == a (DIAG); low bits: u */
+    const unsigned p1b = ((A4b - Z4b + NWB_HX_B8) & NWB_HX_B8) | NUb;
+    const unsigned zva = st.nu_a - Z4a + NWB_HX_B8;                   /* 8 - v: bit 3 set iff v == 0 (UP)  */
+    const unsigned zvb = st.nu_b - Z4b + NWB_HX_B8;
+    st.nu_a = NUa;
+    st.nu_b = NUb;
+    unsigned ta, tb;
+    const unsigned ca = nwb_hx_code(p1a, zva, ta);
+    const unsigned cb = nwb_hx_code(p1b, zvb, tb);
+    ring_l[roff] = __byte_perm(ca, cb, 0x5410);                      /* pair 2q:   my 8 cells of row j */
+    ring_l[roff + NWB_BX_RING_WORDS] = __byte_perm(ca, cb, 0x7632);  /* pair 2q+1                      */
+    roff = (roff + 32u) & (unsigned)(NWB_BX_RING_WORDS - 1);
+    ta &= cm_a;
+    tb &= cm_b;
+    if (EDGE) {
+        unsigned rm = 0u;
+        if ((unsigned)(j - 1) < (unsigned)B0) rm |= 0x0000FFFFu;
+        if ((unsigned)(j - 1) < (unsigned)B1) rm |= 0xFFFF0000u;
+        ta &= rm;
+        tb &= rm;
+        /* bottom row of a pair: r(A,B) = sum_i u(i,B) over the pair's columns */
+        if (j >= 1 && (j == B0 || j == B1)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (j == B0 && k < na0) rs0 += st.u[k] & 0xFFFFu;
+                if (j == B1 && k < na1) rs1 += st.u[k] >> 16;
+            }
+        }
+    }
+    br0 += (unsigned)__popc(__byte_perm(ta, tb, 0x5410));
+    br1 += (unsigned)__popc(__byte_perm(ta, tb, 0x7632));
+}
+
+/* Rows (from, upto] of both pairs leave the rings: lane x moves 16 bytes (chunk x & 7) of row rb + (x >> 3). */
+__device__ __forceinline__ void nwb_bx_flush(const unsigned *ring, const int from, const int upto, const int B0, const int B1,
+                                              uint8_t *tab0, uint8_t *tab1, const int lane)
+{
+    const int sub = lane >> 3, chunk = lane & 7;
+    for (int rb = from + 1; rb <= upto; rb += 4) {
+        const int r = rb + sub;
+        if (r <= upto) {
+            const unsigned *src = ring + (r & (NWB_BX_RING_ROWS - 1)) * 32 + chunk * 4;
+            const size_t dst = (size_t)(r - 1) * 128 + (size_t)chunk * 16;
+            if (r <= B0) *reinterpret_cast<uint4 *>(tab0 + dst) = *reinterpret_cast<const uint4 *>(src);
+            if (r <= B1) *reinterpret_cast<uint4 *>(tab1 + dst) = *reinterpret_cast<const uint4 *>(src + NWB_BX_RING_WORDS);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(const NwbBatchParams bp, const NwbPkConsts pc)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_BX_SMEM_PER_WARP(bp.max_B));
+    unsigned *sidew = ring + 2 * NWB_BX_RING_WORDS;
+    unsigned *ring_l = ring + lane;
+    const unsigned *side_l = sidew + NWB_BX_SPADF + 1 - lane; /* side_l[t] = the word of my row at step t */
+
+    for (long long q = gwarp; 2 * q < bp.n_pairs; q += nwarps) {
+        const long long p0 = 2 * q, p1 = 2 * q + 1;
+        const bool have1 = p1 < bp.n_pairs;
+        const long long t0o = bp.top_off[p0], s0o = bp.side_off[p0];
+        const long long t1o = have1 ? bp.top_off[p1] : 0, s1o = have1 ? bp.side_off[p1] : 0;
+        int A0 = (int)(bp.top_off[p0 + 1] - t0o), B0 = (int)(bp.side_off[p0 + 1] - s0o);
+        int A1 = have1 ? (int)(bp.top_off[p1 + 1] - t1o) : 0, B1 = have1 ? (int)(bp.side_off[p1 + 1] - s1o) : 0;
+        if (A0 == 0 || B0 == 0) { /* borders only (computation.c:97-124) */
+            if (lane == 0) {
+                bp.out_score[p0] = (A0 == 0) ? -B0 * bp.d : -A0 * bp.d;
+                if (bp.out_branch) bp.out_branch[p0] = 0u;
+            }
+            A0 = 0; B0 = 0;
+        }
+        if (have1 && (A1 == 0 || B1 == 0)) {
+            if (lane == 0) {
+                bp.out_score[p1] = (A1 == 0) ? -B1 * bp.d : -A1 * bp.d;
+                if (bp.out_branch) bp.out_branch[p1] = 0u;
+            }
+            A1 = 0; B1 = 0;
+        }
+        const int Bmax = B0 > B1 ? B0 : B1;
+        if (Bmax == 0) continue;
+        /* rows every non-empty pair of the warp has */
+        const int Bmin = (B0 == 0) ? B1 : ((B1 == 0) ? B0 : (B0 < B1 ? B0 : B1));
+
+        __syncwarp(); /* the previous pairs' reads of sidew and the rings are done */
+        const int nwords = Bmax + NWB_BX_SPADF + NWB_BX_STAIL;
+        for (int e = lane; e < nwords; e += 32) {
+            const int j = e - NWB_BX_SPADF;
+            unsigned lo = 0xFFFFu, hi = 0xFFFFu;
+            if (j >= 1 && j <= B0) lo = (~((unsigned)bp.sides[s0o + j - 1] << pc.shift)) & 0xFFFFu;
+            if (j >= 1 && j <= B1) hi = (~((unsigned)bp.sides[s1o + j - 1] << pc.shift)) & 0xFFFFu;
+            sidew[e] = lo | (hi << 16);
+        }
+        NwbBxState st;
+        const int c0 = 8 * lane; /* my first column, 0-based */
+        int na0 = A0 - c0, na1 = A1 - c0;
+        na0 = na0 < 0 ? 0 : (na0 > 8 ? 8 : na0);
+        na1 = na1 < 0 ? 0 : (na1 > 8 ? 8 : na1);
+        unsigned cm_a = 0u, cm_b = 0u; /* bit 3 of the nibbles whose column is inside the pair's table */
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned lo = (k < na0) ? (unsigned)bp.tops[t0o + c0 + k] : 0u;
+            const unsigned hi = (k < na1) ? (unsigned)bp.tops[t1o + c0 + k] : 0u;
+            st.tpw[k] = (lo << pc.shift) | ((hi << pc.shift) << 16);
+            st.u[k] = 0u;
+            const unsigned bit = 8u << (4 * (k & 3));
+            const unsigned m = ((k < na0) ? bit : 0u) | ((k < na1) ? (bit << 16) : 0u);
+            if (k < 4) cm_a |= m;
+            else cm_b |= m;
+        }
+        st.send = NWB_PK_BIG * 0x00010001u;
+        st.nu_a = 0u;
+        st.nu_b = 0u;
+        uint8_t *tab0 = bp.arrows + bp.arrow_off[p0];
+        uint8_t *tab1 = have1 ? bp.arrows + bp.arrow_off[p1] : tab0;
+        unsigned br0 = 0u, br1 = 0u, rs0 = 0u, rs1 = 0u;
+        unsigned roff = (unsigned)((1 - lane) & (NWB_BX_RING_ROWS - 1)) * 32u; /* slot of row 1 - lane */
+        __syncwarp();
+
+        int flushed = 0;
+        const int nsteps = Bmax + 31; /* lane 31 finishes row Bmax at step Bmax + 30 */
+        int t = 0;
+        /* head: steps 0 .. 30, lanes l > t are still above row 1 */
+#pragma unroll 1
+        for (; t < 31; t++)
+            nwb_bx_step<true>(st, pc, lane, side_l[t], ring_l, roff, cm_a, cm_b, t - lane + 1, B0, B1, na0, na1, br0, br1, rs0, rs1);
+        while (t < nsteps) {
+            /* steps t .. t+31: lane 0 reaches row t + 32, lane 31 starts at row t - 30 >= 1 */
+            if (t + 32 < Bmin) {
+#pragma unroll 1
+                for (int sub = 0; sub < 4; sub++) {
+                    unsigned sw[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) sw[i] = side_l[t + 8 * sub + i];
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        nwb_bx_step<false>(st, pc, lane, sw[i], ring_l, roff, cm_a, cm_b, 0, B0, B1, na0, na1, br0, br1, rs0, rs1);
+                }
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < 32; i++)
+                    nwb_bx_step<true>(st, pc, lane, side_l[t + i], ring_l, roff, cm_a, cm_b, t + i - lane + 1, B0, B1, na0, na1,
+                                      br0, br1, rs0, rs1);
+            }
+            t += 32;
+            /* rows <= t - 31 are complete in every lane */
+            int upto = t - 31;
+            if (upto > Bmax) upto = Bmax;
+            __syncwarp();
+            nwb_bx_flush(ring, flushed, upto, B0, B1, tab0, tab1, lane);
+            flushed = upto;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rs0 += __shfl_xor_sync(NWB_FULL_MASK, rs0, o);
+            rs1 += __shfl_xor_sync(NWB_FULL_MASK, rs1, o);
+            br0 += __shfl_xor_sync(NWB_FULL_MASK, br0, o);
+            br1 += __shfl_xor_sync(NWB_FULL_MASK, br1, o);
+        }
+        if (lane == 0) {
+            /* score(A,B) = sum_i u(i,B) - d*(A+B) */
+            if (B0 > 0) {
+                bp.out_score[p0] = (int)(rs0 - (unsigned)bp.d * (unsigned)(A0 + B0));
+                if (bp.out_branch) bp.out_branch[p0] = br0;
+            }
+            if (B1 > 0) {
+                bp.out_score[p1] = (int)(rs1 - (unsigned)bp.d * (unsigned)(A1 + B1));
+                if (bp.out_branch) bp.out_branch[p1] = br1;
+            }
+        }
+    }
+}

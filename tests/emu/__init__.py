@@ -129,8 +129,9 @@ def fill_pk_rank(top, side, m, k, d, *, rank, world, inbox=None, hx=True, grid=2
                 strip_begin=info[0], strip_end=info[1], n_strips=info[2], pitch=pitch)
 
 
-def fill_batch(tops, sides, m, k, d, *, grid=1):
-    """Run nwb_batch_pk_kernel + nwb_batch_branch_kernel under the emulator."""
+def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1):
+    """Run the batch kernel under the emulator.  bx: 0 = nwb_batch_pk_kernel (one pair per warp), 1 =
+    nwb_batch_bx_kernel (two pairs per warp), -1 = the library's own choice; the result's "bx" says which ran."""
     n = len(tops)
     toff = np.zeros(n + 1, np.int64)
     soff = np.zeros(n + 1, np.int64)
@@ -144,16 +145,18 @@ def fill_batch(tops, sides, m, k, d, *, grid=1):
     L = lib()
     L.emu_fill_batch.restype = C.c_int
     L.emu_fill_batch.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
-                                 C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                 C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_int)]
     p = lambda x: x.ctypes.data_as(C.c_void_p)
-    rc = L.emu_fill_batch(b"".join(tops), p(toff), b"".join(sides), p(soff), n, m, k, d, grid, p(arrows), p(aoff),
-                          p(scores), p(branches))
+    used = C.c_int(0)
+    rc = L.emu_fill_batch(b"".join(tops), p(toff), b"".join(sides), p(soff), n, m, k, d, grid, bx, p(arrows), p(aoff),
+                          p(scores), p(branches), C.byref(used))
     assert rc == 0, rc
     tabs = []
     for i in range(n):
         pitch = max(1, (len(tops[i]) + 255) // 256) * 128
         tabs.append(arrows[aoff[i]:aoff[i] + pitch * len(sides[i])].reshape(len(sides[i]), pitch))
-    return dict(scores=scores, branches=branches, tables=tabs)
+    return dict(scores=scores, branches=branches, tables=tabs, bx=bool(used.value))
 
 
 def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:

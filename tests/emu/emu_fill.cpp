@@ -11,6 +11,7 @@
 #include "nwb_fill_hx.cuh"
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
+#include "nwb_batch_bx.cuh"
 
 #include <vector>
 
@@ -327,9 +328,11 @@ int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int
 }
 
 /* batch kernel under the emulator: arrows = concatenated per-pair tables (offsets returned in arrow_off) */
+/* bx: 0 = nwb_batch_pk_kernel (one pair per warp), 1 = nwb_batch_bx_kernel (two pairs per warp; -6 when the
+ * batch does not qualify), -1 = whatever nwb_batch_run() would pick.  *used_bx reports the choice. */
 int emu_fill_batch(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
-                   long long n, int m, int k, int d, unsigned grid, uint8_t *arrows, long long *arrow_off,
-                   int *scores, unsigned *branches)
+                   long long n, int m, int k, int d, unsigned grid, int bx, uint8_t *arrows, long long *arrow_off,
+                   int *scores, unsigned *branches, int *used_bx)
 {
     NwbPkConsts pc;
     if (!nwb_pk_supported(m, k, d, &pc)) return -5;
@@ -346,6 +349,20 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
         aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
     }
     arrow_off[n] = aoff;
+    long long maxA = 0;
+    for (long long p = 0; p < n; p++)
+        if (top_off[p + 1] - top_off[p] > maxA) maxA = top_off[p + 1] - top_off[p];
+    const bool can_bx = nwb_bx_usable(pc, maxA, maxB);
+    if (bx == 1 && !can_bx) return -6;
+    const bool use_bx = (bx != 0) && can_bx;
+    if (used_bx) *used_bx = use_bx ? 1 : 0;
+    if (use_bx) {
+        bp.tops = (const uint8_t *)tops; bp.top_off = top_off; bp.sides = (const uint8_t *)sides; bp.side_off = side_off;
+        bp.n_pairs = n; bp.m = m; bp.k = k; bp.d = d; bp.max_B = maxB;
+        bp.arrows = arrows; bp.arrow_off = arrow_off; bp.out_score = scores; bp.out_branch = branches;
+        emu_launch(grid, 32 * NWB_BX_WARPS, NWB_BX_SMEM_PER_WARP(maxB) * NWB_BX_WARPS, [&]() { nwb_batch_bx_kernel(bp, pc); });
+        return 0;
+    }
     const long long nwarps = (long long)grid * NWB_BATCH_WARPS;
     bp.bpitch = nwb_round_up((size_t)maxB + 1 + 64 + 256, 32);
     bp.scratch_per_warp = (maxS > 1) ? (size_t)(maxS - 1) * bp.bpitch : 0;

@@ -15,7 +15,7 @@ def test_batch_ragged(oracle):
     tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
     sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
     for (m, k, d), grid in (((1, 1, 1), 1), ((2, 1, 2), 2)):
-        r = emu.fill_batch(tops, sides, m, k, d, grid=grid)
+        r = emu.fill_batch(tops, sides, m, k, d, grid=grid, bx=0)
         for i, (t, s) in enumerate(zip(tops, sides)):
             o = oracle.fill(t, s, m, k, d, want_codes=True)
             assert r["scores"][i] == o.final_score, (i, len(t), len(s))
@@ -31,6 +31,58 @@ def test_batch_config4_goldens(oracle):
         t, s = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
         tops.append(t)
         sides.append(s)
-    r = emu.fill_batch(tops, sides, 1, 1, 1, grid=1)
+    r = emu.fill_batch(tops, sides, 1, 1, 1, grid=1, bx=0)
     assert list(r["scores"]) == [19, 29, 19]
     assert list(r["branches"]) == [23713, 22912, 22090]
+
+
+# ---- two pairs per warp (csrc/nwb_batch_bx.cuh) ---------------------------------------------------------
+
+def _check_batch(oracle, tops, sides, m, k, d, *, grid, bx):
+    r = emu.fill_batch(tops, sides, m, k, d, grid=grid, bx=bx)
+    assert r["bx"] == bool(bx)
+    for i, (t, s) in enumerate(zip(tops, sides)):
+        o = oracle.fill(t, s, m, k, d, want_codes=True)
+        assert r["scores"][i] == o.final_score, (i, len(t), len(s))
+        assert r["branches"][i] == o.branch_count, (i, len(t), len(s))
+        if len(t) and len(s):
+            assert np.array_equal(emu.unpack_arrows(r["tables"][i], len(t)) & 7, o.codes[1:, 1:] & 7), (i, len(t), len(s))
+    return r
+
+
+def test_bx_config4_goldens(oracle):
+    tops, sides = [], []
+    for p in (0, 1, 999999):   # an odd number of pairs: the last warp sweeps one pair alone
+        t, s = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
+        tops.append(t)
+        sides.append(s)
+    r = _check_batch(oracle, tops, sides, 1, 1, 1, grid=1, bx=1)
+    assert list(r["scores"]) == [19, 29, 19]
+    assert list(r["branches"]) == [23713, 22912, 22090]
+
+
+def test_bx_ragged_pairs_share_a_warp(oracle):
+    # partners of different shapes (the shorter one finishes early), empty strings, single cells, tall and
+    # flat tables, 31/32/33 and 63/64/65 rows (block and ring-slot boundaries), more pair-pairs than warps
+    rng = random.Random(23)
+    lens = [(256, 256), (1, 1), (255, 257), (3, 40), (17, 130), (0, 5), (200, 90), (64, 64), (256, 1), (33, 33),
+            (256, 31), (100, 300), (5, 0), (8, 32), (9, 33), (249, 63), (250, 64), (7, 65), (1, 200), (256, 2),
+            (0, 0), (31, 31), (130, 95), (96, 128)] + [(rng.randint(1, 256), rng.randint(1, 150)) for _ in range(9)]
+    for alpha in (b"ACGT", bytes(range(1, 256))):
+        tops = [bytes(rng.choice(alpha) for _ in range(a)) for a, _ in lens]
+        sides = [bytes(rng.choice(alpha) for _ in range(b)) for _, b in lens]
+        for (m, k, d), grid in (((1, 1, 1), 1), ((2, 1, 2), 2), ((0, 0, 0), 1), ((1, 1, 3), 1), ((3, -1, 0), 2)):
+            _check_batch(oracle, tops, sides, m, k, d, grid=grid, bx=1)
+
+
+def test_bx_is_the_default_when_it_applies(oracle):
+    t, s = oracle.generate_pair(0x5EED0B01, 200, 70)
+    assert emu.fill_batch([t, t], [s, s], 1, 1, 1)["bx"]                 # short top strings, nibble differences
+    assert not emu.fill_batch([t + t, t], [s, s], 1, 1, 1)["bx"]         # a 400-column pair: strips, one pair per warp
+    assert not emu.fill_batch([t, t], [s, s], 2, 1, 3)["bx"]             # 2d + m = 8 does not fit a nibble
+    # the two kernels agree wherever both apply
+    a = emu.fill_batch([t, s], [s, t], 2, 1, 2, bx=1)
+    b = emu.fill_batch([t, s], [s, t], 2, 1, 2, bx=0)
+    assert list(a["scores"]) == list(b["scores"]) and list(a["branches"]) == list(b["branches"])
+    for x, y, top in zip(a["tables"], b["tables"], (t, s)):
+        assert np.array_equal(emu.unpack_arrows(x, len(top)) & 7, emu.unpack_arrows(y, len(top)) & 7)

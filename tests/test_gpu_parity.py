@@ -235,6 +235,7 @@ def test_batch_config4_shard(oracle, nwb):
     idx = list(range(n - 1)) + [999999]
     tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
     bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST)
+    assert bt.kernel_name() == "nwb_batch_bx_kernel"
     bt.run()
     bt.fetch()
     assert (bt.opt_score(0), bt.branch_count(0)) == (19, 23713)
@@ -245,6 +246,57 @@ def test_batch_config4_shard(oracle, nwb):
         o = oracle.fill(tops[i], sides[i], 1, 1, 1, want_packed=True, pitch=128)
         assert bt.opt_score(i) == o.final_score and bt.branch_count(i) == o.branch_count
         assert np.array_equal(bt.arrow_rows(i) & 0x77, o.packed)
+    bt.close()
+
+
+def _batch_check(oracle, nwb, bt, tops, sides, m, k, d, sample):
+    for i in sample:
+        t, s = tops[i], sides[i]
+        o = oracle.fill(t, s, m, k, d, want_packed=True, pitch=max(1, (len(t) + 255) // 256) * 128)
+        assert bt.opt_score(i) == o.final_score, (i, len(t), len(s))
+        assert bt.branch_count(i) == o.branch_count, (i, len(t), len(s))
+        if len(t) and len(s):
+            nb = (len(t) + 1) // 2
+            got = bt.arrow_rows(i)[:, :nb] & 0x77
+            if len(t) & 1:
+                got[:, nb - 1] &= 0x07
+            assert np.array_equal(got, o.packed[:, :nb]), (i, len(t), len(s))
+
+
+def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
+    """csrc/nwb_batch_bx.cuh: top strings of at most 256 characters, ragged partners sharing a warp,
+    empty strings, an odd number of pairs, more pair-pairs than warps; and the same batch through the
+    one-pair-per-warp kernel (NWB_BATCH_BX=0)."""
+    rng = random.Random(29)
+    lens = [(256, 256), (1, 1), (255, 257), (3, 40), (17, 130), (0, 5), (200, 90), (64, 64), (256, 1), (33, 33),
+            (256, 31), (100, 300), (5, 0), (8, 32), (9, 33), (249, 63), (250, 64), (7, 65), (1, 200), (256, 2),
+            (0, 0), (31, 31), (130, 95), (96, 128), (256, 1000)] + \
+           [(rng.randint(1, 256), rng.randint(1, 400)) for _ in range(4000)]
+    for alpha, schemes in ((b"ACGT", ((1, 1, 1), (0, 0, 0))), (bytes(range(1, 256)), ((2, 1, 2), (1, 1, 3)))):
+        tops = [bytes(rng.choice(alpha) for _ in range(a)) for a, _ in lens]
+        sides = [bytes(rng.choice(alpha) for _ in range(b)) for _, b in lens]
+        sample = list(range(25)) + rng.sample(range(25, len(lens)), 120) + [len(lens) - 1]
+        for m, k, d in schemes:
+            bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+            assert bt.kernel_name() == "nwb_batch_bx_kernel"
+            bt.run()
+            bt.fetch()
+            _batch_check(oracle, nwb, bt, tops, sides, m, k, d, sample)
+            scores = [bt.opt_score(i) for i in range(len(lens))]
+            branches = [bt.branch_count(i) for i in range(len(lens))]
+            bt.close()
+            monkeypatch.setenv("NWB_BATCH_BX", "0")
+            b0 = nwb.Batch(tops, sides, m, k, d, 0)
+            monkeypatch.delenv("NWB_BATCH_BX")
+            assert b0.kernel_name() == "nwb_batch_pk_kernel"
+            b0.run()
+            b0.fetch()
+            assert scores == [b0.opt_score(i) for i in range(len(lens))]
+            assert branches == [b0.branch_count(i) for i in range(len(lens))]
+            b0.close()
+    # 2d + m = 8 does not fit a nibble: the one-pair-per-warp kernel takes the batch
+    bt = nwb.Batch(tops[:4], sides[:4], 2, 1, 3, 0)
+    assert bt.kernel_name() == "nwb_batch_pk_kernel"
     bt.close()
 
 

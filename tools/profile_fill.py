@@ -44,7 +44,7 @@ if args.batch:
         bt.run()
         bt.fetch()
         ms = bt.kernel_ms()
-        print(f"rep {r}: batch {n} x {a}x{b} kernel_ms={ms:.3f} GCUPS={n * a * b / ms / 1e6:.1f} "
+        print(f"rep {r}: {bt.kernel_name()} batch {n} x {a}x{b} kernel_ms={ms:.3f} GCUPS={n * a * b / ms / 1e6:.1f} "
               f"score0={bt.opt_score(0)} branches0={bt.branch_count(0)}", flush=True)
     bt.close()
     sys.exit(0)
