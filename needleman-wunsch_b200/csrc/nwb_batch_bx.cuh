@@ -29,6 +29,9 @@
 #pragma once
 #include "nwb_fill_hx.cuh"
 #include "nwb_batch.cuh"
+#ifndef NWB_EMU
+#include <cuda_fp16.h>
+#endif
 
 #define NWB_BX_WARPS 12
 #define NWB_BX_MAX_A 256
@@ -45,30 +48,55 @@ static inline bool nwb_bx_usable(const NwbPkConsts &pc, long long max_A, int max
     return nwb_hx_supported(pc) && max_A <= NWB_BX_MAX_A && NWB_BX_SMEM_PER_WARP(max_B) <= 220 * 1024;
 }
 
+/* Characters travel as fp16 bit patterns 0x3C00 + c (1.0 + c/1024: distinct normal numbers), rows outside a
+ * table as 0xFFFF (a NaN: equal to nothing), so that one HSET2.EQ on the half-precision pipe -- not the ALU pipe
+ * the DPX instructions and the bit logic compete for -- yields 0xFFFF / 0 per pair, and one LOP3 selects
+ * a_match / a_mis from it. */
+#define NWB_BX_CHAR(c) (0x3C00u + (unsigned)(c))
+#define NWB_BX_NOCHAR 0xFFFFu
+__device__ __forceinline__ unsigned nwb_bx_eq_mask(const unsigned x, const unsigned y)
+{
+#ifdef NWB_EMU
+    unsigned m = 0u;
+    for (int h = 0; h < 2; h++) {
+        const unsigned a = (x >> (16 * h)) & 0xFFFFu, b = (y >> (16 * h)) & 0xFFFFu;
+        const bool nan_a = (a & 0x7C00u) == 0x7C00u && (a & 0x03FFu), nan_b = (b & 0x7C00u) == 0x7C00u && (b & 0x03FFu);
+        const bool zero = !(a & 0x7FFFu) && !(b & 0x7FFFu);
+        if (!nan_a && !nan_b && (a == b || zero)) m |= 0xFFFFu << (16 * h);
+    }
+    return m;
+#else
+    return __heq2_mask(*reinterpret_cast<const __half2 *>(&x), *reinterpret_cast<const __half2 *>(&y));
+#endif
+}
+
 struct NwbBxState {
-    unsigned tpw[8]; /* pre-shifted top characters of my 8 columns (pair 2q | pair 2q+1)       */
+    unsigned tpw[8]; /* top characters of my 8 columns as fp16 patterns (pair 2q | pair 2q+1)   */
     unsigned u[8];   /* u of my columns in the row above                                        */
     unsigned send;   /* v of my last column in the row I just finished (rows above row 1: BIG) */
     unsigned nu_a;   /* u of columns 0..3 / 4..7 in the row above, one nibble per column       */
     unsigned nu_b;
 };
 
-/* One step of one lane: row j = t - lane + 1 of both pairs, 8 cells each.  sp = ~(side char << shift) of
- * row j (pair 2q | pair 2q+1).  roff = word offset of row j's slot in the rings.  EDGE: j may lie outside
- * either table. */
-template <bool EDGE>
+/* One step of one lane: row j = t - lane + 1 of both pairs, 8 cells each.  sp = the side characters of
+ * row j as fp16 patterns (pair 2q | pair 2q+1).  roff = byte offset of row j's slot in the rings.
+ * MODE 0: every lane is strictly inside both tables (1 <= j < B);  MODE 1: the first steps of a pair of
+ * pairs, `live` = this lane has reached row 1 (j <= 0 otherwise; j < B for every lane);  MODE 2: j may lie
+ * anywhere -- row masks for the branch counter and the capture of the bottom row. */
+template <int MODE>
 __device__ __forceinline__ void nwb_bx_step(NwbBxState &st, const NwbPkConsts &pc, const int lane, const unsigned sp,
-                                             unsigned *ring_l, unsigned &roff, const unsigned cm_a, const unsigned cm_b,
-                                             const int j, const int B0, const int B1, const int na0, const int na1,
+                                             const nwb_smem_addr ring_l, unsigned &roff, unsigned cm_a, unsigned cm_b,
+                                             const bool live, const int j, const int B0, const int B1,
                                              unsigned &br0, unsigned &br1, unsigned &rs0, unsigned &rs1)
 {
-    unsigned v = __shfl_up_sync(NWB_FULL_MASK, st.send, 1);
-    if (lane == 0) v = 0u; /* column 0: r(0,j) = 0 */
+    const unsigned nl0 = lane ? 1u : 0u;
+    const unsigned AM = pc.TT1 - 0x00010001u; /* a_match in both halves */
+    unsigned v = __shfl_up_sync(NWB_FULL_MASK, st.send, 1) * nl0; /* lane 0: column 0, r(0,j) = 0 */
     unsigned z[8], a[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const unsigned nx = st.tpw[k] ^ sp;                 /* -1 per half on a match  */
-        a[k] = __viaddmax_s16x2(nx, pc.TT1, pc.AMIS);       /* a_match or a_mis        */
+        const unsigned eq = nwb_bx_eq_mask(st.tpw[k], sp);  /* 0xFFFF per half on a match */
+        a[k] = (eq & AM) | (~eq & pc.AMIS);                 /* a_match or a_mis           */
         z[k] = __vimax3_s16x2(a[k], v, st.u[k]);
         const unsigned un = z[k] - v;
         const unsigned vn = z[k] - st.u[k];
@@ -92,26 +120,30 @@ __device__ __forceinline__ void nwb_bx_step(NwbBxState &st, const NwbPkConsts &p
     unsigned ta, tb;
     const unsigned ca = nwb_hx_code(p1a, zva, ta);
     const unsigned cb = nwb_hx_code(p1b, zvb, tb);
-    ring_l[roff] = __byte_perm(ca, cb, 0x5410);                      /* pair 2q:   my 8 cells of row j */
-    ring_l[roff + NWB_BX_RING_WORDS] = __byte_perm(ca, cb, 0x7632);  /* pair 2q+1                      */
-    roff = (roff + 32u) & (unsigned)(NWB_BX_RING_WORDS - 1);
-    ta &= cm_a;
-    tb &= cm_b;
-    if (EDGE) {
+    nwb_sts<uint32_t>(ring_l + roff, 0, __byte_perm(ca, cb, 0x5410));                     /* pair 2q: my 8 cells of row j */
+    nwb_sts<uint32_t>(ring_l + roff, NWB_BX_RING_WORDS * 4, __byte_perm(ca, cb, 0x7632)); /* pair 2q+1                    */
+    roff = (roff + 128u) & (unsigned)(NWB_BX_RING_WORDS * 4 - 1);
+    if (MODE == 1) {
+        cm_a = live ? cm_a : 0u;
+        cm_b = live ? cm_b : 0u;
+    }
+    if (MODE == 2) {
         unsigned rm = 0u;
         if ((unsigned)(j - 1) < (unsigned)B0) rm |= 0x0000FFFFu;
         if ((unsigned)(j - 1) < (unsigned)B1) rm |= 0xFFFF0000u;
-        ta &= rm;
-        tb &= rm;
-        /* bottom row of a pair: r(A,B) = sum_i u(i,B) over the pair's columns */
+        /* bottom row of a pair: r(A,B) = sum_i u(i,B) over the pair's columns, from the nibble words */
         if (j >= 1 && (j == B0 || j == B1)) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (j == B0 && k < na0) rs0 += st.u[k] & 0xFFFFu;
-                if (j == B1 && k < na1) rs1 += st.u[k] >> 16;
-            }
+            const unsigned xa = NUa & ((cm_a >> 3) * 15u), xb = NUb & ((cm_b >> 3) * 15u);
+            unsigned sb = (xa & 0x0F0F0F0Fu) + ((xa >> 4) & 0x0F0F0F0Fu) + (xb & 0x0F0F0F0Fu) + ((xb >> 4) & 0x0F0F0F0Fu);
+            sb = (sb & 0x00FF00FFu) + ((sb >> 8) & 0x00FF00FFu);
+            if (j == B0) rs0 += sb & 0xFFFFu;
+            if (j == B1) rs1 += sb >> 16;
         }
+        cm_a &= rm;
+        cm_b &= rm;
     }
+    ta &= cm_a;
+    tb &= cm_b;
     br0 += (unsigned)__popc(__byte_perm(ta, tb, 0x5410));
     br1 += (unsigned)__popc(__byte_perm(ta, tb, 0x7632));
 }
@@ -140,7 +172,7 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
     const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_BX_SMEM_PER_WARP(bp.max_B));
     unsigned *sidew = ring + 2 * NWB_BX_RING_WORDS;
-    unsigned *ring_l = ring + lane;
+    const nwb_smem_addr ring_l = nwb_smem_address(reinterpret_cast<unsigned char *>(ring + lane));
     const unsigned *side_l = sidew + NWB_BX_SPADF + 1 - lane; /* side_l[t] = the word of my row at step t */
 
     for (long long q = gwarp; 2 * q < bp.n_pairs; q += nwarps) {
@@ -173,9 +205,9 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
         const int nwords = Bmax + NWB_BX_SPADF + NWB_BX_STAIL;
         for (int e = lane; e < nwords; e += 32) {
             const int j = e - NWB_BX_SPADF;
-            unsigned lo = 0xFFFFu, hi = 0xFFFFu;
-            if (j >= 1 && j <= B0) lo = (~((unsigned)bp.sides[s0o + j - 1] << pc.shift)) & 0xFFFFu;
-            if (j >= 1 && j <= B1) hi = (~((unsigned)bp.sides[s1o + j - 1] << pc.shift)) & 0xFFFFu;
+            unsigned lo = NWB_BX_NOCHAR, hi = NWB_BX_NOCHAR;
+            if (j >= 1 && j <= B0) lo = NWB_BX_CHAR(bp.sides[s0o + j - 1]);
+            if (j >= 1 && j <= B1) hi = NWB_BX_CHAR(bp.sides[s1o + j - 1]);
             sidew[e] = lo | (hi << 16);
         }
         NwbBxState st;
@@ -188,7 +220,7 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
         for (int k = 0; k < 8; k++) {
             const unsigned lo = (k < na0) ? (unsigned)bp.tops[t0o + c0 + k] : 0u;
             const unsigned hi = (k < na1) ? (unsigned)bp.tops[t1o + c0 + k] : 0u;
-            st.tpw[k] = (lo << pc.shift) | ((hi << pc.shift) << 16);
+            st.tpw[k] = NWB_BX_CHAR(lo) | (NWB_BX_CHAR(hi) << 16);
             st.u[k] = 0u;
             const unsigned bit = 8u << (4 * (k & 3));
             const unsigned m = ((k < na0) ? bit : 0u) | ((k < na1) ? (bit << 16) : 0u);
@@ -201,16 +233,22 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
         uint8_t *tab0 = bp.arrows + bp.arrow_off[p0];
         uint8_t *tab1 = have1 ? bp.arrows + bp.arrow_off[p1] : tab0;
         unsigned br0 = 0u, br1 = 0u, rs0 = 0u, rs1 = 0u;
-        unsigned roff = (unsigned)((1 - lane) & (NWB_BX_RING_ROWS - 1)) * 32u; /* slot of row 1 - lane */
+        unsigned roff = (unsigned)((1 - lane) & (NWB_BX_RING_ROWS - 1)) * 128u; /* slot of row 1 - lane */
         __syncwarp();
 
         int flushed = 0;
         const int nsteps = Bmax + 31; /* lane 31 finishes row Bmax at step Bmax + 30 */
         int t = 0;
-        /* head: steps 0 .. 30, lanes l > t are still above row 1 */
+        /* head: steps 0 .. 30, lanes l > t are still above row 1 (lane 0 reaches row 31) */
+        if (Bmin > 31) {
 #pragma unroll 1
-        for (; t < 31; t++)
-            nwb_bx_step<true>(st, pc, lane, side_l[t], ring_l, roff, cm_a, cm_b, t - lane + 1, B0, B1, na0, na1, br0, br1, rs0, rs1);
+            for (; t < 31; t++)
+                nwb_bx_step<1>(st, pc, lane, side_l[t], ring_l, roff, cm_a, cm_b, t >= lane, 0, B0, B1, br0, br1, rs0, rs1);
+        } else {
+#pragma unroll 1
+            for (; t < 31; t++)
+                nwb_bx_step<2>(st, pc, lane, side_l[t], ring_l, roff, cm_a, cm_b, true, t - lane + 1, B0, B1, br0, br1, rs0, rs1);
+        }
         while (t < nsteps) {
             /* steps t .. t+31: lane 0 reaches row t + 32, lane 31 starts at row t - 30 >= 1 */
             if (t + 32 < Bmin) {
@@ -221,13 +259,13 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
                     for (int i = 0; i < 8; i++) sw[i] = side_l[t + 8 * sub + i];
 #pragma unroll
                     for (int i = 0; i < 8; i++)
-                        nwb_bx_step<false>(st, pc, lane, sw[i], ring_l, roff, cm_a, cm_b, 0, B0, B1, na0, na1, br0, br1, rs0, rs1);
+                        nwb_bx_step<0>(st, pc, lane, sw[i], ring_l, roff, cm_a, cm_b, true, 0, B0, B1, br0, br1, rs0, rs1);
                 }
             } else {
 #pragma unroll 1
                 for (int i = 0; i < 32; i++)
-                    nwb_bx_step<true>(st, pc, lane, side_l[t + i], ring_l, roff, cm_a, cm_b, t + i - lane + 1, B0, B1, na0, na1,
-                                      br0, br1, rs0, rs1);
+                    nwb_bx_step<2>(st, pc, lane, side_l[t + i], ring_l, roff, cm_a, cm_b, true, t + i - lane + 1, B0, B1,
+                                   br0, br1, rs0, rs1);
             }
             t += 32;
             /* rows <= t - 31 are complete in every lane */
