@@ -186,10 +186,11 @@ def run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) -> dict | 
     if rank == 0:
         ok4 = (bt.opt_score(0), bt.branch_count(0), bt.opt_score(1), bt.branch_count(1)) == (19, 23713, 29, 22912)
     kms = bt.kernel_ms()
+    kname4 = bt.kernel_name()
     bt.close()
     out["config4_batch"] = {"pairs_total": per * world, "pairs_per_gpu": per, "ms_per_pass": ms,
-                            "gcups_total": per * world * 65536 / (ms * 1e-3) / 1e9, "fill_kernel_ms": kms,
-                            "includes": "fill + per-pair branch-count pass, strings and 4.1 GB of arrow tables resident",
+                            "gcups_total": per * world * 65536 / (ms * 1e-3) / 1e9, "fill_kernel_ms": kms, "kernel": kname4,
+                            "includes": "fill + per-pair branch counter, strings and 4.1 GB of arrow tables resident",
                             "golden_pairs_ok": bool(ok4), "scaling": "weak (125,000 pairs per GPU; 8 GPUs = the 1M-pair config)"}
     if rank != 0:
         return None

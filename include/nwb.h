@@ -241,8 +241,10 @@ uint64_t nwb_batch_count_u64(const nwb_batch *b, int64_t pair);
 const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair, size_t *pitch);
 float nwb_batch_kernel_ms(const nwb_batch *b);
 int64_t nwb_batch_launches(const nwb_batch *b);
-/* Name of the kernel nwb_batch_run() launches for this batch ("nwb_batch_bx_kernel": two pairs per warp, top
- * strings of at most 256 characters and 2d + m <= 7; "nwb_batch_pk_kernel" otherwise): for logs and profiles. */
+/* Name of the kernel nwb_batch_run() launches for this batch: "nwb_batch_bx_kernel" (two pairs per warp: top
+ * strings of at most 256 characters and 2d + m <= 7), "nwb_batch_cx_kernel" (the same, pairs swept back to back:
+ * every pair has the same shape and the side length is a multiple of 32), "nwb_batch_pk_kernel" otherwise.
+ * For logs and profiles. */
 const char *nwb_batch_kernel_name(const nwb_batch *b);
 void *nwb_batch_arrows_device(nwb_batch *b);
 

@@ -8,6 +8,9 @@ struct nwb_batch {
     int max_B = 0, max_strips = 1;
     long long max_A = 0;
     bool use_bx = false; /* two pairs per warp (nwb_batch_bx.cuh) */
+    bool use_cx = false; /* ... swept back to back: every pair has the same shape */
+    bool uniform = true;
+    long long uni_A = -1, uni_B = -1;
     NwbPkConsts pc = {};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -73,6 +76,8 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
         if (ns > b->max_strips) b->max_strips = ns;
         if ((int)B > b->max_B) b->max_B = (int)B;
         if (A > b->max_A) b->max_A = A;
+        if (p == 0) { b->uni_A = A; b->uni_B = B; }
+        else if (A != b->uni_A || B != b->uni_B) b->uniform = false;
         b->h_arrow_off[(size_t)p] = aoff;
         aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
     }
@@ -83,6 +88,8 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
          * one-pair-per-warp kernel (diagnostics) */
         const char *e = getenv("NWB_BATCH_BX");
         b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && !(e && atoi(e) == 0);
+        const char *ec = getenv("NWB_BATCH_CX");
+        b->use_cx = b->use_bx && n_pairs > 0 && nwb_cx_usable(pc, b->uniform, b->uni_A, (int)b->uni_B) && !(ec && atoi(ec) == 0);
     }
     if (!b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
@@ -126,6 +133,16 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
         bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
         bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p;
         bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
+        if (b->use_cx) {
+            const size_t smem = NWB_CX_SMEM_PER_WARP(b->max_B) * (size_t)NWB_BX_WARPS;
+            CK(cudaFuncSetAttribute(nwb_batch_cx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaEventRecord(b->ev0, st));
+            nwb_batch_cx_kernel<<<grid, 32 * NWB_BX_WARPS, smem, st>>>(bp, b->pc, (int)b->uni_A, (int)b->uni_B);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(b->ev1, st));
+            b->launches += 1;
+            return NWB_OK;
+        }
         const size_t smem = NWB_BX_SMEM_PER_WARP(b->max_B) * (size_t)warps;
         CK(cudaFuncSetAttribute(nwb_batch_bx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaEventRecord(b->ev0, st));
@@ -227,7 +244,7 @@ extern "C" float nwb_batch_kernel_ms(const nwb_batch *b)
 extern "C" const char *nwb_batch_kernel_name(const nwb_batch *b)
 {
     if (!b) return "";
-    return b->use_bx ? "nwb_batch_bx_kernel" : "nwb_batch_pk_kernel";
+    return b->use_cx ? "nwb_batch_cx_kernel" : (b->use_bx ? "nwb_batch_bx_kernel" : "nwb_batch_pk_kernel");
 }
 extern "C" int64_t nwb_batch_launches(const nwb_batch *b) { return b ? b->launches : 0; }
 extern "C" void *nwb_batch_arrows_device(nwb_batch *b) { return b ? (void *)b->arrows.p : nullptr; }

@@ -296,3 +296,209 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
         }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Uniform batches ("cx"): every pair is A x B with B a multiple of 32 (BASELINE config 4: 256 x 256).
+ *
+ * nwb_batch_bx_kernel drains its 32-lane anti-diagonal at the end of every pair of pairs and refills it for
+ * the next one: 31 + 32 of the 287 steps of a 256-row table run a checked body with half of the lanes idle.
+ * Here a warp sweeps its pairs of pairs BACK TO BACK as one tall table of n_q * B rows: lane l starts row 1 of
+ * the next pair of pairs in the step after it finished row B of the current one.  Row 1 needs nothing from the
+ * rows above but u = 0, so the hand-over is a per-lane reset at step n*B + l: capture sum_i u(i,B) and the
+ * branch counter of the finished pair of pairs, clear u, take the next top characters (prefetched into
+ * registers a whole table earlier).  Every step of every block runs the unchecked body; the 32 steps in which
+ * the lanes reset one after the other ("transition block") add a short divergent branch.  Side characters are
+ * double-buffered in shared memory (the next pair of pairs' words are written right after a transition block),
+ * arrow rows leave the rings in aligned groups of 32 rows, which never straddle two tables.
+ * --------------------------------------------------------------------------------------------------------- */
+#define NWB_CX_SMEM_PER_WARP(B) (2 * NWB_BX_RING_WORDS * 4 + (((size_t)(B) * 2 * 4 + 15) / 16) * 16)
+
+static inline bool nwb_cx_usable(const NwbPkConsts &pc, bool uniform, long long A, int B)
+{
+    return uniform && nwb_hx_supported(pc) && A >= 1 && A <= NWB_BX_MAX_A && B >= 64 && B % 32 == 0 &&
+           NWB_CX_SMEM_PER_WARP(B) <= 220 * 1024 / NWB_BX_WARPS;
+}
+
+__device__ __forceinline__ unsigned nwb_warp_sum(unsigned x)
+{
+#ifdef NWB_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(NWB_FULL_MASK, x, o);
+    return x;
+#else
+    return __reduce_add_sync(NWB_FULL_MASK, x);
+#endif
+}
+
+__global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_cx_kernel(const NwbBatchParams bp, const NwbPkConsts pc,
+                                                                             const int A, const int B)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long NQ = (bp.n_pairs + 1) / 2; /* pairs of pairs in the batch */
+    if (gwarp >= NQ) return;
+    const int n_q = (int)((NQ - gwarp + nwarps - 1) / nwarps); /* ... in this warp's chain */
+    unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_CX_SMEM_PER_WARP(B));
+    unsigned *sidew = ring + 2 * NWB_BX_RING_WORDS; /* [2][B]: chain element n reads buffer n & 1 */
+    const nwb_smem_addr ring_l = nwb_smem_address(reinterpret_cast<unsigned char *>(ring + lane));
+    const size_t tab_bytes = (size_t)128 * (size_t)B;
+
+    int na = A - 8 * lane;
+    na = na < 0 ? 0 : (na > 8 ? 8 : na);
+    unsigned cm_a = 0u, cm_b = 0u; /* bit 3 of the nibbles whose column is inside the tables (both halves) */
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned bit = (k < na) ? ((8u << (4 * (k & 3))) * 0x00010001u) : 0u;
+        if (k < 4) cm_a |= bit;
+        else cm_b |= bit;
+    }
+    const unsigned nm_a = (cm_a >> 3) * 15u, nm_b = (cm_b >> 3) * 15u; /* the same as whole nibbles */
+
+    /* pairs of chain element n; a missing partner (odd batch) is swept as a copy of the first pair and dropped */
+    auto pair_of = [&](const int n, long long &p0, long long &p1) -> bool {
+        const long long q = gwarp + (long long)n * nwarps;
+        p0 = 2 * q;
+        p1 = 2 * q + 1;
+        const bool have1 = p1 < bp.n_pairs;
+        if (!have1) p1 = p0;
+        return have1;
+    };
+    auto load_tops = [&](const int n, unsigned (&tn)[8]) {
+        long long p0, p1;
+        pair_of(n, p0, p1);
+        const uint8_t *t0 = bp.tops + bp.top_off[p0] + 8 * lane, *t1 = bp.tops + bp.top_off[p1] + 8 * lane;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned lo = (k < na) ? (unsigned)t0[k] : 0u, hi = (k < na) ? (unsigned)t1[k] : 0u;
+            tn[k] = NWB_BX_CHAR(lo) | (NWB_BX_CHAR(hi) << 16);
+        }
+    };
+    auto write_sides = [&](const int n) {
+        long long p0, p1;
+        pair_of(n, p0, p1);
+        const uint8_t *s0 = bp.sides + bp.side_off[p0], *s1 = bp.sides + bp.side_off[p1];
+        unsigned *dst = sidew + (n & 1) * B;
+#pragma unroll 4
+        for (int r = lane; r < B; r += 32) dst[r] = NWB_BX_CHAR(s0[r]) | (NWB_BX_CHAR(s1[r]) << 16);
+    };
+
+    NwbBxState st;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        st.tpw[k] = NWB_BX_CHAR(0) * 0x00010001u;
+        st.u[k] = 0u;
+    }
+    st.send = 0u;
+    st.nu_a = 0u;
+    st.nu_b = 0u;
+    unsigned tn[8];
+    load_tops(0, tn);
+    write_sides(0);
+    unsigned br0 = 0u, br1 = 0u, rs0 = 0u, rs1 = 0u; /* rs*: unused by the unchecked step */
+    unsigned roff = (unsigned)((1 - lane) & (NWB_BX_RING_ROWS - 1)) * 128u; /* slot of virtual row 1 - lane */
+    __syncwarp();
+
+    const int nb = B / 32;
+    int flushed = 0; /* virtual rows 1 .. flushed are in memory */
+    int t = 0;       /* steps done */
+    auto flush_to = [&](const int upto) { /* whole groups of 32 virtual rows; a group lies inside one table */
+        __syncwarp();
+        while (flushed < upto) {
+            const int n = flushed / B;
+            long long p0, p1;
+            const bool have1 = pair_of(n, p0, p1);
+            const int r0 = flushed - n * B; /* local rows r0+1 .. r0+32 */
+            uint8_t *tab0 = bp.arrows + (size_t)p0 * tab_bytes, *tab1 = bp.arrows + (size_t)p1 * tab_bytes;
+            const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const int lr = r0 + 4 * g + sub; /* local row - 1 */
+                const unsigned *src = ring + ((flushed + 4 * g + sub + 1) & (NWB_BX_RING_ROWS - 1)) * 32 + chunk * 4;
+                const size_t dst = (size_t)lr * 128 + (size_t)chunk * 16;
+                const uint4 w0 = *reinterpret_cast<const uint4 *>(src);
+                const uint4 w1 = *reinterpret_cast<const uint4 *>(src + NWB_BX_RING_WORDS);
+                *reinterpret_cast<uint4 *>(tab0 + dst) = w0;
+                if (have1) *reinterpret_cast<uint4 *>(tab1 + dst) = w1;
+            }
+            flushed += 32;
+        }
+        __syncwarp();
+    };
+
+    for (int n = 0; n <= n_q; n++) {
+        /* ---- transition block: steps n*B .. n*B+31, lane l moves on to chain element n at step n*B + l ---- */
+        const unsigned *bufn = sidew + (n & 1) * B, *bufp = sidew + ((n + 1) & 1) * B;
+        unsigned rc0 = 0u, rc1 = 0u, bc0 = 0u, bc1 = 0u;
+#pragma unroll 1
+        for (int i = 0; i < 32; i++) {
+            const int li = i - lane; /* my row of element n, minus 1; negative: still in element n - 1 */
+            const unsigned sp = (li >= 0) ? bufn[li] : bufp[B + li];
+            if (li == 0) {
+                /* my last row of element n - 1 is behind me: r(A,B) = sum_i u(i,B), from the nibble words */
+                const unsigned xa = st.nu_a & nm_a, xb = st.nu_b & nm_b;
+                unsigned sb = (xa & 0x0F0F0F0Fu) + ((xa >> 4) & 0x0F0F0F0Fu) + (xb & 0x0F0F0F0Fu) + ((xb >> 4) & 0x0F0F0F0Fu);
+                sb = (sb & 0x00FF00FFu) + ((sb >> 8) & 0x00FF00FFu);
+                rc0 = sb & 0xFFFFu;
+                rc1 = sb >> 16;
+                bc0 = br0;
+                bc1 = br1;
+                br0 = 0u;
+                br1 = 0u;
+                st.nu_a = 0u;
+                st.nu_b = 0u;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    st.u[k] = 0u; /* row 0 of the new tables: r(i,0) = 0 */
+                    st.tpw[k] = tn[k];
+                }
+            }
+            nwb_bx_step<0>(st, pc, lane, sp, ring_l, roff, cm_a, cm_b, true, 0, B, B, br0, br1, rs0, rs1);
+        }
+        t += 32;
+        flush_to(t - 32);
+        if (n >= 1) { /* element n - 1 is complete in every lane */
+            rc0 = nwb_warp_sum(rc0);
+            rc1 = nwb_warp_sum(rc1);
+            bc0 = nwb_warp_sum(bc0);
+            bc1 = nwb_warp_sum(bc1);
+            long long p0, p1;
+            const bool have1 = pair_of(n - 1, p0, p1);
+            if (lane == 0) {
+                /* score(A,B) = sum_i u(i,B) - d*(A+B) */
+                const unsigned off = (unsigned)bp.d * (unsigned)(A + B);
+                bp.out_score[p0] = (int)(rc0 - off);
+                if (bp.out_branch) bp.out_branch[p0] = bc0;
+                if (have1) {
+                    bp.out_score[p1] = (int)(rc1 - off);
+                    if (bp.out_branch) bp.out_branch[p1] = bc1;
+                }
+            }
+        }
+        if (n == n_q) break;
+        if (n + 1 < n_q) {
+            write_sides(n + 1); /* its buffer was last read in the transition block that just ended */
+            load_tops(n + 1, tn);
+        }
+        __syncwarp();
+        /* ---- the rest of element n: every lane strictly inside the tables ---- */
+        const unsigned *side_l = bufn + 32 - lane; /* side_l[s] = my row's word at step n*B + 32 + s */
+#pragma unroll 1
+        for (int blk = 1; blk < nb; blk++) {
+#pragma unroll 1
+            for (int sub = 0; sub < 4; sub++) {
+                unsigned sw[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) sw[i] = side_l[i];
+                side_l += 8;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    nwb_bx_step<0>(st, pc, lane, sw[i], ring_l, roff, cm_a, cm_b, true, 0, B, B, br0, br1, rs0, rs1);
+            }
+            t += 32;
+            flush_to(t - 32);
+        }
+    }
+    flush_to(n_q * B);
+}

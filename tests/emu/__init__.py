@@ -131,7 +131,8 @@ def fill_pk_rank(top, side, m, k, d, *, rank, world, inbox=None, hx=True, grid=2
 
 def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1):
     """Run the batch kernel under the emulator.  bx: 0 = nwb_batch_pk_kernel (one pair per warp), 1 =
-    nwb_batch_bx_kernel (two pairs per warp), -1 = the library's own choice; the result's "bx" says which ran."""
+    nwb_batch_bx_kernel (two pairs per warp), 2 = nwb_batch_cx_kernel (uniform shapes, pairs back to back),
+    -1 = the library's own choice; the result's "kernel" says which ran ("pk", "bx", "cx")."""
     n = len(tops)
     toff = np.zeros(n + 1, np.int64)
     soff = np.zeros(n + 1, np.int64)
@@ -156,7 +157,7 @@ def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1):
     for i in range(n):
         pitch = max(1, (len(tops[i]) + 255) // 256) * 128
         tabs.append(arrows[aoff[i]:aoff[i] + pitch * len(sides[i])].reshape(len(sides[i]), pitch))
-    return dict(scores=scores, branches=branches, tables=tabs, bx=bool(used.value))
+    return dict(scores=scores, branches=branches, tables=tabs, bx=used.value >= 1, kernel=("pk", "bx", "cx")[used.value])
 
 
 def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:

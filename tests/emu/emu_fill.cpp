@@ -329,7 +329,8 @@ int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int
 
 /* batch kernel under the emulator: arrows = concatenated per-pair tables (offsets returned in arrow_off) */
 /* bx: 0 = nwb_batch_pk_kernel (one pair per warp), 1 = nwb_batch_bx_kernel (two pairs per warp; -6 when the
- * batch does not qualify), -1 = whatever nwb_batch_run() would pick.  *used_bx reports the choice. */
+ * batch does not qualify), 2 = nwb_batch_cx_kernel (uniform shapes, pairs back to back; -6 likewise), -1 =
+ * whatever nwb_batch_run() would pick.  *used_bx reports the choice (0, 1 or 2). */
 int emu_fill_batch(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
                    long long n, int m, int k, int d, unsigned grid, int bx, uint8_t *arrows, long long *arrow_off,
                    int *scores, unsigned *branches, int *used_bx)
@@ -353,14 +354,25 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
     for (long long p = 0; p < n; p++)
         if (top_off[p + 1] - top_off[p] > maxA) maxA = top_off[p + 1] - top_off[p];
     const bool can_bx = nwb_bx_usable(pc, maxA, maxB);
-    if (bx == 1 && !can_bx) return -6;
+    bool uniform = n > 0;
+    for (long long p = 1; p < n; p++)
+        if (top_off[p + 1] - top_off[p] != top_off[1] - top_off[0] || side_off[p + 1] - side_off[p] != side_off[1] - side_off[0])
+            uniform = false;
+    const bool can_cx = can_bx && n > 0 && nwb_cx_usable(pc, uniform, top_off[1] - top_off[0], (int)(side_off[1] - side_off[0]));
+    if ((bx == 1 && !can_bx) || (bx == 2 && !can_cx)) return -6;
+    const bool use_cx = (bx == 2 || bx == -1) && can_cx;
     const bool use_bx = (bx != 0) && can_bx;
-    if (used_bx) *used_bx = use_bx ? 1 : 0;
+    if (used_bx) *used_bx = use_cx ? 2 : (use_bx ? 1 : 0);
     if (use_bx) {
         bp.tops = (const uint8_t *)tops; bp.top_off = top_off; bp.sides = (const uint8_t *)sides; bp.side_off = side_off;
         bp.n_pairs = n; bp.m = m; bp.k = k; bp.d = d; bp.max_B = maxB;
         bp.arrows = arrows; bp.arrow_off = arrow_off; bp.out_score = scores; bp.out_branch = branches;
-        emu_launch(grid, 32 * NWB_BX_WARPS, NWB_BX_SMEM_PER_WARP(maxB) * NWB_BX_WARPS, [&]() { nwb_batch_bx_kernel(bp, pc); });
+        if (use_cx) {
+            const int A = (int)(top_off[1] - top_off[0]), B = (int)(side_off[1] - side_off[0]);
+            emu_launch(grid, 32 * NWB_BX_WARPS, NWB_CX_SMEM_PER_WARP(B) * NWB_BX_WARPS, [&]() { nwb_batch_cx_kernel(bp, pc, A, B); });
+        } else {
+            emu_launch(grid, 32 * NWB_BX_WARPS, NWB_BX_SMEM_PER_WARP(maxB) * NWB_BX_WARPS, [&]() { nwb_batch_bx_kernel(bp, pc); });
+        }
         return 0;
     }
     const long long nwarps = (long long)grid * NWB_BATCH_WARPS;

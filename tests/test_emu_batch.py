@@ -86,3 +86,41 @@ def test_bx_is_the_default_when_it_applies(oracle):
     assert list(a["scores"]) == list(b["scores"]) and list(a["branches"]) == list(b["branches"])
     for x, y, top in zip(a["tables"], b["tables"], (t, s)):
         assert np.array_equal(emu.unpack_arrows(x, len(top)) & 7, emu.unpack_arrows(y, len(top)) & 7)
+
+
+# ---- uniform shapes: pairs swept back to back (nwb_batch_cx_kernel) --------------------------------------
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("a,b,n,grid", [(256, 256, 3, 1), (40, 64, 61, 1), (100, 96, 50, 2), (8, 128, 27, 1), (1, 64, 26, 1),
+                                        (255, 64, 49, 1), (9, 160, 30, 1)])
+def test_cx_uniform_chains(oracle, a, b, n, grid):
+    # several pairs of pairs per warp (12 warps per block): resets, side double-buffering, aligned flush groups,
+    # odd batches (the last pair is swept with a copy of itself as partner)
+    rng = random.Random(a * 1000 + b + n)
+    for alpha, (m, k, d) in ((b"ACGT", (1, 1, 1)), (bytes(range(1, 256)), (2, 1, 2)), (b"AC", (0, 0, 0))):
+        tops = [bytes(rng.choice(alpha) for _ in range(a)) for _ in range(n)]
+        sides = [bytes(rng.choice(alpha) for _ in range(b)) for _ in range(n)]
+        r = emu.fill_batch(tops, sides, m, k, d, grid=grid, bx=2)
+        assert r["kernel"] == "cx"
+        for i, (t, s) in enumerate(zip(tops, sides)):
+            o = oracle.fill(t, s, m, k, d, want_codes=True)
+            assert r["scores"][i] == o.final_score, i
+            assert r["branches"][i] == o.branch_count, i
+            assert np.array_equal(emu.unpack_arrows(r["tables"][i], a) & 7, o.codes[1:, 1:] & 7), i
+
+
+def test_cx_config4_goldens_and_default(oracle):
+    tops, sides = [], []
+    for p in (0, 1, 999999):
+        t, s = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
+        tops.append(t)
+        sides.append(s)
+    r = emu.fill_batch(tops, sides, 1, 1, 1, grid=1)   # the library's own choice
+    assert r["kernel"] == "cx"
+    assert list(r["scores"]) == [19, 29, 19]
+    assert list(r["branches"]) == [23713, 22912, 22090]
+    # not uniform, or rows not a multiple of 32: the general two-pairs-per-warp kernel
+    assert emu.fill_batch(tops, [sides[0], sides[1], sides[2][:200]], 1, 1, 1)["kernel"] == "bx"
+    assert emu.fill_batch([t[:100] for t in tops], [s[:70] for s in sides], 1, 1, 1)["kernel"] == "bx"

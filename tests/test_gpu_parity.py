@@ -235,7 +235,7 @@ def test_batch_config4_shard(oracle, nwb):
     idx = list(range(n - 1)) + [999999]
     tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
     bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST)
-    assert bt.kernel_name() == "nwb_batch_bx_kernel"
+    assert bt.kernel_name() == "nwb_batch_cx_kernel"
     bt.run()
     bt.fetch()
     assert (bt.opt_score(0), bt.branch_count(0)) == (19, 23713)
@@ -298,6 +298,39 @@ def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
     bt = nwb.Batch(tops[:4], sides[:4], 2, 1, 3, 0)
     assert bt.kernel_name() == "nwb_batch_pk_kernel"
     bt.close()
+
+
+def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
+    """csrc/nwb_batch_bx.cuh nwb_batch_cx_kernel: uniform shapes, a warp sweeps its pairs of pairs back to back
+    (long chains: more pairs than 2 x 12 x 148 warps), odd batches, narrow and short tables; the same batches
+    through the drained two-pairs-per-warp kernel (NWB_BATCH_CX=0) must agree."""
+    rng = random.Random(31)
+    for a, b, n, alpha, (m, k, d) in ((256, 256, 12001, b"ACGT", (1, 1, 1)), (100, 96, 9000, bytes(range(1, 256)), (2, 1, 2)),
+                                      (7, 64, 20001, b"AC", (0, 0, 0)), (255, 160, 5000, b"ACGT", (1, 1, 3))):
+        tops = [bytes(rng.choice(alpha) for _ in range(a)) for _ in range(n)]
+        sides = [bytes(rng.choice(alpha) for _ in range(b)) for _ in range(n)]
+        bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+        assert bt.kernel_name() == "nwb_batch_cx_kernel"
+        bt.run()
+        bt.fetch()
+        sample = [0, 1, 2, n - 3, n - 2, n - 1] + rng.sample(range(n), 60)
+        _batch_check(oracle, nwb, bt, tops, sides, m, k, d, sample)
+        scores = [bt.opt_score(i) for i in range(n)]
+        branches = [bt.branch_count(i) for i in range(n)]
+        tabs = [bt.arrow_rows(i).copy() for i in sample]
+        bt.close()
+        monkeypatch.setenv("NWB_BATCH_CX", "0")
+        b0 = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+        monkeypatch.delenv("NWB_BATCH_CX")
+        assert b0.kernel_name() == "nwb_batch_bx_kernel"
+        b0.run()
+        b0.fetch()
+        assert scores == [b0.opt_score(i) for i in range(n)]
+        assert branches == [b0.branch_count(i) for i in range(n)]
+        nb = (a + 1) // 2
+        for i, tab in zip(sample, tabs):
+            assert np.array_equal(tab[:, :nb] & 0x77, b0.arrow_rows(i)[:, :nb] & 0x77)
+        b0.close()
 
 
 def test_count_prefix_property(oracle, nwb):
