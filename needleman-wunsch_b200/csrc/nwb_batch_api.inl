@@ -134,10 +134,14 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
         bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p;
         bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
         if (b->use_cx) {
-            const size_t smem = NWB_CX_SMEM_PER_WARP(b->max_B) * (size_t)NWB_BX_WARPS;
-            CK(cudaFuncSetAttribute(nwb_batch_cx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const char *ew = getenv("NWB_CX_WARPS"); /* diagnostics: 12 or 16 warps per SM */
+            const bool w16 = ew && atoi(ew) == 16 && nwb_cx_usable(b->pc, true, b->uni_A, (int)b->uni_B, 16);
+            const int cw = w16 ? 16 : NWB_BX_WARPS;
+            const size_t smem = NWB_CX_SMEM_PER_WARP(b->max_B, cw) * (size_t)cw;
+            auto kern = w16 ? nwb_batch_cx_kernel<16> : nwb_batch_cx_kernel<NWB_BX_WARPS>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaEventRecord(b->ev0, st));
-            nwb_batch_cx_kernel<<<grid, 32 * NWB_BX_WARPS, smem, st>>>(bp, b->pc, (int)b->uni_A, (int)b->uni_B);
+            kern<<<grid, 32 * cw, smem, st>>>(bp, b->pc, (int)b->uni_A, (int)b->uni_B);
             CK(cudaGetLastError());
             CK(cudaEventRecord(b->ev1, st));
             b->launches += 1;

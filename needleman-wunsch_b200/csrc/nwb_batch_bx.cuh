@@ -83,7 +83,7 @@ struct NwbBxState {
  * MODE 0: every lane is strictly inside both tables (1 <= j < B);  MODE 1: the first steps of a pair of
  * pairs, `live` = this lane has reached row 1 (j <= 0 otherwise; j < B for every lane);  MODE 2: j may lie
  * anywhere -- row masks for the branch counter and the capture of the bottom row. */
-template <int MODE>
+template <int MODE, int RING_ROWS = NWB_BX_RING_ROWS>
 __device__ __forceinline__ void nwb_bx_step(NwbBxState &st, const NwbPkConsts &pc, const int lane, const unsigned sp,
                                              const nwb_smem_addr ring_l, unsigned &roff, unsigned cm_a, unsigned cm_b,
                                              const bool live, const int j, const int B0, const int B1,
@@ -121,8 +121,13 @@ __device__ __forceinline__ void nwb_bx_step(NwbBxState &st, const NwbPkConsts &p
     const unsigned ca = nwb_hx_code(p1a, zva, ta);
     const unsigned cb = nwb_hx_code(p1b, zvb, tb);
     nwb_sts<uint32_t>(ring_l + roff, 0, __byte_perm(ca, cb, 0x5410));                     /* pair 2q: my 8 cells of row j */
-    nwb_sts<uint32_t>(ring_l + roff, NWB_BX_RING_WORDS * 4, __byte_perm(ca, cb, 0x7632)); /* pair 2q+1                    */
-    roff = (roff + 128u) & (unsigned)(NWB_BX_RING_WORDS * 4 - 1);
+    nwb_sts<uint32_t>(ring_l + roff, RING_ROWS * 128, __byte_perm(ca, cb, 0x7632));       /* pair 2q+1                    */
+    if ((RING_ROWS & (RING_ROWS - 1)) == 0) {
+        roff = (roff + 128u) & (unsigned)(RING_ROWS * 128 - 1);
+    } else {
+        roff += 128u;
+        if (roff == (unsigned)(RING_ROWS * 128)) roff = 0u;
+    }
     if (MODE == 1) {
         cm_a = live ? cm_a : 0u;
         cm_b = live ? cm_b : 0u;
@@ -311,12 +316,15 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_bx_kernel(cons
  * double-buffered in shared memory (the next pair of pairs' words are written right after a transition block),
  * arrow rows leave the rings in aligned groups of 32 rows, which never straddle two tables.
  * --------------------------------------------------------------------------------------------------------- */
-#define NWB_CX_SMEM_PER_WARP(B) (2 * NWB_BX_RING_WORDS * 4 + (((size_t)(B) * 2 * 4 + 15) / 16) * 16)
+/* WARPS = 12: rings of 64 rows, flushed every 32 steps; WARPS = 16: rings of 48 rows (32 rows of lane skew + 16),
+ * flushed every 16 steps, 128 registers per thread. */
+#define NWB_CX_RING_ROWS(WARPS) ((WARPS) == 16 ? 48 : 64)
+#define NWB_CX_SMEM_PER_WARP(B, WARPS) (2 * NWB_CX_RING_ROWS(WARPS) * 128 + (((size_t)(B) * 2 * 4 + 15) / 16) * 16)
 
-static inline bool nwb_cx_usable(const NwbPkConsts &pc, bool uniform, long long A, int B)
+static inline bool nwb_cx_usable(const NwbPkConsts &pc, bool uniform, long long A, int B, int warps = NWB_BX_WARPS)
 {
     return uniform && nwb_hx_supported(pc) && A >= 1 && A <= NWB_BX_MAX_A && B >= 64 && B % 32 == 0 &&
-           NWB_CX_SMEM_PER_WARP(B) <= 220 * 1024 / NWB_BX_WARPS;
+           NWB_CX_SMEM_PER_WARP(B, warps) * (size_t)warps <= 226 * 1024;
 }
 
 __device__ __forceinline__ unsigned nwb_warp_sum(unsigned x)
@@ -330,9 +338,12 @@ __device__ __forceinline__ unsigned nwb_warp_sum(unsigned x)
 #endif
 }
 
-__global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_cx_kernel(const NwbBatchParams bp, const NwbPkConsts pc,
-                                                                             const int A, const int B)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) nwb_batch_cx_kernel(const NwbBatchParams bp, const NwbPkConsts pc,
+                                                                      const int A, const int B)
 {
+    constexpr int RR = NWB_CX_RING_ROWS(WARPS); /* ring rows */
+    constexpr int BLK = RR - 32;                /* steps between flushes */
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -340,8 +351,8 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_cx_kernel(cons
     const long long NQ = (bp.n_pairs + 1) / 2; /* pairs of pairs in the batch */
     if (gwarp >= NQ) return;
     const int n_q = (int)((NQ - gwarp + nwarps - 1) / nwarps); /* ... in this warp's chain */
-    unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_CX_SMEM_PER_WARP(B));
-    unsigned *sidew = ring + 2 * NWB_BX_RING_WORDS; /* [2][B]: chain element n reads buffer n & 1 */
+    unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_CX_SMEM_PER_WARP(B, WARPS));
+    unsigned *sidew = ring + 2 * RR * 32; /* [2][B]: chain element n reads buffer n & 1 */
     const nwb_smem_addr ring_l = nwb_smem_address(reinterpret_cast<unsigned char *>(ring + lane));
     const size_t tab_bytes = (size_t)128 * (size_t)B;
 
@@ -397,32 +408,32 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_cx_kernel(cons
     load_tops(0, tn);
     write_sides(0);
     unsigned br0 = 0u, br1 = 0u, rs0 = 0u, rs1 = 0u; /* rs*: unused by the unchecked step */
-    unsigned roff = (unsigned)((1 - lane) & (NWB_BX_RING_ROWS - 1)) * 128u; /* slot of virtual row 1 - lane */
+    unsigned roff = (unsigned)((1 - lane + RR) % RR) * 128u; /* slot of virtual row 1 - lane */
     __syncwarp();
 
     const int nb = B / 32;
     int flushed = 0; /* virtual rows 1 .. flushed are in memory */
     int t = 0;       /* steps done */
-    auto flush_to = [&](const int upto) { /* whole groups of 32 virtual rows; a group lies inside one table */
+    auto flush_to = [&](const int upto) { /* whole groups of BLK virtual rows; a group lies inside one table */
         __syncwarp();
         while (flushed < upto) {
             const int n = flushed / B;
             long long p0, p1;
             const bool have1 = pair_of(n, p0, p1);
-            const int r0 = flushed - n * B; /* local rows r0+1 .. r0+32 */
+            const int r0 = flushed - n * B; /* local rows r0+1 .. r0+BLK */
             uint8_t *tab0 = bp.arrows + (size_t)p0 * tab_bytes, *tab1 = bp.arrows + (size_t)p1 * tab_bytes;
             const int sub = lane >> 3, chunk = lane & 7;
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
+            for (int g = 0; g < BLK / 4; g++) {
                 const int lr = r0 + 4 * g + sub; /* local row - 1 */
-                const unsigned *src = ring + ((flushed + 4 * g + sub + 1) & (NWB_BX_RING_ROWS - 1)) * 32 + chunk * 4;
+                const unsigned *src = ring + ((flushed + 4 * g + sub + 1) % RR) * 32 + chunk * 4;
                 const size_t dst = (size_t)lr * 128 + (size_t)chunk * 16;
                 const uint4 w0 = *reinterpret_cast<const uint4 *>(src);
-                const uint4 w1 = *reinterpret_cast<const uint4 *>(src + NWB_BX_RING_WORDS);
+                const uint4 w1 = *reinterpret_cast<const uint4 *>(src + RR * 32);
                 *reinterpret_cast<uint4 *>(tab0 + dst) = w0;
                 if (have1) *reinterpret_cast<uint4 *>(tab1 + dst) = w1;
             }
-            flushed += 32;
+            flushed += BLK;
         }
         __syncwarp();
     };
@@ -454,7 +465,8 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_cx_kernel(cons
                     st.tpw[k] = tn[k];
                 }
             }
-            nwb_bx_step<0>(st, pc, lane, sp, ring_l, roff, cm_a, cm_b, true, 0, B, B, br0, br1, rs0, rs1);
+            nwb_bx_step<0, RR>(st, pc, lane, sp, ring_l, roff, cm_a, cm_b, true, 0, B, B, br0, br1, rs0, rs1);
+            if (BLK < 32 && i == BLK - 1) flush_to(t + BLK - 32);
         }
         t += 32;
         flush_to(t - 32);
@@ -485,18 +497,18 @@ __global__ void __launch_bounds__(32 * NWB_BX_WARPS, 1) nwb_batch_cx_kernel(cons
         /* ---- the rest of element n: every lane strictly inside the tables ---- */
         const unsigned *side_l = bufn + 32 - lane; /* side_l[s] = my row's word at step n*B + 32 + s */
 #pragma unroll 1
-        for (int blk = 1; blk < nb; blk++) {
+        for (int blk = 32 / BLK; blk < nb * (32 / BLK); blk++) {
 #pragma unroll 1
-            for (int sub = 0; sub < 4; sub++) {
+            for (int sub = 0; sub < BLK / 8; sub++) {
                 unsigned sw[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) sw[i] = side_l[i];
                 side_l += 8;
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    nwb_bx_step<0>(st, pc, lane, sw[i], ring_l, roff, cm_a, cm_b, true, 0, B, B, br0, br1, rs0, rs1);
+                    nwb_bx_step<0, RR>(st, pc, lane, sw[i], ring_l, roff, cm_a, cm_b, true, 0, B, B, br0, br1, rs0, rs1);
             }
-            t += 32;
+            t += BLK;
             flush_to(t - 32);
         }
     }

@@ -369,7 +369,11 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
         bp.arrows = arrows; bp.arrow_off = arrow_off; bp.out_score = scores; bp.out_branch = branches;
         if (use_cx) {
             const int A = (int)(top_off[1] - top_off[0]), B = (int)(side_off[1] - side_off[0]);
-            emu_launch(grid, 32 * NWB_BX_WARPS, NWB_CX_SMEM_PER_WARP(B) * NWB_BX_WARPS, [&]() { nwb_batch_cx_kernel(bp, pc, A, B); });
+            if (getenv("NWB_CX_WARPS") && atoi(getenv("NWB_CX_WARPS")) == 16)
+                emu_launch(grid, 32 * 16, NWB_CX_SMEM_PER_WARP(B, 16) * 16, [&]() { nwb_batch_cx_kernel<16>(bp, pc, A, B); });
+            else
+                emu_launch(grid, 32 * NWB_BX_WARPS, NWB_CX_SMEM_PER_WARP(B, NWB_BX_WARPS) * NWB_BX_WARPS,
+                           [&]() { nwb_batch_cx_kernel<NWB_BX_WARPS>(bp, pc, A, B); });
         } else {
             emu_launch(grid, 32 * NWB_BX_WARPS, NWB_BX_SMEM_PER_WARP(maxB) * NWB_BX_WARPS, [&]() { nwb_batch_bx_kernel(bp, pc); });
         }
