@@ -217,10 +217,12 @@ typedef struct nwb_batch nwb_batch;
 /* Pair p has top = tops + top_off[p] .. top_off[p+1], side likewise (offset
  * arrays hold n_pairs + 1 entries).  Results per pair: optimal score, branch
  * count (unless NWB_NO_BRANCH_COUNT) and, with NWB_WANT_ARROWS_HOST, the pair's
- * arrow table (layout of section 1 with pitch 128 * ceil(A/256) bytes).
- * The batch path runs the packed 16x2 kernel only: schemes outside its range
- * (see nwb_fill_pk.cuh) and NWB_WANT_COUNT / NWB_WANT_SCORES / NWB_TRACK_ABS
- * return NWB_ERR_UNSUPPORTED -- use nwb_fill() per pair for those.
+ * arrow table (layout of section 1 with pitch 128 * ceil(A/256) bytes); with
+ * NWB_WANT_COUNT the number of optimal alignments mod 2^64 (a second pass over
+ * the arrow codes, nwb_batch_count.cuh; nwb_batch_count_u64()).
+ * The batch path runs the packed 16x2 kernels only: schemes outside their range
+ * (see nwb_fill_pk.cuh) and NWB_WANT_SCORES / NWB_TRACK_ABS return
+ * NWB_ERR_UNSUPPORTED -- use nwb_fill() per pair for those.
  * nwb_fill_batch() = nwb_batch_create() + nwb_batch_run() + nwb_batch_fetch(). */
 int nwb_fill_batch(const char *tops, const int64_t *top_off,
                    const char *sides, const int64_t *side_off, int64_t n_pairs,

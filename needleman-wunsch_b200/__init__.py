@@ -395,6 +395,10 @@ class Batch:
     def kernel_name(self) -> str:
         return (load_library().nwb_batch_kernel_name(self._h) or b"").decode()
 
+    def count(self, p: int) -> int:
+        """Optimal alignments of pair p mod 2^64 (NWB_WANT_COUNT; after fetch())."""
+        return int(load_library().nwb_batch_count_u64(self._h, p))
+
     def launches(self) -> int:
         return load_library().nwb_batch_launches(self._h)
 

@@ -24,6 +24,7 @@
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
+#include "nwb_batch_count.cuh"
 #include "nwb_peak.cuh"
 
 #define NWB_ABI_VERSION 1

@@ -19,6 +19,8 @@ struct nwb_batch {
     DevBuf<int> score;
     DevBuf<unsigned> branch;
     DevBuf<uint32_t> scratch;
+    DevBuf<unsigned long long> count, cscratch; /* NWB_WANT_COUNT */
+    std::vector<unsigned long long> h_count;
     std::vector<long long> h_top_off, h_side_off, h_arrow_off;
     std::vector<int> h_score;
     std::vector<unsigned> h_branch;
@@ -35,6 +37,7 @@ extern "C" void nwb_batch_free(nwb_batch *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->tops.release(); b->sides.release(); b->arrows.release(); b->top_off.release(); b->side_off.release();
     b->arrow_off.release(); b->score.release(); b->branch.release(); b->scratch.release();
+    b->count.release(); b->cscratch.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -47,7 +50,7 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     if (!out) return NWB_ERR_INVALID;
     *out = nullptr;
     if (n_pairs < 0 || !top_off || !side_off) return NWB_ERR_INVALID;
-    if (flags & (NWB_WANT_SCORES | NWB_WANT_COUNT | NWB_WANT_COUNT_MATRIX | NWB_TRACK_ABS | NWB_FORCE_GENERAL))
+    if (flags & (NWB_WANT_SCORES | NWB_WANT_COUNT_MATRIX | NWB_TRACK_ABS | NWB_FORCE_GENERAL))
         return NWB_ERR_UNSUPPORTED; /* the batch path runs the packed kernel only */
     const int ndev = nwb_device_count();
     if (ndev <= 0) return NWB_ERR_NO_DEVICE;
@@ -101,6 +104,7 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     if (rc == NWB_OK) rc = b->arrows.ensure(b->arrows_bytes + 16);
     if (rc == NWB_OK) rc = b->score.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK) rc = b->branch.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = b->count.ensure((size_t)n_pairs + 1);
     if (rc != NWB_OK) { nwb_batch_free(b); return rc; }
     e = cudaSuccess;
     if (tbytes) e = cudaMemcpyAsync(b->tops.p, tops, tbytes, cudaMemcpyHostToDevice, b->stream);
@@ -114,6 +118,30 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     return NWB_OK;
 }
 
+/* the count behind -s: a second pass over the arrow codes the fill has just written (nwb_batch_count.cuh) */
+static int batch_count_pass(nwb_batch *b, cudaStream_t st)
+{
+    NwbBatchCountParams cp;
+    memset(&cp, 0, sizeof(cp));
+    const int grid = b->sm_count;
+    cp.top_off = b->top_off.p; cp.side_off = b->side_off.p; cp.n_pairs = b->n;
+    cp.arrows = b->arrows.p; cp.arrow_off = b->arrow_off.p; cp.out_count = b->count.p;
+    if (b->max_strips > 1) {
+        cp.scratch_per_warp = nwb_round_up((size_t)b->max_B + 1, 16);
+        int rc = b->cscratch.ensure((size_t)grid * NWB_BCNT_WARPS * cp.scratch_per_warp);
+        if (rc != NWB_OK) return rc;
+        cp.scratch = b->cscratch.p;
+    }
+    const size_t smem = (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS;
+    CK(cudaFuncSetAttribute(nwb_batch_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nwb_batch_count_kernel<<<grid, 32 * NWB_BCNT_WARPS, smem, st>>>(cp);
+    CK(cudaGetLastError());
+    b->launches += 1;
+    return NWB_OK;
+}
+
+static int batch_fill_pass(nwb_batch *b, cudaStream_t st);
+
 extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
 {
     if (!b) return NWB_ERR_INVALID;
@@ -122,6 +150,16 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     b->ran = true;
     b->fetched = false;
     if (b->n == 0) return NWB_OK;
+    CK(cudaEventRecord(b->ev0, st));
+    int rc = batch_fill_pass(b, st);
+    if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st);
+    if (rc != NWB_OK) return rc;
+    CK(cudaEventRecord(b->ev1, st));
+    return NWB_OK;
+}
+
+static int batch_fill_pass(nwb_batch *b, cudaStream_t st)
+{
     NwbBatchParams bp;
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
@@ -140,19 +178,15 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
             const size_t smem = NWB_CX_SMEM_PER_WARP(b->max_B, cw) * (size_t)cw;
             auto kern = w16 ? nwb_batch_cx_kernel<16> : nwb_batch_cx_kernel<NWB_BX_WARPS>;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaEventRecord(b->ev0, st));
             kern<<<grid, 32 * cw, smem, st>>>(bp, b->pc, (int)b->uni_A, (int)b->uni_B);
             CK(cudaGetLastError());
-            CK(cudaEventRecord(b->ev1, st));
             b->launches += 1;
             return NWB_OK;
         }
         const size_t smem = NWB_BX_SMEM_PER_WARP(b->max_B) * (size_t)warps;
         CK(cudaFuncSetAttribute(nwb_batch_bx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaEventRecord(b->ev0, st));
         nwb_batch_bx_kernel<<<grid, 32 * warps, smem, st>>>(bp, b->pc);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(b->ev1, st));
         b->launches += 1;
         return NWB_OK;
     }
@@ -173,10 +207,8 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
     const size_t smem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * (size_t)warps;
     CK(cudaFuncSetAttribute(nwb_batch_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaEventRecord(b->ev0, st));
     nwb_batch_pk_kernel<<<grid, 32 * warps, smem, st>>>(bp, b->pc);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(b->ev1, st));
     b->launches += 1;
     return NWB_OK;
 }
@@ -192,6 +224,10 @@ extern "C" int nwb_batch_fetch(nwb_batch *b)
         CK(cudaMemcpy(b->h_score.data(), b->score.p, (size_t)b->n * sizeof(int), cudaMemcpyDeviceToHost));
         if (!(b->flags & NWB_NO_BRANCH_COUNT))
             CK(cudaMemcpy(b->h_branch.data(), b->branch.p, (size_t)b->n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (b->flags & NWB_WANT_COUNT) {
+            b->h_count.resize((size_t)b->n);
+            CK(cudaMemcpy(b->h_count.data(), b->count.p, (size_t)b->n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        }
         if (b->flags & NWB_WANT_ARROWS_HOST) {
             b->h_arrows.resize(b->arrows_bytes);
             if (b->arrows_bytes) CK(cudaMemcpy(b->h_arrows.data(), b->arrows.p, b->arrows_bytes, cudaMemcpyDeviceToHost));
@@ -225,8 +261,7 @@ extern "C" uint32_t nwb_batch_branch_count(const nwb_batch *b, int64_t pair)
 }
 extern "C" uint64_t nwb_batch_count_u64(const nwb_batch *b, int64_t pair)
 {
-    (void)b; (void)pair;
-    return 0; /* NWB_WANT_COUNT is not available on the batch path yet */
+    return (b && b->fetched && (b->flags & NWB_WANT_COUNT) && pair >= 0 && pair < b->n) ? b->h_count[(size_t)pair] : 0ull;
 }
 extern "C" const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair, size_t *pitch)
 {

@@ -1,0 +1,100 @@
+/*
+ * nwb_batch_count.cuh -- the optimal-alignment count behind `-s` for a batch of pairs.
+ *
+ * Per pair the number of arrow paths from (A,B) to (0,0), mod 2^64:
+ *     cnt(0,0) = cnt(i,0) = cnt(0,j) = 1,
+ *     cnt(i,j) = [DIAG] cnt(i-1,j-1) + [LEFT] cnt(i-1,j) + [UP] cnt(i,j-1)
+ * (the reference enumerates every alignment, needleman-wunsch.c:209-331, and keeps the low 32 bits,
+ * computation.c:223-260).  Same recurrence and row kernel as nwb_count.cuh (nwb_count_row<8>: six selects and
+ * one three-input add with carry per cell), here as a second pass over the 4-bit codes a batch fill kernel
+ * has written: one warp per pair, lane l owns columns 8l+1 .. 8l+8 of a 256-column strip and works on row
+ * t - l + 1 at step t; the strips of a wider pair are swept left to right by the same warp, the last column's
+ * counts of a strip waiting in a per-warp scratch line for the next one.  Arrow rows come in with coalesced
+ * 16-byte loads (four whole 128-byte strip rows per instruction) four steps ahead of lane 0 and are handed
+ * to the skewed lanes through a 64-row shared-memory ring.  No inter-warp synchronisation.
+ */
+#pragma once
+#include "nwb_count.cuh"
+#include "nwb_batch.cuh"
+
+#define NWB_BCNT_WARPS 16
+#define NWB_BCNT_RING_ROWS 64
+#define NWB_BCNT_SMEM_PER_WARP (NWB_BCNT_RING_ROWS * 128)
+
+struct NwbBatchCountParams {
+    const long long *top_off;   /* n_pairs + 1 */
+    const long long *side_off;  /* n_pairs + 1 */
+    long long n_pairs;
+    const uint8_t *arrows;      /* all pairs' nibble tables */
+    const long long *arrow_off; /* byte offset of pair p's table; its pitch is 128 * ceil(A_p / 256) */
+    unsigned long long *out_count; /* [n_pairs] */
+    unsigned long long *scratch;   /* pairs wider than one strip: per warp max_B + 1 boundary counts */
+    size_t scratch_per_warp;       /* elements */
+};
+
+__global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel(const NwbBatchCountParams cp)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_BCNT_SMEM_PER_WARP);
+    unsigned long long *bnd = cp.scratch ? cp.scratch + (size_t)gwarp * cp.scratch_per_warp : nullptr;
+    const int sub = lane >> 3, chunk = lane & 7;
+
+    for (long long pr = gwarp; pr < cp.n_pairs; pr += nwarps) {
+        const int A = (int)(cp.top_off[pr + 1] - cp.top_off[pr]), B = (int)(cp.side_off[pr + 1] - cp.side_off[pr]);
+        if (A == 0 || B == 0) {
+            if (lane == 0) cp.out_count[pr] = 1ull; /* borders only: one path along the border */
+            continue;
+        }
+        const int n_strips = (A + 255) / 256;
+        const size_t pitch = (size_t)n_strips * 128;
+        const uint8_t *tab = cp.arrows + cp.arrow_off[pr];
+        for (int c = 0; c < n_strips; c++) {
+            const uint8_t *src = tab + (size_t)c * 128 + (size_t)chunk * 16;
+            /* the cell (A,B): lane / column that owns it, in the last strip */
+            const int kfin = (c == n_strips - 1) ? (A - 1 - c * 256) - 8 * lane : -1;
+            unsigned long long cnt[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) cnt[k] = 1ull; /* border row */
+            unsigned long long send = 1ull, left_above = 1ull;
+            __syncwarp(); /* the previous strip's / pair's ring reads and boundary writes are done */
+            /* rows 1..4 into the ring (slot = row mod 64) */
+            {
+                const int r = 1 + sub;
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (r <= B) w = nwb_ldg_u128(src + (size_t)(r - 1) * pitch);
+                *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = w;
+            }
+            uint4 wnext = make_uint4(0u, 0u, 0u, 0u); /* rows 5..8, stored before step 4 */
+            if (5 + sub <= B) wnext = nwb_ldg_u128(src + (size_t)(4 + sub) * pitch);
+            __syncwarp();
+            const int nsteps = B + 31;
+            for (int t = 0; t < nsteps; t++) {
+                if ((t & 3) == 0 && t > 0) {
+                    /* rows t+1 .. t+4 (loaded four steps ago) into the ring; rows t+5 .. t+8 on their way.  The slots
+                     * they overwrite held rows t-63 .. t-60, last read by lane 31 at step t-30 at the latest. */
+                    const int r = t + 1 + sub;
+                    *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = wnext;
+                    const int r2 = r + 4;
+                    wnext = (r2 <= B) ? nwb_ldg_u128(src + (size_t)(r2 - 1) * pitch) : make_uint4(0u, 0u, 0u, 0u);
+                    __syncwarp();
+                }
+                const int j = t - lane + 1; /* my row at this step */
+                unsigned long long cl = __shfl_up_sync(NWB_FULL_MASK, send, 1);
+                if (lane == 0) cl = (c == 0 || j > B) ? 1ull : bnd[j]; /* column 0 of the table / the strip to my left */
+                if (j >= 1 && j <= B) {
+                    const unsigned x = ring[(j & (NWB_BCNT_RING_ROWS - 1)) * 32 + lane];
+                    nwb_count_row<8>(x, cnt, left_above, cl, send);
+                    if (j == B && kfin >= 0 && kfin < 8) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (k == kfin) cp.out_count[pr] = cnt[k];
+                    }
+                    if (lane == 31 && c + 1 < n_strips) bnd[j] = send; /* read by lane 0 in the next strip */
+                }
+            }
+        }
+    }
+}

@@ -129,7 +129,7 @@ def fill_pk_rank(top, side, m, k, d, *, rank, world, inbox=None, hx=True, grid=2
                 strip_begin=info[0], strip_end=info[1], n_strips=info[2], pitch=pitch)
 
 
-def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1):
+def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1, count=False):
     """Run the batch kernel under the emulator.  bx: 0 = nwb_batch_pk_kernel (one pair per warp), 1 =
     nwb_batch_bx_kernel (two pairs per warp), 2 = nwb_batch_cx_kernel (uniform shapes, pairs back to back),
     -1 = the library's own choice; the result's "kernel" says which ran ("pk", "bx", "cx")."""
@@ -153,11 +153,18 @@ def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1):
     rc = L.emu_fill_batch(b"".join(tops), p(toff), b"".join(sides), p(soff), n, m, k, d, grid, bx, p(arrows), p(aoff),
                           p(scores), p(branches), C.byref(used))
     assert rc == 0, rc
+    counts = None
+    if count:
+        counts = np.zeros(n, np.uint64)
+        L.emu_batch_count.restype = C.c_int
+        L.emu_batch_count.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert L.emu_batch_count(p(toff), p(soff), n, grid, p(arrows), p(aoff), p(counts)) == 0
     tabs = []
     for i in range(n):
         pitch = max(1, (len(tops[i]) + 255) // 256) * 128
         tabs.append(arrows[aoff[i]:aoff[i] + pitch * len(sides[i])].reshape(len(sides[i]), pitch))
-    return dict(scores=scores, branches=branches, tables=tabs, bx=used.value >= 1, kernel=("pk", "bx", "cx")[used.value])
+    return dict(scores=scores, branches=branches, tables=tabs, bx=used.value >= 1, kernel=("pk", "bx", "cx")[used.value],
+                counts=counts)
 
 
 def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:

@@ -12,6 +12,7 @@
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
+#include "nwb_batch_count.cuh"
 
 #include <vector>
 
@@ -324,6 +325,30 @@ int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int
     }
     *partial_r = sum.rsum;
     *branches = sum.branch_count;
+    return 0;
+}
+
+/* the batch count pass (nwb_batch_count.cuh) over tables a batch fill has written */
+int emu_batch_count(const long long *top_off, const long long *side_off, long long n, unsigned grid,
+                    const uint8_t *arrows, const long long *arrow_off, unsigned long long *counts)
+{
+    NwbBatchCountParams cp;
+    memset(&cp, 0, sizeof(cp));
+    int maxB = 0, maxS = 1;
+    for (long long p = 0; p < n; p++) {
+        const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
+        if ((A + 255) / 256 > maxS) maxS = (int)((A + 255) / 256);
+        if (B > maxB) maxB = (int)B;
+    }
+    cp.top_off = top_off; cp.side_off = side_off; cp.n_pairs = n;
+    cp.arrows = arrows; cp.arrow_off = arrow_off; cp.out_count = counts;
+    std::vector<unsigned long long> scratch;
+    if (maxS > 1) {
+        cp.scratch_per_warp = nwb_round_up((size_t)maxB + 1, 16);
+        scratch.assign((size_t)grid * NWB_BCNT_WARPS * cp.scratch_per_warp, 0xdeadbeefdeadbeefULL);
+        cp.scratch = scratch.data();
+    }
+    emu_launch(grid, 32 * NWB_BCNT_WARPS, (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS, [&]() { nwb_batch_count_kernel(cp); });
     return 0;
 }
 

@@ -124,3 +124,37 @@ def test_cx_config4_goldens_and_default(oracle):
     # not uniform, or rows not a multiple of 32: the general two-pairs-per-warp kernel
     assert emu.fill_batch(tops, [sides[0], sides[1], sides[2][:200]], 1, 1, 1)["kernel"] == "bx"
     assert emu.fill_batch([t[:100] for t in tops], [s[:70] for s in sides], 1, 1, 1)["kernel"] == "bx"
+
+
+# ---- the count behind -s for a batch (csrc/nwb_batch_count.cuh) -----------------------------------------
+
+def test_batch_count_pass(oracle):
+    # after each of the three fill kernels; ragged shapes, pairs wider than one strip (boundary counts through
+    # the per-warp scratch line), empty strings, counts that wrap 2^64 (0/0/0: Delannoy numbers)
+    rng = random.Random(41)
+    lens = [(256, 256), (1, 1), (255, 257), (300, 40), (17, 130), (0, 5), (700, 90), (64, 64), (256, 1), (33, 33),
+            (257, 31), (100, 300), (5, 0), (513, 70)] + [(rng.randint(1, 280), rng.randint(1, 150)) for _ in range(12)]
+    tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
+    sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
+    for (m, k, d), grid in (((1, 1, 1), 1), ((0, 0, 0), 2), ((2, 1, 2), 1)):
+        r = emu.fill_batch(tops, sides, m, k, d, grid=grid, count=True)
+        assert r["kernel"] == "pk"
+        for i, (t, s) in enumerate(zip(tops, sides)):
+            assert int(r["counts"][i]) == oracle.fill(t, s, m, k, d).count, (i, len(t), len(s))
+    short = [i for i, (a, _) in enumerate(lens) if a <= 256]
+    r = emu.fill_batch([tops[i] for i in short], [sides[i] for i in short], 1, 1, 1, grid=1, count=True)
+    assert r["kernel"] == "bx"
+    for q, i in enumerate(short):
+        assert int(r["counts"][q]) == oracle.fill(tops[i], sides[i], 1, 1, 1).count, i
+
+
+def test_batch_count_config4_goldens(oracle):
+    # the three sample pairs of config 4
+    tops, sides = [], []
+    for p in (0, 1, 999999):
+        t, s = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
+        tops.append(t)
+        sides.append(s)
+    r = emu.fill_batch(tops, sides, 1, 1, 1, grid=1, count=True)
+    assert r["kernel"] == "cx"
+    assert [int(c) for c in r["counts"]] == [387701138034524160, 108460706365440, 4971798065203200]

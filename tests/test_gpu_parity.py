@@ -333,6 +333,35 @@ def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
         b0.close()
 
 
+def test_batch_count(oracle, nwb):
+    """NWB_WANT_COUNT on the batch path (csrc/nwb_batch_count.cuh): SURVEY 8c's config 4 counts, ragged shapes,
+    pairs wider than one strip, empty strings, wrap-around mod 2^64 (0/0/0)."""
+    n = 3000
+    idx = list(range(n - 1)) + [999999]
+    tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
+    bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_COUNT)
+    assert bt.kernel_name() == "nwb_batch_cx_kernel"
+    bt.run()
+    bt.fetch()
+    assert [bt.count(i) for i in (0, 1, n - 1)] == [387701138034524160, 108460706365440, 4971798065203200]
+    rng = random.Random(43)
+    for i in rng.sample(range(n), 40):
+        assert bt.count(i) == oracle.fill(tops[i], sides[i], 1, 1, 1).count, i
+    bt.close()
+    lens = [(256, 256), (1, 1), (255, 257), (300, 40), (17, 130), (0, 5), (700, 90), (64, 64), (256, 1), (33, 33),
+            (257, 31), (100, 300), (5, 0), (1500, 700)] + [(rng.randint(1, 600), rng.randint(1, 500)) for _ in range(400)]
+    tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
+    sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
+    for m, k, d in ((1, 1, 1), (0, 0, 0)):
+        bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_COUNT)
+        bt.run()
+        bt.fetch()
+        for i in list(range(14)) + rng.sample(range(14, len(lens)), 60):
+            o = oracle.fill(tops[i], sides[i], m, k, d)
+            assert (bt.count(i), bt.opt_score(i), bt.branch_count(i)) == (o.count, o.final_score, o.branch_count), i
+        bt.close()
+
+
 def test_count_prefix_property(oracle, nwb):
     """Intermediate counts of the packed count kernel through the public ABI: the count of cell
     (i, j) equals the final count of the sub-problem (top[:i], side[:j]).  The final count of the

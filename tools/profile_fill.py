@@ -21,7 +21,7 @@ ap.add_argument("--alphabet", default="dna")
 ap.add_argument("--m", type=int, default=1)
 ap.add_argument("--k", type=int, default=1)
 ap.add_argument("--d", type=int, default=1)
-ap.add_argument("--flags", type=lambda x: int(x, 0), default=nwb.NO_BRANCH_COUNT)
+ap.add_argument("--flags", type=lambda x: int(x, 0), default=nwb.NO_BRANCH_COUNT, help="include/nwb.h flag bits; WANT_COUNT = 0x2")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--batch", type=int, default=0, help="run a batch of this many pairs (config 4 generator) instead")
 args = ap.parse_args()
