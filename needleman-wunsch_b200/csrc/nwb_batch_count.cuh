@@ -71,19 +71,21 @@ __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel
             if (5 + sub <= B) wnext = nwb_ldg_u128(src + (size_t)(4 + sub) * pitch);
             __syncwarp();
             const int nsteps = B + 31;
-            for (int t = 0; t < nsteps; t++) {
-                if ((t & 3) == 0 && t > 0) {
-                    /* rows t+1 .. t+4 (loaded four steps ago) into the ring; rows t+5 .. t+8 on their way.  The slots
-                     * they overwrite held rows t-63 .. t-60, last read by lane 31 at step t-30 at the latest. */
-                    const int r = t + 1 + sub;
-                    *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = wnext;
-                    const int r2 = r + 4;
-                    wnext = (r2 <= B) ? nwb_ldg_u128(src + (size_t)(r2 - 1) * pitch) : make_uint4(0u, 0u, 0u, 0u);
-                    __syncwarp();
-                }
-                const int j = t - lane + 1; /* my row at this step */
+            const bool has_left = (c > 0), publish = (lane == 31) && (c + 1 < n_strips);
+            /* rows t+1 .. t+4 (loaded four steps ago) into the ring; rows t+5 .. t+8 on their way.  The slots they
+             * overwrite held rows t-63 .. t-60, last read by lane 31 at step t-30 at the latest. */
+            auto stage = [&](const int t) {
+                const int r = t + 1 + sub;
+                *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = wnext;
+                const int r2 = r + 4;
+                wnext = (r2 <= B) ? nwb_ldg_u128(src + (size_t)(r2 - 1) * pitch) : make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+            };
+            /* checked step: my row may lie above row 1 or below row B */
+            auto step_checked = [&](const int t) {
+                const int j = t - lane + 1;
                 unsigned long long cl = __shfl_up_sync(NWB_FULL_MASK, send, 1);
-                if (lane == 0) cl = (c == 0 || j > B) ? 1ull : bnd[j]; /* column 0 of the table / the strip to my left */
+                if (lane == 0) cl = (!has_left || j > B) ? 1ull : bnd[j]; /* column 0 of the table / the strip to my left */
                 if (j >= 1 && j <= B) {
                     const unsigned x = ring[(j & (NWB_BCNT_RING_ROWS - 1)) * 32 + lane];
                     nwb_count_row<8>(x, cnt, left_above, cl, send);
@@ -92,8 +94,34 @@ __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel
                         for (int k = 0; k < 8; k++)
                             if (k == kfin) cp.out_count[pr] = cnt[k];
                     }
-                    if (lane == 31 && c + 1 < n_strips) bnd[j] = send; /* read by lane 0 in the next strip */
+                    if (publish) bnd[j] = send; /* read by lane 0 in the next strip */
                 }
+            };
+            int t = 0;
+#pragma unroll 1
+            for (; t < 32 && t < nsteps; t++) { /* head: lanes l > t are still above row 1 */
+                if ((t & 3) == 0 && t > 0) stage(t);
+                step_checked(t);
+            }
+            /* steps 32 .. B-2: every lane strictly inside rows 1 .. B-1, four steps per staged block of rows */
+            const unsigned *rq = ring + lane;
+#pragma unroll 1
+            for (; t + 4 <= B - 1; t += 4) {
+                stage(t);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int j = t + i - lane + 1;
+                    unsigned long long cl = __shfl_up_sync(NWB_FULL_MASK, send, 1);
+                    if (lane == 0) cl = has_left ? bnd[j] : 1ull;
+                    const unsigned x = rq[(j & (NWB_BCNT_RING_ROWS - 1)) * 32];
+                    nwb_count_row<8>(x, cnt, left_above, cl, send);
+                    if (publish) bnd[j] = send;
+                }
+            }
+#pragma unroll 1
+            for (; t < nsteps; t++) { /* tail: the last rows, lanes running out of the table */
+                if ((t & 3) == 0) stage(t);
+                step_checked(t);
             }
         }
     }
