@@ -103,3 +103,45 @@ def test_summary_beyond_32_bits(cli, oracle):
     rc, out, err = run(OURS, ["-q", "-s", "1", "1", "1"], t + b" " + s + b"\n")
     assert (rc, out) == (0, b"")
     assert err == b"-2087714816 optimal alignments\nOptimal score is 19\n"
+
+
+# ---- batch front-end: needleman-wunsch-batch vs the reference CLI looped per pair -----
+
+BATCH = os.path.join(ROOT, "needleman-wunsch_b200", "host", "needleman-wunsch-batch")
+
+
+def run_batch(args, stdin=b""):
+    p = subprocess.run(["needleman-wunsch-batch"] + list(args), executable=BATCH, input=stdin, capture_output=True)
+    return p.returncode, p.stdout, p.stderr
+
+
+def test_batch_cli_usage_and_input_errors(cli):
+    for args in (["-h"], ["-x", "1", "1", "1"], [], ["1", "1"], ["1", "1", "1", "1"]):
+        rc, out, err = run_batch(args, b"GT GA\n")
+        assert rc == 1 and out == b"" and b"usage: needleman-wunsch-batch" in err
+    for stdin in (b"", b"ACG", b"ACG GT\nAC", b"  \n"):
+        rc, out, err = run_batch(["1", "1", "1"], stdin)
+        assert rc == 1 and out == b"" and b"got EOF too early when reading input strings" in err
+
+
+@pytest.mark.gpu
+def test_batch_cli_matches_the_reference_looped_per_pair(cli):
+    rng = random.Random(77)
+    pairs = [("GCATGCU", "GATTACA"), ("GAT", "GTA"), ("GT", "GT"), ("A", "C")] + \
+            [("".join(rng.choice("ACGT") for _ in range(rng.randint(1, 11))),
+              "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 11)))) for _ in range(40)]
+    text = "\n".join(f"{a} {b}" for a, b in pairs).encode() + b"\n"
+    for mkd in (("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0")):
+        for flags in ([], ["-s"]):
+            rc, out, err = run_batch(flags + list(mkd), text)
+            assert rc == 0 and out == b""
+            want = b""
+            for a, b in pairs:
+                r = run(cli, ["-q"] + flags + list(mkd), f"{a} {b}\n".encode())
+                assert r[0] == 0
+                # without -s the reference prints nothing under -q; the batch front-end always prints the score
+                want += r[2] if flags else b"Optimal score is %d\n" % int(run(cli, ["-q", "-s"] + list(mkd), f"{a} {b}\n".encode())[2].split()[-1])
+            assert err == want, (mkd, flags)
+    # a scheme outside the packed kernels' range is refused with the reference-style error text
+    rc, out, err = run_batch(["1", "3", "1"], text)
+    assert rc == 1 and b"score-table fill failed" in err
