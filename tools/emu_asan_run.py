@@ -31,5 +31,28 @@ for (a,b) in [(7,7),(300,100),(513,70),(600,260),(90,700)]:
         assert r['count']==o.count
 tops=[bytes(random.choice(b"ACGT") for _ in range(n)) for n in (256,300,17,700)]
 sides=[bytes(random.choice(b"ACGT") for _ in range(n)) for n in (256,40,130,90)]
-r=emu.fill_batch(tops,sides,1,1,1,grid=1)
+r=emu.fill_batch(tops,sides,1,1,1,grid=1,count=True)
+assert r['kernel']=='pk'
+for i in range(4):
+    assert int(r['counts'][i])==oracle.fill(tops[i],sides[i],1,1,1).count
+# two pairs per warp (ragged partners, odd batch, table edges at the pitch boundary) and the batch count pass
+lens=[(256,256),(1,1),(255,257),(3,40),(0,5),(256,31),(100,300),(5,0),(250,64),(7,65),(256,2)]
+tops=[bytes(random.choice(b"ACGT") for _ in range(a)) for a,_ in lens]
+sides=[bytes(random.choice(b"ACGT") for _ in range(b)) for _,b in lens]
+r=emu.fill_batch(tops,sides,2,1,2,grid=1,bx=1,count=True)
+for i in range(len(lens)):
+    o=oracle.fill(tops[i],sides[i],2,1,2)
+    assert (r['scores'][i],r['branches'][i],int(r['counts'][i]))==(o.final_score,o.branch_count,o.count), i
+# uniform shapes swept back to back, 12 and 16 warps per block (64- and 48-row rings)
+for (a,b,n) in ((256,256,3),(40,64,61),(255,96,27)):
+    tops=[bytes(random.choice(b"ACGT") for _ in range(a)) for _ in range(n)]
+    sides=[bytes(random.choice(b"ACGT") for _ in range(b)) for _ in range(n)]
+    for w in ("12","16"):
+        os.environ["NWB_CX_WARPS"]=w
+        r=emu.fill_batch(tops,sides,1,1,1,grid=1,bx=2,count=True)
+        assert r['kernel']=='cx'
+        for i in range(n):
+            o=oracle.fill(tops[i],sides[i],1,1,1)
+            assert (r['scores'][i],r['branches'][i],int(r['counts'][i]))==(o.final_score,o.branch_count,o.count), i
+    del os.environ["NWB_CX_WARPS"]
 print("asan run ok")
