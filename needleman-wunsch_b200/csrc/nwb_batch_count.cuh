@@ -67,8 +67,7 @@ __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel
                 if (r <= B) w = nwb_ldg_u128(src + (size_t)(r - 1) * pitch);
                 *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = w;
             }
-            uint4 wnext = make_uint4(0u, 0u, 0u, 0u); /* rows 5..8, stored before step 4 */
-            if (5 + sub <= B) wnext = nwb_ldg_u128(src + (size_t)(4 + sub) * pitch);
+            uint4 wnext = nwb_ldg_u128(src + (size_t)((5 + sub <= B ? 5 + sub : B) - 1) * pitch); /* rows 5..8, stored before step 4 */
             __syncwarp();
             const int nsteps = B + 31;
             const bool has_left = (c > 0), publish = (lane == 31) && (c + 1 < n_strips);
@@ -78,7 +77,9 @@ __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel
                 const int r = t + 1 + sub;
                 *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = wnext;
                 const int r2 = r + 4;
-                wnext = (r2 <= B) ? nwb_ldg_u128(src + (size_t)(r2 - 1) * pitch) : make_uint4(0u, 0u, 0u, 0u);
+                /* unconditional (rows below the table re-read row B and are never looked at): a conditional load
+                 * goes through a temporary whose copy waits for the load right here */
+                wnext = nwb_ldg_u128(src + (size_t)((r2 <= B ? r2 : B) - 1) * pitch);
                 __syncwarp();
             };
             /* checked step: my row may lie above row 1 or below row B */

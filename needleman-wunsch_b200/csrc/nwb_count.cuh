@@ -194,12 +194,17 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
     }
 
     const int nsteps = B + 31;
-    for (int ss = 0; ss < nsteps; ss += NWB_CNT_SUB) {
+    /* One sub-block of 8 steps.  cwslot holds the stream words of this sub-block (fetched two sub-blocks ago) and
+     * takes the words of the sub-block after next: the two slots alternate (the caller's loop is unrolled by two),
+     * so the fresh load lands in a register nobody reads for two sub-blocks.  With one rotating pair of variables
+     * the compiler keeps the load in a temporary and copies it at the end of the prologue, and that copy waits for
+     * the L2 round trip in every sub-block: 22 % of the sweep's time (ncu source view). */
+    auto sub_block = [&](const int ss, unsigned long long &cwslot) {
         if (has_left) {
             /* lane 0's left inputs for rows ss+1 .. ss+8: 16 stream words, lane i takes word i */
             const int row = ss + (lane >> 1) + 1;
             const bool need = (lane < 2 * NWB_CNT_SUB) && (row <= B);
-            unsigned long long cw = cw_next;
+            unsigned long long cw = cwslot;
             bool ok = !need || (cw & NWB_PK_CVALID) || (p.debug_nowait & 1);
             while (!__all_sync(NWB_FULL_MASK, ok)) {
                 if (!ok) {
@@ -210,10 +215,9 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 nwb_pause();
 #endif
             }
-            cw_next = cw_next2; /* words are fetched two sub-blocks ahead: a word that is not valid yet costs an L2 round trip */
-            cw_next2 = 0ull;
-            if (lane < 2 * NWB_CNT_SUB && row + 2 * NWB_CNT_SUB <= B)
-                cw_next2 = nwb_ld_relaxed_u64(in_c + (size_t)(ss + 2 * NWB_CNT_SUB) * 2 + lane, left_remote);
+            /* words are fetched two sub-blocks ahead (a word that is not valid yet costs an L2 round trip);
+             * unconditional: rows beyond B land in the stream's padding and are never looked at */
+            cwslot = nwb_ld_relaxed_u64(in_c + (size_t)(ss + 2 * NWB_CNT_SUB) * 2 + lane, left_remote);
             const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
             __syncwarp(); /* the previous sub-block's reads of cstage are done */
             if (lane < 2 * NWB_CNT_SUB && !(lane & 1)) cstage[lane >> 1] = (cw & ~NWB_PK_CVALID) | (hi << 63);
@@ -282,6 +286,10 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 }
             }
         }
+    };
+    for (int ss = 0; ss < nsteps; ss += 2 * NWB_CNT_SUB) {
+        sub_block(ss, cw_next);
+        if (ss + NWB_CNT_SUB < nsteps) sub_block(ss + NWB_CNT_SUB, cw_next2);
     }
 }
 
