@@ -215,9 +215,6 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 nwb_pause();
 #endif
             }
-            /* words are fetched two sub-blocks ahead (a word that is not valid yet costs an L2 round trip);
-             * unconditional: rows beyond B land in the stream's padding and are never looked at */
-            cwslot = nwb_ld_relaxed_u64(in_c + (size_t)(ss + 2 * NWB_CNT_SUB) * 2 + lane, left_remote);
             const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
             __syncwarp(); /* the previous sub-block's reads of cstage are done */
             if (lane < 2 * NWB_CNT_SUB && !(lane & 1)) cstage[lane >> 1] = (cw & ~NWB_PK_CVALID) | (hi << 63);
@@ -231,15 +228,22 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 const int need = ss + 3 * NWB_CNT_SUB;
                 wait_rows(need < B ? need : B);
             }
-            stage_load(ss + 1 + 2 * NWB_CNT_SUB);
             const unsigned *rq = ring + (ss & (NWB_CNT_RING - 1)) * 32 + lane;
 #pragma unroll
             for (int t = 0; t < NWB_CNT_SUB; t++) w[t] = rq[t * 32];
             __syncwarp(); /* this sub-block's ring reads are issued before the next sub-block's stores */
+            /* every global load of the sub-block is issued here, AFTER the last use of the previous sub-block's
+             * loads (stage_store above, cw at the top): loads retire through a counting scoreboard, so a use that
+             * follows a younger load waits for that one too -- an L2 round trip per sub-block, 22 % of the sweep
+             * (ncu source view), when the stream-word prefetch was issued before stage_store */
+            stage_load(ss + 1 + 2 * NWB_CNT_SUB);
         } else {
 #pragma unroll
             for (int t = 0; t < NWB_CNT_SUB; t++) w[t] = wnext[t];
         }
+        /* stream words are fetched two sub-blocks ahead (a word that is not valid yet costs an L2 round trip);
+         * unconditional: rows beyond B land in the stream's padding and are never looked at */
+        if (has_left) cwslot = nwb_ld_relaxed_u64(in_c + (size_t)(ss + 2 * NWB_CNT_SUB) * 2 + lane, left_remote);
         /* every lane strictly inside rows 1 .. B-1 for this sub-block and the next one's loads inside the table */
         const bool lean = (ss >= 31) && (ss + 2 * NWB_CNT_SUB < B);
         if (lean) {
