@@ -83,7 +83,7 @@ def test_flag_combinations(cli, tmp_path):
     schemes = [("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0"), ("-1", "3", "-2"), ("5", "4", "3"), ("1", "3", "1")]
     n = 0
     for stdin in inputs:
-        for flags in rng.sample(FLAG_SETS, 5):
+        for flags in rng.sample(FLAG_SETS, 3):   # every run of ours pays a CUDA context: keep the GPU suite short
             mkd = rng.choice(schemes)
             same(cli, flags + list(mkd), stdin)
             n += 1
@@ -92,7 +92,7 @@ def test_flag_combinations(cli, tmp_path):
     f.write_bytes(b"GATTACA\nGCATGCU\nmore\n")
     same(cli, ["-f", str(f), "-s", "-t", "1", "1", "1"], b"GT GA\n")
     same(cli, ["-p", "2", "-s", "1", "1", "1"], b"GCATGCU GATTACA\n")
-    assert n >= 50
+    assert n >= 30
 
 
 @pytest.mark.gpu
