@@ -93,7 +93,7 @@ def test_bx_is_the_default_when_it_applies(oracle):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("a,b,n,grid", [(256, 256, 3, 1), (40, 64, 61, 1), (100, 96, 50, 2), (8, 128, 27, 1), (1, 64, 26, 1),
+@pytest.mark.parametrize("a,b,n,grid", [(256, 256, 3, 1), (64, 64, 1, 1), (256, 96, 2, 1), (40, 64, 61, 1), (100, 96, 50, 2), (8, 128, 27, 1), (1, 64, 26, 1),
                                         (255, 64, 49, 1), (9, 160, 30, 1)])
 def test_cx_uniform_chains(oracle, a, b, n, grid):
     # several pairs of pairs per warp (12 warps per block): resets, side double-buffering, aligned flush groups,

@@ -294,6 +294,15 @@ def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
             assert scores == [b0.opt_score(i) for i in range(len(lens))]
             assert branches == [b0.branch_count(i) for i in range(len(lens))]
             b0.close()
+    # batches of one pair (a warp sweeps it alone), uniform and not
+    for t1, s1, name in ((tops[0], sides[0], "nwb_batch_cx_kernel"), (tops[6], sides[6], "nwb_batch_bx_kernel")):
+        bt = nwb.Batch([t1], [s1], 2, 1, 2, nwb.WANT_ARROWS_HOST | nwb.WANT_COUNT)
+        assert bt.kernel_name() == name
+        bt.run()
+        bt.fetch()
+        _batch_check(oracle, nwb, bt, [t1], [s1], 2, 1, 2, [0])
+        assert bt.count(0) == oracle.fill(t1, s1, 2, 1, 2).count
+        bt.close()
     # 2d + m = 8 does not fit a nibble: the one-pair-per-warp kernel takes the batch
     bt = nwb.Batch(tops[:4], sides[:4], 2, 1, 3, 0)
     assert bt.kernel_name() == "nwb_batch_pk_kernel"
