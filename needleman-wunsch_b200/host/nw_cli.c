@@ -49,7 +49,7 @@ static void usage_and_exit(void)
 
 int main(int argc, char **argv)
 {
-    int list_counts = 0, quiet = 0, summary = 0, table = 0, unicode = 0;
+    int list_counts = 0, quiet = 0, summary = 0, table = 0, unicode = 0, workers = 1;
     const char *path = NULL;
 
     /* reference dbg.c:7-15: a leading "./" is dropped from the program name */
@@ -64,9 +64,11 @@ int main(int argc, char **argv)
         case 'f': path = optarg; break;
         case 'l': list_counts = 1; break;
         case 'p': {
-            /* accepted for compatibility; the GPU fill has no thread count */
+            /* the reference's worker count (needleman-wunsch.c:738-742, same check and message); here the
+             * workers are GPUs: the table is split into column strips over up to that many devices */
             const int threads = atoi(optarg);
             nw_require(threads > 1, "num-threads == %d; num-threads must be greater than 1", threads);
+            workers = threads;
             break;
         }
         case 'q': quiet = 1; break;
@@ -98,7 +100,18 @@ int main(int argc, char **argv)
     if (table) flags |= NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_WANT_ARROWS_HOST;
     if (!quiet || list_counts) flags |= NWB_WANT_ARROWS_HOST;
     nwb_table *t = NULL;
-    const int rc = nwb_fill(top, (int)strlen(top), side, (int)strlen(side), m, k, d, flags, &t);
+    /* -p N: column strips over min(N, devices present) GPUs, boundary columns pipelined over NVLink peer
+     * memory (include/nwb.h, nwb_fill_on).  The int32 score matrix behind -t lives on one device, and a
+     * box whose GPUs cannot map one another's memory still has every single GPU: both fill on device 0. */
+    int gpus = 1;
+    if (workers > 1 && !table) {
+        const int ndev = nwb_device_count();
+        gpus = workers < ndev ? workers : ndev;
+        if (gpus < 1) gpus = 1;
+    }
+    int rc = NWB_ERR_CUDA;
+    if (gpus > 1) rc = nwb_fill_on(top, (int)strlen(top), side, (int)strlen(side), m, k, d, flags, 0, gpus, &t);
+    if (rc != NWB_OK) rc = nwb_fill(top, (int)strlen(top), side, (int)strlen(side), m, k, d, flags, &t);
     if (rc != NWB_OK) {
         errno = 0;
         nw_require(0, "score-table fill failed: %s (%s)", nwb_strerror(rc), nwb_last_cuda_error());

@@ -105,6 +105,29 @@ def test_summary_beyond_32_bits(cli, oracle):
     assert err == b"-2087714816 optimal alignments\nOptimal score is 19\n"
 
 
+@pytest.mark.gpu
+def test_p_splits_the_table_over_gpus(cli, oracle, nwb):
+    """-p N: the reference's worker count (needleman-wunsch.c:738-742) selects min(N, devices) GPUs here, the table
+    split into column strips (nwb_fill_on).  Same text as the reference; with one GPU the flag changes nothing."""
+    rng = random.Random(77)
+    top = bytearray(rng.choice(b"ACGT") for _ in range(700))          # 3 strips of 256 columns
+    side = bytearray(top)
+    for pos in (90, 333, 610):
+        side[pos] = ord("A") if side[pos] != ord("A") else ord("C")    # substitutions: few optimal alignments
+    stdin = bytes(top) + b"\n" + bytes(side) + b"\n"
+    for flags in (["-l"], ["-q", "-l"], []):
+        a = same(cli, ["-p", "2"] + flags + ["1", "1", "1"], stdin)
+        assert a[0] == 0
+    same(cli, ["-p", "8", "-s", "-t", "1", "1", "1"], b"GCATGCU GATTACA\n")   # -t keeps the fill on one device
+    same(cli, ["-p", "8", "-l", "2", "1", "2"], b"GCATGCU GATTACA\n")         # more GPUs asked for than strips
+    # count and score beyond what the reference can enumerate: against the one-GPU run and the oracle
+    t, s = oracle.generate_pair(0x5EED0B10, 3000, 2000)
+    one = run(OURS, ["-q", "-s", "1", "1", "1"], t + b" " + s + b"\n")
+    two = run(OURS, ["-p", "2", "-q", "-s", "1", "1", "1"], t + b" " + s + b"\n")
+    assert one == two and one[0] == 0
+    assert b"Optimal score is %d\n" % oracle.fill(t, s, 1, 1, 1).final_score in one[2]
+
+
 # ---- batch front-end (SURVEY.md 8f row 4): needleman-wunsch-batch vs the reference CLI looped per pair -----
 
 BATCH = os.path.join(ROOT, "needleman-wunsch_b200", "host", "needleman-wunsch-batch")
