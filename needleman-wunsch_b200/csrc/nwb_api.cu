@@ -21,6 +21,7 @@
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
 #include "nwb_fill_hx.cuh"
+#include "nwb_fill_hy.cuh"
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
@@ -143,6 +144,7 @@ struct nwb_plan {
     cudaStream_t last_stream = nullptr;
     int m = 0, k = 0, d = 0;
     bool pk_hx = false; /* packed kernel variant with flush warps (nwb_fill_hx.cuh) */
+    bool pk_hy = false; /* ... with one row of skew per virtual lane (nwb_fill_hy.cuh) */
     bool count_pass = false; /* the count runs as a second sweep over the arrow codes (nwb_count.cuh) */
 };
 
@@ -312,6 +314,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     const bool fused_count = (flags & NWB_WANT_COUNT) && !p->count_pass;
     int strip_w = NWB_I32_STRIP_W, pk_k = 0, pk_r = 1;
     p->pk_hx = false;
+    p->pk_hy = false;
     if (p->kind == NWB_KIND_PK) {
         pk_k = nwb_pk_choose_k(A, B, p->world);
         /* two rows per step once the table is tall enough to amortise the doubled lane skew */
@@ -332,6 +335,10 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
             p->pk_hx = hx_ok && atoi(eh) != 0;
             if (p->pk_hx) { pk_k = 4; pk_r = 2; }
         }
+        /* diagnostics: NWB_PK_HY=1 selects the 3-rows-per-lane geometry of nwb_fill_hy.cuh (48 instead of 64 steps
+         * of skew per strip; measured 4-6 % SLOWER than hx on B200 because its step is one dependent chain) */
+        p->pk_hy = false;
+        if (const char *ey = getenv("NWB_PK_HY")) p->pk_hy = p->pk_hx && atoi(ey) != 0;
         strip_w = 64 * pk_k;
     }
     p->L = nwb_make_layout(A, B, p->kind, pk_k, strip_w);
@@ -477,7 +484,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
                          grid + cnt_grid_wanted <= p->sm_count && !getenv("NWB_COUNT_SERIAL");
     sp.publish_rows = overlap ? 1 : 0;
     if (overlap) CK(cudaEventRecord(p->ev_fork, st)); /* buffers are zeroed, strings uploaded */
-    if (hx) rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
+    if (hx) rc = p->pk_hy ? nwb_hy_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, grid, st, cuda_fail);
     else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
     else rc = run_i32(p, sp, grid, st);
     if (rc != NWB_OK) return rc;
@@ -610,7 +617,7 @@ extern "C" const char *nwb_plan_kernel_name(const nwb_plan *p)
 {
     if (!p || !p->ran) return "";
     if (p->kind == NWB_KIND_I32) return "nwb_fill_i32_kernel";
-    return p->pk_hx ? "nwb_fill_hx_kernel" : "nwb_fill_pk_kernel";
+    return p->pk_hx ? (p->pk_hy ? "nwb_fill_hy_kernel" : "nwb_fill_hx_kernel") : "nwb_fill_pk_kernel";
 }
 /* Host-only partition helpers (no device needed): what a launcher with one process per GPU uses to
  * shard the work the same way nwb_plan_create() / nwb_fill_on() do. */

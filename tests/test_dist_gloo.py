@@ -102,19 +102,19 @@ def _strips_rank(rank, world, seed, a, b, mkd, hx):
     assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
 
 
-@pytest.mark.parametrize("hx", [True, False])
+@pytest.mark.parametrize("hx", [2, 1, 0], ids=["hy", "hx", "pk"])
 def test_column_strips_two_ranks(hx):
     # 5 strips: ranks own 3 + 2; DNA 1/1/1
     _run(2, _strips_rank, 0x5EED0A01, 1200, 90, (1, 1, 1), hx)
 
 
 def test_column_strips_two_ranks_protein_scheme():
-    _run(2, _strips_rank, 0x5EED0A05, 700, 140, (2, 1, 2), True)
+    _run(2, _strips_rank, 0x5EED0A05, 700, 140, (2, 1, 2), 2)
 
 
 def test_column_strips_three_ranks_uneven():
     # 4 strips over 3 ranks: 2 + 2 + 0 -- the last rank owns nothing and must not disturb the sums
-    _run(3, _strips_rank, 0x5EED0A03, 1000, 70, (1, 1, 1), True)
+    _run(3, _strips_rank, 0x5EED0A03, 1000, 70, (1, 1, 1), 2)
 
 
 # ----------------------------------------------------------------------------- batch of pairs, no communication

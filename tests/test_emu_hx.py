@@ -14,13 +14,17 @@ import emu
 SCHEMES = [(1, 1, 1), (2, 1, 2), (0, 0, 0), (1, 2, 3), (1, 0, 0), (3, -1, 0), (3, 1, 2), (1, 1, 3)]
 
 
+VARIANTS = (1, 2)   # 1 = nwb_fill_hx.cuh (a row group of skew per virtual lane), 2 = nwb_fill_hy.cuh (one row)
+
+
 def check(oracle, t, s, m, k, d, grid=2, split=0):
     assert emu.hx_supported(m, k, d)
-    r = emu.fill_pk(t, s, m, k, d, K=4, R=2, grid=grid, split=split, hx=True)
     o = oracle.fill(t, s, m, k, d, want_codes=True)
-    assert np.array_equal(emu.unpack_arrows(r["arrows"], len(t)) & 7, o.codes[1:, 1:] & 7)
-    assert r["opt_score"] == o.final_score
-    assert r["branch_count"] == o.branch_count
+    for hx in VARIANTS:
+        r = emu.fill_pk(t, s, m, k, d, K=4, R=2, grid=grid, split=split, hx=hx)
+        assert np.array_equal(emu.unpack_arrows(r["arrows"], len(t)) & 7, o.codes[1:, 1:] & 7), hx
+        assert r["opt_score"] == o.final_score, hx
+        assert r["branch_count"] == o.branch_count, hx
 
 
 def test_supported():

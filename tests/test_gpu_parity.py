@@ -453,6 +453,29 @@ def test_hx_variant_big_and_multi_pass(oracle, nwb, force_hx):
         assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b)
 
 
+def test_hy_geometry_experiment(oracle, nwb, force_hx):
+    """NWB_PK_HY=1: the three-rows-per-lane geometry (csrc/nwb_fill_hy.cuh; an experiment, not the default) gives the
+    same table, score, branch counter and count as the oracle, also with several strips per warp."""
+    os.environ["NWB_PK_HY"] = "1"
+    try:
+        rng = random.Random(29)
+        for a, b, mkd in [(1, 1, (1, 1, 1)), (257, 2, (1, 1, 1)), (513, 3, (2, 1, 2)), (700, 333, (1, 1, 1)),
+                          (2049, 1025, (2, 1, 2)), (64, 4097, (1, 1, 3)), (3000, 3001, (1, 1, 1))]:
+            t = bytes(rng.choice(b"ACGT") for _ in range(a))
+            s = bytes(rng.choice(b"ACGT") for _ in range(b))
+            tab = nwb.fill(t, s, *mkd, nwb.WANT_ARROWS_HOST)
+            o = check_arrows(oracle, nwb, tab, t, s, *mkd)
+            assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, mkd)
+            tabc = nwb.fill(t, s, *mkd, nwb.WANT_COUNT)
+            assert (tabc.opt_score, tabc.branch_count, tabc.count) == (o.final_score, o.branch_count, o.count), (a, b, mkd)
+        t, s = oracle.generate_pair(0x5EED0E06, 160000, 200)   # 625 strips on 444 sweeping warps
+        tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_ARROWS_HOST)
+        o = check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
+        assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count)
+    finally:
+        del os.environ["NWB_PK_HY"]
+
+
 def test_plain_packed_kernel_without_hx(oracle, nwb):
     """NWB_PK_HX=0 keeps the one-warp-per-strip packed kernel (the path for 2d + m > 7) covered at 10k x 10k."""
     old = os.environ.get("NWB_PK_HX")
