@@ -26,6 +26,11 @@ for (a,b) in [(7,7),(300,100),(513,70),(600,260),(90,700)]:
     for cpl in (0,2,4,8):
         r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=2,count=cpl,hx=True)
         assert r['opt_score']==o.final_score and (cpl==0 or r['count']==o.count)
+    # the three-rows-per-lane geometry (nwb_fill_hy.cuh): stream words from step 0 on, 47 groups early; per-lane row parity
+    for cpl in (0,8):
+        r=emu.fill_pk(t,s,2,1,2,K=4,R=2,grid=2,count=cpl,hx=2,split=(1 if a>256 else 0))
+        o2=oracle.fill(t,s,2,1,2)
+        assert r['opt_score']==o2.final_score and r['branch_count']==o2.branch_count and (cpl==0 or r['count']==o2.count)
     if a>256:
         r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=1,split=1,count=8,hx=True)
         assert r['count']==o.count
