@@ -133,6 +133,16 @@ static int batch_count_pass(nwb_batch *b, cudaStream_t st)
         cp.scratch = b->cscratch.p;
     }
     const size_t smem = (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS;
+    /* every pair the same one-strip shape: the tables of a warp's run of pairs are swept back to back
+     * (NWB_BCNT_CHAIN=0, diagnostics: one pair at a time) */
+    const char *ech = getenv("NWB_BCNT_CHAIN");
+    if (nwb_bcount_chain_usable(b->uniform, b->uni_A, b->uni_B, b->n, (long long)grid * NWB_BCNT_WARPS) && !(ech && atoi(ech) == 0)) {
+        CK(cudaFuncSetAttribute(nwb_batch_count_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nwb_batch_count_chain_kernel<<<grid, 32 * NWB_BCNT_WARPS, smem, st>>>(cp, (int)b->uni_A, (int)b->uni_B);
+        CK(cudaGetLastError());
+        b->launches += 1;
+        return NWB_OK;
+    }
     CK(cudaFuncSetAttribute(nwb_batch_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nwb_batch_count_kernel<<<grid, 32 * NWB_BCNT_WARPS, smem, st>>>(cp);
     CK(cudaGetLastError());

@@ -127,3 +127,102 @@ __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel
         }
     }
 }
+
+/*
+ * Uniform batches (every pair A x B with A <= 256, B >= 64, B a multiple of 4 -- BASELINE config 4): a warp takes a
+ * contiguous run of pairs and sweeps their arrow tables BACK TO BACK as one tall table of n * B rows (the tables of
+ * consecutive pairs are contiguous in memory: one strip, pitch 128).  Row 1 of a table needs nothing from the table
+ * above but the border values, so lane l simply resets its counts when it enters a new table (tall row = 1 mod B) and
+ * stores the finished pair's count when it leaves one (tall row = 0 mod B): the 31 steps of lane skew are paid once per
+ * warp instead of once per pair (B + 31 -> B steps per pair), the ring is primed once, and only the chunks of four
+ * steps in which some lane crosses a table boundary (9 of B / 4) run the checked body.
+ */
+static inline bool nwb_bcount_chain_usable(bool uniform, long long A, long long B, long long n_pairs, long long nwarps)
+{
+    return uniform && A >= 1 && A <= 256 && B >= 64 && B % 4 == 0 && nwarps > 0 && (n_pairs / nwarps + 1) * B < (1LL << 30);
+}
+
+__global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_chain_kernel(const NwbBatchCountParams cp, const int A, const int B)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    unsigned *ring = reinterpret_cast<unsigned *>(NWB_SMEM_BASE() + (size_t)warp * NWB_BCNT_SMEM_PER_WARP);
+    const int sub = lane >> 3, chunk = lane & 7;
+    /* my run of pairs: the first n_pairs % nwarps warps take one more */
+    const long long per = cp.n_pairs / nwarps, rem = cp.n_pairs % nwarps;
+    const long long first = gwarp * per + (gwarp < rem ? gwarp : rem);
+    const long long npairs = per + (gwarp < rem ? 1 : 0);
+    if (npairs == 0) return;
+    const int T = (int)(npairs * B); /* rows of the tall table (the host checks that it fits an int) */
+    const uint8_t *src = cp.arrows + cp.arrow_off[first] + (size_t)chunk * 16;
+    const int kfin = (A - 1) - 8 * lane; /* the column of cell (A, B), 0..7 in the lane that owns it */
+    unsigned long long *out = cp.out_count + first;
+
+    unsigned long long cnt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) cnt[k] = 1ull;
+    unsigned long long send = 1ull, left_above = 1ull;
+    /* rows 1..4 into the ring (slot = tall row mod 64), rows 5..8 on their way */
+    {
+        const int r = 1 + sub;
+        *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = nwb_ldg_u128(src + (size_t)(r - 1) * 128);
+    }
+    uint4 wnext = nwb_ldg_u128(src + (size_t)((5 + sub <= T ? 5 + sub : T) - 1) * 128);
+    __syncwarp();
+    auto stage = [&](const int t) { /* rows t+1 .. t+4 (loaded four steps ago) into the ring; t+5 .. t+8 on their way */
+        const int r = t + 1 + sub;
+        *reinterpret_cast<uint4 *>(ring + (r & (NWB_BCNT_RING_ROWS - 1)) * 32 + chunk * 4) = wnext;
+        const int r2 = r + 4;
+        wnext = nwb_ldg_u128(src + (size_t)((r2 <= T ? r2 : T) - 1) * 128);
+        __syncwarp();
+    };
+    int jrow = -lane;        /* my row inside its table, 0-based, at the next step (negative: above the first table) */
+    int pair = 0;            /* index of the table my row is in */
+    const unsigned *rq = ring + lane;
+    const int nsteps = T + 31;
+    int c = 0;               /* t mod B */
+    for (int t = 0; t < nsteps; t += 4, c = (c + 4 == B) ? 0 : c + 4) {
+        if (t > 0) stage(t);
+        if (c < 32 || c == B - 4) {
+            /* some lane enters or leaves a table in these four steps (or is above the first / below the last one) */
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int tau = t + i - lane + 1; /* my tall row */
+                unsigned long long cl = __shfl_up_sync(NWB_FULL_MASK, send, 1);
+                if (lane == 0) cl = 1ull; /* column 0 */
+                if (tau >= 1 && tau <= T) {
+                    if (jrow == 0) { /* row 1 of a table: the border row above it */
+#pragma unroll
+                        for (int k = 0; k < 8; k++) cnt[k] = 1ull;
+                        left_above = 1ull;
+                    }
+                    const unsigned x = rq[(tau & (NWB_BCNT_RING_ROWS - 1)) * 32];
+                    nwb_count_row<8>(x, cnt, left_above, cl, send);
+                    if (jrow == B - 1) {
+                        if (kfin >= 0 && kfin < 8) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                if (k == kfin) out[pair] = cnt[k];
+                        }
+                        jrow = -1;
+                        pair++;
+                    }
+                }
+                jrow++;
+            }
+        } else {
+            /* every lane strictly inside rows 2 .. B-1 of its table */
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int tau = t + i - lane + 1;
+                unsigned long long cl = __shfl_up_sync(NWB_FULL_MASK, send, 1);
+                if (lane == 0) cl = 1ull;
+                const unsigned x = rq[(tau & (NWB_BCNT_RING_ROWS - 1)) * 32];
+                nwb_count_row<8>(x, cnt, left_above, cl, send);
+            }
+            jrow += 4;
+        }
+    }
+}

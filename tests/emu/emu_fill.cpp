@@ -353,7 +353,16 @@ int emu_batch_count(const long long *top_off, const long long *side_off, long lo
         scratch.assign((size_t)grid * NWB_BCNT_WARPS * cp.scratch_per_warp, 0xdeadbeefdeadbeefULL);
         cp.scratch = scratch.data();
     }
-    emu_launch(grid, 32 * NWB_BCNT_WARPS, (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS, [&]() { nwb_batch_count_kernel(cp); });
+    /* as batch_count_pass() in csrc/nwb_batch_api.inl: uniform one-strip batches are swept back to back */
+    bool uniform = n > 0;
+    const long long A0 = n > 0 ? top_off[1] - top_off[0] : 0, B0 = n > 0 ? side_off[1] - side_off[0] : 0;
+    for (long long p = 1; p < n; p++)
+        if (top_off[p + 1] - top_off[p] != A0 || side_off[p + 1] - side_off[p] != B0) uniform = false;
+    if (nwb_bcount_chain_usable(uniform, A0, B0, n, (long long)grid * NWB_BCNT_WARPS))
+        emu_launch(grid, 32 * NWB_BCNT_WARPS, (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS,
+                   [&]() { nwb_batch_count_chain_kernel(cp, (int)A0, (int)B0); });
+    else
+        emu_launch(grid, 32 * NWB_BCNT_WARPS, (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS, [&]() { nwb_batch_count_kernel(cp); });
     return 0;
 }
 

@@ -158,3 +158,17 @@ def test_batch_count_config4_goldens(oracle):
     r = emu.fill_batch(tops, sides, 1, 1, 1, grid=1, count=True)
     assert r["kernel"] == "cx"
     assert [int(c) for c in r["counts"]] == [387701138034524160, 108460706365440, 4971798065203200]
+
+
+def test_batch_count_chained_uniform(oracle):
+    # uniform one-strip batches: nwb_batch_count_chain_kernel sweeps a warp's run of pairs back to back (lanes reset at
+    # table boundaries); more pairs than warps (runs of 3 and 2 pairs on 16 warps), B not a multiple of 32, A < 256,
+    # counts that wrap 2^64, and a single run longer than the 64-row ring several times over
+    rng = random.Random(43)
+    for (a, b, n, mkd, grid) in ((100, 68, 40, (1, 1, 1), 1), (256, 64, 37, (0, 0, 0), 1), (9, 128, 70, (2, 1, 2), 2),
+                                 (256, 256, 19, (1, 1, 1), 1)):
+        tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for _ in range(n)]
+        sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _ in range(n)]
+        r = emu.fill_batch(tops, sides, *mkd, grid=grid, count=True)
+        for i, (t, s) in enumerate(zip(tops, sides)):
+            assert int(r["counts"][i]) == oracle.fill(t, s, *mkd).count, (a, b, i)
