@@ -207,7 +207,7 @@ def run_extras(nwb, oracle, torch, dist, world, rank, local, barrier) -> dict | 
         cms = float(tt.item())
     out["config4_batch_with_count"] = {"pairs_total": per * world, "ms_per_pass": cms,
                                        "gcups_total": per * world * 65536 / (cms * 1e-3) / 1e9,
-                                       "kernels": "fill + nwb_batch_count_kernel", "golden_counts_ok": bool(okc)}
+                                       "kernels": "fill + nwb_batch_count_chain_kernel", "golden_counts_ok": bool(okc)}
     out["config4_batch"] = {"pairs_total": per * world, "pairs_per_gpu": per, "ms_per_pass": ms,
                             "gcups_total": per * world * 65536 / (ms * 1e-3) / 1e9, "fill_kernel_ms": kms, "kernel": kname4,
                             "includes": "fill + per-pair branch counter, strings and 4.1 GB of arrow tables resident",

@@ -371,6 +371,31 @@ def test_batch_count(oracle, nwb):
         bt.close()
 
 
+def test_batch_count_chained_runs(oracle, nwb):
+    """Uniform one-strip batches: nwb_batch_count_chain_kernel sweeps a warp's run of pairs back to back.  Runs of 5-6
+    pairs per warp (12,000 pairs on 2,368 warps), A < 256, B a multiple of 4 but not of 32; every count against the
+    one-pair-at-a-time kernel (NWB_BCNT_CHAIN=0) and a sample against the oracle, also mod 2^64 (0/0/0)."""
+    rng = random.Random(47)
+    n = 12000
+    tops = [bytes(rng.choice(b"ACGT") for _ in range(100)) for _ in range(n)]
+    sides = [bytes(rng.choice(b"ACGT") for _ in range(68)) for _ in range(n)]
+    for m, k, d in ((1, 1, 1), (0, 0, 0)):
+        got = {}
+        for chain in ("1", "0"):
+            os.environ["NWB_BCNT_CHAIN"] = chain
+            try:
+                bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_COUNT)
+                bt.run()
+                bt.fetch()
+                got[chain] = [bt.count(i) for i in range(n)]
+                bt.close()
+            finally:
+                del os.environ["NWB_BCNT_CHAIN"]
+        assert got["1"] == got["0"]
+        for i in [0, 1, 5, 6, n - 1] + rng.sample(range(n), 25):
+            assert got["1"][i] == oracle.fill(tops[i], sides[i], m, k, d).count, i
+
+
 def test_count_prefix_property(oracle, nwb):
     """Intermediate counts of the packed count kernel through the public ABI: the count of cell
     (i, j) equals the final count of the sub-problem (top[:i], side[:j]).  The final count of the
