@@ -67,6 +67,12 @@ extern "C" {
  * reference only prints from debug builds, needleman-wunsch.c:624).  The packed
  * kernel obtains it with a second pass over the arrow table; this skips it. */
 #define NWB_NO_BRANCH_COUNT 0x40u
+/* Verification aid: obtain the count with the dense forward sweep and also return the digests of the count
+ * matrix's bottom row and last column (nwb_summary.lastrow_count_digest / lastcol_count_digest).  Implies
+ * NWB_WANT_COUNT. */
+#define NWB_WANT_COUNT_DIGEST 0x80u
+/* nwb_fill()/nwb_fill_on(): compute the arrow-table digest on the device before returning (nwb_arrow_digest()). */
+#define NWB_WANT_DIGEST 0x100u
 
 /* ---- error codes ---------------------------------------------------------- */
 #define NWB_OK 0
@@ -77,6 +83,17 @@ extern "C" {
 #define NWB_ERR_UNSUPPORTED (-5) /* flag combination not available             */
 
 const char *nwb_strerror(int err);
+/* Explicit overrides for tests and measurements; the library reads NO environment variables.  Every key
+ * selects between kernels that produce identical results ("pk_k", "pk_r", "pk_warps", "pk_hx", "count_mode"
+ * 0 auto / 1 fused into the fill / 2 dense sweep after the fill / 3 dense sweep trailing the fill on a second
+ * stream, "cnt_cpl", "batch_bx", "batch_cx", "bcnt_chain", "bcnt_sparse", "cx_warps"; 0 or -1 = automatic,
+ * see nwb_api.cu) except "watchdog_ms" (how long a device-side wait may see no progress before the fill
+ * fails with NWB_ERR_CUDA; default 4000) and "inject_fault" (test only: 1 makes the next fills lose a
+ * strip's boundary stream so that the watchdog path can be exercised -- the fill FAILS, it never returns a
+ * wrong result).  Process-wide; set before creating the plan/batch that should see it.  Unknown key:
+ * NWB_ERR_INVALID.  nwb_tune_reset() restores the defaults. */
+int nwb_tune(const char *key, int value);
+void nwb_tune_reset(void);
 /* Text of the last CUDA error seen by this thread ("" if none). */
 const char *nwb_last_cuda_error(void);
 /* Number of usable CUDA devices (0 if none), ABI version. */
@@ -140,6 +157,12 @@ const uint64_t *nwb_count_rows(const nwb_table *t, size_t *pitch_elems);
  * launching stream), and which kernel ran: 0 = general int32, 1 = packed 16x2. */
 float nwb_kernel_ms(const nwb_table *t);
 int nwb_kernel_kind(const nwb_table *t);
+/* Parity aid (NWB_WANT_DIGEST): an order-independent 64-bit digest of the whole arrow table, computed on the
+ * device: the sum mod 2^64 over rows j = 1..B and 32-bit words w of the table of
+ * mix64((j << 32) | w, word(j,w) & 0x77777777 with the cells beyond column A zeroed), mix64(p, x) = the
+ * SplitMix64 finaliser of (p + 1) * 0x9E3779B97F4A7C15 + x.  The CPU oracle computes the same sum from the
+ * reference's definition of every cell (needleman-wunsch.c:485-503). */
+int nwb_arrow_digest(const nwb_table *t, uint64_t *digest);
 
 /* ========================================================================== *
  * 2. Device-resident plan -- the same fill with the strings already in HBM and
@@ -158,11 +181,23 @@ typedef struct nwb_summary {
      * plan opt_score is already final; in a strip group the true score is
      * sum over ranks of partial_r, minus d*(A+B). */
     int64_t partial_r;
+    /* How the count was obtained: 0 none, 1 fused into the fill, 2 dense forward sweep over the arrow codes,
+     * 3 sparse backward sweep from (A,B) over the cells on optimal paths, 4 = 3 gave up (live band wider than
+     * its window) and the dense sweep produced the count.  count_rows: rows the sparse sweep visited. */
+    int32_t count_path;
+    uint32_t count_rows;
+    /* NWB_WANT_COUNT_DIGEST: sum_i mix64(i, cnt(i,B)) over this rank's columns i, and sum_j mix64(j, cnt(A,j))
+     * (non-zero only on the rank that owns column A); in a strip group the ranks' values add up. */
+    uint64_t lastrow_count_digest;
+    uint64_t lastcol_count_digest;
 } nwb_summary;
+/* The summary of a finished nwb_fill()/nwb_fill_on() table (strip groups already combined). */
+int nwb_table_summary(const nwb_table *t, nwb_summary *out);
 
 /* Allocate device workspace for fills up to max_top x max_side on `device`.
  * strip_rank/strip_world != (0,1) makes this plan one rank of a column-strip
- * group: rank r owns columns (r*A/world, (r+1)*A/world]. */
+ * group: the table's 256-column strips are dealt out in contiguous runs of ceil(n_strips / world) strips, rank r
+ * taking run r (nwb_strip_partition() below is the same rule; trailing ranks can be empty). */
 int nwb_plan_create(int max_top, int max_side, unsigned flags, int device,
                     int strip_rank, int strip_world, nwb_plan **out);
 void nwb_plan_destroy(nwb_plan *p);
@@ -171,8 +206,14 @@ int nwb_plan_upload(nwb_plan *p, const char *top, int top_len, const char *side,
 /* Launch the fill on `stream` (a cudaStream_t; NULL = the plan's own stream).
  * Asynchronous; inputs and outputs stay on the device. */
 int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream);
-/* Wait for the plan's work and fetch the 32-byte summary (device -> host). */
+/* Wait for the plan's work and fetch the summary (device -> host).  Returns NWB_ERR_CUDA if a device-side
+ * wait gave up (watchdog): the results of that run are invalid. */
 int nwb_plan_summary(nwb_plan *p, nwb_summary *out);
+/* Digest of this plan's share of the arrow table on the device (definition: nwb_arrow_digest() above; the
+ * shares of a strip group add up mod 2^64).  Blocking. */
+int nwb_plan_arrow_digest(nwb_plan *p, uint64_t *digest);
+/* "" / "fused" / "dense" / "sparse": how the last run obtained the count (nwb_summary.count_path). */
+const char *nwb_plan_count_path_name(const nwb_plan *p);
 /* Device pointer / pitch of the arrow table (layout above). */
 void *nwb_plan_arrows_device(nwb_plan *p);
 size_t nwb_plan_arrow_pitch(const nwb_plan *p);
@@ -249,6 +290,11 @@ int64_t nwb_batch_launches(const nwb_batch *b);
  * For logs and profiles. */
 const char *nwb_batch_kernel_name(const nwb_batch *b);
 void *nwb_batch_arrows_device(nwb_batch *b);
+/* Parity aid: digests of the whole batch computed on the device (after nwb_batch_run): out[0..3] = the sums
+ * mod 2^64 over the pairs p of mix64(first_pair + p, x_p), x_p = the pair's arrow digest (nwb_arrow_digest) /
+ * optimal score (sign-extended) / branch count / alignment count (0 terms when not produced).  first_pair
+ * = the global index of this batch's pair 0, so that the shards of a sharded batch add up.  Blocking. */
+int nwb_batch_digest(nwb_batch *b, int64_t first_pair, uint64_t out[4]);
 
 /* ========================================================================== *
  * 4. Measurement aid (not on the fill path): INT/DPX issue rate of `device`,

@@ -34,7 +34,11 @@ TRACK_ABS = 0x08
 FORCE_GENERAL = 0x10
 WANT_COUNT_MATRIX = 0x20
 NO_BRANCH_COUNT = 0x40
+WANT_COUNT_DIGEST = 0x80
+WANT_DIGEST = 0x100
 KIND_I32, KIND_PK = 0, 1
+# nwb_summary.count_path
+COUNT_NONE, COUNT_FUSED, COUNT_DENSE, COUNT_SPARSE, COUNT_SPARSE_BAILED = 0, 1, 2, 3, 4
 
 
 class NwbError(RuntimeError):
@@ -51,7 +55,9 @@ class NwbError(RuntimeError):
 
 class Summary(C.Structure):
     _fields_ = [("opt_score", C.c_int32), ("branch_count", C.c_uint32), ("greatest_abs", C.c_int32),
-                ("kernel_kind", C.c_int32), ("count", C.c_uint64), ("partial_r", C.c_int64)]
+                ("kernel_kind", C.c_int32), ("count", C.c_uint64), ("partial_r", C.c_int64),
+                ("count_path", C.c_int32), ("count_rows", C.c_uint32),
+                ("lastrow_count_digest", C.c_uint64), ("lastcol_count_digest", C.c_uint64)]
 
 
 _lib = None
@@ -61,6 +67,13 @@ _SIGS = {
     "nwb_last_cuda_error": (C.c_char_p, []),
     "nwb_device_count": (C.c_int, []),
     "nwb_abi_version": (C.c_int, []),
+    "nwb_tune": (C.c_int, [C.c_char_p, C.c_int]),
+    "nwb_tune_reset": (None, []),
+    "nwb_table_summary": (C.c_int, [C.c_void_p, C.POINTER(Summary)]),
+    "nwb_arrow_digest": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "nwb_plan_arrow_digest": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "nwb_plan_count_path_name": (C.c_char_p, [C.c_void_p]),
+    "nwb_batch_digest": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "nwb_fill": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
                            C.POINTER(C.c_void_p)]),
     "nwb_fill_on": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
@@ -132,6 +145,15 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def use_experiments_build() -> None:
+    """Measurement tools only: load libnwb_exp.so (`make -C needleman-wunsch_b200/csrc exp`, -DNWB_EXPERIMENTS: the
+    measured-slower nwb_fill_hy.cuh geometry and the wait-skipping debug bits).  Call before anything else."""
+    global LIB_PATH
+    if _lib is not None:
+        raise RuntimeError("libnwb.so is already loaded")
+    LIB_PATH = os.path.join(HERE, "libnwb_exp.so")
+
+
 def load_library() -> C.CDLL:
     """Load libnwb.so.  Raises if it was not built -- there is nothing to fall back to."""
     global _lib
@@ -159,6 +181,33 @@ def measure_int_issue(mode: int = 1, device: int = 0) -> tuple[float, float]:
     if rc != 0:
         raise NwbError(rc, "nwb_measure_int_issue")
     return a.value, b.value
+
+
+def tune(key: str, value: int) -> None:
+    """nwb_tune(): explicit kernel-selection / watchdog overrides for tests and measurements (include/nwb.h)."""
+    rc = load_library().nwb_tune(key.encode(), int(value))
+    if rc != 0:
+        raise NwbError(rc, f"nwb_tune({key!r})")
+
+
+def tune_reset() -> None:
+    load_library().nwb_tune_reset()
+
+
+class tuned:
+    """Context manager: `with nwb.tuned(pk_hx=0, count_mode=2): ...` sets the overrides and restores the defaults."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            tune(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        tune_reset()
+        return False
 
 
 def strip_partition(top_len: int, rank: int, world: int, strip_width: int = 256) -> tuple[int, int]:
@@ -206,6 +255,17 @@ class Table:
         self.kernel_ms = L.nwb_kernel_ms(self._h)
         self.kernel_kind = L.nwb_kernel_kind(self._h)
         self.pitch = L.nwb_arrow_pitch(self._h)
+
+    def summary(self) -> Summary:
+        s = Summary()
+        _ck(load_library().nwb_table_summary(self._h, C.byref(s)), "nwb_table_summary")
+        return s
+
+    def arrow_digest(self) -> int:
+        """Digest of the whole arrow table, computed on the device (NWB_WANT_DIGEST)."""
+        d = C.c_uint64()
+        _ck(load_library().nwb_arrow_digest(self._h, C.byref(d)), "nwb_arrow_digest")
+        return d.value
 
     def score(self, i: int, j: int) -> int:
         return load_library().nwb_score(self._h, i, j)
@@ -311,6 +371,15 @@ class Plan:
     def arrow_pitch(self) -> int:
         return load_library().nwb_plan_arrow_pitch(self._h)
 
+    def arrow_digest(self) -> int:
+        """Digest of this plan's share of the arrow table (device kernel; the shares of a strip group add up)."""
+        d = C.c_uint64()
+        _ck(load_library().nwb_plan_arrow_digest(self._h, C.byref(d)), "nwb_plan_arrow_digest")
+        return d.value
+
+    def count_path(self) -> str:
+        return load_library().nwb_plan_count_path_name(self._h).decode()
+
     def arrows_device(self) -> int:
         return load_library().nwb_plan_arrows_device(self._h) or 0
 
@@ -391,6 +460,12 @@ class Batch:
 
     def kernel_ms(self) -> float:
         return load_library().nwb_batch_kernel_ms(self._h)
+
+    def digest(self, first_pair: int = 0) -> tuple[int, int, int, int]:
+        """(arrow, score, branch, count) digests of the whole batch, computed on the device (nwb_batch_digest)."""
+        out = (C.c_uint64 * 4)()
+        _ck(load_library().nwb_batch_digest(self._h, first_pair, out), "nwb_batch_digest")
+        return tuple(int(x) for x in out)
 
     def kernel_name(self) -> str:
         return (load_library().nwb_batch_kernel_name(self._h) or b"").decode()

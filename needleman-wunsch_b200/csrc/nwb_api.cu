@@ -21,14 +21,18 @@
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
 #include "nwb_fill_hx.cuh"
-#include "nwb_fill_hy.cuh"
+#ifdef NWB_EXPERIMENTS
+#include "nwb_fill_hy.cuh" /* measured-slower lane geometry, kept for the record; not in the product build */
+#endif
 #include "nwb_count.cuh"
+#include "nwb_count_sparse.cuh"
+#include "nwb_digest.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
 #include "nwb_batch_count.cuh"
 #include "nwb_peak.cuh"
 
-#define NWB_ABI_VERSION 1
+#define NWB_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------- */
 static thread_local char g_cuda_err[256] = "";
@@ -69,6 +73,54 @@ extern "C" int nwb_device_count(void)
     }
     return n;
 }
+
+/* ---- explicit tuning / test overrides (include/nwb.h: nwb_tune) ---------------
+ * The library reads NO environment variables.  Every override selects between
+ * kernels that produce identical results, except `inject_fault`, which makes a
+ * fill fail with NWB_ERR_CUDA through the device watchdog (never a wrong result). */
+struct NwbTune {
+    int pk_k = 0;        /* 0 = auto; 1, 2, 4 columns per half-lane (nwb_fill_pk.cuh)                       */
+    int pk_r = 0;        /* 0 = auto; 1, 2 rows per step                                                     */
+    int pk_warps = 0;    /* 0 = auto; sweeping warps per block of nwb_fill_pk_kernel                         */
+    int pk_hx = -1;      /* -1 = auto; 0 = never nwb_fill_hx_kernel; 1 = whenever the scheme allows          */
+    int count_mode = 0;  /* 0 = auto (sparse backward sweep, dense sweep behind it); 1 = fused into the fill;
+                          * 2 = dense sweep after the fill; 3 = dense sweep trailing the fill on a 2nd stream */
+    int cnt_cpl = 0;     /* 0 = auto; 2, 4, 8 columns per lane of the dense count sweep                      */
+    int batch_bx = -1;   /* -1 = auto; 0 = never nwb_batch_bx_kernel                                         */
+    int batch_cx = -1;   /* -1 = auto; 0 = never nwb_batch_cx_kernel                                         */
+    int bcnt_chain = -1; /* -1 = auto; 0 = never nwb_batch_count_chain_kernel                                */
+    int bcnt_sparse = -1; /* -1 = auto; 0 = never the sparse backward batch count                            */
+    int cx_warps = 0;    /* 0 = auto (12); 16                                                                */
+    int watchdog_ms = 4000; /* device-side spin loops give up after this long without progress               */
+    int inject_fault = 0;   /* test only: 1 = drop the boundary stream of the fill's second strip            */
+#ifdef NWB_EXPERIMENTS
+    int pk_hy = 0;
+    int debug_nowait = 0;
+#endif
+};
+static NwbTune g_tune;
+
+extern "C" int nwb_tune(const char *key, int value)
+{
+    if (!key) return NWB_ERR_INVALID;
+    struct { const char *name; int *slot; } tab[] = {
+        {"pk_k", &g_tune.pk_k}, {"pk_r", &g_tune.pk_r}, {"pk_warps", &g_tune.pk_warps}, {"pk_hx", &g_tune.pk_hx},
+        {"count_mode", &g_tune.count_mode}, {"cnt_cpl", &g_tune.cnt_cpl}, {"batch_bx", &g_tune.batch_bx},
+        {"batch_cx", &g_tune.batch_cx}, {"bcnt_chain", &g_tune.bcnt_chain}, {"bcnt_sparse", &g_tune.bcnt_sparse},
+        {"cx_warps", &g_tune.cx_warps},
+        {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault},
+#ifdef NWB_EXPERIMENTS
+        {"pk_hy", &g_tune.pk_hy}, {"debug_nowait", &g_tune.debug_nowait},
+#endif
+    };
+    for (auto &t : tab)
+        if (strcmp(t.name, key) == 0) {
+            *t.slot = value;
+            return NWB_OK;
+        }
+    return NWB_ERR_INVALID;
+}
+extern "C" void nwb_tune_reset(void) { g_tune = NwbTune(); }
 
 /* ------------------------------------------------------------------------- */
 template <typename T>
@@ -126,8 +178,8 @@ struct nwb_plan {
     DevBuf<unsigned long long> cntmat, bnd_c;
     DevBuf<uint32_t> bnd_w;
     DevBuf<uint16_t> side_pre;
-    DevBuf<unsigned long long> dbg_times, dbg_trace;
-    int dbg_trace_blocks = 0, dbg_trace_stride = 1;
+    DevBuf<unsigned long long> digest;
+    int count_path = 0;
     DevBuf<int> progress;
     DevBuf<NwbDevSummary> summary;
     Inbox inbox = {};
@@ -201,7 +253,11 @@ extern "C" int nwb_plan_create(int max_top, int max_side, unsigned flags, int de
         make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64 + 512, 32));
         e = cudaMalloc((void **)&p->inbox.base, p->inbox.bytes);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(inbox)");
-        else e = cudaMemset(p->inbox.base, 0, p->inbox.bytes);
+        else {
+            /* on the plan's own (non-blocking) stream, then wait: nothing else orders it against the first run */
+            e = cudaMemsetAsync(p->inbox.base, 0, p->inbox.bytes, p->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        }
         if (rc == NWB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaMemset(inbox)");
     }
     if (rc != NWB_OK) {
@@ -219,7 +275,7 @@ extern "C" void nwb_plan_destroy(nwb_plan *p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     p->top.release(); p->side.release(); p->arrows.release(); p->scores.release();
     p->bnd_s.release(); p->cntmat.release(); p->bnd_c.release(); p->bnd_w.release();
-    p->progress.release(); p->summary.release(); p->side_pre.release(); p->dbg_times.release(); p->dbg_trace.release();
+    p->progress.release(); p->summary.release(); p->side_pre.release(); p->digest.release();
     if (p->inbox.base) cudaFree(p->inbox.base);
     if (p->right_base && p->right_is_ipc) cudaIpcCloseMemHandle(p->right_base);
     if (p->stream2) { cudaStreamSynchronize(p->stream2); cudaStreamDestroy(p->stream2); }
@@ -270,10 +326,11 @@ static int launch_strip_kernel(KernelT kernel, int grid, int block, size_t smem,
     return NWB_OK;
 }
 
-static int run_i32(nwb_plan *p, const NwbStripParams &sp, int grid, cudaStream_t st)
+static int run_i32(nwb_plan *p, unsigned flags, const NwbStripParams &sp, int grid, cudaStream_t st)
 {
-    const bool C = p->flags & NWB_WANT_COUNT, S = p->flags & NWB_WANT_SCORES, AB = p->flags & NWB_TRACK_ABS,
-               CM = p->flags & NWB_WANT_COUNT_MATRIX;
+    (void)p;
+    const bool C = flags & NWB_WANT_COUNT, S = flags & NWB_WANT_SCORES, AB = flags & NWB_TRACK_ABS,
+               CM = flags & NWB_WANT_COUNT_MATRIX;
     const int block = 32 * NWB_I32_WARPS;
     const size_t smem = NWB_I32_SMEM_BYTES;
 #define L_(c, s, a, cm) return launch_strip_kernel(nwb_fill_i32_kernel<c, s, a, cm>, grid, block, smem, st, sp)
@@ -294,6 +351,18 @@ static int run_i32(nwb_plan *p, const NwbStripParams &sp, int grid, cudaStream_t
 static int run_pk(nwb_plan *p, const NwbStripParams &sp, const NwbPkConsts &pc, bool count, int grid, int warps,
                   cudaStream_t st);
 
+/* zero `n` 16-byte words unless *state == NWB_SPC_DONE (the dense count sweep's streams, when the sparse
+ * backward sweep has not already produced the count) */
+__global__ void __launch_bounds__(256) nwb_zero_unless_done_kernel(const int *state, uint4 *dst, size_t n)
+{
+    if (*reinterpret_cast<const volatile int *>(state) == NWB_SPC_DONE) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+/* where the count behind -s comes from (nwb_summary.count_path) */
+enum { NWB_CNT_NONE = 0, NWB_CNT_FUSED = 1, NWB_CNT_DENSE = 2, NWB_CNT_SPARSE = 3, NWB_CNT_SPARSE_BAILED = 4 };
+
 extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
 {
     if (!p) return NWB_ERR_INVALID;
@@ -304,41 +373,48 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     const int A = p->A, B = p->B;
     unsigned flags = p->flags;
     if (flags & NWB_WANT_COUNT_MATRIX) flags |= NWB_WANT_COUNT;
+    if (flags & NWB_WANT_COUNT_DIGEST) flags |= NWB_WANT_COUNT;
+    const NwbTune tn = g_tune;
 
     NwbPkConsts pc;
     memset(&pc, 0, sizeof(pc));
     p->kind = choose_kind(flags, m, k, d, &pc);
-    /* packed kernels: the count behind -s is a second sweep over the finished arrow codes (nwb_count.cuh);
-     * NWB_COUNT_FUSED=1 (diagnostics) keeps it inside the fill (nwb_fill_pk.cuh, COUNT) */
-    p->count_pass = (p->kind == NWB_KIND_PK) && (flags & NWB_WANT_COUNT) && !getenv("NWB_COUNT_FUSED");
-    const bool fused_count = (flags & NWB_WANT_COUNT) && !p->count_pass;
+    /* The count behind -s.  Default: the sparse backward sweep over the finished arrow codes
+     * (nwb_count_sparse.cuh) with the dense forward sweep (nwb_count.cuh) launched behind it, which returns at
+     * once unless the sparse sweep gave up.  A strip group (world > 1) keeps its arrow columns on different
+     * GPUs and runs the dense sweep, whose strips hand their counts on like the fill's; the count matrix comes
+     * from the general kernel's fused count. */
+    int cpath = NWB_CNT_NONE;
+    if (flags & NWB_WANT_COUNT) {
+        if (flags & NWB_WANT_COUNT_MATRIX) cpath = NWB_CNT_FUSED;
+        else if (tn.count_mode == 1) cpath = NWB_CNT_FUSED;
+        else if (p->kind == NWB_KIND_I32 && p->world > 1) cpath = NWB_CNT_FUSED;
+        else if (tn.count_mode >= 2 || (flags & NWB_WANT_COUNT_DIGEST) || p->world > 1) cpath = NWB_CNT_DENSE;
+        else cpath = NWB_CNT_SPARSE;
+    }
+    if ((flags & NWB_WANT_COUNT_DIGEST) && cpath != NWB_CNT_DENSE) return NWB_ERR_UNSUPPORTED;
+    p->count_path = cpath;
+    p->count_pass = (cpath == NWB_CNT_DENSE || cpath == NWB_CNT_SPARSE);
+    const bool fused_count = (cpath == NWB_CNT_FUSED);
+    /* the kernels take the count request from the flags they are instantiated with */
+    unsigned kflags = flags;
+    if (!fused_count) kflags &= ~(unsigned)NWB_WANT_COUNT;
     int strip_w = NWB_I32_STRIP_W, pk_k = 0, pk_r = 1;
     p->pk_hx = false;
     p->pk_hy = false;
     if (p->kind == NWB_KIND_PK) {
-        pk_k = nwb_pk_choose_k(A, B, p->world);
+        pk_k = (tn.pk_k == 1 || tn.pk_k == 2 || tn.pk_k == 4) ? tn.pk_k : nwb_pk_choose_k(A, B, p->world);
+        if (p->count_pass) pk_k = 4; /* the count sweeps walk 256-column strips */
         /* two rows per step once the table is tall enough to amortise the doubled lane skew */
-        pk_r = (B >= 4096) ? 2 : 1;
-        if (const char *ek = getenv("NWB_PK_K")) { /* diagnostics */
-            const int v = atoi(ek);
-            if (v == 1 || v == 2 || v == 4) pk_k = v;
-        }
-        if (p->count_pass) pk_k = 4; /* the count sweep walks 256-column strips */
-        if (const char *er = getenv("NWB_PK_R")) { /* diagnostics */
-            const int v = atoi(er);
-            if (v == 1 || v == 2) pk_r = v;
-        }
+        pk_r = (tn.pk_r == 1 || tn.pk_r == 2) ? tn.pk_r : ((B >= 4096) ? 2 : 1);
         /* sweeping + flush warps (nwb_fill_hx.cuh) when every difference fits a nibble */
         const bool hx_ok = !fused_count && nwb_hx_supported(pc);
         p->pk_hx = hx_ok && pk_k == 4 && pk_r == 2;
-        if (const char *eh = getenv("NWB_PK_HX")) { /* diagnostics: 0 = never, 1 = whenever the scheme allows */
-            p->pk_hx = hx_ok && atoi(eh) != 0;
-            if (p->pk_hx) { pk_k = 4; pk_r = 2; }
-        }
-        /* diagnostics: NWB_PK_HY=1 selects the 3-rows-per-lane geometry of nwb_fill_hy.cuh (48 instead of 64 steps
-         * of skew per strip; measured 4-6 % SLOWER than hx on B200 because its step is one dependent chain) */
-        p->pk_hy = false;
-        if (const char *ey = getenv("NWB_PK_HY")) p->pk_hy = p->pk_hx && atoi(ey) != 0;
+        if (tn.pk_hx == 0) p->pk_hx = false;
+        if (tn.pk_hx == 1 && hx_ok) { p->pk_hx = true; pk_k = 4; pk_r = 2; }
+#ifdef NWB_EXPERIMENTS
+        p->pk_hy = p->pk_hx && tn.pk_hy != 0;
+#endif
         strip_w = 64 * pk_k;
     }
     p->L = nwb_make_layout(A, B, p->kind, pk_k, strip_w);
@@ -368,41 +444,41 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     if (rc == NWB_OK) rc = p->progress.ensure((size_t)nloc);
     if (rc == NWB_OK && p->kind == NWB_KIND_I32) {
         rc = p->bnd_s.ensure((size_t)nloc * L.bpitch);
-        if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
+        if (rc == NWB_OK && fused_count) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
     }
     if (rc == NWB_OK && p->kind == NWB_KIND_PK) {
         rc = p->bnd_w.ensure((size_t)nloc * L.bpitch);
         if (rc == NWB_OK) rc = p->side_pre.ensure(NWB_PK_SPRE_LEN(B));
         if (rc == NWB_OK && fused_count) rc = p->bnd_c.ensure((size_t)nloc * 2 * L.bpitch);
     }
-    /* the count sweep's own strips: 32 * cpl columns wide, aligned with this rank's 256-column fill strips */
+    /* the dense count sweep's own strips: 32 * cpl columns wide, aligned with this rank's 256-column fill strips */
     NwbCountParams cp;
     memset(&cp, 0, sizeof(cp));
     int cnt_cpl = 8;
+    size_t cnt_stream_words = 0; /* uint64 words of this rank's count streams */
     if (rc == NWB_OK && p->count_pass) {
         long long cols = (long long)nloc * 256;
         if (cols > A) cols = A;
-        cnt_cpl = nwb_count_choose_cpl(cols, p->sm_count);
-        if (const char *ec = getenv("NWB_CNT_CPL")) { /* diagnostics */
-            const int v = atoi(ec);
-            if (v == 2 || v == 4 || v == 8) cnt_cpl = v;
-        }
+        cnt_cpl = (tn.cnt_cpl == 2 || tn.cnt_cpl == 4 || tn.cnt_cpl == 8) ? tn.cnt_cpl : nwb_count_choose_cpl(cols, p->sm_count);
+        if (flags & NWB_WANT_COUNT_DIGEST) cnt_cpl = 8;
         const int wc = 32 * cnt_cpl, ratio = 256 / wc;
+        const int sw_ratio = strip_w / 256 > 0 ? 1 : 256 / strip_w; /* fill strips per 256 columns (pk_k < 4 never has count_pass) */
+        (void)sw_ratio;
         cp.n_strips = (A + wc - 1) / wc;
         cp.strip_begin = p->strip_begin * ratio < cp.n_strips ? p->strip_begin * ratio : cp.n_strips;
         cp.strip_end = p->strip_end * ratio < cp.n_strips ? p->strip_end * ratio : cp.n_strips;
-        rc = p->bnd_c.ensure((size_t)(cp.strip_end - cp.strip_begin) * 2 * L.bpitch);
+        cnt_stream_words = (size_t)(cp.strip_end - cp.strip_begin) * 2 * L.bpitch;
+        rc = p->bnd_c.ensure(cnt_stream_words);
     }
     if (rc != NWB_OK) return rc;
     CK(cudaMemsetAsync(p->progress.p, 0, (size_t)nloc * sizeof(int), st));
     /* the packed kernel's stream words validate themselves (bit 31): start from zero */
-    if (p->kind == NWB_KIND_PK) {
+    if (p->kind == NWB_KIND_PK)
         CK(cudaMemsetAsync(p->bnd_w.p, 0, (size_t)nloc * L.bpitch * sizeof(uint32_t), st));
-        if (fused_count)
-            CK(cudaMemsetAsync(p->bnd_c.p, 0, (size_t)nloc * 2 * L.bpitch * sizeof(unsigned long long), st));
-        if (p->count_pass)
-            CK(cudaMemsetAsync(p->bnd_c.p, 0, (size_t)(cp.strip_end - cp.strip_begin) * 2 * L.bpitch * sizeof(unsigned long long), st));
-    }
+    if (p->kind == NWB_KIND_PK && fused_count)
+        CK(cudaMemsetAsync(p->bnd_c.p, 0, (size_t)nloc * 2 * L.bpitch * sizeof(unsigned long long), st));
+    if (cpath == NWB_CNT_DENSE)
+        CK(cudaMemsetAsync(p->bnd_c.p, 0, cnt_stream_words * sizeof(unsigned long long), st));
 
     NwbStripParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -430,19 +506,11 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     const bool want_branches = !(flags & NWB_NO_BRANCH_COUNT);
     const bool branch_pass = want_branches && p->kind == NWB_KIND_PK && !p->pk_hx && B >= 4096;
     sp.count_branches = (want_branches && !branch_pass) ? 1 : 0;
-    sp.debug_nowait = getenv("NWB_DEBUG_NOWAIT") ? atoi(getenv("NWB_DEBUG_NOWAIT")) : 0;
-    if (getenv("NWB_DEBUG_TIMES") && p->kind == NWB_KIND_PK) { /* diagnostics: per-strip timestamps dumped to a file */
-        if (p->dbg_times.ensure((size_t)L.n_strips * 4) != NWB_OK) return NWB_ERR_NOMEM;
-        CK(cudaMemsetAsync(p->dbg_times.p, 0, (size_t)L.n_strips * 4 * sizeof(unsigned long long), st));
-        sp.debug_times = p->dbg_times.p;
-        p->dbg_trace_blocks = (B / L.pk_r + 63 + 31) / 32 + 1;
-        p->dbg_trace_stride = L.n_strips >= 8 ? (L.n_strips - 1) / 7 : 1;
-        if (p->dbg_trace.ensure((size_t)8 * p->dbg_trace_blocks * 2) != NWB_OK) return NWB_ERR_NOMEM;
-        CK(cudaMemsetAsync(p->dbg_trace.p, 0, (size_t)8 * p->dbg_trace_blocks * 2 * sizeof(unsigned long long), st));
-        sp.debug_trace = p->dbg_trace.p;
-        sp.debug_trace_stride = p->dbg_trace_stride;
-        sp.debug_trace_blocks = p->dbg_trace_blocks;
-    }
+    sp.debug_nowait = tn.inject_fault ? 4 : 0; /* test only: the watchdog turns the lost stream into NWB_ERR_CUDA */
+#ifdef NWB_EXPERIMENTS
+    sp.debug_nowait |= tn.debug_nowait;
+#endif
+    sp.watchdog_ns = (unsigned long long)(tn.watchdog_ms > 0 ? tn.watchdog_ms : 4000) * 1000000ull;
     if (p->strip_begin > 0) {
         if (!p->inbox.base || L.bpitch > p->inbox.bpitch) return NWB_ERR_INVALID;
         sp.in_bnd_s = (const int32_t *)(p->inbox.base + p->inbox.off_s);
@@ -462,10 +530,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     const bool hx = (p->kind == NWB_KIND_PK) && p->pk_hx;
     /* one warp per SM sub-partition; a second one when there are more strips than that */
     int pk_warps = (nloc > p->sm_count * NWB_PK_WARPS) ? NWB_PK_MAX_WARPS : NWB_PK_WARPS;
-    if (const char *ew = getenv("NWB_PK_WARPS")) { /* diagnostics */
-        const int v = atoi(ew);
-        if (v >= 1 && v <= NWB_PK_MAX_WARPS) pk_warps = v;
-    }
+    if (tn.pk_warps >= 1 && tn.pk_warps <= NWB_PK_MAX_WARPS) pk_warps = tn.pk_warps;
     if (p->kind == NWB_KIND_PK)
         while (pk_warps > 1 && NWB_PK_SMEM_BYTES(L.pk_k, L.pk_r, pk_warps) > 200 * 1024) pk_warps--;
     if (p->kind == NWB_KIND_PK && fused_count && pk_warps > NWB_PK_WARPS) pk_warps = NWB_PK_WARPS;
@@ -475,18 +540,24 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         CK(cudaGetLastError());
         p->launches += 1;
     }
-    /* The count sweep trails the hx fill on a second stream: the flush warps publish how many rows of each
-     * strip are in memory, the sweep waits for the rows it is about to read.  It needs SMs the fill does not
-     * occupy (a fill block holds nearly all registers and shared memory of its SM): tables of up to ~118 strips
-     * (30k columns); otherwise, and with NWB_COUNT_SERIAL=1 (diagnostics), it runs after the fill. */
+    /* count_mode 3 (opt-in): the dense count sweep trails the hx fill on a second stream: the flush warps
+     * publish how many rows of each strip are in memory, the sweep waits for the rows it is about to read.  It
+     * needs SMs the fill does not occupy (a fill block holds nearly all registers and shared memory of its SM)
+     * and an otherwise idle GPU: the two kernels are separate cooperative launches, so their co-residency is
+     * not guaranteed by CUDA -- the sweep's waits are bounded by the watchdog. */
     const int cnt_grid_wanted = (cp.strip_end - cp.strip_begin + NWB_CNT_WARPS - 1) / NWB_CNT_WARPS;
-    const bool overlap = hx && p->count_pass && cnt_cpl == 8 && cp.strip_end > cp.strip_begin &&
-                         grid + cnt_grid_wanted <= p->sm_count && !getenv("NWB_COUNT_SERIAL");
+    const bool overlap = hx && cpath == NWB_CNT_DENSE && tn.count_mode == 3 && cnt_cpl == 8 && cp.strip_end > cp.strip_begin &&
+                         !(flags & NWB_WANT_COUNT_DIGEST) && grid + cnt_grid_wanted <= p->sm_count;
     sp.publish_rows = overlap ? 1 : 0;
     if (overlap) CK(cudaEventRecord(p->ev_fork, st)); /* buffers are zeroed, strings uploaded */
-    if (hx) rc = p->pk_hy ? nwb_hy_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, grid, st, cuda_fail);
-    else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
-    else rc = run_i32(p, sp, grid, st);
+    if (hx) {
+#ifdef NWB_EXPERIMENTS
+        rc = p->pk_hy ? nwb_hy_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, grid, st, cuda_fail);
+#else
+        rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
+#endif
+    } else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
+    else rc = run_i32(p, kflags, sp, grid, st);
     if (rc != NWB_OK) return rc;
     if (branch_pass) {
         long long cb = (long long)p->strip_begin * L.strip_w, ce = (long long)p->strip_end * L.strip_w;
@@ -495,6 +566,23 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
                                                                  &p->summary.p->branch_count);
         CK(cudaGetLastError());
         p->launches += 1;
+    }
+    if (cpath == NWB_CNT_SPARSE) {
+        NwbSparseCountParams sc;
+        memset(&sc, 0, sizeof(sc));
+        sc.arrows = p->arrows.p;
+        sc.pitch = L.pitch;
+        sc.A = A; sc.B = B;
+        sc.out_count = &p->summary.p->count;
+        sc.out_state = &p->summary.p->count_state;
+        sc.out_rows = &p->summary.p->sparse_rows;
+        nwb_sparse_count_kernel<<<1, 32, 0, st>>>(sc);
+        CK(cudaGetLastError());
+        /* the dense sweep's streams are zeroed only if it is going to run */
+        nwb_zero_unless_done_kernel<<<p->sm_count * 4, 256, 0, st>>>(&p->summary.p->count_state, (uint4 *)p->bnd_c.p,
+                                                                    cnt_stream_words * sizeof(unsigned long long) / 16);
+        CK(cudaGetLastError());
+        p->launches += 2;
     }
     if (p->count_pass && cp.strip_end > cp.strip_begin) {
         cp.arrows = p->arrows.p;
@@ -505,8 +593,10 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         cp.in_bnd_c = sp.in_bnd_c;
         cp.out_bnd_c = sp.out_bnd_c;
         cp.summary = p->summary.p;
-        cp.debug_nowait = sp.debug_nowait;
+        cp.debug_nowait = sp.debug_nowait & 1;
+        cp.watchdog_ns = sp.watchdog_ns;
         cp.fill_progress = overlap ? p->progress.p : nullptr;
+        cp.skip_state = (cpath == NWB_CNT_SPARSE) ? &p->summary.p->count_state : nullptr;
         const int nlocc = cp.strip_end - cp.strip_begin;
         /* one warp per SM sub-partition on as few SMs as that takes */
         int cgrid = (nlocc + NWB_CNT_WARPS - 1) / NWB_CNT_WARPS;
@@ -516,7 +606,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
             cst = p->stream2;
             CK(cudaStreamWaitEvent(cst, p->ev_fork, 0));
         }
-        rc = nwb_count_launch(cp, cnt_cpl, cgrid, cst, cuda_fail);
+        rc = nwb_count_launch(cp, cnt_cpl, (flags & NWB_WANT_COUNT_DIGEST) != 0, cgrid, cst, cuda_fail);
         if (rc != NWB_OK) return rc;
         p->launches += 1;
         if (overlap) {
@@ -570,33 +660,46 @@ extern "C" int nwb_plan_summary(nwb_plan *p, nwb_summary *out)
         out->opt_score = (int32_t)(uint32_t)((unsigned long long)p->last.rsum -
                                              (unsigned long long)((long long)p->d * ((long long)p->A + p->B)));
     }
-    if (const char *path = getenv("NWB_DEBUG_TIMES")) {
-        if (p->dbg_times.p && p->L.n_strips > 0) {
-            std::vector<unsigned long long> h((size_t)p->L.n_strips * 4);
-            cudaMemcpy(h.data(), p->dbg_times.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-            if (FILE *f = fopen(path, "w")) {
-                for (int i = 0; i < p->L.n_strips; i++)
-                    fprintf(f, "%d %llu %llu %llu %llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-                fclose(f);
-            }
-            if (p->dbg_trace.p) {
-                std::vector<unsigned long long> ht((size_t)8 * p->dbg_trace_blocks * 2);
-                cudaMemcpy(ht.data(), p->dbg_trace.p, ht.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-                std::string tp = std::string(path) + ".trace";
-                if (FILE *f = fopen(tp.c_str(), "w")) {
-                    for (int sl = 0; sl < 8; sl++)
-                        for (int b = 0; b < p->dbg_trace_blocks; b++)
-                            fprintf(f, "%d %d %llu %llu\n", sl * p->dbg_trace_stride, b,
-                                    ht[((size_t)sl * p->dbg_trace_blocks + b) * 2], ht[((size_t)sl * p->dbg_trace_blocks + b) * 2 + 1]);
-                    fclose(f);
-                }
-            }
-        }
-    }
     out->branch_count = p->last.branch_count;
     out->greatest_abs = p->last.greatest_abs;
     out->kernel_kind = p->last.kernel_kind;
     out->count = p->last.count;
+    out->count_path = p->count_path;
+    if (p->count_path == NWB_CNT_SPARSE && p->last.count_state != NWB_SPC_DONE && p->A > 0 && p->B > 0 &&
+        p->strip_end > p->strip_begin)
+        out->count_path = NWB_CNT_SPARSE_BAILED;
+    out->count_rows = p->last.sparse_rows;
+    out->lastrow_count_digest = p->last.dig_row;
+    out->lastcol_count_digest = p->last.dig_col;
+    if (p->last.error != 0) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err),
+                 "device watchdog: a strip waited more than the watchdog time for its left neighbour (code %d)", p->last.error);
+        return NWB_ERR_CUDA;
+    }
+    return NWB_OK;
+}
+
+/* Digest of this plan's share of the arrow table (include/nwb.h, nwb_digest.cuh): rank digests add up. */
+extern "C" int nwb_plan_arrow_digest(nwb_plan *p, uint64_t *out)
+{
+    if (!p || !out || !p->ran) return NWB_ERR_INVALID;
+    *out = 0;
+    if (p->A == 0 || p->B == 0 || p->strip_end <= p->strip_begin) return NWB_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->last_stream ? p->last_stream : p->stream;
+    int rc = p->digest.ensure(1);
+    if (rc != NWB_OK) return rc;
+    CK(cudaMemsetAsync(p->digest.p, 0, sizeof(unsigned long long), st));
+    long long cb = (long long)p->strip_begin * p->L.strip_w, ce = (long long)p->strip_end * p->L.strip_w;
+    if (ce > p->A) ce = p->A;
+    const int wb = (int)(cb / 8), we = (int)((ce + 7) / 8);
+    nwb_arrow_digest_kernel<<<p->sm_count * 8, 256, 0, st>>>(p->arrows.p, p->L.pitch, p->A, p->B, wb, we, p->digest.p);
+    CK(cudaGetLastError());
+    p->launches += 1;
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, p->digest.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out = h;
     return NWB_OK;
 }
 
@@ -618,6 +721,18 @@ extern "C" const char *nwb_plan_kernel_name(const nwb_plan *p)
     if (!p || !p->ran) return "";
     if (p->kind == NWB_KIND_I32) return "nwb_fill_i32_kernel";
     return p->pk_hx ? (p->pk_hy ? "nwb_fill_hy_kernel" : "nwb_fill_hx_kernel") : "nwb_fill_pk_kernel";
+}
+/* How the last run obtained the count: "" (none), "fused", "dense" (forward sweep), "sparse" (backward sweep;
+ * nwb_plan_summary() reports whether it had to fall back). */
+extern "C" const char *nwb_plan_count_path_name(const nwb_plan *p)
+{
+    if (!p || !p->ran) return "";
+    switch (p->count_path) {
+    case NWB_CNT_FUSED: return "fused";
+    case NWB_CNT_DENSE: return "dense";
+    case NWB_CNT_SPARSE: return "sparse";
+    default: return "";
+    }
 }
 /* Host-only partition helpers (no device needed): what a launcher with one process per GPU uses to
  * shard the work the same way nwb_plan_create() / nwb_fill_on() do. */
@@ -737,6 +852,8 @@ struct nwb_table {
     int32_t *h_scores = nullptr;
     unsigned long long *h_cntmat = nullptr;
     size_t spitch = 0;
+    uint64_t arrow_digest = 0;
+    bool have_digest = false;
 };
 
 extern "C" void nwb_free(nwb_table *t)
@@ -797,6 +914,17 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
         t->sum.partial_r += s.partial_r;
         const float ms = nwb_plan_kernel_ms(p);
         if (ms > t->kernel_ms) t->kernel_ms = ms;
+        t->sum.lastrow_count_digest += s.lastrow_count_digest;
+        t->sum.lastcol_count_digest += s.lastcol_count_digest;
+        t->sum.count_path = s.count_path;
+        t->sum.count_rows = s.count_rows;
+        if (flags & NWB_WANT_DIGEST) {
+            uint64_t dg = 0;
+            rc = nwb_plan_arrow_digest(p, &dg);
+            if (rc != NWB_OK) break;
+            t->arrow_digest += dg;
+            t->have_digest = true;
+        }
     }
     if (rc == NWB_OK && top_len > 0 && side_len > 0 && t->sum.kernel_kind == NWB_KIND_PK)
         t->sum.opt_score = nwb_strip_group_score(t->sum.partial_r, top_len, side_len, d);
@@ -861,6 +989,19 @@ extern "C" float nwb_kernel_ms(const nwb_table *t) { return t ? t->kernel_ms : 0
 extern "C" int nwb_kernel_kind(const nwb_table *t) { return t ? t->sum.kernel_kind : -1; }
 extern "C" const uint8_t *nwb_arrow_rows(const nwb_table *t) { return t ? t->h_arrows : nullptr; }
 extern "C" size_t nwb_arrow_pitch(const nwb_table *t) { return t ? t->pitch : 0; }
+extern "C" int nwb_table_summary(const nwb_table *t, nwb_summary *out)
+{
+    if (!t || !out) return NWB_ERR_INVALID;
+    *out = t->sum;
+    return NWB_OK;
+}
+extern "C" int nwb_arrow_digest(const nwb_table *t, uint64_t *out)
+{
+    if (!t || !out) return NWB_ERR_INVALID;
+    if (!t->have_digest && t->A > 0 && t->B > 0) return NWB_ERR_UNSUPPORTED; /* NWB_WANT_DIGEST was not set */
+    *out = t->arrow_digest;
+    return NWB_OK;
+}
 
 extern "C" int32_t nwb_score(const nwb_table *t, int i, int j)
 {

@@ -20,6 +20,7 @@ struct nwb_batch {
     DevBuf<unsigned> branch;
     DevBuf<uint32_t> scratch;
     DevBuf<unsigned long long> count, cscratch; /* NWB_WANT_COUNT */
+    DevBuf<unsigned long long> digest;
     std::vector<unsigned long long> h_count;
     std::vector<long long> h_top_off, h_side_off, h_arrow_off;
     std::vector<int> h_score;
@@ -37,7 +38,7 @@ extern "C" void nwb_batch_free(nwb_batch *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->tops.release(); b->sides.release(); b->arrows.release(); b->top_off.release(); b->side_off.release();
     b->arrow_off.release(); b->score.release(); b->branch.release(); b->scratch.release();
-    b->count.release(); b->cscratch.release();
+    b->count.release(); b->cscratch.release(); b->digest.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -87,12 +88,10 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     b->h_arrow_off[(size_t)n_pairs] = aoff;
     b->arrows_bytes = (size_t)aoff;
     {
-        /* short top strings and nibble-sized differences: two pairs per warp; NWB_BATCH_BX=0 keeps the
-         * one-pair-per-warp kernel (diagnostics) */
-        const char *e = getenv("NWB_BATCH_BX");
-        b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && !(e && atoi(e) == 0);
-        const char *ec = getenv("NWB_BATCH_CX");
-        b->use_cx = b->use_bx && n_pairs > 0 && nwb_cx_usable(pc, b->uniform, b->uni_A, (int)b->uni_B) && !(ec && atoi(ec) == 0);
+        /* short top strings and nibble-sized differences: two pairs per warp (nwb_tune "batch_bx" / "batch_cx" = 0
+         * keep the simpler kernels, for tests) */
+        b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && g_tune.batch_bx != 0;
+        b->use_cx = b->use_bx && n_pairs > 0 && nwb_cx_usable(pc, b->uniform, b->uni_A, (int)b->uni_B) && g_tune.batch_cx != 0;
     }
     if (!b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
@@ -134,9 +133,8 @@ static int batch_count_pass(nwb_batch *b, cudaStream_t st)
     }
     const size_t smem = (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS;
     /* every pair the same one-strip shape: the tables of a warp's run of pairs are swept back to back
-     * (NWB_BCNT_CHAIN=0, diagnostics: one pair at a time) */
-    const char *ech = getenv("NWB_BCNT_CHAIN");
-    if (nwb_bcount_chain_usable(b->uniform, b->uni_A, b->uni_B, b->n, (long long)grid * NWB_BCNT_WARPS) && !(ech && atoi(ech) == 0)) {
+     * (nwb_tune "bcnt_chain" = 0: one pair at a time) */
+    if (nwb_bcount_chain_usable(b->uniform, b->uni_A, b->uni_B, b->n, (long long)grid * NWB_BCNT_WARPS) && g_tune.bcnt_chain != 0) {
         CK(cudaFuncSetAttribute(nwb_batch_count_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nwb_batch_count_chain_kernel<<<grid, 32 * NWB_BCNT_WARPS, smem, st>>>(cp, (int)b->uni_A, (int)b->uni_B);
         CK(cudaGetLastError());
@@ -182,8 +180,7 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st)
         bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p;
         bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
         if (b->use_cx) {
-            const char *ew = getenv("NWB_CX_WARPS"); /* diagnostics: 12 or 16 warps per SM */
-            const bool w16 = ew && atoi(ew) == 16 && nwb_cx_usable(b->pc, true, b->uni_A, (int)b->uni_B, 16);
+            const bool w16 = g_tune.cx_warps == 16 && nwb_cx_usable(b->pc, true, b->uni_A, (int)b->uni_B, 16);
             const int cw = w16 ? 16 : NWB_BX_WARPS;
             const size_t smem = NWB_CX_SMEM_PER_WARP(b->max_B, cw) * (size_t)cw;
             auto kern = w16 ? nwb_batch_cx_kernel<16> : nwb_batch_cx_kernel<NWB_BX_WARPS>;
@@ -296,4 +293,28 @@ extern "C" const char *nwb_batch_kernel_name(const nwb_batch *b)
     return b->use_cx ? "nwb_batch_cx_kernel" : (b->use_bx ? "nwb_batch_bx_kernel" : "nwb_batch_pk_kernel");
 }
 extern "C" int64_t nwb_batch_launches(const nwb_batch *b) { return b ? b->launches : 0; }
+/* Digests of the whole batch, on the device (include/nwb.h): out[0..3] = sum over pairs p of
+ * mix64(first_pair + p, x_p) with x_p = arrow digest / optimal score / branch count / alignment count. */
+extern "C" int nwb_batch_digest(nwb_batch *b, int64_t first_pair, uint64_t out[4])
+{
+    if (!b || !out || !b->ran) return NWB_ERR_INVALID;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (b->n == 0) return NWB_OK;
+    CK(cudaSetDevice(b->device));
+    CK(cudaDeviceSynchronize());
+    int rc = b->digest.ensure(4);
+    if (rc != NWB_OK) return rc;
+    CK(cudaMemsetAsync(b->digest.p, 0, 4 * sizeof(unsigned long long), b->stream));
+    nwb_batch_digest_kernel<<<b->sm_count * 8, 256, 0, b->stream>>>(
+        b->arrows.p, b->arrow_off.p, b->top_off.p, b->side_off.p, b->n, first_pair, b->score.p,
+        (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p, (b->flags & NWB_WANT_COUNT) ? b->count.p : nullptr,
+        b->digest.p);
+    CK(cudaGetLastError());
+    b->launches += 1;
+    unsigned long long h[4];
+    CK(cudaMemcpyAsync(h, b->digest.p, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < 4; i++) out[i] = h[i];
+    return NWB_OK;
+}
 extern "C" void *nwb_batch_arrows_device(nwb_batch *b) { return b ? (void *)b->arrows.p : nullptr; }

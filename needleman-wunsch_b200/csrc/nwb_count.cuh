@@ -24,6 +24,8 @@
  */
 #pragma once
 #include "nwb_fill_pk.cuh"
+#include "nwb_digest.cuh"
+#include "nwb_count_sparse.cuh"
 
 #define NWB_CNT_WARPS 4   /* one per SM sub-partition */
 #define NWB_CNT_SUB 8     /* rows per sub-block: arrow words and stream words are fetched one sub-block ahead */
@@ -45,7 +47,10 @@ struct NwbCountParams {
     NwbDevSummary *summary;
     const int *fill_progress; /* CPL == 8 only: [strip - strip_begin] arrow rows of the strip the fill has written so
                                * far, when the sweep runs concurrently with nwb_fill_hx_kernel; NULL = table is finished */
+    const int *skip_state; /* if non-NULL and *skip_state == NWB_SPC_DONE the kernel returns at once: the sparse
+                            * backward sweep (nwb_count_sparse.cuh) already produced the count */
     int debug_nowait; /* diagnostics: 1 = do not wait for the left strip's stream (results are wrong) */
+    unsigned long long watchdog_ns; /* bounded waits: see NwbStripParams */
 };
 
 template <int CPL>
@@ -98,9 +103,10 @@ __device__ __forceinline__ void nwb_count_row(const unsigned x, unsigned long lo
 }
 
 /* One strip: columns c*32*CPL+1 .. (c+1)*32*CPL, all rows. */
-template <int CPL>
-__device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const int c, unsigned long long *cstage,
-                                                 unsigned *ring, const int lane)
+template <int CPL, bool DIGEST>
+__device__ __forceinline__ bool nwb_count_strip(const NwbCountParams &p, const int c, unsigned long long *cstage,
+                                                 unsigned *ring, const int lane, unsigned long long &dig_row,
+                                                 unsigned long long &dig_col)
 {
     typedef typename NwbCntWord<CPL>::T word_t;
     const int A = p.A, B = p.B;
@@ -115,7 +121,8 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
     const unsigned long long *in_c = nullptr;
     if (has_left)
         in_c = (left_remote ? p.in_bnd_c : p.bnd_c + (size_t)(lc - 1) * 2 * p.bpitch) + (size_t)NWB_PK_BPAD * 2;
-    const bool pub31 = publish && (lane == 31);
+    const bool pub31 = publish && (lane == 31) && !NWB_FAULT_INJECTED(p);
+    bool aborted = false;
     /* the cell (A, B): the lane / column that owns it */
     const int kfin = (c == p.n_strips - 1) ? (A - 1 - c * W) - CPL * lane : -1; /* 0..CPL-1 in the owning lane */
 
@@ -159,9 +166,14 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
     const int *fillp = (staged && p.fill_progress) ? p.fill_progress + lc : nullptr;
     int rows_seen = 0; /* the fill publishes 64 rows at a time: poll (and fence) only when the cached value is short */
     auto wait_rows = [&](const int need) {
-        if (rows_seen >= need) return;
+        if (rows_seen >= need || aborted) return;
+        NwbWatchdog wd;
         do {
             rows_seen = (int)nwb_ld_relaxed_u32(reinterpret_cast<const uint32_t *>(fillp), false);
+            if (rows_seen < need && wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) {
+                aborted = true; /* the fill on the other stream is not making progress (not co-resident?) */
+                return;
+            }
 #ifdef NWB_EMU
             if (rows_seen < need) nwb_pause();
 #endif
@@ -175,6 +187,7 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
         if (fillp) {
             rows_seen = 0;
             wait_rows(B < 2 * NWB_CNT_SUB ? B : 2 * NWB_CNT_SUB);
+            if (aborted) return false;
         }
         stage_load(1);
         stage_store(1);
@@ -205,11 +218,16 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
             const int row = ss + (lane >> 1) + 1;
             const bool need = (lane < 2 * NWB_CNT_SUB) && (row <= B);
             unsigned long long cw = cwslot;
-            bool ok = !need || (cw & NWB_PK_CVALID) || (p.debug_nowait & 1);
+            bool ok = !need || (cw & NWB_PK_CVALID) || NWB_DBG_BITS(p, 1);
+            NwbWatchdog wd;
             while (!__all_sync(NWB_FULL_MASK, ok)) {
                 if (!ok) {
                     cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * 2 + lane, left_remote);
                     ok = (cw & NWB_PK_CVALID) != 0ull;
+                }
+                if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) {
+                    aborted = true;
+                    return;
                 }
 #ifdef NWB_EMU
                 nwb_pause();
@@ -227,6 +245,7 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
             if (fillp) { /* rows up to ss + 24 are about to be read from the table */
                 const int need = ss + 3 * NWB_CNT_SUB;
                 wait_rows(need < B ? need : B);
+                if (aborted) return;
             }
             const unsigned *rq = ring + (ss & (NWB_CNT_RING - 1)) * 32 + lane;
 #pragma unroll
@@ -258,6 +277,11 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                 unsigned long long cl = __shfl_up_sync(NWB_FULL_MASK, send, 1);
                 if (lane == 0) cl = cstage[t];
                 nwb_count_row<CPL>(w[t], cnt, left_above, cl, send);
+                if (DIGEST && kfin >= 0 && kfin < CPL) { /* the lane that owns column A: cnt(A, j) */
+#pragma unroll
+                    for (int k = 0; k < CPL; k++)
+                        if (k == kfin) dig_col += nwb_mix64((unsigned long long)(ss + t - lane + 1), cnt[k]);
+                }
                 nwb_st_relaxed_sys_pred_u64(oc + 2 * t, send | NWB_PK_CVALID, pub31);
                 nwb_st_relaxed_sys_pred_u64(oc + 2 * t + 1, (send >> 63) | NWB_PK_CVALID, pub31);
             }
@@ -280,6 +304,20 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
                     for (int q = 1; q < NWB_CNT_SUB; q++)
                         if (q == t) x = w[q];
                     nwb_count_row<CPL>(x, cnt, left_above, cl, send);
+                    if (DIGEST) {
+                        if (kfin >= 0 && kfin < CPL) {
+#pragma unroll
+                            for (int k = 0; k < CPL; k++)
+                                if (k == kfin) dig_col += nwb_mix64((unsigned long long)j, cnt[k]);
+                        }
+                        if (j == B) { /* bottom row: cnt(i, B) of my columns inside the table */
+#pragma unroll
+                            for (int k = 0; k < CPL; k++) {
+                                const int col = c * W + CPL * lane + k + 1;
+                                if (col <= A) dig_row += nwb_mix64((unsigned long long)col, cnt[k]);
+                            }
+                        }
+                    }
                     if (j == B && kfin >= 0 && kfin < CPL) {
 #pragma unroll
                         for (int k = 0; k < CPL; k++)
@@ -291,22 +329,34 @@ __device__ __forceinline__ void nwb_count_strip(const NwbCountParams &p, const i
             }
         }
     };
-    for (int ss = 0; ss < nsteps; ss += 2 * NWB_CNT_SUB) {
+    for (int ss = 0; ss < nsteps && !aborted; ss += 2 * NWB_CNT_SUB) {
         sub_block(ss, cw_next);
-        if (ss + NWB_CNT_SUB < nsteps) sub_block(ss + NWB_CNT_SUB, cw_next2);
+        if (ss + NWB_CNT_SUB < nsteps && !aborted) sub_block(ss + NWB_CNT_SUB, cw_next2);
     }
+    return !aborted;
 }
 
-template <int CPL>
+/* DIGEST: also accumulate the digests of the bottom row and of column A of the count matrix
+ * (NwbDevSummary.dig_row / dig_col, nwb_digest.cuh) -- a separate instantiation for parity checks. */
+template <int CPL, bool DIGEST>
 __global__ void __launch_bounds__(32 * NWB_CNT_WARPS, 1) nwb_count_kernel(const NwbCountParams p)
 {
+    if (p.skip_state && *reinterpret_cast<const volatile int *>(p.skip_state) == NWB_SPC_DONE) return;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nworkers = (int)gridDim.x * NWB_CNT_WARPS;
     const int worker = warp * (int)gridDim.x + (int)blockIdx.x;
     unsigned long long *cstage = reinterpret_cast<unsigned long long *>(NWB_SMEM_BASE() + (size_t)warp * NWB_CNT_SMEM_PER_WARP);
     unsigned *ring = reinterpret_cast<unsigned *>(cstage + NWB_CNT_SUB);
-    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) nwb_count_strip<CPL>(p, c, cstage, ring, lane);
+    unsigned long long dig_row = 0ull, dig_col = 0ull;
+    for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
+        if (!nwb_count_strip<CPL, DIGEST>(p, c, cstage, ring, lane, dig_row, dig_col)) return; /* watchdog */
+    if (DIGEST) {
+        dig_row = nwb_warp_sum_u64(dig_row);
+        dig_col = nwb_warp_sum_u64(dig_col);
+        if (lane == 0 && dig_row) atomicAdd(&p.summary->dig_row, dig_row);
+        if (lane == 0 && dig_col) atomicAdd(&p.summary->dig_col, dig_col);
+    }
 }
 
 /* Cells per lane and row.  Narrower strips shorten a row step but add a pipeline hop of ~45 steps per
@@ -321,22 +371,23 @@ static inline int nwb_count_choose_cpl(long long columns, int sm_count)
 }
 
 #ifndef NWB_EMU
-template <int CPL>
+template <int CPL, bool DIGEST>
 static int nwb_count_launch_t(const NwbCountParams &cp, int grid, cudaStream_t st, nwb_fail_fn fail)
 {
     void *args[] = {(void *)&cp};
     /* cooperative launch only for its co-residency guarantee (strips spin-wait on one another) */
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)nwb_count_kernel<CPL>, dim3(grid), dim3(32 * NWB_CNT_WARPS),
-                                                args, NWB_CNT_SMEM_BYTES, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)nwb_count_kernel<CPL, DIGEST>, dim3(grid),
+                                                dim3(32 * NWB_CNT_WARPS), args, NWB_CNT_SMEM_BYTES, st);
     if (e != cudaSuccess) return fail(e, "cudaLaunchCooperativeKernel");
     return 0;
 }
-static inline int nwb_count_launch(const NwbCountParams &cp, int cpl, int grid, cudaStream_t st, nwb_fail_fn fail)
+static inline int nwb_count_launch(const NwbCountParams &cp, int cpl, bool digest, int grid, cudaStream_t st, nwb_fail_fn fail)
 {
+    if (digest) return nwb_count_launch_t<8, true>(cp, grid, st, fail);
     switch (cpl) {
-    case 2: return nwb_count_launch_t<2>(cp, grid, st, fail);
-    case 4: return nwb_count_launch_t<4>(cp, grid, st, fail);
-    default: return nwb_count_launch_t<8>(cp, grid, st, fail);
+    case 2: return nwb_count_launch_t<2, false>(cp, grid, st, fail);
+    case 4: return nwb_count_launch_t<4, false>(cp, grid, st, fail);
+    default: return nwb_count_launch_t<8, false>(cp, grid, st, fail);
     }
 }
 #endif

@@ -172,6 +172,69 @@ __device__ __forceinline__ void nwb_wait_ge(const int *flag, int need, bool sys)
 #endif
 }
 
+/* ---- watchdog for device-side spin loops -------------------------------------
+ * Every wait on another warp / block / GPU is bounded: tick() is called once per poll iteration from a
+ * converged warp; every 1024 polls it looks at the launch's error word and at %globaltimer.  It returns true
+ * (for the whole warp) when the wait must be abandoned: nothing arrived within limit_ns -- then the error word is
+ * set, so that every other waiting warp leaves too and the host reports NWB_ERR_CUDA instead of hanging the GPU
+ * (a lost boundary word, a partner kernel that is not co-resident) -- or some other warp already gave up. */
+#define NWB_DEVERR_WATCHDOG 1
+#ifdef NWB_EXPERIMENTS
+#define NWB_DBG_BITS(p, bits) ((p).debug_nowait & (bits)) /* experiments build: skip waits (results are wrong) */
+#else
+#define NWB_DBG_BITS(p, bits) 0
+#endif
+#define NWB_FAULT_INJECTED(p) (((p).debug_nowait & 4) != 0) /* test only: boundary streams are not published */
+
+#define NWB_ERR_WORD(p) ((p).summary ? &(p).summary->error : (int *)0)
+struct NwbWatchdog {
+    unsigned polls;
+    unsigned long long t0;
+    __device__ __forceinline__ NwbWatchdog() : polls(0u), t0(0ull) {}
+    __device__ __noinline__ bool slow(int *err, unsigned long long limit_ns)
+    {
+        if (!err) return false; /* a launch without a summary block (batch kernels: no cross-warp waits) */
+        bool give_up = (*reinterpret_cast<volatile int *>(err) != 0);
+        const unsigned long long now = nwb_globaltimer();
+        if (t0 == 0ull) t0 = now | 1ull;
+        else if (now - t0 > limit_ns) {
+            atomicExch(err, NWB_DEVERR_WATCHDOG);
+            give_up = true;
+        }
+        return __any_sync(NWB_FULL_MASK, give_up) != 0;
+    }
+    __device__ __forceinline__ bool tick(int *err, unsigned long long limit_ns)
+    {
+        if ((++polls & 1023u) != 0u) return false;
+        return slow(err, limit_ns);
+    }
+};
+
+/* nwb_wait_ge with the watchdog: false = the wait was abandoned (all lanes of the warp call this together) */
+__device__ __forceinline__ bool nwb_wait_ge_wd(const int *flag, int need, bool sys, int *err, unsigned long long limit_ns)
+{
+    NwbWatchdog wd;
+    for (;;) {
+#ifdef NWB_EMU
+        const int v = *(const volatile int *)flag;
+#else
+        int v;
+        if (sys) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
+        else asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
+#endif
+        if (__all_sync(NWB_FULL_MASK, v >= need)) break;
+        if (wd.tick(err, limit_ns)) return false;
+#ifdef NWB_EMU
+        nwb_pause();
+#endif
+    }
+#ifndef NWB_EMU
+    if (sys) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+    return true;
+}
+
 /* ---- 16x2 helpers (DPX / video SIMD; VIMNMX.U16x2, VIMNMX3.U16x2, VIADD.16x2) */
 __device__ __forceinline__ unsigned nwb_min_u16x2(unsigned a, unsigned b) { return __vminu2(a, b); }
 __device__ __forceinline__ unsigned nwb_min3_u16x2(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
@@ -185,6 +248,12 @@ struct NwbDevSummary {
     int kernel_kind;
     unsigned long long count;
     long long rsum; /* packed kernel: sum of bottom-row u differences */
+    int count_state;      /* NWB_SPC_* (nwb_count_sparse.cuh): 1 = the sparse backward sweep produced `count` */
+    unsigned sparse_rows; /* rows the sparse sweep visited before its live set died                            */
+    int error;            /* != 0: a device-side watchdog gave up waiting (NWB_DEVERR_*); results are invalid  */
+    int pad;
+    unsigned long long dig_row; /* dense count sweep with digests: sum_i mix64(i, cnt(i,B)) over this rank's columns */
+    unsigned long long dig_col; /* ... sum_j mix64(j, cnt(A,j)) (the rank that owns column A)                        */
 };
 
 /* ---- launch parameters of the single-pair strip-pipeline kernels ------------
@@ -232,7 +301,10 @@ struct NwbStripParams {
     int count_branches; /* packed kernel: count cells with >= 2 arrows while flushing rows */
     int publish_rows;   /* hx kernel: publish in progress[] how many arrow rows of each strip are in memory
                          * (the count sweep of nwb_count.cuh trails the fill on a second stream) */
-    int debug_nowait; /* diagnostics: skip the inter-strip waits (results are wrong) */
+    int debug_nowait; /* bit 2 (value 4): fault injection for the watchdog test -- the strips' boundary streams are
+                       * not published, so the next strip's wait times out (NWB_ERR_CUDA).  Bits 0, 1 (experiments
+                       * build only): skip the inter-strip waits / the flush (results are wrong) */
+    unsigned long long watchdog_ns; /* a spin loop that sees no progress for this long sets summary->error and leaves */
     unsigned long long *debug_times; /* diagnostics: per strip {entry, first words valid, step 64, exit} in ns, or NULL */
     unsigned long long *debug_trace; /* diagnostics: [8 traced strips][nblocks][2] = {ns at block start, polls so far} */
     int debug_trace_stride;          /* strips c with c % stride == 0 are traced (slot c / stride, < 8) */

@@ -147,7 +147,7 @@ __device__ __forceinline__ void nwb_hx_step(NwbHxState &st, const NwbPkConsts &p
 
 /* A sweeping warp's strip: nwb_pk_strip<4, 2> without the write-back.  seq counts this warp's
  * 32-step blocks over all its strips; ring slot of a step = (32 * seq + step in block) mod 128. */
-__device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
+__device__ __forceinline__ bool nwb_hx_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
                                               unsigned char *ring, volatile int *ready, volatile int *done,
                                               int &seq, const int lane, long long &rsum)
 {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
     uint32_t *out_w = (out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch) + NWB_PK_BPAD;
     const uint32_t *in_w = nullptr;
     if (has_left) in_w = (left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch) + NWB_PK_BPAD;
-    const bool pub31 = publish && (lane == 31) && !(p.debug_nowait & 4);
+    const bool pub31 = publish && (lane == 31) && !NWB_FAULT_INJECTED(p);
     const bool is_last = (c == p.n_strips - 1);
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
 
@@ -211,7 +211,11 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
         /* ring back-pressure: this block overwrites the slots of block seq-4; the rows the flush
          * warp takes after block seq-2 still read them */
         if (seq >= 2) {
-            while (nwb_flag_load(done) < seq - 1) nwb_spin_pause(false);
+            NwbWatchdog wd;
+            while (nwb_flag_load(done) < seq - 1) {
+                nwb_spin_pause(false);
+                if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+            }
         }
         const bool lean = !(is_last && R * (s0 + 32) >= B);
 #pragma unroll 1
@@ -221,12 +225,14 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
                 /* commit the prefetched words of groups ss .. ss+7; re-poll the ones not valid yet */
                 const int gs = ss + lane;
                 unsigned w = bq_next;
-                bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID) || (p.debug_nowait & 1);
+                bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID) || NWB_DBG_BITS(p, 1);
+                NwbWatchdog wd;
                 while (!__all_sync(NWB_FULL_MASK, ok)) {
                     if (!ok) {
                         w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
                         ok = (w & NWB_PK_VALID) != 0u;
                     }
+                    if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
 #ifdef NWB_EMU
                     nwb_pause();
 #endif
@@ -265,6 +271,7 @@ __device__ __forceinline__ void nwb_hx_strip(const NwbStripParams &p, const NwbP
         seq++;
     }
     rsum += (long long)(rs32 & 0xFFFFu) + (long long)(rs32 >> 16);
+    return true;
 }
 
 /* The flush warp of sweeping warp `wslot`.  Flush lane h owns the 8 cells per row that sweeping
@@ -330,11 +337,17 @@ __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int 
         uint8_t *dst = p.arrows + (size_t)c * 128 + (size_t)lane * 4;
         unsigned pc0 = 0u, pc1 = 0u;
         for (int blk = 0; blk < nblocks; blk++) {
-            while (nwb_flag_load(ready) < seq + 1) nwb_spin_pause(true);
+            {
+                NwbWatchdog wd;
+                while (nwb_flag_load(ready) < seq + 1) {
+                    nwb_spin_pause(true);
+                    if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return; /* the sweeping warp gave up (or never came) */
+                }
+            }
 #ifndef NWB_EMU
             __threadfence_block();
 #endif
-            if (!(p.debug_nowait & 2)) {
+            if (!NWB_DBG_BITS(p, 2)) {
                 /* slot of step s holds {low: group s - 2*lane, high: group s - 2*lane - 1}; walk the slots
                  * whose HIGH half is one of this block's groups 32*blk-63 .. 32*blk-32 (clipped to the
                  * table); the slot before the first one only primes pc0/pc1 */
@@ -426,7 +439,8 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
         long long rsum = 0;
         int seq = 0;
         for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
-            nwb_hx_strip(p, pc, c, ring, flags + crit_slot, flags + NWB_HX_CRIT + crit_slot, seq, lane, rsum);
+            if (!nwb_hx_strip(p, pc, c, ring, flags + crit_slot, flags + NWB_HX_CRIT + crit_slot, seq, lane, rsum))
+                return; /* watchdog: summary->error is set, the host reports NWB_ERR_CUDA */
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(NWB_FULL_MASK, rsum, o);
         if (lane == 0 && rsum) atomicAdd((unsigned long long *)&p.summary->rsum, (unsigned long long)rsum);

@@ -31,7 +31,7 @@
 #define NWB_I32_SMEM_BYTES (NWB_I32_WARPS * NWB_I32_STAGE_WORDS * 4)
 
 template <bool COUNT, bool SCORES, bool ABS, bool CNTMAT>
-__device__ __forceinline__ void nwb_i32_strip(const NwbStripParams &p, const int c, uint32_t *stage,
+__device__ __forceinline__ bool nwb_i32_strip(const NwbStripParams &p, const int c, uint32_t *stage,
                                                const int lane, unsigned &branches, int &gabs)
 {
     const int A = p.A, B = p.B;
@@ -80,7 +80,8 @@ __device__ __forceinline__ void nwb_i32_strip(const NwbStripParams &p, const int
         if (has_left) {
             int need = 32 * blk + 32;
             if (need > B) need = B;
-            if (!p.debug_nowait) nwb_wait_ge(in_flag, need, left_remote);
+            if (!NWB_DBG_BITS(p, 1) && !nwb_wait_ge_wd(in_flag, need, left_remote, &p.summary->error, p.watchdog_ns))
+                return false; /* watchdog: the left strip never got there */
             const int jj = 32 * blk + 1 + lane;
             if (jj <= B) {
                 bq_s = in_s[jj];
@@ -193,7 +194,7 @@ __device__ __forceinline__ void nwb_i32_strip(const NwbStripParams &p, const int
             }
         }
         __syncwarp();
-        if (publish && lane == 31) {
+        if (publish && lane == 31 && !NWB_FAULT_INJECTED(p)) {
             int done = 32 * blk + 1;
             if (done > B) done = B;
             if (out_remote) {
@@ -204,6 +205,7 @@ __device__ __forceinline__ void nwb_i32_strip(const NwbStripParams &p, const int
             }
         }
     }
+    return true;
 }
 
 template <bool COUNT, bool SCORES, bool ABS, bool CNTMAT>
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(32 * NWB_I32_WARPS, 1) nwb_fill_i32_kernel(con
     unsigned branches = 0;
     int gabs = 0;
     for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
-        nwb_i32_strip<COUNT, SCORES, ABS, CNTMAT>(p, c, stage, lane, branches, gabs);
+        if (!nwb_i32_strip<COUNT, SCORES, ABS, CNTMAT>(p, c, stage, lane, branches, gabs)) return; /* watchdog */
 
     /* warp-reduce the per-lane counters, one atomic per warp (replaces the
      * rwlock-guarded inc_branch_count(), walk-table.c:108-120) */

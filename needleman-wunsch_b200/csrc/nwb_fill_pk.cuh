@@ -383,7 +383,7 @@ __device__ __forceinline__ unsigned nwb_pk_chars(const uint16_t *q)
 }
 
 template <int K, int R, bool SMEMCH, bool COUNT>
-__device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
+__device__ __forceinline__ bool nwb_pk_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
                                               unsigned char *stage_bytes, const int lane, long long &rsum,
                                               unsigned long long *cstage, unsigned long long &cfinal,
                                               const bool count_branches, unsigned &branches)
@@ -429,7 +429,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     uint32_t *out_w = (out_remote ? p.out_bnd_w : p.bnd_w + (size_t)lc * p.bpitch) + NWB_PK_BPAD;
     const uint32_t *in_w = nullptr;
     if (has_left) in_w = (left_remote ? p.in_bnd_w : p.bnd_w + (size_t)(lc - 1) * p.bpitch) + NWB_PK_BPAD;
-    const bool pub31 = publish && (lane == 31);
+    const bool pub31 = publish && (lane == 31) && !NWB_FAULT_INJECTED(p);
     const bool is_last = (c == p.n_strips - 1);
     /* count streams: 2 x uint64 per row, (BPAD + group) * R + sub-row */
     unsigned long long *out_c = nullptr;
@@ -440,7 +440,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
         if (!has_left && lane < NWB_PK_SUB * R) cstage[lane] = 1ull; /* column 0 of the table */
         __syncwarp();
     }
-    const bool nowait = p.debug_nowait != 0;
+    const bool nowait = NWB_DBG_BITS(p, 1) != 0;
     /* my low block's first row at step s is R*(s - 2*lane) + 1 */
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
 
@@ -509,12 +509,17 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                 unsigned w = bq_next;
                 if (!nowait) {
                     bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID);
+                    NwbWatchdog wd;
                     while (!__all_sync(NWB_FULL_MASK, ok)) {
                         npolls++;
                         if (!ok) { /* plain spin: a sleep quantum here would sit on the strip-to-strip critical path */
                             w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
                             ok = (w & NWB_PK_VALID) != 0u;
                         }
+                        if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+#ifdef NWB_EMU
+                        nwb_pause();
+#endif
                     }
                 }
                 if (dbg && lane == 0 && ss == 0) dbg[1] = nwb_globaltimer();
@@ -533,11 +538,16 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
                     if (need) cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
                     if (!nowait) {
                         bool okc = !need || (cw & NWB_PK_CVALID);
+                        NwbWatchdog wdc;
                         while (!__all_sync(NWB_FULL_MASK, okc)) {
                             if (!okc) {
                                 cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
                                 okc = (cw & NWB_PK_CVALID) != 0ull;
                             }
+                            if (wdc.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+#ifdef NWB_EMU
+                            nwb_pause();
+#endif
                         }
                     }
                     const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
@@ -646,6 +656,7 @@ __device__ __forceinline__ void nwb_pk_strip(const NwbStripParams &p, const NwbP
     }
     rsum += (long long)(rs32 & 0xFFFFu) + (long long)(rs32 >> 16);
     if (dbg && lane == 0) dbg[3] = nwb_globaltimer();
+    return true;
 }
 
 /* per-warp shared memory: the arrow ring, then (count kernel) the staged stream counts */
@@ -667,7 +678,8 @@ __global__ void __launch_bounds__(32 * NWB_PK_MAX_WARPS, 1) nwb_fill_pk_kernel(c
     bool owns_final = false;
     unsigned branches = 0;
     for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers) {
-        nwb_pk_strip<K, R, false, COUNT>(p, pc, c, stage, lane, rsum, cstage, cfinal, p.count_branches != 0, branches);
+        if (!nwb_pk_strip<K, R, false, COUNT>(p, pc, c, stage, lane, rsum, cstage, cfinal, p.count_branches != 0, branches))
+            return; /* watchdog: the results of this launch are invalid (summary->error is set) */
         if (COUNT && c == p.n_strips - 1) {
             /* the block that owns column A wrote cfinal when it passed row B */
             const int W = 64 * K, col_lo = c * W + (2 * lane) * K + 1;

@@ -36,6 +36,9 @@ class _Result(C.Structure):
         ("count_hash", C.c_uint64),
         ("lastrow_count_hash", C.c_uint64),
         ("lastcol_count_hash", C.c_uint64),
+        ("arrow_digest", C.c_uint64),
+        ("lastrow_count_digest", C.c_uint64),
+        ("lastcol_count_digest", C.c_uint64),
     ]
 
 
@@ -50,6 +53,9 @@ class FillResult:
     count_hash: int
     lastrow_count_hash: int
     lastcol_count_hash: int
+    arrow_digest: int = 0          # order-independent digests (nw_oracle.h): what the GPU computes on device
+    lastrow_count_digest: int = 0
+    lastcol_count_digest: int = 0
     scores: np.ndarray | None = None   # (B+1, A+1) int32
     codes: np.ndarray | None = None    # (B+1, A+1) uint8
     counts: np.ndarray | None = None   # (B+1, A+1) uint64
@@ -136,7 +142,8 @@ def packed_pitch(a: int) -> int:
 def _mk(res: _Result, **kw) -> FillResult:
     return FillResult(res.final_score, res.branch_count, res.greatest_abs, res.table_hash,
                       res.arrow_hash, res.count, res.count_hash, res.lastrow_count_hash,
-                      res.lastcol_count_hash, **kw)
+                      res.lastcol_count_hash, res.arrow_digest, res.lastrow_count_digest,
+                      res.lastcol_count_digest, **kw)
 
 
 def fill(top, side, m: int, k: int, d: int, *, want_scores=False, want_codes=False,

@@ -66,6 +66,7 @@ int nwo_fill(const char *top, int A, const char *side, int B,
 
     uint64_t th = FNV_OFFSET, ah = FNV_OFFSET, ch = FNV_OFFSET;
     uint64_t lrh = FNV_OFFSET, lch = FNV_OFFSET;
+    uint64_t adig = 0, lrdig = 0, lcdig = 0;
     uint32_t branches = 0;
     int32_t gabs = 0;
 
@@ -104,6 +105,7 @@ int nwo_fill(const char *top, int A, const char *side, int B,
 
         const char sc = side[j - 1];
         uint8_t *prow = packed ? packed + (j - 1) * pitch : NULL;
+        uint32_t dword = 0; /* the nibble-table word being assembled for the digest */
         for (size_t i = 1; i < M; i++) {
             /* score_cell(), needleman-wunsch.c:418-510 */
             const int32_t up = wsub(prev[i], d);
@@ -138,8 +140,15 @@ int nwo_fill(const char *top, int A, const char *side, int B,
             ah = fnv_word(ah, code & 7u);
             ch = fnv_u64(ch, c);
             if (j == N - 1) lrh = fnv_u64(lrh, c);
+            if (j == N - 1) lrdig += nwo_mix64((uint64_t)i, c);
+            dword |= (uint32_t)(code & 7u) << (((i - 1) & 7) * 4);
+            if (((i - 1) & 7) == 7 || i == M - 1) {
+                adig += nwo_mix64(((uint64_t)j << 32) | (uint64_t)((i - 1) >> 3), dword);
+                dword = 0;
+            }
         }
         lch = fnv_u64(lch, ccur[M - 1]);
+        if (M > 1) lcdig += nwo_mix64((uint64_t)j, ccur[M - 1]);
 
         int32_t *t = prev; prev = cur; cur = t;
         uint64_t *tc = cprev; cprev = ccur; ccur = tc;
@@ -156,6 +165,9 @@ int nwo_fill(const char *top, int A, const char *side, int B,
         res->count_hash = ch;
         res->lastrow_count_hash = lrh;
         res->lastcol_count_hash = lch;
+        res->arrow_digest = adig;
+        res->lastrow_count_digest = lrdig;
+        res->lastcol_count_digest = lcdig;
     }
     free(prev); free(cur); free(cprev); free(ccur);
     return 0;

@@ -50,7 +50,24 @@ typedef struct nwo_result {
     uint64_t count_hash;    /* FNV-1a-64 over every cell's count (lo,hi)     */
     uint64_t lastrow_count_hash; /* same, bottom row only (i = 0..A)         */
     uint64_t lastcol_count_hash; /* same, right column only (j = 0..B)       */
+    /* Order-independent digests (sums mod 2^64 of nwo_mix64 terms): what the GPU
+     * computes on device at full size, where a sequential FNV cannot be used.  */
+    uint64_t arrow_digest;         /* sum over rows j=1..B, words w: mix64(j<<32|w, word(j,w));
+                                    * word(j,w) = the 8 codes&7 of cells i=8w+1..8w+8 as nibbles
+                                    * (nibble n <-> i=8w+1+n; cells beyond A are 0): the 32-bit
+                                    * words of the include/nwb.h nibble table                 */
+    uint64_t lastrow_count_digest; /* sum over i=1..A of mix64(i, cnt(i,B))  */
+    uint64_t lastcol_count_digest; /* sum over j=1..B of mix64(j, cnt(A,j))  */
 } nwo_result;
+
+/* The digest's mixing function (SplitMix64 finaliser over a position/value pair). */
+static inline uint64_t nwo_mix64(uint64_t pos, uint64_t x)
+{
+    uint64_t z = (pos + 1) * 0x9E3779B97F4A7C15ULL + x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
 
 /*
  * Fill the whole table.  Every output pointer may be NULL.

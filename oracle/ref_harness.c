@@ -75,8 +75,9 @@ int nwref_fill(const char *top, const char *side, int m, int k, int d,
     const int M = C->score_table->M, N = C->score_table->N;
     if (res) {
         memset(res, 0, sizeof(*res));
-        uint64_t th = FNV_OFFSET, ah = FNV_OFFSET;
+        uint64_t th = FNV_OFFSET, ah = FNV_OFFSET, adig = 0;
         for (int j = 0; j < N; j++) {
+            uint32_t dword = 0;
             for (int i = 0; i < M; i++) {
                 const score_table_cell_t *sc = &C->score_table->cells[i][j];
                 const walk_table_cell_t *wc = &C->walk_table->cells[i][j];
@@ -86,6 +87,14 @@ int nwref_fill(const char *top, const char *side, int m, int k, int d,
                 ah = fnv_word(ah, code & 7u);
                 if (scores) scores[(size_t)j * M + i] = sc->score;
                 if (codes) codes[(size_t)j * M + i] = (uint8_t)code;
+                /* nwo_result.arrow_digest over the reference's own walk table (interior cells) */
+                if (i >= 1 && j >= 1) {
+                    dword |= (code & 7u) << (((i - 1) & 7) * 4);
+                    if (((i - 1) & 7) == 7 || i == M - 1) {
+                        adig += nwo_mix64(((uint64_t)j << 32) | (uint64_t)((i - 1) >> 3), dword);
+                        dword = 0;
+                    }
+                }
             }
         }
         res->final_score = C->score_table->cells[M - 1][N - 1].score;
@@ -93,6 +102,7 @@ int nwref_fill(const char *top, const char *side, int m, int k, int d,
         res->greatest_abs = C->score_table->greatest_abs_val;
         res->table_hash = th;
         res->arrow_hash = ah;
+        res->arrow_digest = adig;
     }
     if (enumerate) {
         tflag = 0;

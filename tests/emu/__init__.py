@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 class _Out(C.Structure):
     _fields_ = [("opt_score", C.c_int), ("branch_count", C.c_uint), ("greatest_abs", C.c_int),
                 ("pad", C.c_int), ("count", C.c_ulonglong), ("pitch", C.c_ulonglong),
-                ("spitch", C.c_ulonglong)]
+                ("spitch", C.c_ulonglong), ("dig_row", C.c_ulonglong), ("dig_col", C.c_ulonglong)]
 
 
 _lib = None
@@ -89,7 +89,33 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=Fal
     rc = L.emu_fill_pk(top, a, side, b, m, k, d, K, R, int(count), grid, warps, split, int(hx),
                        arrows.ctypes.data_as(C.c_void_p), C.byref(out))
     assert rc == 0, rc
-    return dict(opt_score=out.opt_score, branch_count=out.branch_count, arrows=arrows, pitch=pitch, count=out.count)
+    return dict(opt_score=out.opt_score, branch_count=out.branch_count, arrows=arrows, pitch=pitch, count=out.count,
+                dig_row=out.dig_row, dig_col=out.dig_col)
+
+
+def sparse_count(packed: np.ndarray, a: int) -> dict:
+    """nwb_sparse_count_kernel (csrc/nwb_count_sparse.cuh) over a (B, pitch) nibble table in the include/nwb.h
+    layout.  state: 1 = done (count is final), 2 = gave up (the dense sweep would run)."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    b, pitch = packed.shape
+    assert pitch % 4 == 0 and pitch * 2 >= a
+    res = (C.c_ulonglong * 3)()
+    L = lib()
+    L.emu_sparse_count.restype = C.c_int
+    L.emu_sparse_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+    assert L.emu_sparse_count(packed.ctypes.data_as(C.c_void_p), pitch, a, b, res) == 0
+    return dict(count=int(res[0]), state=int(res[1]), rows=int(res[2]))
+
+
+def arrow_digest(packed: np.ndarray, a: int, w_begin: int = 0, w_end: int | None = None, grid: int = 2) -> int:
+    """nwb_arrow_digest_kernel (csrc/nwb_digest.cuh) over words [w_begin, w_end) of a (B, pitch) nibble table."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    b, pitch = packed.shape
+    w_end = (a + 7) // 8 if w_end is None else w_end
+    L = lib()
+    L.emu_arrow_digest.restype = C.c_ulonglong
+    L.emu_arrow_digest.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
+    return int(L.emu_arrow_digest(packed.ctypes.data_as(C.c_void_p), pitch, a, b, w_begin, w_end, grid))
 
 
 def bpitch_pk(a: int, b: int) -> int:

@@ -145,6 +145,7 @@ static inline int __all_sync(unsigned, int pred)
     emu_warp_barrier();
     return all;
 }
+static inline int __any_sync(unsigned m, int pred) { return !__all_sync(m, !pred); }
 static inline void __syncthreads(void)
 {
     emu_block *b = emu_cur->block;

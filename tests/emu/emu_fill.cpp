@@ -41,6 +41,7 @@ struct emu_out {
     unsigned long long count;
     unsigned long long pitch;
     unsigned long long spitch;
+    unsigned long long dig_row, dig_col; /* dense count sweep (cpl 8): NwbDevSummary.dig_row / dig_col */
 };
 
 /* flags: 1 scores, 2 count, 8 abs, 0x20 cntmat (same bits as include/nwb.h).
@@ -102,10 +103,17 @@ int emu_fill_i32(const char *top, int A, const char *side, int B, int m, int k, 
         p0.out_bnd_s = inbox_s.data();
         p0.out_bnd_c = inbox_c.data();
         p0.out_progress = &inbox_flag;
+        /* the second "GPU" has its own (zeroed) progress words and boundary arrays, as every nwb_plan has */
+        std::vector<int32_t> bnd1_s((size_t)L.n_strips * L.bpitch, 0x7f7f7f7f);
+        std::vector<unsigned long long> bnd1_c((size_t)L.n_strips * L.bpitch, 0xdeadbeefULL);
+        std::vector<int> progress1((size_t)L.n_strips, 0);
         p1.strip_begin = split;
         p1.in_bnd_s = inbox_s.data();
         p1.in_bnd_c = inbox_c.data();
         p1.in_progress = &inbox_flag;
+        p1.bnd_s = bnd1_s.data();
+        p1.bnd_c = bnd1_c.data();
+        p1.progress = progress1.data();
         launch(p0);
         launch(p1);
     } else {
@@ -138,6 +146,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     NwbPkConsts pc;
     if (!nwb_pk_supported(m, k, d, &pc)) return -5;
     if (hx && (!nwb_hx_supported(pc) || K != 4 || R != 2 || count == 1)) return -6;
+    if (count == 1 && K != 4) return -6; /* the fused count exists for K = 4 only (nwb_pk_launch rejects it too) */
     if (count >= 2 && (K != 4 || (count != 2 && count != 4 && count != 8))) return -6;
     NwbLayout L = nwb_make_layout(A, B, NWB_KIND_PK, K, 64 * K);
     std::vector<uint32_t> bnd_w((size_t)L.n_strips * L.bpitch, 0u);
@@ -201,9 +210,9 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         cp.summary = &sum;
         cnt_bnd.assign((size_t)cp.n_strips * 2 * L.bpitch, 0ull);
         auto go = [&](const NwbCountParams &q) {
-            if (cpl == 2) emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<2>(q); });
-            else if (cpl == 4) emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<4>(q); });
-            else emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<8>(q); });
+            if (cpl == 2) emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<2, false>(q); });
+            else if (cpl == 4) emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<4, false>(q); });
+            else emu_launch(grid, 32 * NWB_CNT_WARPS, NWB_CNT_SMEM_BYTES, [&]() { nwb_count_kernel<8, true>(q); }); /* with digests */
         };
         if (split_strip > 0) {
             int sb = split_strip * ratio;
@@ -264,7 +273,33 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     out->count = sum.count;
     out->pitch = L.pitch;
     out->spitch = 0;
+    out->dig_row = sum.dig_row;
+    out->dig_col = sum.dig_col;
     return 0;
+}
+
+/* The sparse backward count (nwb_count_sparse.cuh) over a finished nibble table in the include/nwb.h layout.
+ * res = {count, state (NWB_SPC_*), rows visited}. */
+int emu_sparse_count(const uint8_t *arrows, size_t pitch, int A, int B, unsigned long long *res)
+{
+    unsigned long long count = 0ull;
+    int state = 0;
+    unsigned rows = 0;
+    NwbSparseCountParams sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.arrows = arrows; sc.pitch = pitch; sc.A = A; sc.B = B;
+    sc.out_count = &count; sc.out_state = &state; sc.out_rows = &rows;
+    emu_launch(1, 32, 0, [&]() { nwb_sparse_count_kernel(sc); });
+    res[0] = count; res[1] = (unsigned long long)state; res[2] = rows;
+    return 0;
+}
+
+/* nwb_arrow_digest_kernel over words [w_begin, w_end) of a nibble table */
+unsigned long long emu_arrow_digest(const uint8_t *arrows, size_t pitch, int A, int B, int w_begin, int w_end, unsigned grid)
+{
+    unsigned long long out = 0ull;
+    emu_launch(grid, 256, 0, [&]() { nwb_arrow_digest_kernel(arrows, pitch, A, B, w_begin, w_end, &out); });
+    return out;
 }
 
 /* ONE rank of a column-strip group under the emulator (tests/test_dist_gloo.py: one process per rank, the

@@ -50,3 +50,15 @@ def test_flag_subsets_and_split(oracle):
         check(oracle, t, s, 1, 1, 1, flags=flags)
     check(oracle, t, s, 1, 1, 1, grid=2, split=1)
     check(oracle, t, s, 2, 1, 2, grid=1, split=2, flags=2)
+
+
+def test_split_with_several_strips_per_rank(oracle):
+    """Both halves of an emulated 2-GPU split own two or more strips (each rank has its own progress words and
+    boundary arrays, as every nwb_plan has): A = 1281 is 6 strips."""
+    t, s = oracle.generate_pair(0x5EED0902, 1281, 40)
+    for split in (2, 3, 4):
+        check(oracle, t, s, 1, 1, 1, grid=2, split=split, flags=2 | 8)
+    t, s = oracle.generate_pair(0x5EED0904, 1025, 70)
+    check(oracle, t, s, 2, 1, 2, grid=3, split=3, flags=2)
+    t, s = oracle.generate_pair(0x5EED0906, 1024, 33)
+    check(oracle, t, s, 1, 1, 1, grid=1, split=2, flags=2)

@@ -266,7 +266,7 @@ def _batch_check(oracle, nwb, bt, tops, sides, m, k, d, sample):
 def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
     """csrc/nwb_batch_bx.cuh: top strings of at most 256 characters, ragged partners sharing a warp,
     empty strings, an odd number of pairs, more pair-pairs than warps; and the same batch through the
-    one-pair-per-warp kernel (NWB_BATCH_BX=0)."""
+    one-pair-per-warp kernel (nwb_tune batch_bx = 0)."""
     rng = random.Random(29)
     lens = [(256, 256), (1, 1), (255, 257), (3, 40), (17, 130), (0, 5), (200, 90), (64, 64), (256, 1), (33, 33),
             (256, 31), (100, 300), (5, 0), (8, 32), (9, 33), (249, 63), (250, 64), (7, 65), (1, 200), (256, 2),
@@ -285,9 +285,8 @@ def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
             scores = [bt.opt_score(i) for i in range(len(lens))]
             branches = [bt.branch_count(i) for i in range(len(lens))]
             bt.close()
-            monkeypatch.setenv("NWB_BATCH_BX", "0")
-            b0 = nwb.Batch(tops, sides, m, k, d, 0)
-            monkeypatch.delenv("NWB_BATCH_BX")
+            with nwb.tuned(batch_bx=0):
+                b0 = nwb.Batch(tops, sides, m, k, d, 0)
             assert b0.kernel_name() == "nwb_batch_pk_kernel"
             b0.run()
             b0.fetch()
@@ -312,7 +311,7 @@ def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
 def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
     """csrc/nwb_batch_bx.cuh nwb_batch_cx_kernel: uniform shapes, a warp sweeps its pairs of pairs back to back
     (long chains: more pairs than 2 x 12 x 148 warps), odd batches, narrow and short tables; the same batches
-    through the drained two-pairs-per-warp kernel (NWB_BATCH_CX=0) must agree."""
+    through the drained two-pairs-per-warp kernel (nwb_tune batch_cx = 0) must agree."""
     rng = random.Random(31)
     for a, b, n, alpha, (m, k, d) in ((256, 256, 12001, b"ACGT", (1, 1, 1)), (100, 96, 9000, bytes(range(1, 256)), (2, 1, 2)),
                                       (7, 64, 20001, b"AC", (0, 0, 0)), (255, 160, 5000, b"ACGT", (1, 1, 3))):
@@ -328,9 +327,8 @@ def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
         branches = [bt.branch_count(i) for i in range(n)]
         tabs = [bt.arrow_rows(i).copy() for i in sample]
         bt.close()
-        monkeypatch.setenv("NWB_BATCH_CX", "0")
-        b0 = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
-        monkeypatch.delenv("NWB_BATCH_CX")
+        with nwb.tuned(batch_cx=0):
+            b0 = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
         assert b0.kernel_name() == "nwb_batch_bx_kernel"
         b0.run()
         b0.fetch()
@@ -374,7 +372,7 @@ def test_batch_count(oracle, nwb):
 def test_batch_count_chained_runs(oracle, nwb):
     """Uniform one-strip batches: nwb_batch_count_chain_kernel sweeps a warp's run of pairs back to back.  Runs of 5-6
     pairs per warp (12,000 pairs on 2,368 warps), A < 256, B a multiple of 4 but not of 32; every count against the
-    one-pair-at-a-time kernel (NWB_BCNT_CHAIN=0) and a sample against the oracle, also mod 2^64 (0/0/0)."""
+    one-pair-at-a-time kernel (nwb_tune bcnt_chain = 0) and a sample against the oracle, also mod 2^64 (0/0/0)."""
     rng = random.Random(47)
     n = 12000
     tops = [bytes(rng.choice(b"ACGT") for _ in range(100)) for _ in range(n)]
@@ -382,15 +380,12 @@ def test_batch_count_chained_runs(oracle, nwb):
     for m, k, d in ((1, 1, 1), (0, 0, 0)):
         got = {}
         for chain in ("1", "0"):
-            os.environ["NWB_BCNT_CHAIN"] = chain
-            try:
+            with nwb.tuned(bcnt_chain=int(chain), bcnt_sparse=0):
                 bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_COUNT)
                 bt.run()
                 bt.fetch()
                 got[chain] = [bt.count(i) for i in range(n)]
                 bt.close()
-            finally:
-                del os.environ["NWB_BCNT_CHAIN"]
         assert got["1"] == got["0"]
         for i in [0, 1, 5, 6, n - 1] + rng.sample(range(n), 25):
             assert got["1"][i] == oracle.fill(tops[i], sides[i], m, k, d).count, i
@@ -432,16 +427,12 @@ def test_extreme_aspect_ratios_and_multi_pass(oracle, nwb):
 
 
 @pytest.fixture
-def force_hx():
-    """NWB_PK_HX=1: the sweeping + flush warp variant (csrc/nwb_fill_hx.cuh) at every size the
-    scheme allows, not only for tall tables (diagnostic knob read by libnwb.so at every fill)."""
-    old = os.environ.get("NWB_PK_HX")
-    os.environ["NWB_PK_HX"] = "1"
+def force_hx(nwb):
+    """nwb_tune pk_hx = 1: the sweeping + flush warp variant (csrc/nwb_fill_hx.cuh) at every size the
+    scheme allows, not only for tall tables."""
+    nwb.tune("pk_hx", 1)
     yield
-    if old is None:
-        del os.environ["NWB_PK_HX"]
-    else:
-        os.environ["NWB_PK_HX"] = old
+    nwb.tune_reset()
 
 
 def test_hx_variant_edge_shapes(oracle, nwb, force_hx):
@@ -457,8 +448,13 @@ def test_hx_variant_edge_shapes(oracle, nwb, force_hx):
         o = check_arrows(oracle, nwb, tab, t, s, m, k, d)
         assert tab.kernel_kind == (nwb.KIND_PK if pk_supported(m, k, d) else nwb.KIND_I32)
         assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, m, k, d)
-        # -s: the count sweep trails the hx fill on a second stream (rows published by the flush warps)
+        # -s, default path (sparse backward sweep, dense sweep behind it) and the dense sweep trailing the hx
+        # fill on a second stream (count_mode 3: rows published by the flush warps)
         tabc = nwb.fill(t, s, m, k, d, nwb.WANT_COUNT)
+        assert (tabc.opt_score, tabc.branch_count, tabc.count) == (o.final_score, o.branch_count, o.count), (a, b, m, k, d)
+        nwb.tune("count_mode", 3)
+        tabc = nwb.fill(t, s, m, k, d, nwb.WANT_COUNT)
+        nwb.tune("count_mode", 0)
         assert (tabc.opt_score, tabc.branch_count, tabc.count) == (o.final_score, o.branch_count, o.count), (a, b, m, k, d)
 
 
@@ -478,43 +474,13 @@ def test_hx_variant_big_and_multi_pass(oracle, nwb, force_hx):
         assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b)
 
 
-def test_hy_geometry_experiment(oracle, nwb, force_hx):
-    """NWB_PK_HY=1: the three-rows-per-lane geometry (csrc/nwb_fill_hy.cuh; an experiment, not the default) gives the
-    same table, score, branch counter and count as the oracle, also with several strips per warp."""
-    os.environ["NWB_PK_HY"] = "1"
-    try:
-        rng = random.Random(29)
-        for a, b, mkd in [(1, 1, (1, 1, 1)), (257, 2, (1, 1, 1)), (513, 3, (2, 1, 2)), (700, 333, (1, 1, 1)),
-                          (2049, 1025, (2, 1, 2)), (64, 4097, (1, 1, 3)), (3000, 3001, (1, 1, 1))]:
-            t = bytes(rng.choice(b"ACGT") for _ in range(a))
-            s = bytes(rng.choice(b"ACGT") for _ in range(b))
-            tab = nwb.fill(t, s, *mkd, nwb.WANT_ARROWS_HOST)
-            o = check_arrows(oracle, nwb, tab, t, s, *mkd)
-            assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, mkd)
-            tabc = nwb.fill(t, s, *mkd, nwb.WANT_COUNT)
-            assert (tabc.opt_score, tabc.branch_count, tabc.count) == (o.final_score, o.branch_count, o.count), (a, b, mkd)
-        t, s = oracle.generate_pair(0x5EED0E06, 160000, 200)   # 625 strips on 444 sweeping warps
-        tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_ARROWS_HOST)
-        o = check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
-        assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count)
-    finally:
-        del os.environ["NWB_PK_HY"]
-
-
 def test_plain_packed_kernel_without_hx(oracle, nwb):
-    """NWB_PK_HX=0 keeps the one-warp-per-strip packed kernel (the path for 2d + m > 7) covered at 10k x 10k."""
-    old = os.environ.get("NWB_PK_HX")
-    os.environ["NWB_PK_HX"] = "0"
-    try:
+    """nwb_tune pk_hx = 0 keeps the one-warp-per-strip packed kernel (the path for 2d + m > 7) covered at 10k x 10k."""
+    with nwb.tuned(pk_hx=0):
         t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
         tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_ARROWS_HOST)
         assert (tab.opt_score, tab.branch_count) == (1056, 34377799)
         check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
-    finally:
-        if old is None:
-            del os.environ["NWB_PK_HX"]
-        else:
-            os.environ["NWB_PK_HX"] = old
     # a scheme whose differences do not fit a nibble (2d + m = 11) at a size where hx would otherwise run
     t, s = oracle.generate_pair(0x5EED0F00, 3000, 5000)
     tab = nwb.fill(t, s, 5, 4, 3, nwb.WANT_ARROWS_HOST)
@@ -523,39 +489,154 @@ def test_plain_packed_kernel_without_hx(oracle, nwb):
 
 
 def test_fused_count_kernel_still_matches(oracle, nwb):
-    """NWB_COUNT_FUSED=1: the count fused into nwb_fill_pk_kernel (the default is the count sweep over the
-    arrow codes, csrc/nwb_count.cuh): final counts of sub-problems whose count is not 0 mod 2^64, and config 2."""
-    old = os.environ.get("NWB_COUNT_FUSED")
-    os.environ["NWB_COUNT_FUSED"] = "1"
-    try:
+    """nwb_tune count_mode = 1: the count fused into nwb_fill_pk_kernel: final counts of sub-problems whose count
+    is not 0 mod 2^64, and config 2."""
+    with nwb.tuned(count_mode=1):
         t, s = oracle.generate_pair(0x5EED0D00, 900, 700)
         o = oracle.fill(t, s, 1, 1, 1, want_counts=True)
         for i, j in [(900, 700), (256, 256), (257, 300), (513, 699), (100, 650)]:
             tab = nwb.fill(t[:i], s[:j], 1, 1, 1, nwb.WANT_COUNT)
+            assert tab.summary().count_path == nwb.COUNT_FUSED
             assert tab.count == int(o.counts[j, i]), (i, j)
         t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
         tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_COUNT)
         assert (tab.opt_score, tab.branch_count, tab.count) == (1056, 34377799, 0)
-    finally:
-        if old is None:
-            del os.environ["NWB_COUNT_FUSED"]
-        else:
-            os.environ["NWB_COUNT_FUSED"] = old
 
 
-def test_count_sweep_after_the_fill(oracle, nwb):
-    """NWB_COUNT_SERIAL=1: the count sweep launched after the hx fill instead of trailing it (the order used
-    anyway when the fill occupies every SM): same counts."""
-    old = os.environ.get("NWB_COUNT_SERIAL")
-    os.environ["NWB_COUNT_SERIAL"] = "1"
-    try:
-        t, s = oracle.generate_pair(0x5EED0D10, 900, 4500)
-        o = oracle.fill(t, s, 1, 1, 1, want_counts=True)
-        for i, j in [(900, 4500), (256, 4100), (513, 4499)]:
-            tab = nwb.fill(t[:i], s[:j], 1, 1, 1, nwb.WANT_COUNT)
-            assert tab.count == int(o.counts[j, i]), (i, j)
-    finally:
-        if old is None:
-            del os.environ["NWB_COUNT_SERIAL"]
-        else:
-            os.environ["NWB_COUNT_SERIAL"] = old
+def test_dense_count_sweep_after_and_trailing_the_fill(oracle, nwb):
+    """nwb_tune count_mode = 2 / 3: the dense forward count sweep (csrc/nwb_count.cuh) launched after the hx fill,
+    or trailing it on a second stream: same counts as the oracle, on sub-problems whose count is not 0 mod 2^64."""
+    t, s = oracle.generate_pair(0x5EED0D10, 900, 4500)
+    o = oracle.fill(t, s, 1, 1, 1, want_counts=True)
+    for mode in (2, 3):
+        with nwb.tuned(count_mode=mode):
+            for i, j in [(900, 4500), (256, 4100), (513, 4499)]:
+                tab = nwb.fill(t[:i], s[:j], 1, 1, 1, nwb.WANT_COUNT)
+                assert tab.summary().count_path == nwb.COUNT_DENSE
+                assert tab.count == int(o.counts[j, i]), (mode, i, j)
+
+
+# ---- the sparse backward count (csrc/nwb_count_sparse.cuh), the default behind -s ---------------------------
+def test_sparse_count_is_the_default_and_matches(oracle, nwb):
+    rng = random.Random(61)
+    seen_paths = set()
+    for it in range(40):
+        a, b = rng.randint(1, 3000), rng.randint(1, 3000)
+        alpha = rng.choice([oracle.DNA, oracle.PROTEIN, "AC"])
+        m, k, d = rng.choice([(1, 1, 1), (2, 1, 2), (0, 0, 0), (1, 2, 3), (5, 4, 3), (1, 1, 0)])
+        t, s = oracle.generate_pair(0x5EEDA000 + 2 * it, a, b, alpha)
+        o = oracle.fill(t, s, m, k, d)
+        for ff in (0, nwb.FORCE_GENERAL):
+            tab = nwb.fill(t, s, m, k, d, nwb.WANT_COUNT | ff)
+            sm = tab.summary()
+            assert sm.count_path in (nwb.COUNT_SPARSE, nwb.COUNT_SPARSE_BAILED), (it, sm.count_path)
+            seen_paths.add(sm.count_path)
+            assert (tab.count, tab.opt_score, tab.branch_count) == (o.count, o.final_score, o.branch_count), (it, a, b, m, k, d)
+    # (0,0,0) tables wider than the 256-column window make the sparse sweep give up: the dense sweep behind it ran
+    assert seen_paths == {nwb.COUNT_SPARSE, nwb.COUNT_SPARSE_BAILED}
+
+
+def _mutated(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_big", os.path.join(HERE, "golden", "make_golden_big.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for nm, seed, n, subs, indels, mkd in mod.MUTATED:
+        if nm == name:
+            return mod.mutated_pair(seed, n, subs, indels), mkd
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["mutated_dna_30k", "mutated_dna_100k"])
+def test_sparse_count_nonzero_at_full_size(oracle, nwb, name):
+    """A string against a mutated copy of itself: the number of optimal alignments is NOT 0 mod 2^64, so the
+    sparse sweep must carry live values through every one of the 30,000 / 100,000 rows; the same count from the
+    dense sweep (every intermediate count of the last row and column checked through their digests)."""
+    g = [c for c in golden("golden_big.json") if c["name"] == name][0]
+    (t, s), (m, k, d) = _mutated(name)
+    assert (len(t), len(s)) == (g["top_len"], g["side_len"])
+    assert g["count_u64"] != 0
+    plan = nwb.Plan(len(t), len(s), nwb.WANT_COUNT)
+    plan.upload(t, s)
+    plan.run(m, k, d)
+    sm = plan.summary()
+    assert sm.count_path == nwb.COUNT_SPARSE and sm.count_rows == len(s)
+    assert (sm.opt_score, sm.branch_count, sm.count) == (g["final_score"], g["branch_count"], g["count_u64"])
+    assert plan.arrow_digest() == int(g["arrow_digest"], 16)
+    plan.close()
+    plan = nwb.Plan(len(t), len(s), nwb.WANT_COUNT_DIGEST)
+    plan.upload(t, s)
+    plan.run(m, k, d)
+    sm = plan.summary()
+    assert sm.count_path == nwb.COUNT_DENSE
+    assert sm.count == g["count_u64"]
+    assert (sm.lastrow_count_digest, sm.lastcol_count_digest) == (int(g["lastrow_count_digest"], 16), int(g["lastcol_count_digest"], 16))
+    plan.close()
+
+
+# ---- full-size parity through on-device digests (csrc/nwb_digest.cuh) ---------------------------------------
+@pytest.mark.parametrize("name,alpha,mkd", [("config2_dna_10k", "dna", (1, 1, 1)), ("config5_protein_30k", "protein", (2, 1, 2)),
+                                            ("config3_dna_100k", "dna", (1, 1, 1))])
+@pytest.mark.parametrize("kernel", ["hx", "pk", "i32"])
+def test_full_size_digests(oracle, nwb, name, alpha, mkd, kernel):
+    """EVERY arrow set of configs 2, 5 and 3 at full size (digest of the whole nibble table, computed on the
+    device, against the oracle's), the summary, the default (sparse) count, and every count of the dense sweep's
+    last row and last column (non-zero intermediate values: the final count of these configs is 0 mod 2^64)."""
+    g = [c for c in golden("golden_big.json") if c["name"] == name][0]
+    a, b = g["top_len"], g["side_len"]
+    if kernel != "hx" and a > 30000:
+        pytest.skip("the slower kernels are covered at 10k and 30k")
+    t, s = oracle.generate_pair(g["seed"], a, b, oracle.DNA if alpha == "dna" else oracle.PROTEIN)
+    ff = nwb.FORCE_GENERAL if kernel == "i32" else 0
+    want_kernel = {"hx": "nwb_fill_hx_kernel", "pk": "nwb_fill_pk_kernel", "i32": "nwb_fill_i32_kernel"}[kernel]
+    with nwb.tuned(pk_hx=0 if kernel == "pk" else -1):
+        plan = nwb.Plan(a, b, nwb.WANT_COUNT | ff)
+        plan.upload(t, s)
+        plan.run(*mkd)
+        sm = plan.summary()
+        assert plan.kernel_name() == want_kernel
+        assert (sm.opt_score, sm.branch_count, sm.count) == (g["final_score"], g["branch_count"], g["count_u64"])
+        assert sm.count_path == nwb.COUNT_SPARSE
+        assert plan.arrow_digest() == int(g["arrow_digest"], 16)
+        plan.close()
+        if kernel == "hx":
+            plan = nwb.Plan(a, b, nwb.WANT_COUNT_DIGEST)
+            plan.upload(t, s)
+            plan.run(*mkd)
+            sm = plan.summary()
+            assert sm.count_path == nwb.COUNT_DENSE and sm.count == g["count_u64"]
+            assert sm.lastrow_count_digest == int(g["lastrow_count_digest"], 16)
+            assert sm.lastcol_count_digest == int(g["lastcol_count_digest"], 16)
+            plan.close()
+
+
+def test_table_digest_through_nwb_fill(oracle, nwb):
+    t, s = oracle.generate_pair(0x5EED0C30, 3001, 1777)
+    o = oracle.fill(t, s, 1, 1, 1)
+    for ff in (0, nwb.FORCE_GENERAL):
+        tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_DIGEST | ff)
+        assert tab.arrow_digest() == o.arrow_digest
+    tab = nwb.fill(t, s, 1, 1, 1, 0)
+    with pytest.raises(nwb.NwbError):
+        tab.arrow_digest()
+
+
+def test_config4_full_shard_digest(oracle, nwb):
+    """ALL 125,000 pairs of one GPU's shard of config 4 (every arrow set, score, branch count and alignment count,
+    through the batch digests computed on the device) against the oracle-generated per-shard digests."""
+    g = [c for c in golden("golden_big.json") if c["name"] == "config4_batch_1M"][0]
+    per = g["pairs_per_shard"]
+    for shard in (0, 5):
+        first = shard * per
+        tcat, scat = bytearray(), bytearray()
+        for p in range(first, first + per):
+            tt, ss = oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256)
+            tcat += tt
+            scat += ss
+        off = np.arange(per + 1, dtype=np.int64) * 256
+        bt = nwb.Batch.from_arrays(bytes(tcat), off, bytes(scat), off, 1, 1, 1, nwb.WANT_COUNT)
+        bt.run()
+        dg = bt.digest(first)
+        bt.close()
+        e = g["shard_digests"][shard]
+        assert dg == tuple(int(e[k], 16) for k in ("arrow", "score", "branch", "count")), shard

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the sweeping warps' lane geometry: nwb_fill_hy.cuh (three rows of skew per lane, NWB_PK_HY=1) against the
-default nwb_fill_hx.cuh (four rows) on BASELINE configs 3, 5, 2, with and without the count behind -s.
+default nwb_fill_hx.cuh (four rows); needs the experiments build (make -C needleman-wunsch_b200/csrc exp) on BASELINE configs 3, 5, 2, with and without the count behind -s.
     python tools/ab_hy.py [--reps 5]
 Every run is checked against tests/golden/golden_big.json (score, branch counter)."""
 import argparse
@@ -11,6 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nw_b200 as nwb  # noqa: E402
+nwb.use_experiments_build()
 import oracle  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -29,7 +30,7 @@ for n in [int(x) for x in args.sizes.split(",")]:
     for flags, what in ((0, "fill"), (nwb.WANT_COUNT, "fill+count")):
         res = {}
         for hy in ("0", "1"):
-            os.environ["NWB_PK_HY"] = hy
+            nwb.tune("pk_hy", int(hy))
             plan = nwb.Plan(n, n, flags)
             plan.upload(t, s)
             ms = []

@@ -17,22 +17,21 @@ for a, b in ((7, 7), (300, 100), (700, 260), (1500, 64)):
         if flags & nwb.WANT_COUNT:
             assert tab.count == o.count
         tab.close()
-# the sweeping + flush warp kernel (NWB_PK_HX=1 forces it at small sizes) and the count sweep after it;
+# the sweeping + flush warp kernel (nwb_tune pk_hx = 1 forces it at small sizes) and the count sweep after it;
 # 1500 x 300: 6 strips on one block's three sweeping warps
-os.environ["NWB_PK_HX"] = "1"
-for hy in ("0", "1"):   # 1: the three-rows-per-lane geometry of nwb_fill_hy.cuh (an experiment, not the default)
-    os.environ["NWB_PK_HY"] = hy
+nwb.tune("pk_hx", 1)
+for mode in (0, 2, 3):   # count: sparse backward sweep (default) / dense sweep after / trailing the fill
+    nwb.tune("count_mode", mode)
     for a, b in ((7, 7), (300, 101), (700, 260), (1500, 300)):
         t, s = oracle.generate_pair(0x5EED0F40 + a, a, b)
         o = oracle.fill(t, s, 2, 1, 2)
         for flags in (0, nwb.WANT_COUNT):
             tab = nwb.fill(t, s, 2, 1, 2, flags | nwb.WANT_ARROWS_HOST)
-            assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, flags, hy)
+            assert (tab.opt_score, tab.branch_count) == (o.final_score, o.branch_count), (a, b, flags, mode)
             if flags & nwb.WANT_COUNT:
                 assert tab.count == o.count
             tab.close()
-del os.environ["NWB_PK_HX"]
-del os.environ["NWB_PK_HY"]
+nwb.tune_reset()
 tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256 if p % 3 else 300, 256 if p % 2 else 100) for p in range(40)))
 bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST)
 bt.run()

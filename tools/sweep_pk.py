@@ -39,9 +39,9 @@ for n in [int(x) for x in args.sizes.split(",")]:
                                      [int(x) for x in args.warps.split(",")]):
         if args.count and K != 4:
             continue
-        os.environ["NWB_PK_K"] = str(K)
-        os.environ["NWB_PK_R"] = str(R)
-        os.environ["NWB_PK_WARPS"] = str(W)
+        nwb.tune("pk_k", K)
+        nwb.tune("pk_r", R)
+        nwb.tune("pk_warps", W)
         best = 1e9
         for _ in range(args.reps):
             plan.run(m, k, d)

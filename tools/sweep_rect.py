@@ -31,13 +31,10 @@ for A in [int(x) for x in args.tops.split(",")]:
     combos = [("hx", 4, 2, 0)] + [("pk", K, R, W) for K, R, W in itertools.product(
         [int(x) for x in args.ks.split(",")], [int(x) for x in args.rs.split(",")], [int(x) for x in args.warps.split(",")])]
     for kind, K, R, W in combos:
-        os.environ["NWB_PK_HX"] = "1" if kind == "hx" else "0"
-        os.environ["NWB_PK_K"] = str(K)
-        os.environ["NWB_PK_R"] = str(R)
-        if W:
-            os.environ["NWB_PK_WARPS"] = str(W)
-        else:
-            os.environ.pop("NWB_PK_WARPS", None)
+        nwb.tune("pk_hx", 1 if kind == "hx" else 0)
+        nwb.tune("pk_k", K)
+        nwb.tune("pk_r", R)
+        nwb.tune("pk_warps", W)
         best = 1e9
         for _ in range(args.reps):
             plan.run(1, 1, 1)
