@@ -124,6 +124,10 @@ int nwb_fill_on(const char *top, int top_len, const char *side, int side_len,
                 nwb_table **out);
 /* replaces free_computation(), computation.c:200-214 */
 void nwb_free(nwb_table *t);
+/* nwb_fill()/nwb_fill_on() keep the device workspace (streams, buffers) of the last fills per (device, number of
+ * GPUs) and reuse it when it is large enough, instead of allocating and freeing it on every call.  This releases
+ * whatever is cached (e.g. the 5 GB arrow table of a 100k x 100k fill).  nwb_tune("plan_cache", 0) disables it. */
+void nwb_cache_clear(void);
 
 /* score_table_t.M-1 / N-1 (score-table.h:70-71) */
 int nwb_top_len(const nwb_table *t);

@@ -79,6 +79,7 @@ _SIGS = {
     "nwb_fill_on": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
                               C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "nwb_free": (None, [C.c_void_p]),
+    "nwb_cache_clear": (None, []),
     "nwb_top_len": (C.c_int, [C.c_void_p]),
     "nwb_side_len": (C.c_int, [C.c_void_p]),
     "nwb_opt_score": (C.c_int32, [C.c_void_p]),
@@ -188,6 +189,11 @@ def tune(key: str, value: int) -> None:
     rc = load_library().nwb_tune(key.encode(), int(value))
     if rc != 0:
         raise NwbError(rc, f"nwb_tune({key!r})")
+
+
+def cache_clear() -> None:
+    """Release the device workspace nwb_fill()/nwb_fill_on() keep between calls."""
+    load_library().nwb_cache_clear()
 
 
 def tune_reset() -> None:

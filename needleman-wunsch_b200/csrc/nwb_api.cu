@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -92,7 +93,8 @@ struct NwbTune {
     int bcnt_sparse = -1; /* -1 = auto; 0 = never the sparse backward batch count                            */
     int cx_warps = 0;    /* 0 = auto (12); 16                                                                */
     int watchdog_ms = 4000; /* device-side spin loops give up after this long without progress               */
-    int inject_fault = 0;   /* test only: 1 = drop the boundary stream of the fill's second strip            */
+    int inject_fault = 0;   /* test only: 1 = the fill's strips do not publish their boundary streams        */
+    int plan_cache = 1;     /* 0 = nwb_fill()/nwb_fill_on() create and destroy their device workspace per call */
 #ifdef NWB_EXPERIMENTS
     int pk_hy = 0;
     int debug_nowait = 0;
@@ -108,7 +110,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"count_mode", &g_tune.count_mode}, {"cnt_cpl", &g_tune.cnt_cpl}, {"batch_bx", &g_tune.batch_bx},
         {"batch_cx", &g_tune.batch_cx}, {"bcnt_chain", &g_tune.bcnt_chain}, {"bcnt_sparse", &g_tune.bcnt_sparse},
         {"cx_warps", &g_tune.cx_warps},
-        {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault},
+        {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
 #ifdef NWB_EXPERIMENTS
         {"pk_hy", &g_tune.pk_hy}, {"debug_nowait", &g_tune.debug_nowait},
 #endif
@@ -866,6 +868,128 @@ extern "C" void nwb_free(nwb_table *t)
     delete t;
 }
 
+/* ---- workspace cache behind nwb_fill() / nwb_fill_on() --------------------------
+ * A one-shot fill used to create and destroy its plans (streams, events, a dozen device buffers, their zeroing)
+ * on every call: 3-4 ms of host time around a 0.75 ms kernel at 10k x 10k.  The plans of the last fills are kept
+ * per (device, number of GPUs) and reused when they are large enough; nwb_cache_clear() releases them. */
+struct NwbPlanSet {
+    int device = 0, world = 1, maxA = 0, maxB = 0;
+    bool busy = false, cached = false;
+    std::vector<nwb_plan *> plans;
+};
+static std::mutex g_cache_mu;
+static std::vector<NwbPlanSet *> g_cache;
+#define NWB_CACHE_SETS 2
+
+static void planset_destroy(NwbPlanSet *ps)
+{
+    if (!ps) return;
+    for (nwb_plan *p : ps->plans) nwb_plan_destroy(p);
+    delete ps;
+}
+
+static int planset_acquire(int device, int world, int A, int B, unsigned flags, NwbPlanSet **out)
+{
+    *out = nullptr;
+    NwbPlanSet *ps = nullptr;
+    std::vector<NwbPlanSet *> evict;
+    const bool use_cache = g_tune.plan_cache != 0;
+    if (use_cache) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (NwbPlanSet *c : g_cache)
+            if (!c->busy && c->device == device && c->world == world && c->maxA >= A && c->maxB >= B) { ps = c; break; }
+        if (ps) ps->busy = true;
+        else {
+            /* make room: drop idle sets of the same (device, world) that are too small, then the oldest idle one */
+            for (size_t i = 0; i < g_cache.size();) {
+                NwbPlanSet *c = g_cache[i];
+                const bool same = c->device == device && c->world == world;
+                if (!c->busy && (same || g_cache.size() >= NWB_CACHE_SETS)) {
+                    evict.push_back(c);
+                    g_cache.erase(g_cache.begin() + (long)i);
+                } else i++;
+            }
+        }
+    }
+    for (NwbPlanSet *c : evict) planset_destroy(c);
+    if (ps) {
+        int rc = NWB_OK;
+        for (nwb_plan *p : ps->plans) {
+            p->flags = flags;
+            if (world > 1 && rc == NWB_OK) rc = nwb_plan_reset_inbox(p, nullptr);
+        }
+        for (nwb_plan *p : ps->plans)
+            if (world > 1 && rc == NWB_OK) {
+                cudaSetDevice(p->device);
+                cudaError_t e = cudaStreamSynchronize(p->stream);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+            }
+        if (rc != NWB_OK) {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            ps->busy = false;
+            return rc;
+        }
+        *out = ps;
+        return NWB_OK;
+    }
+    ps = new (std::nothrow) NwbPlanSet();
+    if (!ps) return NWB_ERR_NOMEM;
+    ps->device = device;
+    ps->world = world;
+    ps->maxA = (int)nwb_round_up((size_t)(A > 4096 ? A : 4096), 1024);
+    ps->maxB = (int)nwb_round_up((size_t)(B > 4096 ? B : 4096), 1024);
+    ps->busy = true;
+    int rc = NWB_OK;
+    for (int g = 0; g < world && rc == NWB_OK; g++) {
+        nwb_plan *p = nullptr;
+        rc = nwb_plan_create(ps->maxA, ps->maxB, flags & ~(unsigned)(NWB_WANT_SCORES | NWB_WANT_COUNT_MATRIX), device + g, g, world, &p);
+        if (rc == NWB_OK) {
+            p->flags = flags;
+            ps->plans.push_back(p);
+        }
+    }
+    for (int g = 0; g + 1 < world && rc == NWB_OK; g++) rc = plan_attach_right_local(ps->plans[g], ps->plans[g + 1]);
+    if (rc != NWB_OK) {
+        planset_destroy(ps);
+        return rc;
+    }
+    if (use_cache) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_cache.size() < NWB_CACHE_SETS) {
+            g_cache.push_back(ps);
+            ps->cached = true;
+        }
+    }
+    *out = ps;
+    return NWB_OK;
+}
+
+static void planset_release(NwbPlanSet *ps)
+{
+    if (!ps) return;
+    if (ps->cached) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        ps->busy = false;
+        return;
+    }
+    planset_destroy(ps);
+}
+
+extern "C" void nwb_cache_clear(void)
+{
+    std::vector<NwbPlanSet *> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (!g_cache[i]->busy) {
+                drop.push_back(g_cache[i]);
+                g_cache.erase(g_cache.begin() + (long)i);
+            } else i++;
+        }
+    }
+    for (NwbPlanSet *c : drop) planset_destroy(c);
+}
+
 extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int side_len,
                            int m, int k, int d, unsigned flags, int device, int num_gpus,
                            nwb_table **out)
@@ -878,6 +1002,7 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
     if (ndev <= 0) return NWB_ERR_NO_DEVICE;
     if (device < 0 || device + num_gpus > ndev) return NWB_ERR_INVALID;
     if (flags & NWB_WANT_COUNT_MATRIX) flags |= NWB_WANT_COUNT;
+    if ((flags & (NWB_WANT_SCORES | NWB_WANT_COUNT_MATRIX)) && num_gpus > 1) return NWB_ERR_UNSUPPORTED;
 
     nwb_table *t = new (std::nothrow) nwb_table();
     if (!t) return NWB_ERR_NOMEM;
@@ -885,23 +1010,23 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
     t->top.assign(top, top + top_len);
     t->side.assign(side, side + side_len);
 
-    int rc = NWB_OK;
-    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
-        nwb_plan *p = nullptr;
-        rc = nwb_plan_create(top_len, side_len, flags, device + g, g, num_gpus, &p);
-        if (rc == NWB_OK) t->plans.push_back(p);
+    NwbPlanSet *ps = nullptr;
+    int rc = planset_acquire(device, num_gpus, top_len, side_len, flags, &ps);
+    if (rc != NWB_OK) {
+        nwb_free(t);
+        return rc;
     }
-    for (int g = 0; g + 1 < num_gpus && rc == NWB_OK; g++) rc = plan_attach_right_local(t->plans[g], t->plans[g + 1]);
-    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_upload(t->plans[g], top, top_len, side, side_len);
-    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_run(t->plans[g], m, k, d, nullptr);
+    const std::vector<nwb_plan *> &plans = ps->plans;
+    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_upload(plans[g], top, top_len, side, side_len);
+    for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_run(plans[g], m, k, d, nullptr);
     /* summaries: score/count live on the rank that owns column A (the last
      * non-empty one); branch counts and abs maxima are combined */
     memset(&t->sum, 0, sizeof(t->sum));
     for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
         nwb_summary s;
-        rc = nwb_plan_summary(t->plans[g], &s);
+        rc = nwb_plan_summary(plans[g], &s);
         if (rc != NWB_OK) break;
-        nwb_plan *p = t->plans[g];
+        nwb_plan *p = plans[g];
         t->sum.branch_count += s.branch_count;
         if (s.greatest_abs > t->sum.greatest_abs) t->sum.greatest_abs = s.greatest_abs;
         t->sum.kernel_kind = s.kernel_kind;
@@ -910,14 +1035,14 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
         if (owns_last) {
             t->sum.opt_score = s.opt_score;
             t->sum.count = s.count;
+            t->sum.count_path = s.count_path;
+            t->sum.count_rows = s.count_rows;
         }
         t->sum.partial_r += s.partial_r;
         const float ms = nwb_plan_kernel_ms(p);
         if (ms > t->kernel_ms) t->kernel_ms = ms;
         t->sum.lastrow_count_digest += s.lastrow_count_digest;
         t->sum.lastcol_count_digest += s.lastcol_count_digest;
-        t->sum.count_path = s.count_path;
-        t->sum.count_rows = s.count_rows;
         if (flags & NWB_WANT_DIGEST) {
             uint64_t dg = 0;
             rc = nwb_plan_arrow_digest(p, &dg);
@@ -926,17 +1051,24 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
             t->have_digest = true;
         }
     }
+    if (rc != NWB_OK) {
+        /* a failed run (watchdog) may have left waiters on the other devices: let every stream drain */
+        for (nwb_plan *p : plans) {
+            cudaSetDevice(p->device);
+            cudaStreamSynchronize(p->stream);
+        }
+    }
     if (rc == NWB_OK && top_len > 0 && side_len > 0 && t->sum.kernel_kind == NWB_KIND_PK)
         t->sum.opt_score = nwb_strip_group_score(t->sum.partial_r, top_len, side_len, d);
     if (rc == NWB_OK && top_len > 0 && side_len > 0) {
-        const NwbLayout &L = t->plans[0]->L;
+        const NwbLayout &L = plans[0]->L;
         t->pitch = L.pitch;
         t->spitch = L.spitch;
         if (flags & NWB_WANT_ARROWS_HOST) {
             t->h_arrows = (uint8_t *)malloc(L.pitch * (size_t)side_len);
             if (!t->h_arrows) rc = NWB_ERR_NOMEM;
             for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
-                nwb_plan *p = t->plans[g];
+                nwb_plan *p = plans[g];
                 if (p->strip_end <= p->strip_begin) continue;
                 const size_t off = (size_t)p->strip_begin * L.strip_w / 2;
                 const size_t width = (size_t)(p->strip_end - p->strip_begin) * L.strip_w / 2;
@@ -950,7 +1082,7 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
             t->h_scores = (int32_t *)malloc(L.spitch * (size_t)side_len * sizeof(int32_t));
             if (!t->h_scores) rc = NWB_ERR_NOMEM;
             else {
-                cudaError_t e = cudaMemcpy(t->h_scores, t->plans[0]->scores.p,
+                cudaError_t e = cudaMemcpy(t->h_scores, plans[0]->scores.p,
                                            L.spitch * (size_t)side_len * sizeof(int32_t), cudaMemcpyDeviceToHost);
                 if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(scores)");
             }
@@ -959,12 +1091,13 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
             t->h_cntmat = (unsigned long long *)malloc(L.spitch * (size_t)side_len * sizeof(unsigned long long));
             if (!t->h_cntmat) rc = NWB_ERR_NOMEM;
             else {
-                cudaError_t e = cudaMemcpy(t->h_cntmat, t->plans[0]->cntmat.p,
+                cudaError_t e = cudaMemcpy(t->h_cntmat, plans[0]->cntmat.p,
                                            L.spitch * (size_t)side_len * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
                 if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(cntmat)");
             }
         }
     }
+    planset_release(ps);
     if (rc != NWB_OK) {
         nwb_free(t);
         return rc;

@@ -640,3 +640,24 @@ def test_config4_full_shard_digest(oracle, nwb):
         bt.close()
         e = g["shard_digests"][shard]
         assert dg == tuple(int(e[k], 16) for k in ("arrow", "score", "branch", "count")), shard
+
+
+def test_watchdog_turns_a_lost_boundary_stream_into_an_error(oracle, nwb):
+    """nwb_tune inject_fault = 1 makes every strip keep its boundary stream to itself, so the next strip waits for
+    ever -- the device watchdog must end the wait, and the fill must FAIL (NWB_ERR_CUDA), for every kernel family;
+    the library stays usable afterwards."""
+    t, s = oracle.generate_pair(0x5EED0F50, 3000, 5000)
+    o = oracle.fill(t, s, 1, 1, 1)
+    for pk_hx, ff, flags in ((-1, 0, 0), (0, 0, 0), (-1, nwb.FORCE_GENERAL, 0), (-1, 0, nwb.WANT_COUNT_DIGEST)):
+        nwb.tune("inject_fault", 1)
+        nwb.tune("watchdog_ms", 250)
+        nwb.tune("pk_hx", pk_hx)
+        try:
+            with pytest.raises(nwb.NwbError) as e:
+                nwb.fill(t, s, 1, 1, 1, ff | flags)
+            assert e.value.code == -3, e.value
+            assert "watchdog" in str(e.value)
+        finally:
+            nwb.tune_reset()
+        tab = nwb.fill(t, s, 1, 1, 1, ff | nwb.WANT_COUNT)
+        assert (tab.opt_score, tab.branch_count, tab.count) == (o.final_score, o.branch_count, o.count)
