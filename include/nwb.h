@@ -265,9 +265,11 @@ typedef struct nwb_batch nwb_batch;
  * arrow table (layout of section 1 with pitch 128 * ceil(A/256) bytes); with
  * NWB_WANT_COUNT the number of optimal alignments mod 2^64 (a second pass over
  * the arrow codes, nwb_batch_count.cuh; nwb_batch_count_u64()).
- * The batch path runs the packed 16x2 kernels only: schemes outside their range
- * (see nwb_fill_pk.cuh) and NWB_WANT_SCORES / NWB_TRACK_ABS return
- * NWB_ERR_UNSUPPORTED -- use nwb_fill() per pair for those.
+ * Any m / k / d is accepted, as by the reference (needleman-wunsch.c:783-785): schemes whose per-cell differences
+ * are small run the packed 16x2 batch kernels; everything else, NWB_FORCE_GENERAL, NWB_WANT_SCORES (the int32
+ * score matrix of every pair: nwb_batch_score_rows()) and NWB_TRACK_ABS (nwb_batch_greatest_abs()) run the general
+ * int32 engine with one warp per pair (nwb_batch_i32.cuh).  Only NWB_WANT_COUNT_MATRIX is refused
+ * (NWB_ERR_UNSUPPORTED: use nwb_fill() per pair).
  * nwb_fill_batch() = nwb_batch_create() + nwb_batch_run() + nwb_batch_fetch(). */
 int nwb_fill_batch(const char *tops, const int64_t *top_off,
                    const char *sides, const int64_t *side_off, int64_t n_pairs,
@@ -278,6 +280,10 @@ int nwb_batch_create(const char *tops, const int64_t *top_off,
                      int m, int k, int d, unsigned flags, int device, nwb_batch **out);
 /* Launch the batch on `stream` (NULL = the batch's own); asynchronous. */
 int nwb_batch_run(nwb_batch *b, void *stream);
+/* New strings for the SAME shapes (the offsets given to nwb_batch_create()), from host buffers, and run: the batch
+ * is cut into chunks of pairs and the host-to-device copy of a chunk overlaps the kernels of the previous one.
+ * Asynchronous on the batch's own stream; follow with nwb_batch_fetch().  (nwb_fill_batch() uses it too.) */
+int nwb_batch_refill(nwb_batch *b, const char *tops, const char *sides);
 /* Wait and copy the per-pair results (and arrows if requested) to the host. */
 int nwb_batch_fetch(nwb_batch *b);
 void nwb_batch_free(nwb_batch *b);
@@ -286,6 +292,10 @@ int32_t nwb_batch_opt_score(const nwb_batch *b, int64_t pair);
 uint32_t nwb_batch_branch_count(const nwb_batch *b, int64_t pair);
 uint64_t nwb_batch_count_u64(const nwb_batch *b, int64_t pair);
 const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair, size_t *pitch);
+/* NWB_TRACK_ABS: max |score| over the pair's interior cells (score_table_t.greatest_abs_val under tflag). */
+int32_t nwb_batch_greatest_abs(const nwb_batch *b, int64_t pair);
+/* NWB_WANT_SCORES: interior scores of a pair, element (i,j), i,j >= 1, at rows[(j-1) * (*pitch_elems) + (i-1)]. */
+const int32_t *nwb_batch_score_rows(const nwb_batch *b, int64_t pair, size_t *pitch_elems);
 float nwb_batch_kernel_ms(const nwb_batch *b);
 int64_t nwb_batch_launches(const nwb_batch *b);
 /* Name of the kernel nwb_batch_run() launches for this batch: "nwb_batch_bx_kernel" (two pairs per warp: top

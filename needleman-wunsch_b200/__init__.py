@@ -117,6 +117,7 @@ _SIGS = {
     "nwb_batch_create": (C.c_int, [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]),
     "nwb_batch_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nwb_batch_refill": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "nwb_batch_fetch": (C.c_int, [C.c_void_p]),
     "nwb_batch_launches": (C.c_int64, [C.c_void_p]),
     "nwb_batch_kernel_name": (C.c_char_p, [C.c_void_p]),
@@ -128,6 +129,8 @@ _SIGS = {
     "nwb_batch_count_u64": (C.c_uint64, [C.c_void_p, C.c_int64]),
     "nwb_batch_arrow_rows": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
     "nwb_batch_kernel_ms": (C.c_float, [C.c_void_p]),
+    "nwb_batch_greatest_abs": (C.c_int32, [C.c_void_p, C.c_int64]),
+    "nwb_batch_score_rows": (C.c_void_p, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
     "nwb_strip_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nwb_batch_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nwb_strip_group_score": (C.c_int32, [C.c_int64, C.c_int, C.c_int, C.c_int]),
@@ -234,6 +237,32 @@ def batch_partition(n_pairs: int, rank: int, world: int) -> tuple[int, int]:
 def strip_group_score(partial_r_sum: int, top_len: int, side_len: int, d: int) -> int:
     """Optimal score of a strip group from the sum over ranks of Summary.partial_r (host-only)."""
     return int(load_library().nwb_strip_group_score(partial_r_sum, top_len, side_len, d))
+
+
+DNA = "ACGT"
+PROTEIN = "ARNDCQEGHILKMFPSTWYV"
+
+
+def generate(seed: int, n: int, alphabet: str = DNA, count: int = 1, seed_stride: int = 0) -> bytes:
+    """The benchmark's input generator: SplitMix64 seeded with `seed`, one character per draw,
+    `alphabet[z % len(alphabet)]`.  count > 1 concatenates `count` strings of n characters with seeds
+    seed, seed + seed_stride, ... (config 4: pair p has top seed 0x5EED4000 + 2p and side seed + 1).
+    Vectorised with numpy; tests/test_oracle.py checks it against the oracle's scalar generator."""
+    a = np.frombuffer(alphabet.encode("latin-1"), np.uint8)
+    with np.errstate(over="ignore"):
+        seeds = np.uint64(seed & (2**64 - 1)) + np.arange(count, dtype=np.uint64) * np.uint64(seed_stride & (2**64 - 1))
+        i = np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        z = seeds[:, None] + i[None, :]
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        idx = (z % np.uint64(len(a))).astype(np.intp)
+    return a[idx].tobytes()
+
+
+def generate_pair(seed: int, a: int, b: int, alphabet: str = DNA) -> tuple[bytes, bytes]:
+    """top string from `seed`, side string from `seed + 1`."""
+    return generate(seed, a, alphabet), generate(seed + 1, b, alphabet)
 
 
 def _b(s) -> bytes:
@@ -461,6 +490,10 @@ class Batch:
     def run(self, stream: int | None = None) -> None:
         _ck(load_library().nwb_batch_run(self._h, C.c_void_p(stream or 0)), "nwb_batch_run")
 
+    def refill(self, tcat: bytes, scat: bytes) -> None:
+        """New strings for the same shapes from host buffers, H2D chunks overlapped with the kernels (nwb_batch_refill)."""
+        _ck(load_library().nwb_batch_refill(self._h, tcat, scat), "nwb_batch_refill")
+
     def fetch(self) -> None:
         _ck(load_library().nwb_batch_fetch(self._h), "nwb_batch_fetch")
 
@@ -488,6 +521,20 @@ class Batch:
 
     def branch_count(self, p: int) -> int:
         return load_library().nwb_batch_branch_count(self._h, p)
+
+    def greatest_abs(self, p: int) -> int:
+        return load_library().nwb_batch_greatest_abs(self._h, p)
+
+    def score_rows(self, p: int) -> np.ndarray | None:
+        """(B, A) int32 interior scores of pair p (NWB_WANT_SCORES; after fetch())."""
+        pitch = C.c_size_t()
+        ptr = load_library().nwb_batch_score_rows(self._h, p, C.byref(pitch))
+        a = int(self._toff[p + 1] - self._toff[p])
+        b = int(self._soff[p + 1] - self._soff[p])
+        if not ptr or b == 0:
+            return None
+        buf = (C.c_int32 * (pitch.value * b)).from_address(ptr)
+        return np.frombuffer(buf, np.int32).reshape(b, pitch.value)[:, :a].copy()
 
     def arrow_rows(self, p: int) -> np.ndarray | None:
         pitch = C.c_size_t()

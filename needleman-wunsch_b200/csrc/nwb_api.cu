@@ -31,6 +31,7 @@
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
 #include "nwb_batch_count.cuh"
+#include "nwb_batch_i32.cuh"
 #include "nwb_peak.cuh"
 
 #define NWB_ABI_VERSION 2

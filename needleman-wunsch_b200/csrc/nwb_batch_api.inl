@@ -1,4 +1,5 @@
 /* nwb_batch_api.inl -- host side of the batch entry points (include/nwb.h section 3). */
+#define NWB_BATCH_MAX_CHUNKS 16
 struct nwb_batch {
     int device = 0;
     unsigned flags = 0;
@@ -7,6 +8,7 @@ struct nwb_batch {
     int sm_count = 0;
     int max_B = 0, max_strips = 1;
     long long max_A = 0;
+    bool general = false; /* int32 engine, one warp per pair (nwb_batch_i32.cuh): any m/k/d, scores, |score| maximum */
     bool use_bx = false; /* two pairs per warp (nwb_batch_bx.cuh) */
     bool use_cx = false; /* ... swept back to back: every pair has the same shape */
     bool uniform = true;
@@ -14,6 +16,8 @@ struct nwb_batch {
     NwbPkConsts pc = {};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;              /* nwb_batch_refill(): host-to-device copies of the next chunk */
+    cudaEvent_t ev_chunk[NWB_BATCH_MAX_CHUNKS] = {}; /* ... one "chunk is on the device" event per chunk */
     DevBuf<uint8_t> tops, sides, arrows;
     DevBuf<long long> top_off, side_off, arrow_off;
     DevBuf<int> score;
@@ -21,6 +25,15 @@ struct nwb_batch {
     DevBuf<uint32_t> scratch;
     DevBuf<unsigned long long> count, cscratch; /* NWB_WANT_COUNT */
     DevBuf<unsigned long long> digest;
+    /* general (int32) path */
+    DevBuf<int32_t> gscores, gbnd;
+    DevBuf<long long> score_off;
+    DevBuf<int> gabs, gprogress;
+    DevBuf<NwbDevSummary> gsum;
+    std::vector<long long> h_score_off;
+    std::vector<int32_t> h_gscores;
+    std::vector<int> h_abs;
+    size_t gscores_elems = 0;
     std::vector<unsigned long long> h_count;
     std::vector<long long> h_top_off, h_side_off, h_arrow_off;
     std::vector<int> h_score;
@@ -39,29 +52,37 @@ extern "C" void nwb_batch_free(nwb_batch *b)
     b->tops.release(); b->sides.release(); b->arrows.release(); b->top_off.release(); b->side_off.release();
     b->arrow_off.release(); b->score.release(); b->branch.release(); b->scratch.release();
     b->count.release(); b->cscratch.release(); b->digest.release();
+    b->gscores.release(); b->gbnd.release(); b->score_off.release(); b->gabs.release(); b->gprogress.release(); b->gsum.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    for (int i = 0; i < NWB_BATCH_MAX_CHUNKS; i++)
+        if (b->ev_chunk[i]) cudaEventDestroy(b->ev_chunk[i]);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
 
-extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const char *sides, const int64_t *side_off,
-                                int64_t n_pairs, int m, int k, int d, unsigned flags, int device, nwb_batch **out)
+static int batch_create_impl(const char *tops, const int64_t *top_off, const char *sides, const int64_t *side_off,
+                             int64_t n_pairs, int m, int k, int d, unsigned flags, int device, bool upload_strings,
+                             nwb_batch **out)
 {
     if (!out) return NWB_ERR_INVALID;
     *out = nullptr;
     if (n_pairs < 0 || !top_off || !side_off) return NWB_ERR_INVALID;
-    if (flags & (NWB_WANT_SCORES | NWB_WANT_COUNT_MATRIX | NWB_TRACK_ABS | NWB_FORCE_GENERAL))
-        return NWB_ERR_UNSUPPORTED; /* the batch path runs the packed kernel only */
+    if (flags & NWB_WANT_COUNT_MATRIX) return NWB_ERR_UNSUPPORTED; /* per-cell counts: nwb_fill() per pair */
     const int ndev = nwb_device_count();
     if (ndev <= 0) return NWB_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return NWB_ERR_INVALID;
     NwbPkConsts pc;
-    if (!nwb_pk_supported(m, k, d, &pc)) return NWB_ERR_UNSUPPORTED;
+    memset(&pc, 0, sizeof(pc));
+    /* schemes outside the packed kernels' range (the reference takes whatever atoi() yields,
+     * needleman-wunsch.c:783-785), the score matrix and the |score| maximum run on the int32 engine */
+    const bool general = (flags & (NWB_WANT_SCORES | NWB_TRACK_ABS | NWB_FORCE_GENERAL)) != 0 || !nwb_pk_supported(m, k, d, &pc);
     CK(cudaSetDevice(device));
     nwb_batch *b = new (std::nothrow) nwb_batch();
     if (!b) return NWB_ERR_NOMEM;
     b->device = device; b->flags = flags; b->n = n_pairs; b->m = m; b->k = k; b->d = d; b->pc = pc;
+    b->general = general;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
@@ -72,7 +93,8 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     b->h_top_off.assign(top_off, top_off + n_pairs + 1);
     b->h_side_off.assign(side_off, side_off + n_pairs + 1);
     b->h_arrow_off.resize((size_t)n_pairs + 1);
-    long long aoff = 0;
+    if (general && (flags & NWB_WANT_SCORES)) b->h_score_off.resize((size_t)n_pairs + 1);
+    long long aoff = 0, soff = 0;
     for (int64_t p = 0; p < n_pairs; p++) {
         const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
         if (A < 0 || B < 0 || A > INT_MAX / 2 || B > 60000) { nwb_batch_free(b); return NWB_ERR_INVALID; }
@@ -84,16 +106,22 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
         else if (A != b->uni_A || B != b->uni_B) b->uniform = false;
         b->h_arrow_off[(size_t)p] = aoff;
         aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
+        if (!b->h_score_off.empty()) {
+            b->h_score_off[(size_t)p] = soff;
+            soff += (long long)(ns > 0 ? ns : 1) * 256 * B;
+        }
     }
     b->h_arrow_off[(size_t)n_pairs] = aoff;
     b->arrows_bytes = (size_t)aoff;
-    {
+    if (!b->h_score_off.empty()) b->h_score_off[(size_t)n_pairs] = soff;
+    b->gscores_elems = (size_t)soff;
+    if (!general) {
         /* short top strings and nibble-sized differences: two pairs per warp (nwb_tune "batch_bx" / "batch_cx" = 0
          * keep the simpler kernels, for tests) */
         b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && g_tune.batch_bx != 0;
         b->use_cx = b->use_bx && n_pairs > 0 && nwb_cx_usable(pc, b->uniform, b->uni_A, (int)b->uni_B) && g_tune.batch_cx != 0;
     }
-    if (!b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
+    if (!general && !b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
     int rc = b->tops.ensure(tbytes + 16);
     if (rc == NWB_OK) rc = b->sides.ensure(sbytes + 16);
@@ -104,27 +132,48 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
     if (rc == NWB_OK) rc = b->score.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK) rc = b->branch.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = b->count.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK && general) {
+        const size_t nwarps = (size_t)b->sm_count * 2 * NWB_BI32_WARPS;
+        const size_t bpitch = nwb_round_up((size_t)b->max_B + 2, 32);
+        rc = b->gbnd.ensure(nwarps * (size_t)b->max_strips * bpitch);
+        if (rc == NWB_OK) rc = b->gprogress.ensure(nwarps * (size_t)b->max_strips);
+        if (rc == NWB_OK) rc = b->gsum.ensure(nwarps);
+        if (rc == NWB_OK && (flags & NWB_TRACK_ABS)) rc = b->gabs.ensure((size_t)n_pairs + 1);
+        if (rc == NWB_OK && (flags & NWB_WANT_SCORES)) {
+            rc = b->gscores.ensure(b->gscores_elems + 16);
+            if (rc == NWB_OK) rc = b->score_off.ensure((size_t)n_pairs + 1);
+        }
+    }
     if (rc != NWB_OK) { nwb_batch_free(b); return rc; }
     e = cudaSuccess;
-    if (tbytes) e = cudaMemcpyAsync(b->tops.p, tops, tbytes, cudaMemcpyHostToDevice, b->stream);
-    if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(b->sides.p, sides, sbytes, cudaMemcpyHostToDevice, b->stream);
+    if (upload_strings && tbytes) e = cudaMemcpyAsync(b->tops.p, tops, tbytes, cudaMemcpyHostToDevice, b->stream);
+    if (upload_strings && e == cudaSuccess && sbytes) e = cudaMemcpyAsync(b->sides.p, sides, sbytes, cudaMemcpyHostToDevice, b->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(b->top_off.p, b->h_top_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(b->side_off.p, b->h_side_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(b->arrow_off.p, b->h_arrow_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
+    if (e == cudaSuccess && !b->h_score_off.empty())
+        e = cudaMemcpyAsync(b->score_off.p, b->h_score_off.data(), ((size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, b->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) { rc = cuda_fail(e, "batch upload"); nwb_batch_free(b); return rc; }
     *out = b;
     return NWB_OK;
 }
 
+extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const char *sides, const int64_t *side_off,
+                                int64_t n_pairs, int m, int k, int d, unsigned flags, int device, nwb_batch **out)
+{
+    if (n_pairs > 0 && (!tops || !sides) && top_off && side_off && (top_off[n_pairs] > 0 || side_off[n_pairs] > 0)) return NWB_ERR_INVALID;
+    return batch_create_impl(tops, top_off, sides, side_off, n_pairs, m, k, d, flags, device, true, out);
+}
+
 /* the count behind -s: a second pass over the arrow codes the fill has just written (nwb_batch_count.cuh) */
-static int batch_count_pass(nwb_batch *b, cudaStream_t st)
+static int batch_count_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1)
 {
     NwbBatchCountParams cp;
     memset(&cp, 0, sizeof(cp));
     const int grid = b->sm_count;
-    cp.top_off = b->top_off.p; cp.side_off = b->side_off.p; cp.n_pairs = b->n;
-    cp.arrows = b->arrows.p; cp.arrow_off = b->arrow_off.p; cp.out_count = b->count.p;
+    cp.top_off = b->top_off.p + c0; cp.side_off = b->side_off.p + c0; cp.n_pairs = c1 - c0;
+    cp.arrows = b->arrows.p; cp.arrow_off = b->arrow_off.p + c0; cp.out_count = b->count.p + c0;
     if (b->max_strips > 1) {
         cp.scratch_per_warp = nwb_round_up((size_t)b->max_B + 1, 16);
         int rc = b->cscratch.ensure((size_t)grid * NWB_BCNT_WARPS * cp.scratch_per_warp);
@@ -134,7 +183,7 @@ static int batch_count_pass(nwb_batch *b, cudaStream_t st)
     const size_t smem = (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS;
     /* every pair the same one-strip shape: the tables of a warp's run of pairs are swept back to back
      * (nwb_tune "bcnt_chain" = 0: one pair at a time) */
-    if (nwb_bcount_chain_usable(b->uniform, b->uni_A, b->uni_B, b->n, (long long)grid * NWB_BCNT_WARPS) && g_tune.bcnt_chain != 0) {
+    if (nwb_bcount_chain_usable(b->uniform, b->uni_A, b->uni_B, c1 - c0, (long long)grid * NWB_BCNT_WARPS) && g_tune.bcnt_chain != 0) {
         CK(cudaFuncSetAttribute(nwb_batch_count_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nwb_batch_count_chain_kernel<<<grid, 32 * NWB_BCNT_WARPS, smem, st>>>(cp, (int)b->uni_A, (int)b->uni_B);
         CK(cudaGetLastError());
@@ -148,7 +197,7 @@ static int batch_count_pass(nwb_batch *b, cudaStream_t st)
     return NWB_OK;
 }
 
-static int batch_fill_pass(nwb_batch *b, cudaStream_t st);
+static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1);
 
 extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
 {
@@ -159,15 +208,85 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     b->fetched = false;
     if (b->n == 0) return NWB_OK;
     CK(cudaEventRecord(b->ev0, st));
-    int rc = batch_fill_pass(b, st);
-    if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st);
+    int rc = batch_fill_pass(b, st, 0, b->n);
+    if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, 0, b->n);
     if (rc != NWB_OK) return rc;
     CK(cudaEventRecord(b->ev1, st));
     return NWB_OK;
 }
 
-static int batch_fill_pass(nwb_batch *b, cudaStream_t st)
+/* New strings for the same shapes, from HOST buffers: the batch is cut into chunks of pairs, the host-to-device
+ * copy of chunk i+1 (copy stream) overlaps the kernels of chunk i (the batch's own stream).  tops/sides hold the
+ * pairs' strings at the offsets given to nwb_batch_create(). */
+extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *sides)
 {
+    if (!b || (b->n > 0 && (!tops || !sides))) return NWB_ERR_INVALID;
+    CK(cudaSetDevice(b->device));
+    b->ran = true;
+    b->fetched = false;
+    if (b->n == 0) return NWB_OK;
+    if (!b->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < NWB_BATCH_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
+    }
+    cudaStream_t st = b->stream;
+    int64_t nchunks = b->n / 16384;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 8) nchunks = 8;
+    /* two pairs share a warp in the bx/cx kernels: keep chunk boundaries even */
+    int64_t per = (b->n + nchunks - 1) / nchunks;
+    per += per & 1;
+    CK(cudaEventRecord(b->ev0, st));
+    int rc = NWB_OK;
+    int ci = 0;
+    for (int64_t c0 = 0; c0 < b->n && rc == NWB_OK; c0 += per, ci++) {
+        const int64_t c1 = (c0 + per < b->n) ? c0 + per : b->n;
+        const long long tb = b->h_top_off[(size_t)c0], te = b->h_top_off[(size_t)c1];
+        const long long sb = b->h_side_off[(size_t)c0], se = b->h_side_off[(size_t)c1];
+        if (te > tb) CK(cudaMemcpyAsync(b->tops.p + tb, tops + tb, (size_t)(te - tb), cudaMemcpyHostToDevice, b->copy_stream));
+        if (se > sb) CK(cudaMemcpyAsync(b->sides.p + sb, sides + sb, (size_t)(se - sb), cudaMemcpyHostToDevice, b->copy_stream));
+        CK(cudaEventRecord(b->ev_chunk[ci], b->copy_stream));
+        CK(cudaStreamWaitEvent(st, b->ev_chunk[ci], 0));
+        rc = batch_fill_pass(b, st, c0, c1);
+        if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, c0, c1);
+    }
+    if (rc != NWB_OK) return rc;
+    CK(cudaEventRecord(b->ev1, st));
+    return NWB_OK;
+}
+
+static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1)
+{
+    if (b->general) {
+        NwbBatchI32Params gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.tops = b->tops.p; gp.top_off = b->top_off.p + c0; gp.sides = b->sides.p; gp.side_off = b->side_off.p + c0;
+        gp.n_pairs = c1 - c0; gp.m = b->m; gp.k = b->k; gp.d = b->d;
+        gp.arrows = b->arrows.p; gp.arrow_off = b->arrow_off.p + c0;
+        gp.scores = b->gscores.p; gp.score_off = b->score_off.p ? b->score_off.p + c0 : nullptr;
+        gp.out_score = b->score.p + c0;
+        gp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
+        gp.out_abs = (b->flags & NWB_TRACK_ABS) ? b->gabs.p + c0 : nullptr;
+        gp.bnd_s = b->gbnd.p;
+        gp.bpitch = nwb_round_up((size_t)b->max_B + 2, 32);
+        gp.progress = b->gprogress.p;
+        gp.max_strips = b->max_strips;
+        gp.wsum = b->gsum.p;
+        const int ggrid = b->sm_count * 2;
+        const size_t smem = (size_t)NWB_BI32_WARPS * NWB_I32_STAGE_WORDS * 4;
+        const bool S = (b->flags & NWB_WANT_SCORES) != 0, AB = (b->flags & NWB_TRACK_ABS) != 0;
+#define NWB_BI32_GO(s_, a_)                                                                                          \
+    do {                                                                                                             \
+        CK(cudaFuncSetAttribute(nwb_batch_i32_kernel<s_, a_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        nwb_batch_i32_kernel<s_, a_><<<ggrid, 32 * NWB_BI32_WARPS, smem, st>>>(gp);                                    \
+    } while (0)
+        if (S) { if (AB) NWB_BI32_GO(true, true); else NWB_BI32_GO(true, false); }
+        else { if (AB) NWB_BI32_GO(false, true); else NWB_BI32_GO(false, false); }
+#undef NWB_BI32_GO
+        CK(cudaGetLastError());
+        b->launches += 1;
+        return NWB_OK;
+    }
     NwbBatchParams bp;
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
@@ -175,10 +294,10 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st)
         int warps = (int)((220 * 1024) / NWB_BX_SMEM_PER_WARP(b->max_B));
         if (warps > NWB_BX_WARPS) warps = NWB_BX_WARPS;
         if (warps < 1) return NWB_ERR_UNSUPPORTED;
-        bp.tops = b->tops.p; bp.top_off = b->top_off.p; bp.sides = b->sides.p; bp.side_off = b->side_off.p;
-        bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
-        bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p;
-        bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
+        bp.tops = b->tops.p; bp.top_off = b->top_off.p + c0; bp.sides = b->sides.p; bp.side_off = b->side_off.p + c0;
+        bp.n_pairs = c1 - c0; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
+        bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p + c0; bp.out_score = b->score.p + c0;
+        bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
         if (b->use_cx) {
             const bool w16 = g_tune.cx_warps == 16 && nwb_cx_usable(b->pc, true, b->uni_A, (int)b->uni_B, 16);
             const int cw = w16 ? 16 : NWB_BX_WARPS;
@@ -208,10 +327,10 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st)
         int rc = b->scratch.ensure((size_t)nwarps * bp.scratch_per_warp);
         if (rc != NWB_OK) return rc;
     }
-    bp.tops = b->tops.p; bp.top_off = b->top_off.p; bp.sides = b->sides.p; bp.side_off = b->side_off.p;
-    bp.n_pairs = b->n; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
-    bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p; bp.out_score = b->score.p; bp.scratch = b->scratch.p;
-    bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p;
+    bp.tops = b->tops.p; bp.top_off = b->top_off.p + c0; bp.sides = b->sides.p; bp.side_off = b->side_off.p + c0;
+    bp.n_pairs = c1 - c0; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
+    bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p + c0; bp.out_score = b->score.p + c0; bp.scratch = b->scratch.p;
+    bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
     const size_t smem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * (size_t)warps;
     CK(cudaFuncSetAttribute(nwb_batch_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nwb_batch_pk_kernel<<<grid, 32 * warps, smem, st>>>(bp, b->pc);
@@ -235,6 +354,14 @@ extern "C" int nwb_batch_fetch(nwb_batch *b)
             b->h_count.resize((size_t)b->n);
             CK(cudaMemcpy(b->h_count.data(), b->count.p, (size_t)b->n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         }
+        if (b->general && (b->flags & NWB_TRACK_ABS)) {
+            b->h_abs.resize((size_t)b->n);
+            CK(cudaMemcpy(b->h_abs.data(), b->gabs.p, (size_t)b->n * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        if (b->general && (b->flags & NWB_WANT_SCORES) && b->gscores_elems) {
+            b->h_gscores.resize(b->gscores_elems);
+            CK(cudaMemcpy(b->h_gscores.data(), b->gscores.p, b->gscores_elems * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        }
         if (b->flags & NWB_WANT_ARROWS_HOST) {
             b->h_arrows.resize(b->arrows_bytes);
             if (b->arrows_bytes) CK(cudaMemcpy(b->h_arrows.data(), b->arrows.p, b->arrows_bytes, cudaMemcpyDeviceToHost));
@@ -249,8 +376,9 @@ extern "C" int nwb_fill_batch(const char *tops, const int64_t *top_off, const ch
 {
     if (!out) return NWB_ERR_INVALID;
     nwb_batch *b = nullptr;
-    int rc = nwb_batch_create(tops, top_off, sides, side_off, n_pairs, m, k, d, flags, device, &b);
-    if (rc == NWB_OK) rc = nwb_batch_run(b, nullptr);
+    /* the strings go up chunk by chunk, overlapped with the kernels of the previous chunk */
+    int rc = batch_create_impl(tops, top_off, sides, side_off, n_pairs, m, k, d, flags, device, false, &b);
+    if (rc == NWB_OK) rc = nwb_batch_refill(b, tops, sides);
     if (rc == NWB_OK) rc = nwb_batch_fetch(b);
     if (rc != NWB_OK) { nwb_batch_free(b); *out = nullptr; return rc; }
     *out = b;
@@ -278,6 +406,18 @@ extern "C" const uint8_t *nwb_batch_arrow_rows(const nwb_batch *b, int64_t pair,
     if (!b->fetched || b->h_arrows.empty()) return nullptr;
     return b->h_arrows.data() + b->h_arrow_off[(size_t)pair];
 }
+extern "C" int32_t nwb_batch_greatest_abs(const nwb_batch *b, int64_t pair)
+{
+    return (b && b->fetched && !b->h_abs.empty() && pair >= 0 && pair < b->n) ? b->h_abs[(size_t)pair] : 0;
+}
+extern "C" const int32_t *nwb_batch_score_rows(const nwb_batch *b, int64_t pair, size_t *pitch_elems)
+{
+    if (!b || pair < 0 || pair >= b->n) return nullptr;
+    const long long A = b->h_top_off[(size_t)pair + 1] - b->h_top_off[(size_t)pair];
+    if (pitch_elems) *pitch_elems = (size_t)((A + 255) / 256 > 0 ? (A + 255) / 256 : 1) * 256;
+    if (!b->fetched || b->h_gscores.empty()) return nullptr;
+    return b->h_gscores.data() + b->h_score_off[(size_t)pair];
+}
 extern "C" float nwb_batch_kernel_ms(const nwb_batch *b)
 {
     if (!b || !b->ran || b->n == 0) return 0.f;
@@ -290,6 +430,7 @@ extern "C" float nwb_batch_kernel_ms(const nwb_batch *b)
 extern "C" const char *nwb_batch_kernel_name(const nwb_batch *b)
 {
     if (!b) return "";
+    if (b->general) return "nwb_batch_i32_kernel";
     return b->use_cx ? "nwb_batch_cx_kernel" : (b->use_bx ? "nwb_batch_bx_kernel" : "nwb_batch_pk_kernel");
 }
 extern "C" int64_t nwb_batch_launches(const nwb_batch *b) { return b ? b->launches : 0; }

@@ -193,6 +193,38 @@ def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1, count=False):
                 counts=counts)
 
 
+def fill_batch_i32(tops, sides, m, k, d, *, grid=1, want_scores=False, want_abs=True):
+    """nwb_batch_i32_kernel (csrc/nwb_batch_i32.cuh: any m / k / d, one warp per pair) under the emulator."""
+    n = len(tops)
+    toff = np.zeros(n + 1, np.int64)
+    soff = np.zeros(n + 1, np.int64)
+    np.cumsum([len(t) for t in tops], out=toff[1:])
+    np.cumsum([len(s) for s in sides], out=soff[1:])
+    total = sum(max(1, (len(t) + 255) // 256) * 128 * len(s) for t, s in zip(tops, sides))
+    arrows = np.full(total + 16, 0xEE, np.uint8)
+    aoff = np.zeros(n + 1, np.int64)
+    scores = np.zeros(n, np.int32)
+    branches = np.zeros(n, np.uint32)
+    gabs = np.zeros(n, np.int32) if want_abs else None
+    smat = np.zeros(2 * total + 16, np.int32) if want_scores else None
+    scoff = np.zeros(n + 1, np.int64) if want_scores else None
+    L = lib()
+    L.emu_fill_batch_i32.restype = C.c_int
+    L.emu_fill_batch_i32.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                     C.c_uint] + [C.c_void_p] * 7
+    p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    rc = L.emu_fill_batch_i32(b"".join(tops), p(toff), b"".join(sides), p(soff), n, m, k, d, grid, p(arrows), p(aoff),
+                              p(scores), p(branches), p(gabs), p(smat), p(scoff))
+    assert rc == 0, rc
+    tabs, mats = [], []
+    for i in range(n):
+        ns = max(1, (len(tops[i]) + 255) // 256)
+        tabs.append(arrows[aoff[i]:aoff[i] + ns * 128 * len(sides[i])].reshape(len(sides[i]), ns * 128))
+        if want_scores:
+            mats.append(smat[scoff[i]:scoff[i] + ns * 256 * len(sides[i])].reshape(len(sides[i]), ns * 256)[:, :len(tops[i])])
+    return dict(scores=scores, branches=branches, abs=gabs, tables=tabs, score_rows=mats)
+
+
 def unpack_arrows(packed: np.ndarray, a: int) -> np.ndarray:
     """(B, pitch) nibble table -> (B, A) uint8 codes (DIAG|LEFT|UP)."""
     lo = packed & 0xF

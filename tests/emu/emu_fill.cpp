@@ -14,6 +14,7 @@
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
 #include "nwb_batch_count.cuh"
+#include "nwb_batch_i32.cuh"
 
 #include <vector>
 
@@ -405,6 +406,47 @@ int emu_batch_count(const long long *top_off, const long long *side_off, long lo
 /* bx: 0 = nwb_batch_pk_kernel (one pair per warp), 1 = nwb_batch_bx_kernel (two pairs per warp; -6 when the
  * batch does not qualify), 2 = nwb_batch_cx_kernel (uniform shapes, pairs back to back; -6 likewise), -1 =
  * whatever nwb_batch_run() would pick.  *used_bx reports the choice (0, 1 or 2). */
+/* nwb_batch_i32_kernel<scores, abs>: any m / k / d.  out_abs / scores may be NULL. */
+int emu_fill_batch_i32(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
+                       long long n, int m, int k, int d, unsigned grid, uint8_t *arrows, long long *arrow_off,
+                       int *out_score, unsigned *out_branch, int *out_abs, int32_t *scores, long long *score_off)
+{
+    int maxB = 0, maxS = 1;
+    long long aoff = 0, soff = 0;
+    for (long long p = 0; p < n; p++) {
+        const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
+        const int ns = (int)((A + 255) / 256);
+        if (ns > maxS) maxS = ns;
+        if (B > maxB) maxB = (int)B;
+        arrow_off[p] = aoff;
+        aoff += (long long)(ns > 0 ? ns : 1) * 128 * B;
+        if (score_off) { score_off[p] = soff; soff += (long long)(ns > 0 ? ns : 1) * 256 * B; }
+    }
+    arrow_off[n] = aoff;
+    if (score_off) score_off[n] = soff;
+    const size_t nwarps = (size_t)grid * NWB_BI32_WARPS;
+    NwbBatchI32Params gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.tops = (const uint8_t *)tops; gp.top_off = top_off; gp.sides = (const uint8_t *)sides; gp.side_off = side_off;
+    gp.n_pairs = n; gp.m = m; gp.k = k; gp.d = d;
+    gp.arrows = arrows; gp.arrow_off = arrow_off; gp.scores = scores; gp.score_off = score_off;
+    gp.out_score = out_score; gp.out_branch = out_branch; gp.out_abs = out_abs;
+    gp.bpitch = nwb_round_up((size_t)maxB + 2, 32);
+    std::vector<int32_t> bnd(nwarps * (size_t)maxS * gp.bpitch, 0x7f7f7f7f);
+    std::vector<int> prog(nwarps * (size_t)maxS, 12345);
+    std::vector<NwbDevSummary> wsum(nwarps);
+    gp.bnd_s = bnd.data(); gp.progress = prog.data(); gp.max_strips = maxS; gp.wsum = wsum.data();
+    const size_t smem = (size_t)NWB_BI32_WARPS * NWB_I32_STAGE_WORDS * 4;
+    if (scores) {
+        if (out_abs) emu_launch(grid, 32 * NWB_BI32_WARPS, smem, [&]() { nwb_batch_i32_kernel<true, true>(gp); });
+        else emu_launch(grid, 32 * NWB_BI32_WARPS, smem, [&]() { nwb_batch_i32_kernel<true, false>(gp); });
+    } else {
+        if (out_abs) emu_launch(grid, 32 * NWB_BI32_WARPS, smem, [&]() { nwb_batch_i32_kernel<false, true>(gp); });
+        else emu_launch(grid, 32 * NWB_BI32_WARPS, smem, [&]() { nwb_batch_i32_kernel<false, false>(gp); });
+    }
+    return 0;
+}
+
 int emu_fill_batch(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
                    long long n, int m, int k, int d, unsigned grid, int bx, uint8_t *arrows, long long *arrow_off,
                    int *scores, unsigned *branches, int *used_bx)

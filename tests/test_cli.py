@@ -154,7 +154,8 @@ def test_batch_cli_matches_the_reference_looped_per_pair(cli):
             [("".join(rng.choice("ACGT") for _ in range(rng.randint(1, 11))),
               "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 11)))) for _ in range(40)]
     text = "\n".join(f"{a} {b}" for a, b in pairs).encode() + b"\n"
-    for mkd in (("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0")):
+    # any m k d the reference takes (needleman-wunsch.c:783-785): the last three run the int32 batch engine
+    for mkd in (("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0"), ("1", "3", "1"), ("5", "4", "3"), ("-1", "3", "-2")):
         for flags in ([], ["-s"]):
             rc, out, err = run_batch(flags + list(mkd), text)
             assert rc == 0 and out == b""
@@ -165,6 +166,3 @@ def test_batch_cli_matches_the_reference_looped_per_pair(cli):
                 # without -s the reference prints nothing under -q; the batch front-end always prints the score
                 want += r[2] if flags else b"Optimal score is %d\n" % int(run(cli, ["-q", "-s"] + list(mkd), f"{a} {b}\n".encode())[2].split()[-1])
             assert err == want, (mkd, flags)
-    # a scheme outside the packed kernels' range is refused with the reference-style error text
-    rc, out, err = run_batch(["1", "3", "1"], text)
-    assert rc == 1 and b"score-table fill failed" in err

@@ -172,3 +172,22 @@ def test_batch_count_chained_uniform(oracle):
         r = emu.fill_batch(tops, sides, *mkd, grid=grid, count=True)
         for i, (t, s) in enumerate(zip(tops, sides)):
             assert int(r["counts"][i]) == oracle.fill(t, s, *mkd).count, (a, b, i)
+
+
+def test_batch_general_int32_engine(oracle):
+    """csrc/nwb_batch_i32.cuh: schemes outside the packed range, the score matrix and the |score| maximum, one warp
+    per pair; pairs wider than one strip, empty strings, more pairs than warps."""
+    rng = random.Random(83)
+    lens = [(256, 40), (1, 1), (257, 33), (0, 5), (5, 0), (600, 70), (64, 64), (33, 100), (300, 9)] + \
+           [(rng.randint(1, 300), rng.randint(1, 90)) for _ in range(20)]
+    tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
+    sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
+    for (m, k, d), ws in (((1, 3, 1), False), ((5, 4, 3), True), ((-1, 3, -2), False), ((1, 1, 1), True)):
+        r = emu.fill_batch_i32(tops, sides, m, k, d, grid=1, want_scores=ws)
+        for i, (t, s) in enumerate(zip(tops, sides)):
+            o = oracle.fill(t, s, m, k, d, want_codes=True, want_scores=True)
+            assert (r["scores"][i], r["branches"][i], r["abs"][i]) == (o.final_score, o.branch_count, o.greatest_abs), (i, m, k, d)
+            if len(t) and len(s):
+                assert np.array_equal(emu.unpack_arrows(r["tables"][i], len(t)) & 7, o.codes[1:, 1:] & 7), i
+                if ws:
+                    assert np.array_equal(r["score_rows"][i], o.scores[1:, 1:]), i

@@ -223,9 +223,44 @@ def test_batch_ragged(oracle, nwb):
                     got[:, nb - 1] &= 0x07
                 assert np.array_equal(got, o.packed[:, :nb]), i
         bt.close()
-    # schemes outside the packed kernel's range are refused, not silently mis-scored
+
+
+def test_batch_general_schemes_scores_and_abs(oracle, nwb):
+    """Schemes outside the packed kernels' range ((1,3,1), (5,4,3), negative penalties), NWB_FORCE_GENERAL,
+    NWB_WANT_SCORES and NWB_TRACK_ABS through nwb_fill_batch: the int32 batch engine (csrc/nwb_batch_i32.cuh)
+    against the oracle -- every arrow set, score matrix, |score| maximum, branch count and alignment count."""
+    rng = random.Random(71)
+    lens = [(256, 256), (1, 1), (255, 257), (300, 40), (17, 130), (0, 5), (700, 90), (64, 64), (256, 1), (33, 33),
+            (257, 31), (5, 0), (1100, 300)] + [(rng.randint(1, 600), rng.randint(1, 400)) for _ in range(120)]
+    tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
+    sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
+    for (m, k, d), flags in (((1, 3, 1), 0), ((5, 4, 3), nwb.WANT_COUNT), ((-1, 3, -2), nwb.WANT_COUNT),
+                             ((1, 1, 1), nwb.FORCE_GENERAL | nwb.WANT_COUNT),
+                             ((2, 1, 2), nwb.WANT_SCORES | nwb.TRACK_ABS | nwb.WANT_COUNT)):
+        bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST | flags)
+        assert bt.kernel_name() == "nwb_batch_i32_kernel"
+        bt.run()
+        bt.fetch()
+        for i in list(range(13)) + rng.sample(range(13, len(lens)), 40):
+            t, s = tops[i], sides[i]
+            o = oracle.fill(t, s, m, k, d, want_packed=True, want_scores=True, pitch=max(1, (len(t) + 255) // 256) * 128)
+            assert bt.opt_score(i) == o.final_score, (i, len(t), len(s), m, k, d)
+            assert bt.branch_count(i) == o.branch_count, i
+            if flags & nwb.WANT_COUNT:
+                assert bt.count(i) == o.count, i
+            if flags & nwb.TRACK_ABS:
+                assert bt.greatest_abs(i) == o.greatest_abs, i
+            if len(t) and len(s):
+                nb = (len(t) + 1) // 2
+                got = bt.arrow_rows(i)[:, :nb] & 0x77
+                if len(t) & 1:
+                    got[:, nb - 1] &= 0x07
+                assert np.array_equal(got, o.packed[:, :nb]), i
+                if flags & nwb.WANT_SCORES:
+                    assert np.array_equal(bt.score_rows(i), o.scores[1:, 1:]), i
+        bt.close()
     with pytest.raises(nwb.NwbError):
-        nwb.Batch(tops[:2], sides[:2], 1, 3, 1)
+        nwb.Batch(tops[:2], sides[:2], 1, 1, 1, nwb.WANT_COUNT_MATRIX)
 
 
 def test_batch_config4_shard(oracle, nwb):
@@ -661,3 +696,33 @@ def test_watchdog_turns_a_lost_boundary_stream_into_an_error(oracle, nwb):
             nwb.tune_reset()
         tab = nwb.fill(t, s, 1, 1, 1, ff | nwb.WANT_COUNT)
         assert (tab.opt_score, tab.branch_count, tab.count) == (o.final_score, o.branch_count, o.count)
+
+
+def test_batch_refill_chunked_pipeline(oracle, nwb):
+    """nwb_batch_refill(): new strings for the same shapes from host buffers, uploaded chunk by chunk while the
+    previous chunk's kernels run (several chunks: > 32768 pairs).  Results must equal a fresh batch of the new
+    strings: uniform shapes (back-to-back kernel), ragged shapes (two pairs per warp, odd count), with the count."""
+    rng = random.Random(91)
+    for shapes in ([(64, 64)] * 40000, [(rng.randint(1, 80), rng.randint(1, 70)) for _ in range(40001)]):
+        n = len(shapes)
+        def strings(seed):
+            r = random.Random(seed)
+            return ([bytes(r.choice(b"ACGT") for _ in range(a)) for a, _ in shapes],
+                    [bytes(r.choice(b"ACGT") for _ in range(b)) for _, b in shapes])
+        t0, s0 = strings(1)
+        t1, s1 = strings(2)
+        bt = nwb.Batch(t0, s0, 1, 1, 1, nwb.WANT_COUNT)
+        bt.run()
+        bt.fetch()
+        bt.refill(b"".join(t1), b"".join(s1))
+        bt.fetch()
+        fresh = nwb.Batch(t1, s1, 1, 1, 1, nwb.WANT_COUNT)
+        fresh.run()
+        fresh.fetch()
+        assert bt.digest(0) == fresh.digest(0)
+        for i in [0, 1, n // 2, n - 2, n - 1] + rng.sample(range(n), 30):
+            assert (bt.opt_score(i), bt.branch_count(i), bt.count(i)) == (fresh.opt_score(i), fresh.branch_count(i), fresh.count(i)), i
+            o = oracle.fill(t1[i], s1[i], 1, 1, 1)
+            assert (bt.opt_score(i), bt.branch_count(i), bt.count(i)) == (o.final_score, o.branch_count, o.count), i
+        bt.close()
+        fresh.close()
