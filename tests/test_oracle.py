@@ -189,3 +189,17 @@ def test_reference_cli_readme_example(oracle):
                        capture_output=True, check=True)
     assert p.stderr == b"3 optimal alignments\nOptimal score is 0\n"  # README:153-155, on stderr
     assert p.stdout == b""
+
+
+def test_package_generator_matches_the_oracle_generator(oracle):
+    """bench.py and the tools make their inputs with the product package's own SplitMix64 generator
+    (needleman-wunsch_b200.generate, numpy); it must produce exactly the oracle's strings."""
+    import nw_b200 as nwb
+    for seed, n, alpha in [(0x5EED0002, 1000, nwb.DNA), (0x5EED0003, 999, nwb.DNA), (0x5EED0005, 777, nwb.PROTEIN),
+                           (0x5EED0030, 4096, nwb.DNA), (2**64 - 5, 100, "AB"), (0, 1, nwb.DNA)]:
+        assert nwb.generate(seed, n, alpha) == oracle.generate(seed, n, alpha)
+    assert nwb.generate(0x5EED0002, 16) == b"CTTTCCTTAGCAGTTA" and nwb.generate(0x5EED0006, 16, nwb.PROTEIN) == b"PDGAGPEFMCEANPWA"
+    many = nwb.generate(0x5EED4000, 256, nwb.DNA, count=50, seed_stride=2)
+    for p in (0, 1, 7, 49):
+        assert many[256 * p:256 * (p + 1)] == oracle.generate(0x5EED4000 + 2 * p, 256)
+    assert nwb.generate_pair(0x5EED0030, 33, 17) == oracle.generate_pair(0x5EED0030, 33, 17)
