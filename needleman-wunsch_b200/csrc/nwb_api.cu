@@ -91,7 +91,6 @@ struct NwbTune {
     int batch_bx = -1;   /* -1 = auto; 0 = never nwb_batch_bx_kernel                                         */
     int batch_cx = -1;   /* -1 = auto; 0 = never nwb_batch_cx_kernel                                         */
     int bcnt_chain = -1; /* -1 = auto; 0 = never nwb_batch_count_chain_kernel                                */
-    int bcnt_sparse = -1; /* -1 = auto; 0 = never the sparse backward batch count                            */
     int cx_warps = 0;    /* 0 = auto (12); 16                                                                */
     int watchdog_ms = 4000; /* device-side spin loops give up after this long without progress               */
     int inject_fault = 0;   /* test only: 1 = the fill's strips do not publish their boundary streams        */
@@ -109,7 +108,7 @@ extern "C" int nwb_tune(const char *key, int value)
     struct { const char *name; int *slot; } tab[] = {
         {"pk_k", &g_tune.pk_k}, {"pk_r", &g_tune.pk_r}, {"pk_warps", &g_tune.pk_warps}, {"pk_hx", &g_tune.pk_hx},
         {"count_mode", &g_tune.count_mode}, {"cnt_cpl", &g_tune.cnt_cpl}, {"batch_bx", &g_tune.batch_bx},
-        {"batch_cx", &g_tune.batch_cx}, {"bcnt_chain", &g_tune.bcnt_chain}, {"bcnt_sparse", &g_tune.bcnt_sparse},
+        {"batch_cx", &g_tune.batch_cx}, {"bcnt_chain", &g_tune.bcnt_chain},
         {"cx_warps", &g_tune.cx_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
 #ifdef NWB_EXPERIMENTS

@@ -219,19 +219,30 @@ __device__ __forceinline__ bool nwb_count_strip(const NwbCountParams &p, const i
             const bool need = (lane < 2 * NWB_CNT_SUB) && (row <= B);
             unsigned long long cw = cwslot;
             bool ok = !need || (cw & NWB_PK_CVALID) || NWB_DBG_BITS(p, 1);
-            NwbWatchdog wd;
-            while (!__all_sync(NWB_FULL_MASK, ok)) {
-                if (!ok) {
-                    cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * 2 + lane, left_remote);
-                    ok = (cw & NWB_PK_CVALID) != 0ull;
-                }
-                if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) {
-                    aborted = true;
-                    return;
-                }
+            if (!__all_sync(NWB_FULL_MASK, ok)) {
+                NwbWatchdog wd; /* its bookkeeping stays outside the inner poll loop (see nwb_fill_hx.cuh) */
+                for (;;) {
+                    bool arrived = false;
+#pragma unroll 1
+                    for (int it = 0; it < NWB_WD_POLLS; it++) {
+                        if (!ok) {
+                            cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * 2 + lane, left_remote);
+                            ok = (cw & NWB_PK_CVALID) != 0ull;
+                        }
 #ifdef NWB_EMU
-                nwb_pause();
+                        nwb_pause();
 #endif
+                        if (__all_sync(NWB_FULL_MASK, ok)) {
+                            arrived = true;
+                            break;
+                        }
+                    }
+                    if (arrived) break;
+                    if (wd.slow(NWB_ERR_WORD(p), p.watchdog_ns)) {
+                        aborted = true;
+                        return;
+                    }
+                }
             }
             const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
             __syncwarp(); /* the previous sub-block's reads of cstage are done */

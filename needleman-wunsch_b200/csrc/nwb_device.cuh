@@ -106,6 +106,18 @@ __device__ __forceinline__ unsigned long long nwb_globaltimer()
 #endif
 }
 
+/* A register copy the compiler can neither elide nor move across memory operations (see nwb_fill_hx.cuh). */
+__device__ __forceinline__ unsigned nwb_pin_copy(unsigned v)
+{
+#ifdef NWB_EMU
+    return v;
+#else
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v) : "memory");
+    return r;
+#endif
+}
+
 /* read-only (non-coherent) 16-bit load */
 __device__ __forceinline__ unsigned short nwb_ldg_u16(const uint16_t *p)
 {
@@ -187,11 +199,19 @@ __device__ __forceinline__ void nwb_wait_ge(const int *flag, int need, bool sys)
 #define NWB_FAULT_INJECTED(p) (((p).debug_nowait & 4) != 0) /* test only: boundary streams are not published */
 
 #define NWB_ERR_WORD(p) ((p).summary ? &(p).summary->error : (int *)0)
+#ifndef NWB_WD_MODE
+#define NWB_WD_MODE 2
+#endif
+#define NWB_WD_POLLS 1024 /* polls between two looks at the clock */
 struct NwbWatchdog {
     unsigned polls;
     unsigned long long t0;
     __device__ __forceinline__ NwbWatchdog() : polls(0u), t0(0ull) {}
+#if NWB_WD_MODE == 1
     __device__ __noinline__ bool slow(int *err, unsigned long long limit_ns)
+#else
+    __device__ __forceinline__ bool slow(int *err, unsigned long long limit_ns)
+#endif
     {
         if (!err) return false; /* a launch without a summary block (batch kernels: no cross-warp waits) */
         bool give_up = (*reinterpret_cast<volatile int *>(err) != 0);
@@ -205,8 +225,13 @@ struct NwbWatchdog {
     }
     __device__ __forceinline__ bool tick(int *err, unsigned long long limit_ns)
     {
+#if NWB_WD_MODE == 0
+        (void)err; (void)limit_ns;
+        return false;
+#else
         if ((++polls & 1023u) != 0u) return false;
         return slow(err, limit_ns);
+#endif
     }
 };
 
@@ -215,18 +240,26 @@ __device__ __forceinline__ bool nwb_wait_ge_wd(const int *flag, int need, bool s
 {
     NwbWatchdog wd;
     for (;;) {
+        bool arrived = false;
+#pragma unroll 1
+        for (int it = 0; it < NWB_WD_POLLS; it++) {
 #ifdef NWB_EMU
-        const int v = *(const volatile int *)flag;
+            const int v = *(const volatile int *)flag;
 #else
-        int v;
-        if (sys) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
-        else asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
+            int v;
+            if (sys) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
+            else asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag));
 #endif
-        if (__all_sync(NWB_FULL_MASK, v >= need)) break;
-        if (wd.tick(err, limit_ns)) return false;
+            if (__all_sync(NWB_FULL_MASK, v >= need)) {
+                arrived = true;
+                break;
+            }
 #ifdef NWB_EMU
-        nwb_pause();
+            nwb_pause();
 #endif
+        }
+        if (arrived) break;
+        if (wd.slow(err, limit_ns)) return false;
     }
 #ifndef NWB_EMU
     if (sys) asm volatile("fence.acq_rel.sys;" ::: "memory");

@@ -210,11 +210,25 @@ __device__ __forceinline__ bool nwb_hx_strip(const NwbStripParams &p, const NwbP
         const int s0 = 32 * blk;
         /* ring back-pressure: this block overwrites the slots of block seq-4; the rows the flush
          * warp takes after block seq-2 still read them */
-        if (seq >= 2) {
-            NwbWatchdog wd;
-            while (nwb_flag_load(done) < seq - 1) {
-                nwb_spin_pause(false);
-                if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+        if (seq >= 2 && nwb_flag_load(done) < seq - 1) {
+            /* The flush warp only ever waits for THIS warp, so it always gets there -- unless it left because some
+             * watchdog fired: look at the error word now and then.  (A full watchdog tick in this loop changed the
+             * sweeping warp's schedule and cost 33 % of the whole fill.) */
+            for (;;) {
+                bool freed = false;
+#pragma unroll 1
+                for (int it = 0; it < NWB_WD_POLLS; it++) {
+                    if (nwb_flag_load(done) >= seq - 1) {
+                        freed = true;
+                        break;
+                    }
+#ifdef NWB_EMU
+                    nwb_pause();
+#endif
+                }
+                if (freed) break;
+                const int *ew = NWB_ERR_WORD(p);
+                if (ew && *reinterpret_cast<const volatile int *>(ew) != 0) return false;
             }
         }
         const bool lean = !(is_last && R * (s0 + 32) >= B);
@@ -226,25 +240,44 @@ __device__ __forceinline__ bool nwb_hx_strip(const NwbStripParams &p, const NwbP
                 const int gs = ss + lane;
                 unsigned w = bq_next;
                 bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID) || NWB_DBG_BITS(p, 1);
-                NwbWatchdog wd;
-                while (!__all_sync(NWB_FULL_MASK, ok)) {
-                    if (!ok) {
-                        w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
-                        ok = (w & NWB_PK_VALID) != 0u;
-                    }
-                    if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+                if (!__all_sync(NWB_FULL_MASK, ok)) {
+                    /* The wake-up latency of this loop sits on the strip-to-strip critical path (391 hops at 100k):
+                     * the inner loop is load, vote, leave; the watchdog's bookkeeping runs outside it, once per
+                     * NWB_WD_POLLS polls (inside the loop it cost 33 % of the whole fill). */
+                    NwbWatchdog wd;
+                    for (;;) {
+                        bool arrived = false;
+#pragma unroll 1
+                        for (int it = 0; it < NWB_WD_POLLS; it++) {
+                            if (!ok) {
+                                w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
+                                ok = (w & NWB_PK_VALID) != 0u;
+                            }
 #ifdef NWB_EMU
-                    nwb_pause();
+                            nwb_pause();
 #endif
+                            if (__all_sync(NWB_FULL_MASK, ok)) {
+                                arrived = true;
+                                break;
+                            }
+                        }
+                        if (arrived) break;
+                        if (wd.slow(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+                    }
                 }
                 bq = w & VMASK;
                 bq_next = 0u;
                 if (lane < NWB_PK_SUB && gs + NWB_PK_SUB < ngroups)
                     bq_next = nwb_ld_relaxed_u32(in_w + gs + NWB_PK_SUB, left_remote);
             }
+            /* The side characters of this sub-block were loaded one sub-block ago; they are COPIED out of their load
+             * registers here, before the next sub-block's loads are issued.  Global loads retire through a counting
+             * scoreboard: a step that read a load register directly would also wait for the younger loads issued
+             * just below -- an L2 round trip per sub-block, +33 % on the whole fill (measured when ptxas renamed the
+             * registers instead of copying).  The volatile move pins the copy and its place. */
             unsigned chars[NWB_PK_SUB];
 #pragma unroll
-            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = chars_next[t];
+            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = nwb_pin_copy(chars_next[t]);
             {
                 const uint16_t *spn = sp_lane + R * (ss + NWB_PK_SUB);
 #pragma unroll

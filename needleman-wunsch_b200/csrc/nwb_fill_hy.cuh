@@ -203,7 +203,7 @@ __device__ __forceinline__ void nwb_hy_strip(const NwbStripParams &p, const NwbP
             }
             unsigned chars[NWB_PK_SUB];
 #pragma unroll
-            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = chars_next[t];
+            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = nwb_pin_copy(chars_next[t]); /* before the next loads are issued: see nwb_fill_hx.cuh */
             {
                 const uint16_t *spn = sp_lane + R * (ss + NWB_PK_SUB);
 #pragma unroll

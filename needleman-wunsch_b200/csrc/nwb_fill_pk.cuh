@@ -509,17 +509,30 @@ __device__ __forceinline__ bool nwb_pk_strip(const NwbStripParams &p, const NwbP
                 unsigned w = bq_next;
                 if (!nowait) {
                     bool ok = (lane >= NWB_PK_SUB) || (gs >= ngroups) || (w & NWB_PK_VALID);
-                    NwbWatchdog wd;
-                    while (!__all_sync(NWB_FULL_MASK, ok)) {
-                        npolls++;
-                        if (!ok) { /* plain spin: a sleep quantum here would sit on the strip-to-strip critical path */
-                            w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
-                            ok = (w & NWB_PK_VALID) != 0u;
-                        }
-                        if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+                    if (!__all_sync(NWB_FULL_MASK, ok)) {
+                        /* plain spin, no sleep quantum and no bookkeeping inside the inner loop: its wake-up latency
+                         * sits on the strip-to-strip critical path (see nwb_fill_hx.cuh) */
+                        NwbWatchdog wd;
+                        for (;;) {
+                            bool arrived = false;
+#pragma unroll 1
+                            for (int it = 0; it < NWB_WD_POLLS; it++) {
+                                if (!ok) {
+                                    w = nwb_ld_relaxed_u32(in_w + gs, left_remote);
+                                    ok = (w & NWB_PK_VALID) != 0u;
+                                }
 #ifdef NWB_EMU
-                        nwb_pause();
+                                nwb_pause();
 #endif
+                                if (__all_sync(NWB_FULL_MASK, ok)) {
+                                    arrived = true;
+                                    break;
+                                }
+                            }
+                            npolls += NWB_WD_POLLS;
+                            if (arrived) break;
+                            if (wd.slow(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+                        }
                     }
                 }
                 if (dbg && lane == 0 && ss == 0) dbg[1] = nwb_globaltimer();
@@ -538,16 +551,27 @@ __device__ __forceinline__ bool nwb_pk_strip(const NwbStripParams &p, const NwbP
                     if (need) cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
                     if (!nowait) {
                         bool okc = !need || (cw & NWB_PK_CVALID);
-                        NwbWatchdog wdc;
-                        while (!__all_sync(NWB_FULL_MASK, okc)) {
-                            if (!okc) {
-                                cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
-                                okc = (cw & NWB_PK_CVALID) != 0ull;
-                            }
-                            if (wdc.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+                        if (!__all_sync(NWB_FULL_MASK, okc)) {
+                            NwbWatchdog wdc;
+                            for (;;) {
+                                bool arrived = false;
+#pragma unroll 1
+                                for (int it = 0; it < NWB_WD_POLLS; it++) {
+                                    if (!okc) {
+                                        cw = nwb_ld_relaxed_u64(in_c + (size_t)ss * R * 2 + lane, left_remote);
+                                        okc = (cw & NWB_PK_CVALID) != 0ull;
+                                    }
 #ifdef NWB_EMU
-                            nwb_pause();
+                                    nwb_pause();
 #endif
+                                    if (__all_sync(NWB_FULL_MASK, okc)) {
+                                        arrived = true;
+                                        break;
+                                    }
+                                }
+                                if (arrived) break;
+                                if (wdc.slow(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
+                            }
                         }
                     }
                     const unsigned long long hi = __shfl_down_sync(NWB_FULL_MASK, cw, 1);
@@ -559,7 +583,7 @@ __device__ __forceinline__ bool nwb_pk_strip(const NwbStripParams &p, const NwbP
             /* side characters of the NEXT sub-block's steps are loaded one sub-block ahead */
             unsigned chars[NWB_PK_SUB];
 #pragma unroll
-            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = chars_next[t];
+            for (int t = 0; t < NWB_PK_SUB; t++) chars[t] = nwb_pin_copy(chars_next[t]); /* before the next loads are issued: see nwb_fill_hx.cuh */
             {
                 const uint16_t *spn = sp_lane + R * (ss + NWB_PK_SUB);
 #pragma unroll

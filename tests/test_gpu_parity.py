@@ -415,7 +415,7 @@ def test_batch_count_chained_runs(oracle, nwb):
     for m, k, d in ((1, 1, 1), (0, 0, 0)):
         got = {}
         for chain in ("1", "0"):
-            with nwb.tuned(bcnt_chain=int(chain), bcnt_sparse=0):
+            with nwb.tuned(bcnt_chain=int(chain)):
                 bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_COUNT)
                 bt.run()
                 bt.fetch()

@@ -27,7 +27,6 @@ off = np.arange(n + 1, dtype=np.int64) * 256
 res = {}
 for chain in ("0", "1"):
     nwb.tune("bcnt_chain", int(chain))
-    nwb.tune("bcnt_sparse", 0)
     for flags, what in ((0, "fill"), (nwb.WANT_COUNT, "fill+count")):
         b = nwb.Batch.from_arrays(bytes(tcat), off, bytes(scat), off, 1, 1, 1, flags)
         ms = []
