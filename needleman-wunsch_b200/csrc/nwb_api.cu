@@ -23,7 +23,9 @@
 #include "nwb_fill_pk.cuh"
 #include "nwb_fill_hx.cuh"
 #ifdef NWB_EXPERIMENTS
-#include "nwb_fill_hy.cuh" /* measured-slower lane geometry, kept for the record; not in the product build */
+/* built, verified and measured SLOWER than nwb_fill_hx.cuh; kept for the record, not in the product build */
+#include "nwb_fill_hy.cuh" /* one row of skew per virtual lane */
+#include "nwb_fill_hz.cuh" /* packing warps next to the sweeping and flush warps, two strips per SM */
 #endif
 #include "nwb_count.cuh"
 #include "nwb_count_sparse.cuh"
@@ -97,6 +99,7 @@ struct NwbTune {
     int plan_cache = 1;     /* 0 = nwb_fill()/nwb_fill_on() create and destroy their device workspace per call */
 #ifdef NWB_EXPERIMENTS
     int pk_hy = 0;
+    int pk_hz = 0;
     int debug_nowait = 0;
 #endif
 };
@@ -112,7 +115,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"cx_warps", &g_tune.cx_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
 #ifdef NWB_EXPERIMENTS
-        {"pk_hy", &g_tune.pk_hy}, {"debug_nowait", &g_tune.debug_nowait},
+        {"pk_hy", &g_tune.pk_hy}, {"pk_hz", &g_tune.pk_hz}, {"debug_nowait", &g_tune.debug_nowait},
 #endif
     };
     for (auto &t : tab)
@@ -199,6 +202,7 @@ struct nwb_plan {
     int m = 0, k = 0, d = 0;
     bool pk_hx = false; /* packed kernel variant with flush warps (nwb_fill_hx.cuh) */
     bool pk_hy = false; /* ... with one row of skew per virtual lane (nwb_fill_hy.cuh) */
+    bool pk_hz = false; /* ... with packing warps as well, two strips per SM (nwb_fill_hz.cuh) */
     bool count_pass = false; /* the count runs as a second sweep over the arrow codes (nwb_count.cuh) */
 };
 
@@ -404,6 +408,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     int strip_w = NWB_I32_STRIP_W, pk_k = 0, pk_r = 1;
     p->pk_hx = false;
     p->pk_hy = false;
+    p->pk_hz = false;
     if (p->kind == NWB_KIND_PK) {
         pk_k = (tn.pk_k == 1 || tn.pk_k == 2 || tn.pk_k == 4) ? tn.pk_k : nwb_pk_choose_k(A, B, p->world);
         if (p->count_pass) pk_k = 4; /* the count sweeps walk 256-column strips */
@@ -530,6 +535,10 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
 
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
     const bool hx = (p->kind == NWB_KIND_PK) && p->pk_hx;
+#ifdef NWB_EXPERIMENTS
+    /* every strip of this launch can have an SM half (sweeping warp + packing warp + flush warp) to itself */
+    p->pk_hz = hx && !p->pk_hy && tn.pk_hz != 0 && nwb_hz_usable(nloc, p->sm_count);
+#endif
     /* one warp per SM sub-partition; a second one when there are more strips than that */
     int pk_warps = (nloc > p->sm_count * NWB_PK_WARPS) ? NWB_PK_MAX_WARPS : NWB_PK_WARPS;
     if (tn.pk_warps >= 1 && tn.pk_warps <= NWB_PK_MAX_WARPS) pk_warps = tn.pk_warps;
@@ -554,7 +563,8 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     if (overlap) CK(cudaEventRecord(p->ev_fork, st)); /* buffers are zeroed, strings uploaded */
     if (hx) {
 #ifdef NWB_EXPERIMENTS
-        rc = p->pk_hy ? nwb_hy_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, grid, st, cuda_fail);
+        rc = p->pk_hy ? nwb_hy_launch(sp, pc, grid, st, cuda_fail)
+                      : (p->pk_hz ? nwb_hz_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, grid, st, cuda_fail));
 #else
         rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
 #endif
@@ -722,7 +732,7 @@ extern "C" const char *nwb_plan_kernel_name(const nwb_plan *p)
 {
     if (!p || !p->ran) return "";
     if (p->kind == NWB_KIND_I32) return "nwb_fill_i32_kernel";
-    return p->pk_hx ? (p->pk_hy ? "nwb_fill_hy_kernel" : "nwb_fill_hx_kernel") : "nwb_fill_pk_kernel";
+    return p->pk_hx ? (p->pk_hy ? "nwb_fill_hy_kernel" : (p->pk_hz ? "nwb_fill_hz_kernel" : "nwb_fill_hx_kernel")) : "nwb_fill_pk_kernel";
 }
 /* How the last run obtained the count: "" (none), "fused", "dense" (forward sweep), "sparse" (backward sweep;
  * nwb_plan_summary() reports whether it had to fall back). */

@@ -64,7 +64,7 @@ __device__ __forceinline__ void nwb_sts128(nwb_smem_addr a, unsigned x, unsigned
 __device__ __forceinline__ int nwb_flag_load(const volatile int *p) { return *p; }
 __device__ __forceinline__ void nwb_flag_store(volatile int *p, int v)
 {
-#ifndef NWB_EMU
+#if !defined(NWB_EMU) && !defined(NWB_TEST_NOFENCE)
     __threadfence_block();
 #endif
     *p = v;
@@ -348,13 +348,13 @@ __device__ __forceinline__ void nwb_hx_flush_slot(const uint4 w, unsigned &pc0, 
     pc1 = c1;
 }
 
-template <bool PUBLISH>
+template <bool PUBLISH, int NCRIT = NWB_HX_CRIT>
 __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int wslot, const unsigned char *ring,
                                               volatile int *ready, volatile int *done, const int lane,
                                               unsigned &branches)
 {
     const int B = p.B, A = p.A;
-    const int nworkers = (int)gridDim.x * NWB_HX_CRIT;
+    const int nworkers = (int)gridDim.x * NCRIT; /* sweeping warps per block: 3 here, 2 in nwb_fill_hz.cuh */
     const int worker = wslot * (int)gridDim.x + (int)blockIdx.x;
     const int ngroups = (B + 1) / 2;
     const int nfull = B / 2; /* groups with both rows inside the table */

@@ -9,6 +9,7 @@
 #include "nwb_fill_i32.cuh"
 #include "nwb_fill_pk.cuh"
 #include "nwb_fill_hx.cuh"
+#include "nwb_fill_hz.cuh"
 #include "nwb_fill_hy.cuh"
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
@@ -176,7 +177,10 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     p.side_pre = side_pre.data();
     const uint32_t *last_stream = nullptr; /* the stream consumed by the last strip, when it is not in bnd_w */
     auto launch = [&](const NwbStripParams &q) {
-        if (hx == 2) { /* one row of skew per virtual lane (nwb_fill_hy.cuh) */
+        if (hx == 3) { /* sweeping + packing + flush warps, two strips per block (nwb_fill_hz.cuh) */
+            if (q.publish_rows) emu_launch(grid, 32 * NWB_HZ_WARPS, NWB_HZ_SMEM_BYTES, [&]() { nwb_fill_hz_kernel<true>(q, pc); });
+            else emu_launch(grid, 32 * NWB_HZ_WARPS, NWB_HZ_SMEM_BYTES, [&]() { nwb_fill_hz_kernel<false>(q, pc); });
+        } else if (hx == 2) { /* one row of skew per virtual lane (nwb_fill_hy.cuh) */
             if (q.publish_rows) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<true>(q, pc); });
             else emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<false>(q, pc); });
         } else if (hx) {
@@ -351,7 +355,8 @@ int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int
     std::vector<uint16_t> side_pre(NWB_PK_SPRE_LEN(B), 0x1234);
     emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
     p.side_pre = side_pre.data();
-    if (hx == 2) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<false>(p, pc); });
+    if (hx == 3) emu_launch(grid, 32 * NWB_HZ_WARPS, NWB_HZ_SMEM_BYTES, [&]() { nwb_fill_hz_kernel<false>(p, pc); });
+    else if (hx == 2) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<false>(p, pc); });
     else if (hx) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false>(p, pc); });
     else run_pk_emu<4, 2, false>(grid, 4, p, pc);
     { /* the counter fused into the flush and the stand-alone pass over this rank's columns must agree */

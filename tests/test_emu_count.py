@@ -17,7 +17,7 @@ def chk(oracle, t, s, m, k, d, hx, grid=2, split=0, cpls=(2, 4, 8)):
         assert (r["opt_score"], r["branch_count"], r["count"]) == (o.final_score, o.branch_count, o.count), cpl
 
 
-@pytest.mark.parametrize("hx", [0, 1, 2], ids=["pk", "hx", "hy"])
+@pytest.mark.parametrize("hx", [0, 1, 2, 3], ids=["pk", "hx", "hy", "hz"])
 def test_readme_and_delannoy(oracle, hx):
     chk(oracle, b"GCATGCU", b"GATTACA", 1, 1, 1, hx)          # 3 optimal alignments (README:154)
     chk(oracle, b"GCATGCU", b"GATTACA", 0, 0, 0, hx, grid=1)  # every arrow everywhere: Delannoy(7,7) = 48,639
@@ -25,7 +25,7 @@ def test_readme_and_delannoy(oracle, hx):
     assert r["count"] == 48639
 
 
-@pytest.mark.parametrize("hx", [0, 1, 2], ids=["pk", "hx", "hy"])
+@pytest.mark.parametrize("hx", [0, 1, 2, 3], ids=["pk", "hx", "hy", "hz"])
 def test_shapes(oracle, hx):
     rng = random.Random(31 + hx)
     for a, b in [(1, 1), (5, 40), (63, 33), (256, 64), (257, 130), (513, 70), (600, 201), (130, 256), (256, 256),

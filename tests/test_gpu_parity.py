@@ -463,10 +463,10 @@ def test_extreme_aspect_ratios_and_multi_pass(oracle, nwb):
 
 @pytest.fixture
 def force_hx(nwb):
-    """nwb_tune pk_hx = 1: the sweeping + flush warp variant (csrc/nwb_fill_hx.cuh) at every size the
-    scheme allows, not only for tall tables."""
+    """nwb_tune pk_hx = 1: the sweeping + flush warp kernel (csrc/nwb_fill_hx.cuh) at every size the scheme allows,
+    not only for tall tables."""
     nwb.tune("pk_hx", 1)
-    yield
+    yield "hx"
     nwb.tune_reset()
 
 
@@ -497,6 +497,11 @@ def test_hx_variant_big_and_multi_pass(oracle, nwb, force_hx):
     """Whole tables at 10k x 10k (config 2) and 3k x 3k protein, extreme aspect ratios, and more strips
     than sweeping warps (160,000 columns = 625 strips > 444: several strips per warp, ring across strips)."""
     t, s = oracle.generate_pair(0x5EED0002, 10000, 10000)
+    plan = nwb.Plan(10000, 10000, 0)
+    plan.upload(t, s)
+    plan.run(1, 1, 1)
+    assert plan.kernel_name() == "nwb_fill_hx_kernel"
+    plan.close()
     tab = nwb.fill(t, s, 1, 1, 1, nwb.WANT_ARROWS_HOST)
     assert (tab.opt_score, tab.branch_count) == (1056, 34377799)
     check_arrows(oracle, nwb, tab, t, s, 1, 1, 1)
