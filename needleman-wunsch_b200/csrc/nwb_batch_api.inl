@@ -299,6 +299,8 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
         bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p + c0; bp.out_score = b->score.p + c0;
         bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
         if (b->use_cx) {
+            /* uniform shapes: the kernel addresses pair p's table as arrows + p * table bytes (not through arrow_off) */
+            bp.arrows = b->arrows.p + b->h_arrow_off[(size_t)c0];
             const bool w16 = g_tune.cx_warps == 16 && nwb_cx_usable(b->pc, true, b->uni_A, (int)b->uni_B, 16);
             const int cw = w16 ? 16 : NWB_BX_WARPS;
             const size_t smem = NWB_CX_SMEM_PER_WARP(b->max_B, cw) * (size_t)cw;

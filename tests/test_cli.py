@@ -155,7 +155,8 @@ def test_batch_cli_matches_the_reference_looped_per_pair(cli):
               "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 11)))) for _ in range(40)]
     text = "\n".join(f"{a} {b}" for a, b in pairs).encode() + b"\n"
     # any m k d the reference takes (needleman-wunsch.c:783-785): the last three run the int32 batch engine
-    for mkd in (("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0"), ("1", "3", "1"), ("5", "4", "3"), ("-1", "3", "-2")):
+    # (negative operands need "--": both front-ends parse their options with getopt, needleman-wunsch.c:723)
+    for mkd in (("1", "1", "1"), ("2", "1", "2"), ("0", "0", "0"), ("1", "3", "1"), ("5", "4", "3"), ("--", "-1", "3", "-2")):
         for flags in ([], ["-s"]):
             rc, out, err = run_batch(flags + list(mkd), text)
             assert rc == 0 and out == b""

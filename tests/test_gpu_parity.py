@@ -234,9 +234,10 @@ def test_batch_general_schemes_scores_and_abs(oracle, nwb):
             (257, 31), (5, 0), (1100, 300)] + [(rng.randint(1, 600), rng.randint(1, 400)) for _ in range(120)]
     tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
     sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
-    for (m, k, d), flags in (((1, 3, 1), 0), ((5, 4, 3), nwb.WANT_COUNT), ((-1, 3, -2), nwb.WANT_COUNT),
-                             ((1, 1, 1), nwb.FORCE_GENERAL | nwb.WANT_COUNT),
+    for (m, k, d), flags in (((1, 3, 1), 0), ((1, 5, 2), nwb.WANT_COUNT), ((-1, 3, -2), nwb.WANT_COUNT),
+                             ((70, 60, 50), nwb.WANT_COUNT), ((1, 1, 1), nwb.FORCE_GENERAL | nwb.WANT_COUNT),
                              ((2, 1, 2), nwb.WANT_SCORES | nwb.TRACK_ABS | nwb.WANT_COUNT)):
+        assert (flags & (nwb.FORCE_GENERAL | nwb.WANT_SCORES)) or not pk_supported(m, k, d)
         bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST | flags)
         assert bt.kernel_name() == "nwb_batch_i32_kernel"
         bt.run()
