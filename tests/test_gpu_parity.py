@@ -200,6 +200,26 @@ def test_two_gpu_strips_match_one(oracle, nwb):
     full_check(oracle, nwb, t, s, 2, 1, 2, nwb.FORCE_GENERAL, num_gpus=2)
 
 
+def test_strip_group_full_size_digests(oracle, nwb):
+    """Column strips over 2 (and 4, 8 when present) GPUs of one process at full size: EVERY arrow set (the ranks' table
+    digests add up to the oracle's), score, branch count and the count (dense sweep handed from GPU to GPU)."""
+    ndev = nwb.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    gold = {c["name"]: c for c in golden("golden_big.json")}
+    for name, seed, alpha, mkd in (("config2_dna_10k", 0x5EED0002, "dna", (1, 1, 1)), ("config5_protein_30k", 0x5EED0005, "protein", (2, 1, 2)),
+                                   ("config3_dna_100k", 0x5EED0030, "dna", (1, 1, 1))):
+        g = gold[name]
+        t, s = oracle.generate_pair(seed, g["top_len"], g["side_len"], oracle.DNA if alpha == "dna" else oracle.PROTEIN)
+        for world in [w for w in (2, 4, 8) if w <= ndev]:
+            tab = nwb.fill(t, s, *mkd, nwb.WANT_DIGEST | nwb.WANT_COUNT, num_gpus=world)
+            assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"]), (name, world)
+            assert tab.arrow_digest() == int(g["arrow_digest"], 16), (name, world)
+            assert tab.summary().count_path == nwb.COUNT_DENSE
+            tab.close()
+            nwb.cache_clear()
+
+
 # ---- batch of independent pairs (BASELINE config 4) ---------------------------------
 def test_batch_ragged(oracle, nwb):
     rng = random.Random(11)
