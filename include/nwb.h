@@ -96,6 +96,10 @@ int nwb_tune(const char *key, int value);
 void nwb_tune_reset(void);
 /* Text of the last CUDA error seen by this thread ("" if none). */
 const char *nwb_last_cuda_error(void);
+/* Page-locked ("pinned") host memory for input strings: host-to-device copies from it run at full link speed and
+ * overlap with the kernels (nwb_batch_refill); any other host memory works too, only slower.  NULL on failure. */
+void *nwb_host_alloc(size_t bytes);
+void nwb_host_free(void *p);
 /* Number of usable CUDA devices (0 if none), ABI version. */
 int nwb_device_count(void);
 int nwb_abi_version(void);

@@ -67,6 +67,8 @@ _SIGS = {
     "nwb_last_cuda_error": (C.c_char_p, []),
     "nwb_device_count": (C.c_int, []),
     "nwb_abi_version": (C.c_int, []),
+    "nwb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "nwb_host_free": (None, [C.c_void_p]),
     "nwb_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "nwb_tune_reset": (None, []),
     "nwb_table_summary": (C.c_int, [C.c_void_p, C.POINTER(Summary)]),
@@ -117,7 +119,7 @@ _SIGS = {
     "nwb_batch_create": (C.c_int, [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]),
     "nwb_batch_run": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "nwb_batch_refill": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "nwb_batch_refill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nwb_batch_fetch": (C.c_int, [C.c_void_p]),
     "nwb_batch_launches": (C.c_int64, [C.c_void_p]),
     "nwb_batch_kernel_name": (C.c_char_p, [C.c_void_p]),
@@ -192,6 +194,34 @@ def tune(key: str, value: int) -> None:
     rc = load_library().nwb_tune(key.encode(), int(value))
     if rc != 0:
         raise NwbError(rc, f"nwb_tune({key!r})")
+
+
+class PinnedBuffer:
+    """Page-locked host memory (nwb_host_alloc) holding a copy of `data`; pass it where host strings are expected."""
+
+    def __init__(self, data: bytes):
+        self.nbytes = len(data)
+        self.ptr = load_library().nwb_host_alloc(max(1, self.nbytes))
+        if not self.ptr:
+            raise NwbError(-2, "nwb_host_alloc")
+        C.memmove(self.ptr, data, self.nbytes)
+
+    def close(self) -> None:
+        if self.ptr:
+            load_library().nwb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _host_ptr(x):
+    if isinstance(x, PinnedBuffer):
+        return C.c_void_p(x.ptr)
+    return C.cast(C.c_char_p(x), C.c_void_p)
 
 
 def cache_clear() -> None:
@@ -492,7 +522,9 @@ class Batch:
 
     def refill(self, tcat: bytes, scat: bytes) -> None:
         """New strings for the same shapes from host buffers, H2D chunks overlapped with the kernels (nwb_batch_refill)."""
-        _ck(load_library().nwb_batch_refill(self._h, tcat, scat), "nwb_batch_refill")
+        keep = (tcat, scat)  # the copies are asynchronous: keep the buffers alive until fetch()
+        self._refill_src = keep
+        _ck(load_library().nwb_batch_refill(self._h, _host_ptr(tcat), _host_ptr(scat)), "nwb_batch_refill")
 
     def fetch(self) -> None:
         _ck(load_library().nwb_batch_fetch(self._h), "nwb_batch_fetch")
