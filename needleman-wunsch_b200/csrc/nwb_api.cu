@@ -605,6 +605,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
         sc.out_count = &p->summary.p->count;
         sc.out_state = &p->summary.p->count_state;
         sc.out_rows = &p->summary.p->sparse_rows;
+        sc.mode = 0;
         nwb_sparse_count_kernel<<<1, 32, 0, st>>>(sc);
         CK(cudaGetLastError());
         /* the dense sweep's streams are zeroed only if it is going to run */

@@ -16,9 +16,9 @@
  * left the sweep stops (on random DNA/protein the 2-adic valuation of P grows by
  * about one bit per dozen rows, so the live set dies ~1000 rows above (A,B)).
  *
- * One warp walks the rows j = B .. 1.  Lane l owns one 8-column block (one 32-bit
- * word of the arrow row): the block b == l (mod 32) inside a window of 32 blocks
- * (256 columns) that follows the live cells to the left.  Per row: P along the row
+ * One warp walks the rows j = B .. 1.  Lane l owns one unit of CPL consecutive columns
+ * (CPL = 2: a byte of the arrow row, CPL = 8: a 32-bit word): the unit b == l (mod 32)
+ * inside a window of 32 units (64 or 256 columns) that follows the live cells to the left.  Per row: P along the row
  * (right to left through runs of LEFT arrows: a local pass per lane, then carries
  * between lanes until none is left), then the flow into row j-1 (UP, DIAG).  Arrow
  * words are fetched one chunk of 8 rows ahead; a lane whose block has fallen off the
@@ -43,60 +43,69 @@ struct NwbSparseCountParams {
     unsigned long long *out_count; /* where the count goes                                  */
     int *out_state;                /* NWB_SPC_*                                             */
     unsigned *out_rows;            /* rows visited before the live set died (or NULL)       */
+    int mode;                      /* tests: 1 = skip the 64-column attempt, 2 = skip the 256-column attempt */
 };
 
-__device__ __forceinline__ unsigned nwb_spc_load(const uint8_t *arrows, size_t pitch, int j, int blk, unsigned colmask)
+/* the CPL arrow nibbles of unit `unit` (CPL consecutive columns) in row j; 0 outside the table */
+template <int CPL>
+__device__ __forceinline__ unsigned nwb_spc_load(const uint8_t *arrows, size_t pitch, int j, int unit, unsigned colmask)
 {
-    if (j < 1 || blk < 0) return 0u;
-    const unsigned *q = reinterpret_cast<const unsigned *>(arrows + (size_t)(j - 1) * pitch) + blk;
+    if (j < 1 || unit < 0) return 0u;
+    const int col0 = unit * CPL; /* 0-based first column of the unit */
+    const unsigned *q = reinterpret_cast<const unsigned *>(arrows + (size_t)(j - 1) * pitch) + (col0 >> 3);
 #ifdef NWB_EMU
-    return *q & colmask;
+    const unsigned w = *q;
 #else
-    return __ldca(q) & colmask; /* a row's 32 words are one 128-byte line */
+    const unsigned w = __ldca(q); /* a row's words sit in one or two 128-byte lines */
 #endif
+    return (w >> (4 * (col0 & 7))) & colmask;
 }
 
 __device__ __forceinline__ unsigned long long nwb_spc_sel(unsigned flag, unsigned long long v) { return flag ? v : 0ull; }
 
-/* One pair: the warp's 32 lanes.  Returns NWB_SPC_DONE / NWB_SPC_BAILED (uniform); *count and *rows valid in lane 0. */
+/* One pair: the warp's 32 lanes, CPL columns per lane (window of 32 * CPL columns).  Returns NWB_SPC_DONE /
+ * NWB_SPC_BAILED (uniform); *count and *rows valid in every lane. */
+template <int CPL>
 __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, const size_t pitch, const int A, const int B,
                                                      const int lane, unsigned long long *count, unsigned *rows)
 {
-    const int rb0 = (A - 1) >> 3;                 /* block of column A */
-    int myb = rb0 - ((rb0 - lane) & 31);          /* my block: == lane (mod 32), inside [rb0-31, rb0]; < 0: none */
-    const int right = (lane + 1) & 31;            /* the lane that owns block myb + 1 (cyclically)               */
+    const unsigned FULL = (CPL == 8) ? 0x77777777u : (0x77777777u & ((1u << (4 * CPL)) - 1u));
+    const int rb0 = (A - 1) / CPL;                /* unit of column A */
+    int myb = rb0 - ((rb0 - lane) & 31);          /* my unit: == lane (mod 32), inside [rb0-31, rb0]; < 0: none */
+    const int right = (lane + 1) & 31;            /* the lane that owns unit myb + 1 (cyclically)               */
     auto colmask_of = [&](const int b) -> unsigned {
-        if (b != rb0) return 0x77777777u;
-        const int n = ((A - 1) & 7) + 1;          /* cells of the last block that are inside the table */
-        return n >= 8 ? 0x77777777u : (0x77777777u & ((1u << (4 * n)) - 1u));
+        if (b != rb0) return FULL;
+        const int n = ((A - 1) % CPL) + 1;        /* cells of the last unit that are inside the table */
+        return n >= CPL ? FULL : (FULL & ((1u << (4 * n)) - 1u));
     };
 
-    unsigned long long inc[8], P[8];
+    unsigned long long inc[CPL], P[CPL];
     {
         /* P(A,B) = 1 (as selects: an indexed store would put inc[] into local memory) */
-        const int kA = (myb == rb0) ? ((A - 1) & 7) : -1;
+        const int kA = (myb == rb0) ? ((A - 1) % CPL) : -1;
 #pragma unroll
-        for (int k = 0; k < 8; k++) inc[k] = (k == kA) ? 1ull : 0ull;
+        for (int k = 0; k < CPL; k++) inc[k] = (k == kA) ? 1ull : 0ull;
     }
     unsigned long long total = 0ull; /* flow that has reached the border */
     unsigned w[NWB_SPC_CHUNK], wn[NWB_SPC_CHUNK];
     int jtop = B;
 #pragma unroll
-    for (int t = 0; t < NWB_SPC_CHUNK; t++) w[t] = nwb_spc_load(arrows, pitch, jtop - t, myb, colmask_of(myb));
-    int rlb = rb0; /* rightmost live block */
+    for (int t = 0; t < NWB_SPC_CHUNK; t++) w[t] = nwb_spc_load<CPL>(arrows, pitch, jtop - t, myb, colmask_of(myb));
+    int rlb = rb0; /* rightmost live unit */
     int state = NWB_SPC_NONE;
     unsigned nrows = 0;
 
     while (state == NWB_SPC_NONE) {
-        /* next chunk: a lane right of the live band moves 32 blocks to the left */
+        /* next chunk: a lane right of the live band moves 32 units to the left */
         const int nextb = (myb > rlb) ? myb - 32 : myb;
         {
             const unsigned cm = colmask_of(nextb);
 #pragma unroll
-            for (int t = 0; t < NWB_SPC_CHUNK; t++) wn[t] = nwb_spc_load(arrows, pitch, jtop - NWB_SPC_CHUNK - t, nextb, cm);
+            for (int t = 0; t < NWB_SPC_CHUNK; t++) wn[t] = nwb_spc_load<CPL>(arrows, pitch, jtop - NWB_SPC_CHUNK - t, nextb, cm);
         }
         const int nbb = __shfl_sync(NWB_FULL_MASK, myb, right);
         const bool adjacent = (nbb == myb + 1);
+        bool bad = false;
 #pragma unroll
         for (int t = 0; t < NWB_SPC_CHUNK; t++) {
             const int j = jtop - t;
@@ -105,20 +114,21 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
             /* P along the row, right to left: P(i) = inc(i) + [LEFT(i+1)] P(i+1) */
             unsigned long long d = 0ull;
 #pragma unroll
-            for (int k = 7; k >= 0; k--) {
+            for (int k = CPL - 1; k >= 0; k--) {
                 P[k] = inc[k] + d;
                 d = nwb_spc_sel((x >> (4 * k + 1)) & 1u, P[k]);
             }
-            bool bad = false;
             for (;;) {
                 if (myb == 0) { total += d; d = 0ull; } /* LEFT out of column 1: the border column */
                 const unsigned long long cin = __shfl_sync(NWB_FULL_MASK, d, right);
+                /* a carry that arrives from a lane which does not own the unit to my right has left the window: it is
+                 * dropped (so it cannot circulate) and the sweep is given up at the end of the chunk */
+                const bool take = (cin != 0ull) && adjacent;
                 bad = bad || (cin != 0ull && !adjacent);
-                /* no carry left -- or one that would wrap around the window (it would circulate for ever) */
-                if (!__any_sync(NWB_FULL_MASK, cin != 0ull) || __any_sync(NWB_FULL_MASK, bad)) break;
-                d = cin;
+                if (!__any_sync(NWB_FULL_MASK, take)) break;
+                d = take ? cin : 0ull;
 #pragma unroll
-                for (int k = 7; k >= 0; k--) {
+                for (int k = CPL - 1; k >= 0; k--) {
                     P[k] += d;
                     d = nwb_spc_sel((x >> (4 * k + 1)) & 1u, d);
                 }
@@ -129,17 +139,19 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
             const unsigned long long dgin = __shfl_sync(NWB_FULL_MASK, dg, right);
             bad = bad || (dgin != 0ull && !adjacent);
 #pragma unroll
-            for (int k = 0; k < 7; k++)
+            for (int k = 0; k < CPL - 1; k++)
                 inc[k] = nwb_spc_sel((x >> (4 * k + 2)) & 1u, P[k]) + nwb_spc_sel((x >> (4 * k + 4)) & 1u, P[k + 1]);
-            inc[7] = nwb_spc_sel((x >> 30) & 1u, P[7]) + dgin;
+            inc[CPL - 1] = nwb_spc_sel((x >> (4 * (CPL - 1) + 2)) & 1u, P[CPL - 1]) + dgin;
             nrows++;
-            bool live = false;
-#pragma unroll
-            for (int k = 0; k < 8; k++) live = live || (inc[k] != 0ull);
-            if (__any_sync(NWB_FULL_MASK, bad)) { state = NWB_SPC_BAILED; continue; }
-            if (!__any_sync(NWB_FULL_MASK, live)) { state = NWB_SPC_DONE; continue; }
+            /* the votes that end the sweep are taken once per chunk: a few rows without live cells cost nothing, and a
+             * chunk that lost a carry is thrown away anyway */
             if (t == NWB_SPC_CHUNK - 1 || j == 1) {
-                /* rightmost live block, for the re-assignment at the chunk boundary */
+                bool live = false;
+#pragma unroll
+                for (int k = 0; k < CPL; k++) live = live || (inc[k] != 0ull);
+                if (__any_sync(NWB_FULL_MASK, bad)) { state = NWB_SPC_BAILED; continue; }
+                if (!__any_sync(NWB_FULL_MASK, live)) { state = NWB_SPC_DONE; continue; }
+                /* rightmost live unit, for the re-assignment at the chunk boundary */
                 int v = live ? myb : -1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -158,7 +170,7 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
     }
     /* whatever is left has arrived in row 0 (or is zero) */
 #pragma unroll
-    for (int k = 0; k < 8; k++) total += inc[k];
+    for (int k = 0; k < CPL; k++) total += inc[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(NWB_FULL_MASK, total, o);
     *count = total;
@@ -166,12 +178,19 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
     return state;
 }
 
+/* First with 2 columns per lane (a 64-column window: a row costs ~1/3 of the 8-column form, and the live band of the
+ * BASELINE inputs is at most 26 columns wide), then, if that window was too narrow, with 8 (256 columns). */
 __global__ void __launch_bounds__(32, 1) nwb_sparse_count_kernel(const NwbSparseCountParams p)
 {
     const int lane = threadIdx.x & 31;
     unsigned long long count = 0ull;
-    unsigned rows = 0u;
-    const int state = nwb_sparse_count_pair(p.arrows, p.pitch, p.A, p.B, lane, &count, &rows);
+    unsigned rows = 0u, rows2 = 0u;
+    int state = NWB_SPC_BAILED;
+    if (!(p.mode & 1)) state = nwb_sparse_count_pair<2>(p.arrows, p.pitch, p.A, p.B, lane, &count, &rows);
+    if (state != NWB_SPC_DONE && !(p.mode & 2)) {
+        state = nwb_sparse_count_pair<8>(p.arrows, p.pitch, p.A, p.B, lane, &count, &rows2);
+        rows += rows2;
+    }
     if (lane == 0) {
         if (state == NWB_SPC_DONE) *p.out_count = count;
         if (p.out_rows) *p.out_rows = rows;

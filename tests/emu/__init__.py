@@ -93,7 +93,7 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=Fal
                 dig_row=out.dig_row, dig_col=out.dig_col)
 
 
-def sparse_count(packed: np.ndarray, a: int) -> dict:
+def sparse_count(packed: np.ndarray, a: int, mode: int = 0) -> dict:
     """nwb_sparse_count_kernel (csrc/nwb_count_sparse.cuh) over a (B, pitch) nibble table in the include/nwb.h
     layout.  state: 1 = done (count is final), 2 = gave up (the dense sweep would run)."""
     packed = np.ascontiguousarray(packed, np.uint8)
@@ -102,8 +102,9 @@ def sparse_count(packed: np.ndarray, a: int) -> dict:
     res = (C.c_ulonglong * 3)()
     L = lib()
     L.emu_sparse_count.restype = C.c_int
-    L.emu_sparse_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
-    assert L.emu_sparse_count(packed.ctypes.data_as(C.c_void_p), pitch, a, b, res) == 0
+    L.emu_sparse_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+    # mode: 0 = as the product (64-column window first, then 256), 1 = 256-column window only, 2 = 64-column only
+    assert L.emu_sparse_count(packed.ctypes.data_as(C.c_void_p), pitch, a, b, mode, res) == 0
     return dict(count=int(res[0]), state=int(res[1]), rows=int(res[2]))
 
 

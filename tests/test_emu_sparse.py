@@ -43,6 +43,9 @@ CASES = [
 def test_sparse_count_matches_dense_dp(seed, a, b, alpha, mkd):
     top, side = oracle.generate_pair(seed, a, b, alpha)
     o, pk = _packed(top, side, *mkd, garbage=True)
+    for mode in (1, 2):
+        rm = emu.sparse_count(pk, a, mode)
+        assert rm["state"] == 2 or rm["count"] == o.count, mode
     r = emu.sparse_count(pk, a)
     if mkd == (-1, 3, -2):
         # gaps are rewarded: the optimal alignments spread over the whole 300-column table, wider than the
@@ -146,9 +149,11 @@ def test_sparse_count_random_sweep():
         mkd = [(1, 1, 1), (2, 1, 2), (1, 2, 1), (3, 1, 2), (0, 1, 1), (1, 0, 1)][it % 6]
         top, side = oracle.generate_pair(0x5EED9000 + 2 * it, a, b, alpha)
         o, pk = _packed(top, side, *mkd, garbage=bool(it & 1))
-        r = emu.sparse_count(pk, a)
-        assert r["state"] in (1, 2)
-        if r["state"] == 1:
-            assert r["count"] == o.count, (it, a, b, mkd)
-            done += 1
+        # as the product (64-column window, then 256), 256-column window only, 64-column window only
+        for mode in (0, 1, 2):
+            r = emu.sparse_count(pk, a, mode)
+            assert r["state"] in (1, 2)
+            if r["state"] == 1:
+                assert r["count"] == o.count, (it, a, b, mkd, mode)
+                done += mode == 0
     assert done >= 40
