@@ -14,7 +14,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import oracle  # noqa: E402  (input generator only)
+import nw_b200 as oracle  # noqa: E402  (the package's own SURVEY 8d generator: generate_pair, DNA, PROTEIN)
 
 OURS = os.path.join(ROOT, "needleman-wunsch_b200", "host", "needleman-wunsch")
 REF = os.path.join(ROOT, "oracle", "_ref", "needleman-wunsch")
