@@ -35,6 +35,8 @@ struct NwbBatchParams {
     uint32_t *scratch;          /* boundary streams for pairs wider than one strip: per warp n_strips_max * bpitch */
     size_t scratch_per_warp;    /* words */
     size_t bpitch;              /* words per strip boundary */
+    const long long *pair_list; /* NULL, or the pairs to fill (what nwb_batch_bp_kernel left over) ... */
+    const unsigned *pair_count; /* ... and how many of them (device word) */
 };
 
 #define NWB_BATCH_SIDE_ELEMS(maxB) ((size_t)(maxB) + NWB_BATCH_SPADB + NWB_BATCH_STAIL)
@@ -51,7 +53,9 @@ __global__ void __launch_bounds__(32 * NWB_BATCH_WARPS, 1) nwb_batch_pk_kernel(c
     unsigned char *stage = NWB_SMEM_BASE() + (size_t)warp * per_warp;
     uint16_t *side_sm = reinterpret_cast<uint16_t *>(stage + NWB_PK_WARP_SMEM(NWB_BATCH_K, NWB_BATCH_R, false));
 
-    for (long long pr = gwarp; pr < bp.n_pairs; pr += nwarps) {
+    const long long n_todo = bp.pair_list ? (long long)*bp.pair_count : bp.n_pairs;
+    for (long long q = gwarp; q < n_todo; q += nwarps) {
+        const long long pr = bp.pair_list ? bp.pair_list[q] : q;
         const long long t0 = bp.top_off[pr], s0 = bp.side_off[pr];
         const int A = (int)(bp.top_off[pr + 1] - t0), B = (int)(bp.side_off[pr + 1] - s0);
         if (A == 0 || B == 0) {

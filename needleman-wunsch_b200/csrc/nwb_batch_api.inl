@@ -11,6 +11,7 @@ struct nwb_batch {
     bool general = false; /* int32 engine, one warp per pair (nwb_batch_i32.cuh): any m/k/d, scores, |score| maximum */
     bool use_bx = false; /* two pairs per warp (nwb_batch_bx.cuh) */
     bool use_cx = false; /* ... swept back to back: every pair has the same shape */
+    bool use_bp = false; /* bit-parallel rows, one thread per pair (nwb_batch_bp.cuh) */
     bool uniform = true;
     long long uni_A = -1, uni_B = -1;
     NwbPkConsts pc = {};
@@ -25,6 +26,8 @@ struct nwb_batch {
     DevBuf<uint32_t> scratch;
     DevBuf<unsigned long long> count, cscratch; /* NWB_WANT_COUNT */
     DevBuf<unsigned long long> digest;
+    DevBuf<long long> fb_list; /* nwb_batch_bp_kernel: pairs left to nwb_batch_pk_kernel ... */
+    DevBuf<unsigned> fb_count; /* ... and their number, one word per chunk of a refill */
     /* general (int32) path */
     DevBuf<int32_t> gscores, gbnd;
     DevBuf<long long> score_off;
@@ -51,7 +54,7 @@ extern "C" void nwb_batch_free(nwb_batch *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->tops.release(); b->sides.release(); b->arrows.release(); b->top_off.release(); b->side_off.release();
     b->arrow_off.release(); b->score.release(); b->branch.release(); b->scratch.release();
-    b->count.release(); b->cscratch.release(); b->digest.release();
+    b->count.release(); b->cscratch.release(); b->digest.release(); b->fb_list.release(); b->fb_count.release();
     b->gscores.release(); b->gbnd.release(); b->score_off.release(); b->gabs.release(); b->gprogress.release(); b->gsum.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -120,6 +123,9 @@ static int batch_create_impl(const char *tops, const int64_t *top_off, const cha
          * keep the simpler kernels, for tests) */
         b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && g_tune.batch_bx != 0;
         b->use_cx = b->use_bx && n_pairs > 0 && nwb_cx_usable(pc, b->uniform, b->uni_A, (int)b->uni_B) && g_tune.batch_cx != 0;
+        /* small differences (2d + m <= 3: DNA 1/1/1) and one strip: a thread per pair, a row per addition.  Narrow
+         * tables keep the warp kernels (the row vectors are always 256 bits wide). */
+        b->use_bp = n_pairs > 0 && nwb_bp_usable(pc, b->max_A) && g_tune.batch_bp != 0 && (b->max_A > 128 || g_tune.batch_bp == 1);
     }
     if (!general && !b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
@@ -132,6 +138,8 @@ static int batch_create_impl(const char *tops, const int64_t *top_off, const cha
     if (rc == NWB_OK) rc = b->score.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK) rc = b->branch.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = b->count.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK && b->use_bp) rc = b->fb_list.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK && b->use_bp) rc = b->fb_count.ensure(NWB_BATCH_MAX_CHUNKS + 1);
     if (rc == NWB_OK && general) {
         const size_t nwarps = (size_t)b->sm_count * 2 * NWB_BI32_WARPS;
         const size_t bpitch = nwb_round_up((size_t)b->max_B + 2, 32);
@@ -197,7 +205,7 @@ static int batch_count_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c
     return NWB_OK;
 }
 
-static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1);
+static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1, int chunk);
 
 extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
 {
@@ -208,7 +216,7 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     b->fetched = false;
     if (b->n == 0) return NWB_OK;
     CK(cudaEventRecord(b->ev0, st));
-    int rc = batch_fill_pass(b, st, 0, b->n);
+    int rc = batch_fill_pass(b, st, 0, b->n, 0);
     if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, 0, b->n);
     if (rc != NWB_OK) return rc;
     CK(cudaEventRecord(b->ev1, st));
@@ -247,7 +255,7 @@ extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *side
         if (se > sb) CK(cudaMemcpyAsync(b->sides.p + sb, sides + sb, (size_t)(se - sb), cudaMemcpyHostToDevice, b->copy_stream));
         CK(cudaEventRecord(b->ev_chunk[ci], b->copy_stream));
         CK(cudaStreamWaitEvent(st, b->ev_chunk[ci], 0));
-        rc = batch_fill_pass(b, st, c0, c1);
+        rc = batch_fill_pass(b, st, c0, c1, ci);
         if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, c0, c1);
     }
     if (rc != NWB_OK) return rc;
@@ -255,7 +263,7 @@ extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *side
     return NWB_OK;
 }
 
-static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1)
+static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1, int chunk)
 {
     if (b->general) {
         NwbBatchI32Params gp;
@@ -290,6 +298,49 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
     NwbBatchParams bp;
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
+    if (b->use_bp) {
+        /* one thread per pair; whatever it cannot take (more than four letters in a top string) lands on a list
+         * that the one-warp-per-pair kernel works off right behind it (a launch that finds the list empty returns) */
+        unsigned *fbc = b->fb_count.p + chunk; /* every chunk of a refill has its own list and counter */
+        CK(cudaMemsetAsync(fbc, 0, sizeof(unsigned), st));
+        NwbBpParams pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.tops = b->tops.p; pp.top_off = b->top_off.p + c0; pp.sides = b->sides.p; pp.side_off = b->side_off.p + c0;
+        pp.n_pairs = c1 - c0; pp.d = b->d;
+        pp.arrows = b->arrows.p; pp.arrow_off = b->arrow_off.p + c0; pp.out_score = b->score.p + c0;
+        pp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
+        pp.fb_list = b->fb_list.p + c0; pp.fb_count = fbc;
+        int warps = g_tune.bp_warps > 0 ? g_tune.bp_warps : nwb_bp_choose_warps((c1 - c0 + 31) / 32, grid);
+        if (warps > NWB_BP_WARPS) warps = NWB_BP_WARPS;
+        const size_t smem = NWB_BP_SMEM_BYTES(warps);
+        int launched = 0;
+#define NWB_BP_GO(M_, N_)                                                                                            \
+    if (b->pc.a_match == M_ && b->pc.a_mis == N_) {                                                                  \
+        CK(cudaFuncSetAttribute(nwb_batch_bp_kernel<M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        nwb_batch_bp_kernel<M_, N_><<<grid, 32 * warps, smem, st>>>(pp);                                               \
+        launched = 1;                                                                                                \
+    }
+        NWB_BP_GO(1, 0) NWB_BP_GO(1, 1) NWB_BP_GO(2, 0) NWB_BP_GO(2, 1) NWB_BP_GO(2, 2)
+        NWB_BP_GO(3, 0) NWB_BP_GO(3, 1) NWB_BP_GO(3, 2) NWB_BP_GO(3, 3)
+#undef NWB_BP_GO
+        if (!launched) return NWB_ERR_UNSUPPORTED;
+        CK(cudaGetLastError());
+        int pw = (int)((220 * 1024) / NWB_BATCH_SMEM_PER_WARP(b->max_B));
+        if (pw > NWB_BATCH_WARPS) pw = NWB_BATCH_WARPS;
+        if (pw < 1) return NWB_ERR_UNSUPPORTED;
+        bp.tops = b->tops.p; bp.top_off = b->top_off.p + c0; bp.sides = b->sides.p; bp.side_off = b->side_off.p + c0;
+        bp.n_pairs = c1 - c0; bp.m = b->m; bp.k = b->k; bp.d = b->d; bp.max_B = b->max_B;
+        bp.arrows = b->arrows.p; bp.arrow_off = b->arrow_off.p + c0; bp.out_score = b->score.p + c0;
+        bp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
+        bp.bpitch = nwb_round_up((size_t)b->max_B + 1 + 64 + 256, 32);
+        bp.pair_list = pp.fb_list; bp.pair_count = fbc;
+        const size_t psmem = NWB_BATCH_SMEM_PER_WARP(b->max_B) * (size_t)pw;
+        CK(cudaFuncSetAttribute(nwb_batch_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        nwb_batch_pk_kernel<<<grid, 32 * pw, psmem, st>>>(bp, b->pc);
+        CK(cudaGetLastError());
+        b->launches += 2;
+        return NWB_OK;
+    }
     if (b->use_bx) {
         int warps = (int)((220 * 1024) / NWB_BX_SMEM_PER_WARP(b->max_B));
         if (warps > NWB_BX_WARPS) warps = NWB_BX_WARPS;
@@ -433,6 +484,7 @@ extern "C" const char *nwb_batch_kernel_name(const nwb_batch *b)
 {
     if (!b) return "";
     if (b->general) return "nwb_batch_i32_kernel";
+    if (b->use_bp) return "nwb_batch_bp_kernel";
     return b->use_cx ? "nwb_batch_cx_kernel" : (b->use_bx ? "nwb_batch_bx_kernel" : "nwb_batch_pk_kernel");
 }
 extern "C" int64_t nwb_batch_launches(const nwb_batch *b) { return b ? b->launches : 0; }

@@ -1,0 +1,391 @@
+/*
+ * nwb_batch_bp.cuh -- bit-parallel batch fill ("bp"): one THREAD per pair, a table row is a handful of
+ * 256-bit vectors, one addition per difference level resolves a whole row.
+ *
+ * Same results as the reference's score_cell() (needleman-wunsch.c:418-510: the recurrence and "every tie
+ * gets its arrow", :485-503) for top strings of up to 256 characters with at most four distinct letters,
+ * when the per-cell differences are small (M = 2d + m <= 3: DNA 1/1/1 has M = 3).
+ *
+ * With r(i,j) = score(i,j) + d(i+j) (nwb_fill_pk.cuh) the differences u = r(i,j) - r(i-1,j) and
+ * v = r(i,j) - r(i,j-1) lie in [0, M] and per cell
+ *     z = max(a, vL, uU),  u = z - vL,  v = z - uU,       a = M on a match, N = 2d - k otherwise
+ *     DIAG <=> z == a,  LEFT <=> u == 0,  UP <=> v == 0.
+ * Along a row, v(i) = max(y(i), v(i-1) - uU(i)) with y = max(a - uU, 0).  For the level sets
+ * V_k = [v >= k] (bit i-1 = column i) this reads
+ *     V_k = S_k | ((V_k << 1) & P),   P = [uU == 0],
+ *     S_k = [y >= k] | OR_{t>=1} ((V_{k+t} << 1) & [uU <= t]),
+ * and "seeds S run through the runs of P" is ONE multi-word addition (the carry does the running, as in
+ * Myers' bit-vector algorithm):  V_k = S_k | (((S_k & P') + P') ^ P'),  P' = P >> 1.  M additions per
+ * row, levels from M down to 1; u of the new row = v + uU - vL in bit-sliced binary, the three arrow
+ * planes are zero tests on the same vectors.  ~36 logic instructions per 32 cells instead of ~200.
+ *
+ * Mapping: lane = pair.  A warp sweeps 32 pairs row by row; every lane keeps its row state (u as binary
+ * bit-planes, 8 words each) in registers, the match vectors of its top string (one per letter) in shared
+ * memory, and needs no shuffle and no carry from any other lane.  The arrow planes become the ABI's
+ * 4-bit codes (include/nwb.h) through a byte -> 8-nibble table in shared memory (one copy per lane, so
+ * no bank conflicts), and a row of the warp (32 pairs x 128 bytes) leaves through a swizzled staging
+ * buffer so that every store instruction writes whole 128-byte lines.
+ *
+ * Pairs whose top string has more than four distinct letters are not computed here: they are put on a
+ * list that nwb_batch_pk_kernel works off afterwards (nwb_batch_api.inl).  tools/bp_proto.py is the
+ * executable statement of the formulation (Python integers as bit-vectors, checked against the oracle).
+ */
+#pragma once
+#include "nwb_batch.cuh"
+
+#define NWB_BP_NW 8     /* 32-bit words per row vector: up to 256 columns */
+#define NWB_BP_NSYM 4   /* letters with a match vector */
+#define NWB_BP_MAXM 3   /* instantiated difference ranges */
+#define NWB_BP_WARPS 16
+#define NWB_BP_SIDE_ROWS 64
+#define NWB_BP_LUT_BYTES (256 * 32 * 4)
+#define NWB_BP_PEQ_BYTES ((NWB_BP_NSYM + 1) * NWB_BP_NW * 32 * 4)
+#define NWB_BP_STAGE_BYTES (32 * 128)
+#define NWB_BP_SIDE_BYTES (NWB_BP_SIDE_ROWS * 32)
+#define NWB_BP_META_BYTES (32 * 8)
+#define NWB_BP_WARP_SMEM (NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES + NWB_BP_SIDE_BYTES + NWB_BP_META_BYTES)
+#define NWB_BP_SMEM_BYTES(warps) ((size_t)NWB_BP_LUT_BYTES + (size_t)(warps) * NWB_BP_WARP_SMEM)
+
+struct NwbBpParams {
+    const uint8_t *tops;
+    const long long *top_off;   /* n_pairs + 1 */
+    const uint8_t *sides;
+    const long long *side_off;  /* n_pairs + 1 */
+    long long n_pairs;
+    int d;
+    uint8_t *arrows;            /* all pairs' nibble tables (pitch 128: one strip) */
+    const long long *arrow_off; /* byte offset of pair p's table, a multiple of 128 */
+    int *out_score;             /* [n_pairs] */
+    unsigned *out_branch;       /* [n_pairs] or NULL */
+    long long *fb_list;         /* pairs this kernel leaves to nwb_batch_pk_kernel (more than 4 letters) */
+    unsigned *fb_count;
+};
+
+/* usable for this batch?  (m, k, d) inside the packed range, M = 2d + m <= 3, every top string <= 256 */
+static inline bool nwb_bp_usable(const NwbPkConsts &pc, long long max_A)
+{
+    return pc.a_match >= 1 && pc.a_match <= NWB_BP_MAXM && pc.a_mis >= 0 && pc.a_mis <= pc.a_match && max_A <= 32 * NWB_BP_NW;
+}
+
+/* Warps per block: every group of 32 pairs costs the same, so the groups are worked off in rounds of
+ * grid x warps; among the block sizes that need the fewest rounds take the smallest (the last round is the
+ * fullest, and fewer resident warps leave each one more of the SM). */
+static inline int nwb_bp_choose_warps(long long groups, int grid)
+{
+    if (groups <= 0 || grid <= 0) return NWB_BP_WARPS;
+    const long long rounds = (groups + (long long)grid * NWB_BP_WARPS - 1) / ((long long)grid * NWB_BP_WARPS);
+    int w = (int)((groups + rounds * grid - 1) / (rounds * grid));
+    if (w < 4) w = 4;
+    if (w > NWB_BP_WARPS) w = NWB_BP_WARPS;
+    return w;
+}
+
+/* [x >= k] of a bit-sliced value (pl[0] = least significant plane); k is a compile-time constant after unrolling */
+template <int NB>
+__device__ __forceinline__ unsigned nwb_bp_ge(const unsigned (&pl)[NB][NWB_BP_NW], const int k, const int w)
+{
+    if (k <= 0) return 0xFFFFFFFFu;
+    if (k >= (1 << NB)) return 0u;
+    unsigned res = 0xFFFFFFFFu;
+#pragma unroll
+    for (int t = 0; t < NB; t++) res = ((k >> t) & 1) ? (pl[t][w] & res) : (pl[t][w] | res);
+    return res;
+}
+
+/* s = a + b over NWB_BP_NW words (one carry chain) */
+__device__ __forceinline__ void nwb_bp_add(unsigned (&s)[NWB_BP_NW], const unsigned (&a)[NWB_BP_NW], const unsigned (&b)[NWB_BP_NW])
+{
+#ifdef NWB_EMU
+    unsigned long long c = 0ull;
+    for (int w = 0; w < NWB_BP_NW; w++) {
+        c += (unsigned long long)a[w] + b[w];
+        s[w] = (unsigned)c;
+        c >>= 32;
+    }
+#else
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#endif
+}
+
+/* binary planes of a level-set (thermometer) code th[1..M] */
+template <int M, int NB>
+__device__ __forceinline__ void nwb_bp_binary(unsigned (&out)[NB][NWB_BP_NW], const unsigned (&th)[M + 2][NWB_BP_NW])
+{
+#pragma unroll
+    for (int w = 0; w < NWB_BP_NW; w++) {
+#pragma unroll
+        for (int t = 0; t < NB; t++) {
+            unsigned p = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lo = (1 << t) * (2 * q + 1), hi = (1 << t) * (2 * q + 2);
+                if (lo <= M) p |= (hi <= M) ? (th[lo][w] & ~th[hi][w]) : th[lo][w];
+            }
+            out[t][w] = p;
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned nwb_bp_load_word(const uint8_t *s, const long long off, const bool aligned)
+{
+    if (aligned) return *reinterpret_cast<const unsigned *>(s + off);
+    return (unsigned)s[off] | ((unsigned)s[off + 1] << 8) | ((unsigned)s[off + 2] << 16) | ((unsigned)s[off + 3] << 24);
+}
+
+template <int M, int N>
+__global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(const NwbBpParams bp)
+{
+    constexpr int NB = (M >= 4) ? 3 : ((M >= 2) ? 2 : 1);
+    constexpr int NW = NWB_BP_NW;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = (int)(blockDim.x >> 5);
+    const long long nwarps = (long long)gridDim.x * wpb;
+    const long long gwarp = (long long)blockIdx.x * wpb + warp;
+    unsigned char *smem = NWB_SMEM_BASE();
+    unsigned *lut = reinterpret_cast<unsigned *>(smem);
+    unsigned char *mine = smem + NWB_BP_LUT_BYTES + (size_t)warp * NWB_BP_WARP_SMEM;
+    unsigned *peq = reinterpret_cast<unsigned *>(mine);                                  /* [letter 0..4][word][lane] */
+    uint4 *stage = reinterpret_cast<uint4 *>(mine + NWB_BP_PEQ_BYTES);                  /* [lane][8 swizzled 16-byte chunks] */
+    uint8_t *side_sm = mine + NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES;                    /* [row & 63][lane] */
+    uint2 *meta = reinterpret_cast<uint2 *>(mine + NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES + NWB_BP_SIDE_BYTES); /* {table row 0 / 128, rows} */
+
+    /* byte -> 8 nibbles (bit i -> bit 4i), one copy per lane: entry x of lane l sits in bank l */
+    for (int x = warp; x < 256; x += wpb) {
+        unsigned v = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v |= ((unsigned)(x >> i) & 1u) << (4 * i);
+        lut[x * 32 + lane] = v;
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) peq[(NWB_BP_NSYM * NW + w) * 32 + lane] = 0u; /* a side letter the top string does not have */
+    __syncthreads();
+    const unsigned *mylut = lut + lane;
+
+    const long long groups = (bp.n_pairs + 31) / 32;
+    for (long long g = gwarp; g < groups; g += nwarps) {
+        const long long p = g * 32 + lane;
+        const bool valid = p < bp.n_pairs;
+        long long t0 = 0, s0 = 0;
+        int A = 0, B = 0;
+        if (valid) {
+            t0 = bp.top_off[p];
+            s0 = bp.side_off[p];
+            A = (int)(bp.top_off[p + 1] - t0);
+            B = (int)(bp.side_off[p + 1] - s0);
+        }
+        /* ---- match vectors of my top string: at most four distinct letters ---- */
+        unsigned l0 = 0x100u, l1 = 0x101u, l2 = 0x102u, l3 = 0x103u; /* no byte equals an unassigned letter */
+        int nlet = 0;
+        bool over = false;
+        const bool t_al = __all_sync(NWB_FULL_MASK, (t0 & 3) == 0);
+        int maxA = A;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int x = __shfl_xor_sync(NWB_FULL_MASK, maxA, o);
+            maxA = x > maxA ? x : maxA;
+        }
+#pragma unroll 1
+        for (int w = 0; w < NW; w++) {
+            unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+            if (32 * w < maxA) {
+#pragma unroll 1
+                for (int q = 0; q < 8; q++) {
+                    const int col = 32 * w + 4 * q;
+                    unsigned word = 0u;
+                    if (col < A) word = nwb_bp_load_word(bp.tops, t0 + col, t_al);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const unsigned c = (word >> (8 * e)) & 0xFFu;
+                        if (col + e < A) {
+                            bool h0 = c == l0, h1 = c == l1, h2 = c == l2, h3 = c == l3;
+                            if (!(h0 || h1 || h2 || h3)) {
+                                if (nlet == 0) { l0 = c; h0 = true; }
+                                else if (nlet == 1) { l1 = c; h1 = true; }
+                                else if (nlet == 2) { l2 = c; h2 = true; }
+                                else if (nlet == 3) { l3 = c; h3 = true; }
+                                else over = true;
+                                nlet++;
+                            }
+                            const unsigned bit = 1u << (4 * q + e);
+                            if (h0) a0 |= bit;
+                            if (h1) a1 |= bit;
+                            if (h2) a2 |= bit;
+                            if (h3) a3 |= bit;
+                        }
+                    }
+                }
+            }
+            peq[(0 * NW + w) * 32 + lane] = a0;
+            peq[(1 * NW + w) * 32 + lane] = a1;
+            peq[(2 * NW + w) * 32 + lane] = a2;
+            peq[(3 * NW + w) * 32 + lane] = a3;
+        }
+        if (valid && over) { /* not mine: the general batch kernel takes this pair */
+            const unsigned pos = atomicAdd(bp.fb_count, 1u);
+            bp.fb_list[pos] = p;
+        }
+        if (valid && !over && (A == 0 || B == 0)) { /* borders only */
+            bp.out_score[p] = (A == 0) ? -B * bp.d : -A * bp.d;
+            if (bp.out_branch) bp.out_branch[p] = 0u;
+        }
+        const int Brun = (valid && !over && A > 0) ? B : 0; /* rows this lane computes and stores */
+        meta[lane] = make_uint2(valid ? (unsigned)(bp.arrow_off[p] >> 7) : 0u, (unsigned)Brun);
+        int maxB = Brun;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int x = __shfl_xor_sync(NWB_FULL_MASK, maxB, o);
+            maxB = x > maxB ? x : maxB;
+        }
+        const bool full = __all_sync(NWB_FULL_MASK, A == 32 * NW || Brun == 0); /* no column masks needed */
+        const bool s_al = __all_sync(NWB_FULL_MASK, (s0 & 3) == 0);
+        __syncwarp();
+
+        unsigned uu[NB][NW]; /* u of the row above, bit-sliced */
+#pragma unroll
+        for (int t = 0; t < NB; t++)
+#pragma unroll
+            for (int w = 0; w < NW; w++) uu[t][w] = 0u;
+        unsigned branches = 0u;
+        int rsum = 0;
+
+#pragma unroll 1
+        for (int j = 0; j < maxB; j++) {
+            if ((j & (NWB_BP_SIDE_ROWS - 1)) == 0) {
+                /* my next 64 side letters, one byte per row; only I read them back */
+#pragma unroll 1
+                for (int q = 0; q < NWB_BP_SIDE_ROWS / 4; q++) {
+                    const int row = j + 4 * q;
+                    unsigned word = 0u;
+                    if (row < Brun) word = nwb_bp_load_word(bp.sides, s0 + row, s_al);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) side_sm[(4 * q + e) * 32 + lane] = (uint8_t)(word >> (8 * e));
+                }
+            }
+            const unsigned c = side_sm[(j & (NWB_BP_SIDE_ROWS - 1)) * 32 + lane];
+            const int slot = (c == l0) ? 0 : ((c == l1) ? 1 : ((c == l2) ? 2 : ((c == l3) ? 3 : NWB_BP_NSYM)));
+            const unsigned *pe = peq + slot * (NW * 32) + lane;
+            unsigned E[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) E[w] = pe[w * 32];
+
+            /* P' = [uU == 0] >> 1 */
+            unsigned Pp[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const unsigned Pw = ~nwb_bp_ge<NB>(uu, 1, w);
+                const unsigned Pn = (w + 1 < NW) ? ~nwb_bp_ge<NB>(uu, 1, w + 1) : 0u;
+                Pp[w] = __funnelshift_r(Pw, Pn, 1);
+            }
+            unsigned V[M + 2][NW], Vs[M + 2][NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) { V[0][w] = 0xFFFFFFFFu; Vs[0][w] = 0xFFFFFFFFu; V[M + 1][w] = 0u; Vs[M + 1][w] = 0u; }
+#pragma unroll
+            for (int k = M; k >= 1; k--) {
+                unsigned S[NW], T[NW], sum[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    unsigned y = E[w] & ~nwb_bp_ge<NB>(uu, M - k + 1, w);
+                    if (k <= N) y |= ~E[w] & ~nwb_bp_ge<NB>(uu, N - k + 1, w);
+#pragma unroll
+                    for (int t = 1; t <= M - k; t++) y |= Vs[k + t][w] & ~nwb_bp_ge<NB>(uu, t + 1, w);
+                    S[w] = y;
+                    T[w] = y & Pp[w];
+                }
+                nwb_bp_add(sum, T, Pp);
+#pragma unroll
+                for (int w = 0; w < NW; w++) V[k][w] = S[w] | (sum[w] ^ Pp[w]);
+#pragma unroll
+                for (int w = 0; w < NW; w++) Vs[k][w] = (w > 0) ? __funnelshift_l(V[k][w - 1], V[k][w], 1) : (V[k][0] << 1);
+            }
+            unsigned v[NB][NW], vl[NB][NW];
+            nwb_bp_binary<M, NB>(v, V);
+            nwb_bp_binary<M, NB>(vl, Vs);
+            unsigned Dp[NW], Lp[NW], Up[NW];
+            unsigned rowbr = 0u;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                /* u of this row = v + uU - vL (mod 2^NB: the result lies in [0, M]); z = v + uU */
+                unsigned un[NB], z[NB];
+                unsigned borrow = 0u, carry = 0u, zc = 0u;
+#pragma unroll
+                for (int t = 0; t < NB; t++) {
+                    const unsigned x = v[t][w] ^ vl[t][w] ^ borrow; /* v - vL */
+                    borrow = (~v[t][w] & (vl[t][w] | borrow)) | (vl[t][w] & borrow);
+                    un[t] = x ^ uu[t][w] ^ carry;
+                    carry = (x & uu[t][w]) | (carry & (x ^ uu[t][w]));
+                    z[t] = v[t][w] ^ uu[t][w] ^ zc;
+                    zc = (v[t][w] & uu[t][w]) | (zc & (v[t][w] ^ uu[t][w]));
+                }
+                unsigned eqM = 0xFFFFFFFFu, eqN = 0xFFFFFFFFu, nz = 0u;
+#pragma unroll
+                for (int t = 0; t < NB; t++) {
+                    eqM &= ((M >> t) & 1) ? z[t] : ~z[t];
+                    eqN &= ((N >> t) & 1) ? z[t] : ~z[t];
+                    nz |= un[t];
+                }
+                unsigned dg = (E[w] & eqM) | (~E[w] & eqN);
+                unsigned lf = ~nz;
+                unsigned up = ~V[1][w];
+                if (!full) { /* columns beyond my top string: no arrows, no branch cells */
+                    const int left = A - 32 * w;
+                    const unsigned cm = (left >= 32) ? 0xFFFFFFFFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
+                    dg &= cm; lf &= cm; up &= cm;
+                }
+                Dp[w] = dg; Lp[w] = lf; Up[w] = up;
+                rowbr += (unsigned)__popc((dg & lf) | (dg & up) | (lf & up));
+#pragma unroll
+                for (int t = 0; t < NB; t++) uu[t][w] = un[t];
+            }
+            if (j < Brun) branches += rowbr;
+            if (j == Brun - 1) { /* r(A,B) = sum of u(i,B) over my columns */
+                int r = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    const int left = A - 32 * w;
+                    const unsigned cm = (left >= 32) ? 0xFFFFFFFFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
+#pragma unroll
+                    for (int t = 0; t < NB; t++) r += __popc(uu[t][w] & cm) << t;
+                }
+                rsum = r;
+            }
+            /* planes -> 4-bit codes (DIAG | LEFT << 1 | UP << 2), my 128-byte row into the staging buffer */
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                unsigned o[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned xd = (Dp[w] >> (8 * q)) & 0xFFu, xl = (Lp[w] >> (8 * q)) & 0xFFu, xu = (Up[w] >> (8 * q)) & 0xFFu;
+                    o[q] = mylut[xd * 32] + 2u * mylut[xl * 32] + 4u * mylut[xu * 32];
+                }
+                stage[lane * 8 + ((w + lane) & 7)] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+            /* lanes 8h..8h+7 store the row of pair 4i + h: whole 128-byte lines */
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int L = 4 * i + (lane >> 3), ch = lane & 7;
+                const uint4 val = stage[L * 8 + ((ch + L) & 7)];
+                const uint2 mt = meta[L];
+                if ((unsigned)j < mt.y)
+                    *reinterpret_cast<uint4 *>(bp.arrows + (((size_t)mt.x + (size_t)j) << 7) + (size_t)ch * 16) = val;
+            }
+            __syncwarp();
+        }
+        if (Brun > 0) {
+            bp.out_score[p] = rsum - bp.d * (A + B);
+            if (bp.out_branch) bp.out_branch[p] = branches;
+        }
+        __syncwarp();
+    }
+}

@@ -194,6 +194,38 @@ def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1, count=False):
                 counts=counts)
 
 
+def fill_batch_bp(tops, sides, m, k, d, *, grid=1, warps=2):
+    """nwb_batch_bp_kernel (csrc/nwb_batch_bp.cuh: bit-parallel rows, one thread per pair) under the emulator,
+    followed by nwb_batch_pk_kernel over the pairs it left over.  Returns None when the batch does not qualify."""
+    build()
+    L = lib()
+    n = len(tops)
+    tops = [_b(t) for t in tops]
+    sides = [_b(s) for s in sides]
+    toff = np.zeros(n + 1, dtype=np.int64)
+    soff = np.zeros(n + 1, dtype=np.int64)
+    toff[1:] = np.cumsum([len(t) for t in tops])
+    soff[1:] = np.cumsum([len(s) for s in sides])
+    aoff = np.zeros(n + 1, dtype=np.int64)
+    total = int(sum(128 * len(s) for s in sides))
+    arrows = np.full(total + 16, 0xEE, dtype=np.uint8)
+    scores = np.zeros(n + 1, dtype=np.int32)
+    branches = np.zeros(n + 1, dtype=np.uint32)
+    nfb = C.c_longlong(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.emu_fill_batch_bp.restype = C.c_int
+    L.emu_fill_batch_bp.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                    C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]
+    # the kernels read up to 3 bytes past a string (aligned word loads): pad like the product's device buffers
+    rc = L.emu_fill_batch_bp(b"".join(tops) + b"\0" * 16, p(toff), b"".join(sides) + b"\0" * 16, p(soff), n, m, k, d, grid, warps,
+                             p(arrows), p(aoff), p(scores), p(branches), C.byref(nfb))
+    if rc == -6:
+        return None
+    assert rc == 0, rc
+    tables = [arrows[int(aoff[i]):int(aoff[i + 1])].reshape(len(sides[i]), 128) for i in range(n)]
+    return {"tables": tables, "scores": scores[:n].copy(), "branches": branches[:n].copy(), "n_fallback": int(nfb.value)}
+
+
 def fill_batch_i32(tops, sides, m, k, d, *, grid=1, want_scores=False, want_abs=True):
     """nwb_batch_i32_kernel (csrc/nwb_batch_i32.cuh: any m / k / d, one warp per pair) under the emulator."""
     n = len(tops)

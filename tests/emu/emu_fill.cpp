@@ -14,6 +14,7 @@
 #include "nwb_count.cuh"
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
+#include "nwb_batch_bp.cuh"
 #include "nwb_batch_count.cuh"
 #include "nwb_batch_i32.cuh"
 
@@ -31,6 +32,19 @@ static void run_pk_emu(unsigned grid, int warps, const NwbStripParams &p, const 
 {
     emu_launch(grid, 32 * warps, (size_t)warps * NWB_PK_WARP_SMEM(K, R, COUNT),
                [&]() { nwb_fill_pk_kernel<K, R, COUNT>(p, pc); });
+}
+
+template <int M>
+static bool emu_bp_go(int N, unsigned grid, int warps, const NwbBpParams &p)
+{
+    const size_t smem = NWB_BP_SMEM_BYTES(warps);
+    switch (N) {
+    case 0: emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, 0>(p); }); return true;
+    case 1: if (M >= 1) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 1 ? 1 : 0)>(p); }); return true; } break;
+    case 2: if (M >= 2) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 2 ? 2 : 0)>(p); }); return true; } break;
+    case 3: if (M >= 3) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 3 ? 3 : 0)>(p); }); return true; } break;
+    }
+    return false;
 }
 
 extern "C" {
@@ -511,6 +525,54 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
     bp.out_branch = branches;
     emu_launch(grid, 32 * NWB_BATCH_WARPS, NWB_BATCH_SMEM_PER_WARP(maxB) * NWB_BATCH_WARPS,
                [&]() { nwb_batch_pk_kernel(bp, pc); });
+    return 0;
+}
+
+/* nwb_batch_bp_kernel<M, N> (bit-parallel rows, one thread per pair) followed, as in batch_fill_pass(), by
+ * nwb_batch_pk_kernel over the pairs it left on its list (more than four distinct letters in the top string).
+ * *n_fallback reports how many those were.  -6: the batch does not qualify. */
+int emu_fill_batch_bp(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
+                      long long n, int m, int k, int d, unsigned grid, int warps, uint8_t *arrows, long long *arrow_off,
+                      int *scores, unsigned *branches, long long *n_fallback)
+{
+    NwbPkConsts pc;
+    if (!nwb_pk_supported(m, k, d, &pc)) return -5;
+    long long maxA = 0, aoff = 0;
+    int maxB = 0;
+    for (long long p = 0; p < n; p++) {
+        const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
+        if (A > maxA) maxA = A;
+        if (B > maxB) maxB = (int)B;
+        arrow_off[p] = aoff;
+        aoff += 128 * B;
+    }
+    arrow_off[n] = aoff;
+    if (!nwb_bp_usable(pc, maxA)) return -6;
+    std::vector<long long> fb((size_t)n + 1, -1);
+    unsigned fbn = 0;
+    NwbBpParams p;
+    memset(&p, 0, sizeof(p));
+    p.tops = (const uint8_t *)tops; p.top_off = top_off; p.sides = (const uint8_t *)sides; p.side_off = side_off;
+    p.n_pairs = n; p.d = d; p.arrows = arrows; p.arrow_off = arrow_off; p.out_score = scores; p.out_branch = branches;
+    p.fb_list = fb.data(); p.fb_count = &fbn;
+    bool ok = false;
+    switch (pc.a_match) {
+    case 1: ok = emu_bp_go<1>(pc.a_mis, grid, warps, p); break;
+    case 2: ok = emu_bp_go<2>(pc.a_mis, grid, warps, p); break;
+    case 3: ok = emu_bp_go<3>(pc.a_mis, grid, warps, p); break;
+    }
+    if (!ok) return -6;
+    if (n_fallback) *n_fallback = fbn;
+    if (fbn) {
+        NwbBatchParams bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.tops = (const uint8_t *)tops; bp.top_off = top_off; bp.sides = (const uint8_t *)sides; bp.side_off = side_off;
+        bp.n_pairs = n; bp.m = m; bp.k = k; bp.d = d; bp.max_B = maxB;
+        bp.arrows = arrows; bp.arrow_off = arrow_off; bp.out_score = scores; bp.out_branch = branches;
+        bp.bpitch = nwb_round_up((size_t)maxB + 1 + 64 + 256, 32);
+        bp.pair_list = fb.data(); bp.pair_count = &fbn;
+        emu_launch(grid, 32 * NWB_BATCH_WARPS, NWB_BATCH_SMEM_PER_WARP(maxB) * NWB_BATCH_WARPS, [&]() { nwb_batch_pk_kernel(bp, pc); });
+    }
     return 0;
 }
 }

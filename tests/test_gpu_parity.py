@@ -396,6 +396,87 @@ def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
         b0.close()
 
 
+def test_batch_bit_parallel(oracle, nwb):
+    """csrc/nwb_batch_bp.cuh nwb_batch_bp_kernel: one thread per pair, rows as bit-vectors (2d + m <= 3, top strings of
+    at most 256 characters).  Config 4's goldens, ragged shapes, empty strings, unaligned offsets, more groups of 32
+    pairs than warps, side letters the top string does not have, top strings with more than four letters (worked off
+    by nwb_batch_pk_kernel from the kernel's list), every instantiated (2d + m, 2d - k); the same batches through
+    the packed-difference kernels (nwb_tune batch_bp = 0) must agree on every pair."""
+    rng = random.Random(37)
+    n = 9000
+    idx = list(range(n - 1)) + [999999]
+    tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
+    with nwb.tuned(batch_bp=1):
+        bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST | nwb.WANT_COUNT)
+    assert bt.kernel_name() == "nwb_batch_bp_kernel"
+    bt.run()
+    bt.fetch()
+    assert (bt.opt_score(0), bt.branch_count(0), bt.count(0)) == (19, 23713, 387701138034524160)
+    assert (bt.opt_score(1), bt.branch_count(1), bt.count(1)) == (29, 22912, 108460706365440)
+    assert (bt.opt_score(n - 1), bt.branch_count(n - 1), bt.count(n - 1)) == (19, 22090, 4971798065203200)
+    _batch_check(oracle, nwb, bt, tops, sides, 1, 1, 1, rng.sample(range(n), 50))
+    dg = bt.digest(0)
+    bt.close()
+    with nwb.tuned(batch_bp=0):
+        b0 = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_COUNT)
+    assert b0.kernel_name() == "nwb_batch_cx_kernel"
+    b0.run()
+    b0.fetch()
+    assert b0.digest(0) == dg          # every pair: arrow tables, scores, branch counters, counts
+    b0.close()
+    lens = [(256, 256), (1, 1), (255, 257), (3, 40), (17, 130), (0, 5), (200, 90), (64, 64), (256, 1), (33, 33),
+            (256, 31), (100, 300), (5, 0), (8, 32), (9, 33), (249, 63), (250, 64), (7, 65), (1, 200), (256, 2),
+            (0, 0), (31, 31), (130, 95), (96, 128), (256, 1000)] + \
+           [(rng.randint(1, 256), rng.randint(1, 400)) for _ in range(6000)]
+    alphas = [b"ACGT"] * 6 + [b"ACGTN", b"AC", bytes(range(1, 256)), b"ARNDCQEGHILKMFPSTWYV"]
+    tops = [bytes(rng.choice(rng.choice(alphas)) for _ in range(a)) for a, _ in lens]
+    sides = [bytes(rng.choice(b"ACGTNX") for _ in range(b)) for _, b in lens]
+    sample = list(range(25)) + rng.sample(range(25, len(lens)), 150) + [len(lens) - 1]
+    sample += [i for i in range(25, 400) if len(set(tops[i])) > 4][:20]
+    for m, k, d in ((1, 1, 1), (0, 0, 1), (1, -1, 0), (3, 0, 0), (1, 2, 1), (0, 1, 1), (2, -1, 0)):
+        with nwb.tuned(batch_bp=1):
+            bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+        assert bt.kernel_name() == "nwb_batch_bp_kernel", (m, k, d)
+        bt.run()
+        bt.fetch()
+        _batch_check(oracle, nwb, bt, tops, sides, m, k, d, sample if (m, k, d) == (1, 1, 1) else sample[:60])
+        dg = bt.digest(0)
+        bt.close()
+        with nwb.tuned(batch_bp=0):
+            b0 = nwb.Batch(tops, sides, m, k, d, 0)
+        assert b0.kernel_name() != "nwb_batch_bp_kernel"
+        b0.run()
+        b0.fetch()
+        assert b0.digest(0)[:3] == dg[:3], (m, k, d)
+        b0.close()
+    # refill from host buffers in chunks (every chunk has its own left-over list)
+    n = 40000
+    tcat = nwb.generate(0x5EED4000, 256, nwb.DNA, count=n, seed_stride=2)
+    scat = nwb.generate(0x5EED4001, 256, nwb.DNA, count=n, seed_stride=2)
+    tmix = bytearray(tcat)
+    for p in range(0, n, 997):      # some pairs with five letters in the top string
+        tmix[p * 256:p * 256 + 5] = b"ACGTN"
+    off = np.arange(n + 1, dtype=np.int64) * 256
+    res = {}
+    for knob in (1, 0):
+        with nwb.tuned(batch_bp=knob):
+            bt = nwb.Batch.from_arrays(tcat, off, scat, off, 1, 1, 1, 0)
+        bt.refill(bytes(tmix), scat)
+        bt.fetch()
+        res[knob] = (bt.digest(0)[:3], bt.opt_score(997), bt.branch_count(n - 1))
+        bt.close()
+    assert res[1] == res[0]
+    # not for this kernel: 2d + m > 3, strings wider than a strip
+    with nwb.tuned(batch_bp=1):
+        bt = nwb.Batch(tops[:4], sides[:4], 2, 1, 2, 0)
+        assert bt.kernel_name() != "nwb_batch_bp_kernel"
+        bt.close()
+        bt = nwb.Batch([b"A" * 300], [b"C" * 10], 1, 1, 1, 0)
+        assert bt.kernel_name() != "nwb_batch_bp_kernel"
+        bt.close()
+
+
+
 def test_batch_count(oracle, nwb):
     """NWB_WANT_COUNT on the batch path (csrc/nwb_batch_count.cuh): SURVEY 8c's config 4 counts, ragged shapes,
     pairs wider than one strip, empty strings, wrap-around mod 2^64 (0/0/0)."""
