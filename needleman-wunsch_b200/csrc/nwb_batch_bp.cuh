@@ -17,7 +17,8 @@
  * and "seeds S run through the runs of P" is ONE multi-word addition (the carry does the running, as in
  * Myers' bit-vector algorithm):  V_k = S_k | (((S_k & P') + P') ^ P'),  P' = P >> 1.  M additions per
  * row, levels from M down to 1; u of the new row = v + uU - vL in bit-sliced binary, the three arrow
- * planes are zero tests on the same vectors.  ~36 logic instructions per 32 cells instead of ~200.
+ * planes are zero tests on the same vectors: 23 logic instructions, 4 shifts and 3 additions per 32 cells
+ * for DNA 1/1/1 (nwb_bp_row), against ~200 instructions for the packed-difference kernels.
  *
  * Mapping: lane = pair.  A warp sweeps 32 pairs row by row; every lane keeps its row state (u as binary
  * bit-planes, 8 words each) in registers, the match vectors of its top string (one per letter) in shared
@@ -142,6 +143,254 @@ __device__ __forceinline__ unsigned nwb_bp_load_word(const uint8_t *s, const lon
     return (unsigned)s[off] | ((unsigned)s[off + 1] << 8) | ((unsigned)s[off + 2] << 16) | ((unsigned)s[off + 3] << 24);
 }
 
+/* d = f(a, b, c) bit by bit, f given by its truth table over NWB_LOP_A / _B / _C (one LOP3) */
+#define NWB_LOP_A 0xF0
+#define NWB_LOP_B 0xCC
+#define NWB_LOP_C 0xAA
+template <int LUT>
+__device__ __forceinline__ unsigned nwb_lop3(const unsigned a, const unsigned b, const unsigned c)
+{
+#ifdef NWB_EMU
+    unsigned r = 0u;
+    for (int i = 0; i < 8; i++)
+        if (((LUT & 0xFF) >> i) & 1) r |= ((i & 4) ? a : ~a) & ((i & 2) ? b : ~b) & ((i & 1) ? c : ~c);
+    return r;
+#else
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT & 0xFF));
+    return d;
+#endif
+}
+
+/* entry (byte q of x, or of ~x) of the lane's copy of the byte -> nibbles table */
+template <bool INV>
+__device__ __forceinline__ unsigned nwb_bp_lut(const unsigned *mylut, const unsigned x, const int q)
+{
+    const int idx = (int)__byte_perm(x, 0u, 0x4440u + (unsigned)q); /* one PRMT */
+    return INV ? mylut[255 * 32 - idx * 32] : mylut[idx * 32];          /* INV: the entry of ~x */
+}
+
+/* One row of one pair: E = match vector of the row's side letter, uu = u of the row above (bit-sliced; replaced by
+ * this row's u).  Out: D = DIAG plane, Ln = NOT LEFT (u != 0), Un = NOT UP (v != 0). */
+template <int M, int N, int NB>
+__device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsigned (&uu)[NB][NWB_BP_NW], unsigned (&D)[NWB_BP_NW],
+                                            unsigned (&Ln)[NWB_BP_NW], unsigned (&Un)[NWB_BP_NW])
+{
+    constexpr int NW = NWB_BP_NW;
+    if constexpr (M == 3 && N == 1) {
+        /* DNA 1/1/1, written out so that every intermediate is a function of three words, one LOP3 each (the
+         * look-up tables are spelled out: the compiler does not find them from the generic expressions):
+         * 22 logic instructions, 4 funnel shifts and 3 additions per 32 cells.  uU = (b1, b0). */
+        constexpr int A_ = NWB_LOP_A, B_ = NWB_LOP_B, C_ = NWB_LOP_C;
+        unsigned P[NW], Pp[NW], S[NW], T[NW], sum[NW], V3[NW], V2[NW], V1[NW], V3s[NW], V2s[NW], V1s[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) P[w] = nwb_lop3<~(A_ | B_)>(uu[1][w], uu[0][w], 0u);
+#pragma unroll
+        for (int w = 0; w < NW; w++) Pp[w] = __funnelshift_r(P[w], (w + 1 < NW) ? P[w + 1] : 0u, 1);
+        /* level 3: y >= 3 <=> match and uU == 0 */
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            S[w] = nwb_lop3<A_ & B_>(E[w], P[w], 0u);
+            T[w] = nwb_lop3<A_ & B_ & C_>(E[w], P[w], Pp[w]);
+        }
+        nwb_bp_add(sum, T, Pp);
+#pragma unroll
+        for (int w = 0; w < NW; w++) V3[w] = nwb_lop3<A_ | (B_ ^ C_)>(S[w], sum[w], Pp[w]);
+#pragma unroll
+        for (int w = 0; w < NW; w++) V3s[w] = (w > 0) ? __funnelshift_l(V3[w - 1], V3[w], 1) : (V3[0] << 1);
+        /* level 2: (match or v(i-1) >= 3) and uU <= 1 */
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            S[w] = nwb_lop3<(A_ | B_) & ~C_>(E[w], V3s[w], uu[1][w]);
+            T[w] = nwb_lop3<A_ & B_>(S[w], Pp[w], 0u);
+        }
+        nwb_bp_add(sum, T, Pp);
+#pragma unroll
+        for (int w = 0; w < NW; w++) V2[w] = nwb_lop3<A_ | (B_ ^ C_)>(S[w], sum[w], Pp[w]);
+#pragma unroll
+        for (int w = 0; w < NW; w++) V2s[w] = (w > 0) ? __funnelshift_l(V2[w - 1], V2[w], 1) : (V2[0] << 1);
+        /* level 1: y >= 1, or v(i-1) >= 2 and uU <= 1, or v(i-1) >= 3 and uU <= 2 */
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const unsigned b1 = uu[1][w], b0 = uu[0][w];
+            const unsigned y1 = nwb_lop3<(A_ & ~(B_ & C_)) | (~A_ & ~(B_ | C_))>(E[w], b1, b0);
+            const unsigned g = nwb_lop3<A_ & ~B_ & C_>(b1, b0, V3s[w]);     /* uU == 2 and v(i-1) >= 3 */
+            const unsigned h = nwb_lop3<A_ | (~B_ & C_)>(y1, b1, V2s[w]);   /* ... or uU <= 1 and v(i-1) >= 2 */
+            S[w] = nwb_lop3<A_ | B_>(g, h, 0u);
+            T[w] = nwb_lop3<(A_ | B_) & C_>(g, h, Pp[w]);
+        }
+        nwb_bp_add(sum, T, Pp);
+#pragma unroll
+        for (int w = 0; w < NW; w++) V1[w] = nwb_lop3<A_ | (B_ ^ C_)>(S[w], sum[w], Pp[w]);
+#pragma unroll
+        for (int w = 0; w < NW; w++) V1s[w] = (w > 0) ? __funnelshift_l(V1[w - 1], V1[w], 1) : (V1[0] << 1);
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const unsigned b1 = uu[1][w], b0 = uu[0][w];
+            const unsigned v0 = nwb_lop3<A_ ^ B_ ^ C_>(V1[w], V2[w], V3[w]);          /* v = (V2, v0), vL = (V2s, l0) */
+            const unsigned l0 = nwb_lop3<A_ ^ B_ ^ C_>(V1s[w], V2s[w], V3s[w]);
+            const unsigned un0 = nwb_lop3<A_ ^ B_ ^ C_>(v0, l0, b0);                   /* u = v - vL + uU (mod 4) */
+            const unsigned x1 = nwb_lop3<A_ ^ B_ ^ C_>(V2[w], V2s[w], b1);
+            const unsigned x2 = nwb_lop3<(~A_ & B_) ^ ((A_ ^ B_) & C_)>(v0, l0, b0);   /* borrow of v - vL, carry of + uU */
+            const unsigned un1 = nwb_lop3<A_ ^ B_>(x1, x2, 0u);
+            const unsigned w1 = nwb_lop3<A_ ^ B_ ^ C_>(V2[w], b1, E[w]);               /* z = v + uU; DIAG <=> z == (match ? 3 : 1) */
+            D[w] = nwb_lop3<(A_ ^ B_) & ~(C_ ^ (A_ & B_))>(v0, b0, w1);
+            Ln[w] = nwb_lop3<A_ | B_>(un1, un0, 0u);
+            Un[w] = V1[w];
+            uu[0][w] = un0;
+            uu[1][w] = un1;
+        }
+    } else {
+        /* P' = [uU == 0] >> 1 */
+        unsigned Pp[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const unsigned Pw = ~nwb_bp_ge<NB>(uu, 1, w);
+            const unsigned Pn = (w + 1 < NW) ? ~nwb_bp_ge<NB>(uu, 1, w + 1) : 0u;
+            Pp[w] = __funnelshift_r(Pw, Pn, 1);
+        }
+        unsigned V[M + 2][NW], Vs[M + 2][NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) { V[0][w] = 0xFFFFFFFFu; Vs[0][w] = 0xFFFFFFFFu; V[M + 1][w] = 0u; Vs[M + 1][w] = 0u; }
+#pragma unroll
+        for (int k = M; k >= 1; k--) {
+            unsigned S[NW], T[NW], sum[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                unsigned y = E[w] & ~nwb_bp_ge<NB>(uu, M - k + 1, w);
+                if (k <= N) y |= ~E[w] & ~nwb_bp_ge<NB>(uu, N - k + 1, w);
+#pragma unroll
+                for (int t = 1; t <= M - k; t++) y |= Vs[k + t][w] & ~nwb_bp_ge<NB>(uu, t + 1, w);
+                S[w] = y;
+                T[w] = y & Pp[w];
+            }
+            nwb_bp_add(sum, T, Pp);
+#pragma unroll
+            for (int w = 0; w < NW; w++) V[k][w] = S[w] | (sum[w] ^ Pp[w]);
+#pragma unroll
+            for (int w = 0; w < NW; w++) Vs[k][w] = (w > 0) ? __funnelshift_l(V[k][w - 1], V[k][w], 1) : (V[k][0] << 1);
+        }
+        unsigned v[NB][NW], vl[NB][NW];
+        nwb_bp_binary<M, NB>(v, V);
+        nwb_bp_binary<M, NB>(vl, Vs);
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            /* u of this row = v + uU - vL (mod 2^NB: the result lies in [0, M]); z = v + uU */
+            unsigned un[NB], z[NB];
+            unsigned borrow = 0u, carry = 0u, zc = 0u;
+#pragma unroll
+            for (int t = 0; t < NB; t++) {
+                const unsigned x = v[t][w] ^ vl[t][w] ^ borrow; /* v - vL */
+                borrow = (~v[t][w] & (vl[t][w] | borrow)) | (vl[t][w] & borrow);
+                un[t] = x ^ uu[t][w] ^ carry;
+                carry = (x & uu[t][w]) | (carry & (x ^ uu[t][w]));
+                z[t] = v[t][w] ^ uu[t][w] ^ zc;
+                zc = (v[t][w] & uu[t][w]) | (zc & (v[t][w] ^ uu[t][w]));
+            }
+            unsigned eqM = 0xFFFFFFFFu, eqN = 0xFFFFFFFFu, nz = 0u;
+#pragma unroll
+            for (int t = 0; t < NB; t++) {
+                eqM &= ((M >> t) & 1) ? z[t] : ~z[t];
+                eqN &= ((N >> t) & 1) ? z[t] : ~z[t];
+                nz |= un[t];
+            }
+            D[w] = (E[w] & eqM) | (~E[w] & eqN);
+            Ln[w] = nz;
+            Un[w] = V[1][w];
+#pragma unroll
+            for (int t = 0; t < NB; t++) uu[t][w] = un[t];
+        }
+    }
+}
+
+/* The rows of one group of 32 pairs (lane = pair).  FULL: every top string of the group has 256 letters (no
+ * column masks).  A warp-uniform choice made outside the row loop, so that the common case carries no selects. */
+template <int M, int N, int NB, bool FULL>
+__device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, const unsigned *peq, uint4 *stage, uint8_t *side_sm,
+                                             const uint2 *meta, const unsigned *mylut, const int lane, const int A, const int Brun,
+                                             const int maxB, const long long s0, const bool s_al, const unsigned l0,
+                                             const unsigned l1, const unsigned l2, const unsigned l3, unsigned &branches, int &rsum)
+{
+    constexpr int NW = NWB_BP_NW;
+    unsigned uu[NB][NW]; /* u of the row above, bit-sliced */
+#pragma unroll
+    for (int t = 0; t < NB; t++)
+#pragma unroll
+        for (int w = 0; w < NW; w++) uu[t][w] = 0u;
+
+#pragma unroll 1
+    for (int j = 0; j < maxB; j++) {
+        if ((j & (NWB_BP_SIDE_ROWS - 1)) == 0) {
+            /* my next 64 side letters, one byte per row; only I read them back */
+#pragma unroll 1
+            for (int q = 0; q < NWB_BP_SIDE_ROWS / 4; q++) {
+                const int row = j + 4 * q;
+                unsigned word = 0u;
+                if (row < Brun) word = nwb_bp_load_word(bp.sides, s0 + row, s_al);
+#pragma unroll
+                for (int e = 0; e < 4; e++) side_sm[(4 * q + e) * 32 + lane] = (uint8_t)(word >> (8 * e));
+            }
+        }
+        const unsigned c = side_sm[(j & (NWB_BP_SIDE_ROWS - 1)) * 32 + lane];
+        const int slot = (c == l0) ? 0 : ((c == l1) ? 1 : ((c == l2) ? 2 : ((c == l3) ? 3 : NWB_BP_NSYM)));
+        const unsigned *pe = peq + slot * (NW * 32) + lane;
+        unsigned E[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) E[w] = pe[w * 32];
+
+        /* one row: the arrow planes (LEFT and UP inverted) and u of this row */
+        unsigned Dp[NW], Ln[NW], Un[NW];
+        nwb_bp_row<M, N, NB>(E, uu, Dp, Ln, Un);
+        unsigned rowbr = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            if (!FULL) { /* columns beyond my top string: no arrows, no branch cells */
+                const int left = A - 32 * w;
+                const unsigned cm = (left >= 32) ? 0xFFFFFFFFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
+                Dp[w] &= cm; Ln[w] |= ~cm; Un[w] |= ~cm;
+            }
+            /* two or more arrows (walk-table.c:108-120): majority of DIAG, LEFT = ~Ln, UP = ~Un */
+            rowbr += (unsigned)__popc(nwb_lop3<(NWB_LOP_A & ~NWB_LOP_B) | (NWB_LOP_A & ~NWB_LOP_C) | ~(NWB_LOP_B | NWB_LOP_C)>(Dp[w], Ln[w], Un[w]));
+        }
+        if (j < Brun) branches += rowbr;
+        if (j == Brun - 1) { /* r(A,B) = sum of u(i,B) over my columns */
+            int r = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const int left = A - 32 * w;
+                const unsigned cm = (left >= 32) ? 0xFFFFFFFFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
+#pragma unroll
+                for (int t = 0; t < NB; t++) r += __popc(uu[t][w] & cm) << t;
+            }
+            rsum = r;
+        }
+        /* planes -> 4-bit codes (DIAG | LEFT << 1 | UP << 2), my 128-byte row into the staging buffer.  With
+         * T[x] = byte x spread to nibbles: code word = T[d] + 2 T[~ln] + 4 T[~un]; the byte comes out with one
+         * PRMT, the table address (for ~x: counted down from entry 255) and the combination are multiply-adds
+         * on the other pipe. */
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            unsigned o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned td = nwb_bp_lut<false>(mylut, Dp[w], q), tl = nwb_bp_lut<true>(mylut, Ln[w], q), tu = nwb_bp_lut<true>(mylut, Un[w], q);
+                o[q] = tu * 4u + (tl * 2u + td);
+            }
+            stage[lane * 8 + ((w + lane) & 7)] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        /* lanes 8h..8h+7 store the row of pair 4i + h: whole 128-byte lines */
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int L = 4 * i + (lane >> 3), ch = lane & 7;
+            const uint4 val = stage[L * 8 + ((ch + L) & 7)];
+            const uint2 mt = meta[L];
+            if ((unsigned)j < mt.y) gdst[mt.x + (unsigned)(8 * j + ch)] = val;
+        }
+        __syncwarp();
+    }
+}
+
 template <int M, int N>
 __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(const NwbBpParams bp)
 {
@@ -240,7 +489,6 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
             if (bp.out_branch) bp.out_branch[p] = 0u;
         }
         const int Brun = (valid && !over && A > 0) ? B : 0; /* rows this lane computes and stores */
-        meta[lane] = make_uint2(valid ? (unsigned)(bp.arrow_off[p] >> 7) : 0u, (unsigned)Brun);
         int maxB = Brun;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -251,137 +499,15 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         const bool s_al = __all_sync(NWB_FULL_MASK, (s0 & 3) == 0);
         __syncwarp();
 
-        unsigned uu[NB][NW]; /* u of the row above, bit-sliced */
-#pragma unroll
-        for (int t = 0; t < NB; t++)
-#pragma unroll
-            for (int w = 0; w < NW; w++) uu[t][w] = 0u;
         unsigned branches = 0u;
         int rsum = 0;
-
-#pragma unroll 1
-        for (int j = 0; j < maxB; j++) {
-            if ((j & (NWB_BP_SIDE_ROWS - 1)) == 0) {
-                /* my next 64 side letters, one byte per row; only I read them back */
-#pragma unroll 1
-                for (int q = 0; q < NWB_BP_SIDE_ROWS / 4; q++) {
-                    const int row = j + 4 * q;
-                    unsigned word = 0u;
-                    if (row < Brun) word = nwb_bp_load_word(bp.sides, s0 + row, s_al);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) side_sm[(4 * q + e) * 32 + lane] = (uint8_t)(word >> (8 * e));
-                }
-            }
-            const unsigned c = side_sm[(j & (NWB_BP_SIDE_ROWS - 1)) * 32 + lane];
-            const int slot = (c == l0) ? 0 : ((c == l1) ? 1 : ((c == l2) ? 2 : ((c == l3) ? 3 : NWB_BP_NSYM)));
-            const unsigned *pe = peq + slot * (NW * 32) + lane;
-            unsigned E[NW];
-#pragma unroll
-            for (int w = 0; w < NW; w++) E[w] = pe[w * 32];
-
-            /* P' = [uU == 0] >> 1 */
-            unsigned Pp[NW];
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                const unsigned Pw = ~nwb_bp_ge<NB>(uu, 1, w);
-                const unsigned Pn = (w + 1 < NW) ? ~nwb_bp_ge<NB>(uu, 1, w + 1) : 0u;
-                Pp[w] = __funnelshift_r(Pw, Pn, 1);
-            }
-            unsigned V[M + 2][NW], Vs[M + 2][NW];
-#pragma unroll
-            for (int w = 0; w < NW; w++) { V[0][w] = 0xFFFFFFFFu; Vs[0][w] = 0xFFFFFFFFu; V[M + 1][w] = 0u; Vs[M + 1][w] = 0u; }
-#pragma unroll
-            for (int k = M; k >= 1; k--) {
-                unsigned S[NW], T[NW], sum[NW];
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    unsigned y = E[w] & ~nwb_bp_ge<NB>(uu, M - k + 1, w);
-                    if (k <= N) y |= ~E[w] & ~nwb_bp_ge<NB>(uu, N - k + 1, w);
-#pragma unroll
-                    for (int t = 1; t <= M - k; t++) y |= Vs[k + t][w] & ~nwb_bp_ge<NB>(uu, t + 1, w);
-                    S[w] = y;
-                    T[w] = y & Pp[w];
-                }
-                nwb_bp_add(sum, T, Pp);
-#pragma unroll
-                for (int w = 0; w < NW; w++) V[k][w] = S[w] | (sum[w] ^ Pp[w]);
-#pragma unroll
-                for (int w = 0; w < NW; w++) Vs[k][w] = (w > 0) ? __funnelshift_l(V[k][w - 1], V[k][w], 1) : (V[k][0] << 1);
-            }
-            unsigned v[NB][NW], vl[NB][NW];
-            nwb_bp_binary<M, NB>(v, V);
-            nwb_bp_binary<M, NB>(vl, Vs);
-            unsigned Dp[NW], Lp[NW], Up[NW];
-            unsigned rowbr = 0u;
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                /* u of this row = v + uU - vL (mod 2^NB: the result lies in [0, M]); z = v + uU */
-                unsigned un[NB], z[NB];
-                unsigned borrow = 0u, carry = 0u, zc = 0u;
-#pragma unroll
-                for (int t = 0; t < NB; t++) {
-                    const unsigned x = v[t][w] ^ vl[t][w] ^ borrow; /* v - vL */
-                    borrow = (~v[t][w] & (vl[t][w] | borrow)) | (vl[t][w] & borrow);
-                    un[t] = x ^ uu[t][w] ^ carry;
-                    carry = (x & uu[t][w]) | (carry & (x ^ uu[t][w]));
-                    z[t] = v[t][w] ^ uu[t][w] ^ zc;
-                    zc = (v[t][w] & uu[t][w]) | (zc & (v[t][w] ^ uu[t][w]));
-                }
-                unsigned eqM = 0xFFFFFFFFu, eqN = 0xFFFFFFFFu, nz = 0u;
-#pragma unroll
-                for (int t = 0; t < NB; t++) {
-                    eqM &= ((M >> t) & 1) ? z[t] : ~z[t];
-                    eqN &= ((N >> t) & 1) ? z[t] : ~z[t];
-                    nz |= un[t];
-                }
-                unsigned dg = (E[w] & eqM) | (~E[w] & eqN);
-                unsigned lf = ~nz;
-                unsigned up = ~V[1][w];
-                if (!full) { /* columns beyond my top string: no arrows, no branch cells */
-                    const int left = A - 32 * w;
-                    const unsigned cm = (left >= 32) ? 0xFFFFFFFFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
-                    dg &= cm; lf &= cm; up &= cm;
-                }
-                Dp[w] = dg; Lp[w] = lf; Up[w] = up;
-                rowbr += (unsigned)__popc((dg & lf) | (dg & up) | (lf & up));
-#pragma unroll
-                for (int t = 0; t < NB; t++) uu[t][w] = un[t];
-            }
-            if (j < Brun) branches += rowbr;
-            if (j == Brun - 1) { /* r(A,B) = sum of u(i,B) over my columns */
-                int r = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    const int left = A - 32 * w;
-                    const unsigned cm = (left >= 32) ? 0xFFFFFFFFu : ((left <= 0) ? 0u : ((1u << left) - 1u));
-#pragma unroll
-                    for (int t = 0; t < NB; t++) r += __popc(uu[t][w] & cm) << t;
-                }
-                rsum = r;
-            }
-            /* planes -> 4-bit codes (DIAG | LEFT << 1 | UP << 2), my 128-byte row into the staging buffer */
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                unsigned o[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const unsigned xd = (Dp[w] >> (8 * q)) & 0xFFu, xl = (Lp[w] >> (8 * q)) & 0xFFu, xu = (Up[w] >> (8 * q)) & 0xFFu;
-                    o[q] = mylut[xd * 32] + 2u * mylut[xl * 32] + 4u * mylut[xu * 32];
-                }
-                stage[lane * 8 + ((w + lane) & 7)] = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            __syncwarp();
-            /* lanes 8h..8h+7 store the row of pair 4i + h: whole 128-byte lines */
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int L = 4 * i + (lane >> 3), ch = lane & 7;
-                const uint4 val = stage[L * 8 + ((ch + L) & 7)];
-                const uint2 mt = meta[L];
-                if ((unsigned)j < mt.y)
-                    *reinterpret_cast<uint4 *>(bp.arrows + (((size_t)mt.x + (size_t)j) << 7) + (size_t)ch * 16) = val;
-            }
-            __syncwarp();
-        }
+        /* tables of a group lie within 2^32 16-byte chunks of the first one (B <= 60000): 32-bit chunk indices */
+        const long long off0 = __shfl_sync(NWB_FULL_MASK, valid ? bp.arrow_off[p] : 0ll, 0);
+        meta[lane] = make_uint2(valid ? (unsigned)((bp.arrow_off[p] - off0) >> 4) : 0u, (unsigned)Brun);
+        __syncwarp();
+        uint4 *gdst = reinterpret_cast<uint4 *>(bp.arrows + off0);
+        if (full) nwb_bp_rows<M, N, NB, true>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
+        else nwb_bp_rows<M, N, NB, false>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
         if (Brun > 0) {
             bp.out_score[p] = rsum - bp.d * (A + B);
             if (bp.out_branch) bp.out_branch[p] = branches;
