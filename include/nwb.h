@@ -86,7 +86,7 @@ const char *nwb_strerror(int err);
 /* Explicit overrides for tests and measurements; the library reads NO environment variables.  Every key
  * selects between kernels that produce identical results ("pk_k", "pk_r", "pk_warps", "pk_hx", "count_mode"
  * 0 auto / 1 fused into the fill / 2 dense sweep after the fill / 3 dense sweep trailing the fill on a second
- * stream, "cnt_cpl", "batch_bx", "batch_cx", "bcnt_chain", "cx_warps"; 0 or -1 = automatic,
+ * stream, "cnt_cpl", "batch_bx", "batch_cx", "batch_bp", "bp_warps", "bcnt_chain", "cx_warps"; 0 or -1 = automatic,
  * see nwb_api.cu) except "watchdog_ms" (how long a device-side wait may see no progress before the fill
  * fails with NWB_ERR_CUDA; default 4000) and "inject_fault" (test only: 1 makes the next fills lose a
  * strip's boundary stream so that the watchdog path can be exercised -- the fill FAILS, it never returns a
@@ -302,10 +302,12 @@ int32_t nwb_batch_greatest_abs(const nwb_batch *b, int64_t pair);
 const int32_t *nwb_batch_score_rows(const nwb_batch *b, int64_t pair, size_t *pitch_elems);
 float nwb_batch_kernel_ms(const nwb_batch *b);
 int64_t nwb_batch_launches(const nwb_batch *b);
-/* Name of the kernel nwb_batch_run() launches for this batch: "nwb_batch_bx_kernel" (two pairs per warp: top
- * strings of at most 256 characters and 2d + m <= 7), "nwb_batch_cx_kernel" (the same, pairs swept back to back:
- * every pair has the same shape and the side length is a multiple of 32), "nwb_batch_pk_kernel" otherwise.
- * For logs and profiles. */
+/* Name of the kernel nwb_batch_run() launches for this batch: "nwb_batch_bp_kernel" (bit-parallel rows, one thread
+ * per pair: top strings of 129..256 characters and 2d + m <= 3, e.g. DNA 1/1/1; pairs whose top string has more
+ * than four distinct letters are worked off by nwb_batch_pk_kernel right behind it), "nwb_batch_bx_kernel" (two
+ * pairs per warp: top strings of at most 256 characters and 2d + m <= 7), "nwb_batch_cx_kernel" (the same, pairs
+ * swept back to back: every pair has the same shape and the side length is a multiple of 32),
+ * "nwb_batch_i32_kernel" (any m / k / d, scores), "nwb_batch_pk_kernel" otherwise.  For logs and profiles. */
 const char *nwb_batch_kernel_name(const nwb_batch *b);
 void *nwb_batch_arrows_device(nwb_batch *b);
 /* Parity aid: digests of the whole batch computed on the device (after nwb_batch_run): out[0..3] = the sums

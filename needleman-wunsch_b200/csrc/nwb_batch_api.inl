@@ -18,6 +18,8 @@ struct nwb_batch {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_stream = nullptr;              /* nwb_batch_refill(): host-to-device copies of the next chunk */
+    cudaStream_t stream2 = nullptr;                  /* ... odd chunks compute here: the kernels of neighbouring chunks overlap */
+    cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev_chunk[NWB_BATCH_MAX_CHUNKS] = {}; /* ... one "chunk is on the device" event per chunk */
     DevBuf<uint8_t> tops, sides, arrows;
     DevBuf<long long> top_off, side_off, arrow_off;
@@ -61,6 +63,8 @@ extern "C" void nwb_batch_free(nwb_batch *b)
     for (int i = 0; i < NWB_BATCH_MAX_CHUNKS; i++)
         if (b->ev_chunk[i]) cudaEventDestroy(b->ev_chunk[i]);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -235,6 +239,8 @@ extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *side
     if (b->n == 0) return NWB_OK;
     if (!b->copy_stream) {
         CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
         for (int i = 0; i < NWB_BATCH_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
     }
     cudaStream_t st = b->stream;
@@ -247,6 +253,9 @@ extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *side
     CK(cudaEventRecord(b->ev0, st));
     int rc = NWB_OK;
     int ci = 0;
+    /* one-strip pairs on the packed / bit-parallel kernels keep everything per warp in shared memory; wider pairs
+     * and the int32 engine have per-warp scratch in global memory that two launches in flight would share */
+    const bool two_streams = !b->general && b->max_strips == 1;
     for (int64_t c0 = 0; c0 < b->n && rc == NWB_OK; c0 += per, ci++) {
         const int64_t c1 = (c0 + per < b->n) ? c0 + per : b->n;
         const long long tb = b->h_top_off[(size_t)c0], te = b->h_top_off[(size_t)c1];
@@ -254,11 +263,20 @@ extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *side
         if (te > tb) CK(cudaMemcpyAsync(b->tops.p + tb, tops + tb, (size_t)(te - tb), cudaMemcpyHostToDevice, b->copy_stream));
         if (se > sb) CK(cudaMemcpyAsync(b->sides.p + sb, sides + sb, (size_t)(se - sb), cudaMemcpyHostToDevice, b->copy_stream));
         CK(cudaEventRecord(b->ev_chunk[ci], b->copy_stream));
-        CK(cudaStreamWaitEvent(st, b->ev_chunk[ci], 0));
-        rc = batch_fill_pass(b, st, c0, c1, ci);
-        if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, c0, c1);
+        /* A chunk is a fraction of the batch and does not fill the GPU on its own (one thread per pair in
+         * nwb_batch_bp_kernel: 16,000 pairs are 4 warps per SM): odd chunks go to a second stream so that the
+         * kernels of neighbouring chunks run side by side. */
+        cudaStream_t cst = ((ci & 1) && two_streams) ? b->stream2 : st;
+        if (ci == 1 && two_streams) CK(cudaStreamWaitEvent(b->stream2, b->ev0, 0));
+        CK(cudaStreamWaitEvent(cst, b->ev_chunk[ci], 0));
+        rc = batch_fill_pass(b, cst, c0, c1, ci);
+        if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, cst, c0, c1);
     }
     if (rc != NWB_OK) return rc;
+    if (ci > 1 && two_streams) {
+        CK(cudaEventRecord(b->ev_join, b->stream2));
+        CK(cudaStreamWaitEvent(st, b->ev_join, 0));
+    }
     CK(cudaEventRecord(b->ev1, st));
     return NWB_OK;
 }
@@ -309,7 +327,7 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
         pp.n_pairs = c1 - c0; pp.d = b->d;
         pp.arrows = b->arrows.p; pp.arrow_off = b->arrow_off.p + c0; pp.out_score = b->score.p + c0;
         pp.out_branch = (b->flags & NWB_NO_BRANCH_COUNT) ? nullptr : b->branch.p + c0;
-        pp.fb_list = b->fb_list.p + c0; pp.fb_count = fbc;
+        pp.fb_list = b->fb_list.p + c0; pp.fb_count = fbc; pp.k2 = 2u; pp.k4 = 4u;
         int warps = g_tune.bp_warps > 0 ? g_tune.bp_warps : nwb_bp_choose_warps((c1 - c0 + 31) / 32, grid);
         if (warps > NWB_BP_WARPS) warps = NWB_BP_WARPS;
         const size_t smem = NWB_BP_SMEM_BYTES(warps);

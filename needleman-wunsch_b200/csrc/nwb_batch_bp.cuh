@@ -37,7 +37,7 @@
 #define NWB_BP_NW 8     /* 32-bit words per row vector: up to 256 columns */
 #define NWB_BP_NSYM 4   /* letters with a match vector */
 #define NWB_BP_MAXM 3   /* instantiated difference ranges */
-#define NWB_BP_WARPS 16
+#define NWB_BP_WARPS 16  /* at most, per block (128 registers per thread) */
 #define NWB_BP_SIDE_ROWS 64
 #define NWB_BP_LUT_BYTES (256 * 32 * 4)
 #define NWB_BP_PEQ_BYTES ((NWB_BP_NSYM + 1) * NWB_BP_NW * 32 * 4)
@@ -60,6 +60,7 @@ struct NwbBpParams {
     unsigned *out_branch;       /* [n_pairs] or NULL */
     long long *fb_list;         /* pairs this kernel leaves to nwb_batch_pk_kernel (more than 4 letters) */
     unsigned *fb_count;
+    unsigned k2, k4;            /* 2 and 4, as run-time values (see nwb_bp_rows) */
 };
 
 /* usable for this batch?  (m, k, d) inside the packed range, M = 2d + m <= 3, every top string <= 256 */
@@ -303,8 +304,9 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsig
     }
 }
 
-/* The rows of one group of 32 pairs (lane = pair).  FULL: every top string of the group has 256 letters (no
- * column masks).  A warp-uniform choice made outside the row loop, so that the common case carries no selects. */
+/* The rows of one group of 32 pairs (lane = pair).  FULL: every pair of the group is 256 columns wide and all have
+ * the same number of rows: no column masks, no per-pair row count at the stores, tables evenly spaced.  A
+ * warp-uniform choice made outside the row loop, so that the common case carries no selects. */
 template <int M, int N, int NB, bool FULL>
 __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, const unsigned *peq, uint4 *stage, uint8_t *side_sm,
                                              const uint2 *meta, const unsigned *mylut, const int lane, const int A, const int Brun,
@@ -317,18 +319,37 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
     for (int t = 0; t < NB; t++)
 #pragma unroll
         for (int w = 0; w < NW; w++) uu[t][w] = 0u;
+    /* Staging buffer: row = lane, 16-byte chunk w at position w ^ (lane & 7): conflict-free for the writers (a
+     * quarter warp = 8 rows, 8 different positions) and for the readers (8 chunks of one row).  The multipliers of
+     * the code-word combination are run-time values so that they stay multiply-adds (as constants they become
+     * shifts and adds on the ALU pipe, which is the one that limits this kernel). */
+    uint4 *st_w[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) st_w[w] = stage + lane * 8 + (w ^ (lane & 7));
+    const int ch = lane & 7, h = lane >> 3;
+    const uint4 *st_r0 = stage + h * 8 + (ch ^ h), *st_r1 = stage + (h + 4) * 8 + (ch ^ (h + 4));
+    const unsigned k2 = bp.k2, k4 = bp.k4;
 
 #pragma unroll 1
     for (int j = 0; j < maxB; j++) {
         if ((j & (NWB_BP_SIDE_ROWS - 1)) == 0) {
-            /* my next 64 side letters, one byte per row; only I read them back */
+            /* my next 64 side letters, one byte per row; only I read them back.  All 16 loads are issued before
+             * the first store (one memory latency per 64 rows, not sixteen). */
+#ifndef NWB_BP_STAGE_BATCH
+#define NWB_BP_STAGE_BATCH 4 /* loads in flight; 16 measured 7 % slower (the row loop's schedule changes), 1 the same as 4 */
+#endif
 #pragma unroll 1
-            for (int q = 0; q < NWB_BP_SIDE_ROWS / 4; q++) {
-                const int row = j + 4 * q;
-                unsigned word = 0u;
-                if (row < Brun) word = nwb_bp_load_word(bp.sides, s0 + row, s_al);
+            for (int q0 = 0; q0 < NWB_BP_SIDE_ROWS / 4; q0 += NWB_BP_STAGE_BATCH) {
+                unsigned word[NWB_BP_STAGE_BATCH];
 #pragma unroll
-                for (int e = 0; e < 4; e++) side_sm[(4 * q + e) * 32 + lane] = (uint8_t)(word >> (8 * e));
+                for (int q = 0; q < NWB_BP_STAGE_BATCH; q++) {
+                    const int row = j + 4 * (q0 + q);
+                    word[q] = (row < Brun) ? nwb_bp_load_word(bp.sides, s0 + row, s_al) : 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < NWB_BP_STAGE_BATCH; q++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) side_sm[(4 * (q0 + q) + e) * 32 + lane] = (uint8_t)(word[q] >> (8 * e));
             }
         }
         const unsigned c = side_sm[(j & (NWB_BP_SIDE_ROWS - 1)) * 32 + lane];
@@ -374,18 +395,22 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const unsigned td = nwb_bp_lut<false>(mylut, Dp[w], q), tl = nwb_bp_lut<true>(mylut, Ln[w], q), tu = nwb_bp_lut<true>(mylut, Un[w], q);
-                o[q] = tu * 4u + (tl * 2u + td);
+                o[q] = tu * k4 + (tl * k2 + td);
             }
-            stage[lane * 8 + ((w + lane) & 7)] = make_uint4(o[0], o[1], o[2], o[3]);
+            *st_w[w] = make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
         /* lanes 8h..8h+7 store the row of pair 4i + h: whole 128-byte lines */
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int L = 4 * i + (lane >> 3), ch = lane & 7;
-            const uint4 val = stage[L * 8 + ((ch + L) & 7)];
-            const uint2 mt = meta[L];
-            if ((unsigned)j < mt.y) gdst[mt.x + (unsigned)(8 * j + ch)] = val;
+            const int L = 4 * i + h; /* (L & 7) = h or h + 4 */
+            const uint4 val = ((i & 1) ? st_r1 : st_r0)[(i >> 1) * 64];
+            if (FULL) {
+                gdst[(unsigned)L * (unsigned)(8 * maxB) + (unsigned)(8 * j + ch)] = val;
+            } else {
+                const uint2 mt = meta[L];
+                if ((unsigned)j < mt.y) gdst[mt.x + (unsigned)(8 * j + ch)] = val;
+            }
         }
         __syncwarp();
     }
@@ -495,7 +520,6 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
             const int x = __shfl_xor_sync(NWB_FULL_MASK, maxB, o);
             maxB = x > maxB ? x : maxB;
         }
-        const bool full = __all_sync(NWB_FULL_MASK, A == 32 * NW || Brun == 0); /* no column masks needed */
         const bool s_al = __all_sync(NWB_FULL_MASK, (s0 & 3) == 0);
         __syncwarp();
 
@@ -503,6 +527,9 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         int rsum = 0;
         /* tables of a group lie within 2^32 16-byte chunks of the first one (B <= 60000): 32-bit chunk indices */
         const long long off0 = __shfl_sync(NWB_FULL_MASK, valid ? bp.arrow_off[p] : 0ll, 0);
+        /* one shape, 256 columns, tables one after the other */
+        const bool full = __all_sync(NWB_FULL_MASK, A == 32 * NW && Brun == maxB && Brun > 0 &&
+                                                        bp.arrow_off[valid ? p : 0] - off0 == (long long)lane * 128 * maxB);
         meta[lane] = make_uint2(valid ? (unsigned)((bp.arrow_off[p] - off0) >> 4) : 0u, (unsigned)Brun);
         __syncwarp();
         uint4 *gdst = reinterpret_cast<uint4 *>(bp.arrows + off0);

@@ -554,7 +554,7 @@ int emu_fill_batch_bp(const char *tops, const long long *top_off, const char *si
     memset(&p, 0, sizeof(p));
     p.tops = (const uint8_t *)tops; p.top_off = top_off; p.sides = (const uint8_t *)sides; p.side_off = side_off;
     p.n_pairs = n; p.d = d; p.arrows = arrows; p.arrow_off = arrow_off; p.out_score = scores; p.out_branch = branches;
-    p.fb_list = fb.data(); p.fb_count = &fbn;
+    p.fb_list = fb.data(); p.fb_count = &fbn; p.k2 = 2u; p.k4 = 4u;
     bool ok = false;
     switch (pc.a_match) {
     case 1: ok = emu_bp_go<1>(pc.a_mis, grid, warps, p); break;

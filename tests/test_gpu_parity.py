@@ -291,7 +291,7 @@ def test_batch_config4_shard(oracle, nwb):
     idx = list(range(n - 1)) + [999999]
     tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
     bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_ARROWS_HOST)
-    assert bt.kernel_name() == "nwb_batch_cx_kernel"
+    assert bt.kernel_name() == "nwb_batch_bp_kernel"     # the default for 256-column DNA 1/1/1 pairs
     bt.run()
     bt.fetch()
     assert (bt.opt_score(0), bt.branch_count(0)) == (19, 23713)
@@ -333,7 +333,8 @@ def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
         sides = [bytes(rng.choice(alpha) for _ in range(b)) for _, b in lens]
         sample = list(range(25)) + rng.sample(range(25, len(lens)), 120) + [len(lens) - 1]
         for m, k, d in schemes:
-            bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+            with nwb.tuned(batch_bp=0):
+                bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
             assert bt.kernel_name() == "nwb_batch_bx_kernel"
             bt.run()
             bt.fetch()
@@ -341,7 +342,7 @@ def test_batch_two_pairs_per_warp(oracle, nwb, monkeypatch):
             scores = [bt.opt_score(i) for i in range(len(lens))]
             branches = [bt.branch_count(i) for i in range(len(lens))]
             bt.close()
-            with nwb.tuned(batch_bx=0):
+            with nwb.tuned(batch_bx=0, batch_bp=0):
                 b0 = nwb.Batch(tops, sides, m, k, d, 0)
             assert b0.kernel_name() == "nwb_batch_pk_kernel"
             b0.run()
@@ -373,7 +374,8 @@ def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
                                       (7, 64, 20001, b"AC", (0, 0, 0)), (255, 160, 5000, b"ACGT", (1, 1, 3))):
         tops = [bytes(rng.choice(alpha) for _ in range(a)) for _ in range(n)]
         sides = [bytes(rng.choice(alpha) for _ in range(b)) for _ in range(n)]
-        bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
+        with nwb.tuned(batch_bp=0):
+            bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
         assert bt.kernel_name() == "nwb_batch_cx_kernel"
         bt.run()
         bt.fetch()
@@ -383,7 +385,7 @@ def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
         branches = [bt.branch_count(i) for i in range(n)]
         tabs = [bt.arrow_rows(i).copy() for i in sample]
         bt.close()
-        with nwb.tuned(batch_cx=0):
+        with nwb.tuned(batch_cx=0, batch_bp=0):
             b0 = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
         assert b0.kernel_name() == "nwb_batch_bx_kernel"
         b0.run()
@@ -484,7 +486,7 @@ def test_batch_count(oracle, nwb):
     idx = list(range(n - 1)) + [999999]
     tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
     bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_COUNT)
-    assert bt.kernel_name() == "nwb_batch_cx_kernel"
+    assert bt.kernel_name() == "nwb_batch_bp_kernel"
     bt.run()
     bt.fetch()
     assert [bt.count(i) for i in (0, 1, n - 1)] == [387701138034524160, 108460706365440, 4971798065203200]

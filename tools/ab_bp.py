@@ -6,6 +6,7 @@ the batch digests (arrow tables, scores, branch counters) against tests/golden/g
     python tools/ab_bp.py [--pairs 125000] [--warps 0,8,12,14,16]"""
 import argparse
 import json
+import time
 import os
 import sys
 
@@ -19,7 +20,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=125000)
 ap.add_argument("--warps", default="0")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--lib", default=None, help="another build of libnwb.so (variant A/B on the same box)")
 args = ap.parse_args()
+if args.lib:
+    nwb.LIB_PATH = os.path.abspath(args.lib)
 n = args.pairs
 tcat = nwb.generate(0x5EED4000, 256, nwb.DNA, count=n, seed_stride=2)
 scat = nwb.generate(0x5EED4001, 256, nwb.DNA, count=n, seed_stride=2)
@@ -29,6 +33,7 @@ if n == 125000:
     with open(os.path.join(ROOT, "tests", "golden", "golden_big.json")) as f:
         g4 = {c["name"]: c for c in json.load(f)}["config4_batch_1M"]["shard_digests"][0]
     want = tuple(int(g4[k], 16) for k in ("arrow", "score", "branch"))
+tpin, spin = nwb.PinnedBuffer(tcat), nwb.PinnedBuffer(scat)
 ok = True
 ref = None
 runs = [("cx", dict(batch_bp=0))] + [(f"bp warps={w}", dict(batch_bp=1, bp_warps=int(w))) for w in args.warps.split(",")]
@@ -42,11 +47,21 @@ for name, knobs in runs:
             ms.append(b.kernel_ms())
         dg = b.digest(0)[:3]
         kname = b.kernel_name()
+        # end to end from page-locked host buffers: chunked H2D overlapped with the kernels + D2H of the results
+        e2e = []
+        for _ in range(args.reps):
+            t0 = time.perf_counter()
+            b.refill(tpin, spin)
+            b.fetch()
+            e2e.append((time.perf_counter() - t0) * 1e3)
+        dg2 = b.digest(0)[:3]
         b.close()
+        if dg2 != dg:
+            dg = None
     if ref is None:
         ref = dg
     good = dg == ref and (want is None or dg == want)
     ok = ok and good
     print(f"{name:14s} {kname:22s} {min(ms):7.3f} ms  {n * 65536 / min(ms) / 1e6:8.1f} GCUPS  "
-          f"{n * 32768 / min(ms) / 1e6:7.1f} GB/s written  digests {'ok' if good else 'MISMATCH'}", flush=True)
+          f"{n * 32768 / min(ms) / 1e6:7.1f} GB/s written  e2e {min(e2e):6.3f} ms  digests {'ok' if good else 'MISMATCH'}", flush=True)
 sys.exit(0 if ok else 1)
