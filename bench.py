@@ -202,6 +202,12 @@ def run_reference(args) -> None:
 def run_extras(nwb, torch, dist, world, rank, local, barrier, gold) -> tuple[dict | None, bool]:
     out = {}
     ok_all = True
+    hbm_peak = 6650.0
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak = float(json.load(f).get("hbm_gbs", hbm_peak))
+    except OSError:
+        pass
     # ---- config 4: batch of 256 x 256 DNA pairs, pair p seeded 0x5EED4000 + 2p, sharded by rank (no communication)
     per = 125_000
     first, cnt = nwb.batch_partition(per * world, rank, world)
@@ -259,7 +265,14 @@ def run_extras(nwb, torch, dist, world, rank, local, barrier, gold) -> tuple[dic
                       "e2e_ms_from_pageable_host_memory": e2e_pageable_ms,
                       "e2e_h2d_bytes_per_gpu": 2 * per * 256, "e2e_d2h_bytes_per_gpu": per * (8 + (8 if flags else 0)),
                       "e2e_call": "nwb_batch_refill (host strings in page-locked memory from nwb_host_alloc, H2D in 7 chunks overlapped "
-                                  "with the kernels) + nwb_batch_fetch (D2H of every pair's score, branch count, count)",
+                                  "with the kernels, neighbouring chunks on two compute streams) + nwb_batch_fetch (D2H of every pair's "
+                                  "score, branch count, count)",
+                      "roofline_hbm": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                                       "achieved": per * (32768 + 512 + 8) / (ms * 1e-3) / 1e9,
+                                       "frac": per * (32768 + 512 + 8) / (ms * 1e-3) / 1e9 / hbm_peak,
+                                       "algorithmic_bytes_per_pair": 32768 + 512 + 8,
+                                       "note": "per pair: 32 KB of 4-bit arrow codes written + 512 B of strings read + score and "
+                                               "branch counter; fill pass only (the count pass re-reads the codes)"} if not flags else None,
                       "golden_ok": bad == 0.0,
                       "golden": "every pair of every shard: arrow / score / branch / count digests vs golden_big.json config4_batch_1M",
                       "scaling": "weak (125,000 pairs per GPU; 8 GPUs = the 1M-pair config)"}
