@@ -33,6 +33,7 @@
 #include "nwb_batch.cuh"
 #include "nwb_batch_bx.cuh"
 #include "nwb_batch_bp.cuh"
+#include "nwb_batch_lcount.cuh"
 #include "nwb_batch_count.cuh"
 #include "nwb_batch_i32.cuh"
 #include "nwb_peak.cuh"
@@ -97,6 +98,8 @@ struct NwbTune {
     int cx_warps = 0;    /* 0 = auto (12); 16                                                                */
     int batch_bp = -1;   /* -1 = auto; 0 = never nwb_batch_bp_kernel (bit-parallel rows, one thread per pair)      */
     int bp_warps = 0;    /* 0 = auto; warps per block of nwb_batch_bp_kernel (1..16)                          */
+    int batch_lcount = -1; /* -1 = auto; 0 = never nwb_batch_lcount_kernel (sparse count, one thread per pair)      */
+    int lc_warps = 0;    /* 0 = auto; warps per block of nwb_batch_lcount_kernel                              */
     int watchdog_ms = 4000; /* device-side spin loops give up after this long without progress               */
     int inject_fault = 0;   /* test only: 1 = the fill's strips do not publish their boundary streams        */
     int plan_cache = 1;     /* 0 = nwb_fill()/nwb_fill_on() create and destroy their device workspace per call */
@@ -133,6 +136,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"count_mode", &g_tune.count_mode}, {"cnt_cpl", &g_tune.cnt_cpl}, {"batch_bx", &g_tune.batch_bx},
         {"batch_cx", &g_tune.batch_cx}, {"bcnt_chain", &g_tune.bcnt_chain},
         {"cx_warps", &g_tune.cx_warps}, {"batch_bp", &g_tune.batch_bp}, {"bp_warps", &g_tune.bp_warps},
+        {"batch_lcount", &g_tune.batch_lcount}, {"lc_warps", &g_tune.lc_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
 #ifdef NWB_EXPERIMENTS
         {"pk_hy", &g_tune.pk_hy}, {"pk_hz", &g_tune.pk_hz}, {"debug_nowait", &g_tune.debug_nowait},

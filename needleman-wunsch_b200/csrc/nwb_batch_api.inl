@@ -142,8 +142,8 @@ static int batch_create_impl(const char *tops, const int64_t *top_off, const cha
     if (rc == NWB_OK) rc = b->score.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK) rc = b->branch.ensure((size_t)n_pairs + 1);
     if (rc == NWB_OK && (flags & NWB_WANT_COUNT)) rc = b->count.ensure((size_t)n_pairs + 1);
-    if (rc == NWB_OK && b->use_bp) rc = b->fb_list.ensure((size_t)n_pairs + 1);
-    if (rc == NWB_OK && b->use_bp) rc = b->fb_count.ensure(NWB_BATCH_MAX_CHUNKS + 1);
+    if (rc == NWB_OK && (b->use_bp || (flags & NWB_WANT_COUNT))) rc = b->fb_list.ensure((size_t)n_pairs + 1);
+    if (rc == NWB_OK && (b->use_bp || (flags & NWB_WANT_COUNT))) rc = b->fb_count.ensure(NWB_BATCH_MAX_CHUNKS + 1);
     if (rc == NWB_OK && general) {
         const size_t nwarps = (size_t)b->sm_count * 2 * NWB_BI32_WARPS;
         const size_t bpitch = nwb_round_up((size_t)b->max_B + 2, 32);
@@ -179,7 +179,7 @@ extern "C" int nwb_batch_create(const char *tops, const int64_t *top_off, const 
 }
 
 /* the count behind -s: a second pass over the arrow codes the fill has just written (nwb_batch_count.cuh) */
-static int batch_count_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1)
+static int batch_count_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1, int chunk)
 {
     NwbBatchCountParams cp;
     memset(&cp, 0, sizeof(cp));
@@ -193,6 +193,27 @@ static int batch_count_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c
         cp.scratch = b->cscratch.p;
     }
     const size_t smem = (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS;
+    if (g_tune.batch_lcount != 0 && b->fb_list.p && b->fb_count.p) {
+        /* one thread per pair, backwards over the cells on optimal paths (nwb_batch_lcount.cuh); the pairs whose band
+         * does not fit its window land on a list that the dense kernel works off right behind (the list of this chunk:
+         * the fill's own left-over launch, earlier on this stream, is done with it) */
+        unsigned *fbc = b->fb_count.p + chunk;
+        CK(cudaMemsetAsync(fbc, 0, sizeof(unsigned), st));
+        NwbLaneCountParams lp;
+        memset(&lp, 0, sizeof(lp));
+        lp.top_off = cp.top_off; lp.side_off = cp.side_off; lp.n_pairs = cp.n_pairs; lp.arrows = cp.arrows;
+        lp.arrow_off = cp.arrow_off; lp.out_count = cp.out_count; lp.fb_list = b->fb_list.p + c0; lp.fb_count = fbc;
+        int lw = g_tune.lc_warps > 0 ? g_tune.lc_warps : nwb_lc_choose_warps((cp.n_pairs + 31) / 32, grid);
+        if (lw > NWB_LC_WARPS) lw = NWB_LC_WARPS;
+        nwb_batch_lcount_kernel<<<grid, 32 * lw, 0, st>>>(lp);
+        CK(cudaGetLastError());
+        cp.pair_list = lp.fb_list; cp.pair_count = fbc;
+        CK(cudaFuncSetAttribute(nwb_batch_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nwb_batch_count_kernel<<<grid, 32 * NWB_BCNT_WARPS, smem, st>>>(cp);
+        CK(cudaGetLastError());
+        b->launches += 2;
+        return NWB_OK;
+    }
     /* every pair the same one-strip shape: the tables of a warp's run of pairs are swept back to back
      * (nwb_tune "bcnt_chain" = 0: one pair at a time) */
     if (nwb_bcount_chain_usable(b->uniform, b->uni_A, b->uni_B, c1 - c0, (long long)grid * NWB_BCNT_WARPS) && g_tune.bcnt_chain != 0) {
@@ -221,7 +242,7 @@ extern "C" int nwb_batch_run(nwb_batch *b, void *stream)
     if (b->n == 0) return NWB_OK;
     CK(cudaEventRecord(b->ev0, st));
     int rc = batch_fill_pass(b, st, 0, b->n, 0);
-    if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, 0, b->n);
+    if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, st, 0, b->n, 0);
     if (rc != NWB_OK) return rc;
     CK(cudaEventRecord(b->ev1, st));
     return NWB_OK;
@@ -270,7 +291,7 @@ extern "C" int nwb_batch_refill(nwb_batch *b, const char *tops, const char *side
         if (ci == 1 && two_streams) CK(cudaStreamWaitEvent(b->stream2, b->ev0, 0));
         CK(cudaStreamWaitEvent(cst, b->ev_chunk[ci], 0));
         rc = batch_fill_pass(b, cst, c0, c1, ci);
-        if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, cst, c0, c1);
+        if (rc == NWB_OK && (b->flags & NWB_WANT_COUNT)) rc = batch_count_pass(b, cst, c0, c1, ci);
     }
     if (rc != NWB_OK) return rc;
     if (ci > 1 && two_streams) {

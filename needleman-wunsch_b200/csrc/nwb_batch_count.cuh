@@ -30,6 +30,8 @@ struct NwbBatchCountParams {
     unsigned long long *out_count; /* [n_pairs] */
     unsigned long long *scratch;   /* pairs wider than one strip: per warp max_B + 1 boundary counts */
     size_t scratch_per_warp;       /* elements */
+    const long long *pair_list;    /* NULL, or the pairs to count (what nwb_batch_lcount_kernel left over) ... */
+    const unsigned *pair_count;    /* ... and how many of them (device word) */
 };
 
 __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel(const NwbBatchCountParams cp)
@@ -42,7 +44,9 @@ __global__ void __launch_bounds__(32 * NWB_BCNT_WARPS, 1) nwb_batch_count_kernel
     unsigned long long *bnd = cp.scratch ? cp.scratch + (size_t)gwarp * cp.scratch_per_warp : nullptr;
     const int sub = lane >> 3, chunk = lane & 7;
 
-    for (long long pr = gwarp; pr < cp.n_pairs; pr += nwarps) {
+    const long long n_todo = cp.pair_list ? (long long)*cp.pair_count : cp.n_pairs;
+    for (long long q = gwarp; q < n_todo; q += nwarps) {
+        const long long pr = cp.pair_list ? cp.pair_list[q] : q;
         const int A = (int)(cp.top_off[pr + 1] - cp.top_off[pr]), B = (int)(cp.side_off[pr + 1] - cp.side_off[pr]);
         if (A == 0 || B == 0) {
             if (lane == 0) cp.out_count[pr] = 1ull; /* borders only: one path along the border */

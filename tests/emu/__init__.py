@@ -226,6 +226,31 @@ def fill_batch_bp(tops, sides, m, k, d, *, grid=1, warps=2):
     return {"tables": tables, "scores": scores[:n].copy(), "branches": branches[:n].copy(), "n_fallback": int(nfb.value)}
 
 
+def batch_lcount(tops, sides, tables, *, grid=1, warps=2):
+    """nwb_batch_lcount_kernel (csrc/nwb_batch_lcount.cuh: one thread per pair, sparse backward sweep over arrow
+    tables a batch fill has written) under the emulator, followed by the dense kernel over the pairs it gave up on.
+    tables[i]: (B_i, pitch_i) uint8.  Returns (counts, n_fallback)."""
+    build()
+    L = lib()
+    n = len(tops)
+    toff = np.zeros(n + 1, dtype=np.int64)
+    soff = np.zeros(n + 1, dtype=np.int64)
+    toff[1:] = np.cumsum([len(t) for t in tops])
+    soff[1:] = np.cumsum([len(s) for s in sides])
+    aoff = np.zeros(n + 1, dtype=np.int64)
+    aoff[1:] = np.cumsum([t.size for t in tables])
+    arrows = np.concatenate([np.ascontiguousarray(t, np.uint8).ravel() for t in tables] + [np.full(64, 0xEE, np.uint8)])
+    counts = np.zeros(n + 1, dtype=np.uint64)
+    nfb = C.c_longlong(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.emu_batch_lcount.restype = C.c_int
+    L.emu_batch_lcount.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_uint, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.POINTER(C.c_longlong)]
+    rc = L.emu_batch_lcount(p(toff), p(soff), n, grid, warps, p(arrows), p(aoff), p(counts), C.byref(nfb))
+    assert rc == 0, rc
+    return counts[:n].copy(), int(nfb.value)
+
+
 def fill_batch_i32(tops, sides, m, k, d, *, grid=1, want_scores=False, want_abs=True):
     """nwb_batch_i32_kernel (csrc/nwb_batch_i32.cuh: any m / k / d, one warp per pair) under the emulator."""
     n = len(tops)

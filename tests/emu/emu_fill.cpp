@@ -16,6 +16,7 @@
 #include "nwb_batch_bx.cuh"
 #include "nwb_batch_bp.cuh"
 #include "nwb_batch_count.cuh"
+#include "nwb_batch_lcount.cuh"
 #include "nwb_batch_i32.cuh"
 
 #include <vector>
@@ -386,6 +387,42 @@ int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int
     }
     *partial_r = sum.rsum;
     *branches = sum.branch_count;
+    return 0;
+}
+
+/* nwb_batch_lcount_kernel (one thread per pair, sparse backward sweep) followed, as in batch_count_pass(), by the
+ * dense nwb_batch_count_kernel over the pairs it gave up on.  *n_fallback reports how many those were. */
+int emu_batch_lcount(const long long *top_off, const long long *side_off, long long n, unsigned grid, int warps,
+                     const uint8_t *arrows, const long long *arrow_off, unsigned long long *counts, long long *n_fallback)
+{
+    std::vector<long long> fb((size_t)n + 1, -1);
+    unsigned fbn = 0;
+    NwbLaneCountParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.top_off = top_off; lp.side_off = side_off; lp.n_pairs = n; lp.arrows = arrows; lp.arrow_off = arrow_off;
+    lp.out_count = counts; lp.fb_list = fb.data(); lp.fb_count = &fbn;
+    emu_launch(grid, 32 * warps, 0, [&]() { nwb_batch_lcount_kernel(lp); });
+    if (n_fallback) *n_fallback = fbn;
+    if (fbn) {
+        NwbBatchCountParams cp;
+        memset(&cp, 0, sizeof(cp));
+        int maxB = 0, maxS = 1;
+        for (long long p = 0; p < n; p++) {
+            const long long A = top_off[p + 1] - top_off[p], B = side_off[p + 1] - side_off[p];
+            if ((A + 255) / 256 > maxS) maxS = (int)((A + 255) / 256);
+            if (B > maxB) maxB = (int)B;
+        }
+        cp.top_off = top_off; cp.side_off = side_off; cp.n_pairs = n;
+        cp.arrows = arrows; cp.arrow_off = arrow_off; cp.out_count = counts;
+        std::vector<unsigned long long> scratch;
+        if (maxS > 1) {
+            cp.scratch_per_warp = nwb_round_up((size_t)maxB + 1, 16);
+            scratch.assign((size_t)grid * NWB_BCNT_WARPS * cp.scratch_per_warp, 0xdeadbeefdeadbeefULL);
+            cp.scratch = scratch.data();
+        }
+        cp.pair_list = fb.data(); cp.pair_count = &fbn;
+        emu_launch(grid, 32 * NWB_BCNT_WARPS, (size_t)NWB_BCNT_SMEM_PER_WARP * NWB_BCNT_WARPS, [&]() { nwb_batch_count_kernel(cp); });
+    }
     return 0;
 }
 

@@ -479,6 +479,65 @@ def test_batch_bit_parallel(oracle, nwb):
 
 
 
+def test_batch_lane_count(oracle, nwb):
+    """csrc/nwb_batch_lcount.cuh nwb_batch_lcount_kernel: the count behind -s for a batch, one thread per pair sweeping
+    backwards over the cells on optimal paths; pairs whose band does not fit the 40-column window are counted by the
+    dense kernel from the list.  Config 4's golden counts, ragged shapes, pairs wider than a strip, empty strings,
+    schemes where nearly every pair gives up (0/0/0: every cell ties), protein 2/1/2; the dense pass alone
+    (nwb_tune batch_lcount = 0) must agree on every pair, and refill in chunks too."""
+    rng = random.Random(47)
+    n = 6000
+    idx = list(range(n - 1)) + [999999]
+    tops, sides = zip(*(oracle.generate_pair(0x5EED4000 + 2 * p, 256, 256) for p in idx))
+    res = {}
+    for knob in (1, 0):
+        with nwb.tuned(batch_lcount=knob):
+            bt = nwb.Batch(list(tops), list(sides), 1, 1, 1, nwb.WANT_COUNT)
+            bt.run()
+            bt.fetch()
+            res[knob] = (bt.digest(0), [bt.count(i) for i in (0, 1, n - 1)], bt.launches())
+            if knob:
+                for i in rng.sample(range(n), 40):
+                    assert bt.count(i) == oracle.fill(tops[i], sides[i], 1, 1, 1).count, i
+            bt.close()
+    assert res[1][1] == [387701138034524160, 108460706365440, 4971798065203200]
+    assert res[1][:2] == res[0][:2]
+    lens = [(256, 256), (1, 1), (255, 257), (300, 40), (17, 130), (0, 5), (700, 90), (64, 64), (256, 1), (33, 33),
+            (257, 31), (100, 300), (5, 0), (1500, 700), (40, 41), (41, 40)] + \
+           [(rng.randint(1, 600), rng.randint(1, 500)) for _ in range(300)] + \
+           [(a, max(1, a + rng.randint(-8, 8))) for a in (30, 60, 100, 200, 256, 300, 500) for _ in range(20)]
+    for alpha, schemes in ((b"ACGT", ((1, 1, 1), (0, 0, 0))), (b"ARNDCQEGHILKMFPSTWYV", ((2, 1, 2), (5, 4, 3)))):
+        tops = [bytes(rng.choice(alpha) for _ in range(a)) for a, _ in lens]
+        sides = [bytes(rng.choice(alpha) for _ in range(b)) for _, b in lens]
+        for m, k, d in schemes:
+            got = {}
+            for knob in (1, 0):
+                with nwb.tuned(batch_lcount=knob):
+                    bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_COUNT)
+                    bt.run()
+                    bt.fetch()
+                    got[knob] = [bt.count(i) for i in range(len(lens))]
+                    bt.close()
+            assert got[1] == got[0], (m, k, d)
+            for i in list(range(16)) + rng.sample(range(16, len(lens)), 25):
+                assert got[1][i] == oracle.fill(tops[i], sides[i], m, k, d).count, (m, k, d, i, lens[i])
+    # from host buffers in chunks: every chunk has its own left-over list
+    n = 40000
+    tcat = nwb.generate(0x5EED4000, 256, nwb.DNA, count=n, seed_stride=2)
+    scat = nwb.generate(0x5EED4001, 256, nwb.DNA, count=n, seed_stride=2)
+    off = np.arange(n + 1, dtype=np.int64) * 256
+    res = {}
+    for knob in (1, 0):
+        with nwb.tuned(batch_lcount=knob):
+            bt = nwb.Batch.from_arrays(tcat, off, scat, off, 1, 1, 1, nwb.WANT_COUNT)
+            bt.refill(tcat, scat)
+            bt.fetch()
+            res[knob] = bt.digest(0)
+            bt.close()
+    assert res[1] == res[0]
+
+
+
 def test_batch_count(oracle, nwb):
     """NWB_WANT_COUNT on the batch path (csrc/nwb_batch_count.cuh): SURVEY 8c's config 4 counts, ragged shapes,
     pairs wider than one strip, empty strings, wrap-around mod 2^64 (0/0/0)."""
