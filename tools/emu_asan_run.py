@@ -60,4 +60,16 @@ for (a,b,n) in ((256,256,3),(40,64,61),(255,96,27)):
             o=oracle.fill(tops[i],sides[i],1,1,1)
             assert (r['scores'][i],r['branches'][i],int(r['counts'][i]))==(o.final_score,o.branch_count,o.count), i
     del os.environ["NWB_CX_WARPS"]
+# bit-parallel batch kernel (one thread per pair: match vectors, look-up table, staging buffer in shared memory; word
+# loads at the end of the string buffers; the left-over list) and the per-lane sparse count (16-byte loads around the
+# window, the dense kernel over its left-over list)
+lens=[(256,256)]*33+[(200,90),(256,31),(17,130),(1,1),(64,64),(0,3),(5,0),(255,77),(129,300),(3,3),(256,1)]*3
+tops=[bytes(random.choice(b"ACGTN" if i%13==5 else b"ACGT") for _ in range(a)) for i,(a,_) in enumerate(lens)]
+sides=[bytes(random.choice(b"ACGTX") for _ in range(b)) for _,b in lens]
+r=emu.fill_batch_bp(tops,sides,1,1,1,grid=2,warps=2)
+assert r is not None and r['n_fallback']>=1
+counts,nfb=emu.batch_lcount(tops,sides,r['tables'],grid=2,warps=2)
+for i in range(len(lens)):
+    o=oracle.fill(tops[i],sides[i],1,1,1)
+    assert (r['scores'][i],r['branches'][i],int(counts[i]))==(o.final_score,o.branch_count,o.count), i
 print("asan run ok")
