@@ -127,9 +127,9 @@ static int batch_create_impl(const char *tops, const int64_t *top_off, const cha
          * keep the simpler kernels, for tests) */
         b->use_bx = nwb_bx_usable(pc, b->max_A, b->max_B) && g_tune.batch_bx != 0;
         b->use_cx = b->use_bx && n_pairs > 0 && nwb_cx_usable(pc, b->uniform, b->uni_A, (int)b->uni_B) && g_tune.batch_cx != 0;
-        /* small differences (2d + m <= 3: DNA 1/1/1) and one strip: a thread per pair, a row per addition.  Narrow
-         * tables keep the warp kernels (the row vectors are always 256 bits wide). */
-        b->use_bp = n_pairs > 0 && nwb_bp_usable(pc, b->max_A) && g_tune.batch_bp != 0 && (b->max_A > 128 || g_tune.batch_bp == 1);
+        /* small differences (2d + m <= 3: DNA 1/1/1) and one strip: a thread per pair, a row per addition (row vectors
+         * of 64, 128 or 256 bits by the longest top string; very short strings keep the warp kernels) */
+        b->use_bp = n_pairs > 0 && nwb_bp_usable(pc, b->max_A) && g_tune.batch_bp != 0 && (b->max_A > NWB_BP_MIN_AUTO || g_tune.batch_bp == 1);
     }
     if (!general && !b->use_bx && NWB_BATCH_SMEM_PER_WARP(b->max_B) > 220 * 1024) { nwb_batch_free(b); return NWB_ERR_UNSUPPORTED; }
     const size_t tbytes = (size_t)top_off[n_pairs], sbytes = (size_t)side_off[n_pairs];
@@ -353,14 +353,20 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
         if (warps > NWB_BP_WARPS) warps = NWB_BP_WARPS;
         const size_t smem = NWB_BP_SMEM_BYTES(warps);
         int launched = 0;
+#define NWB_BP_GO_W(M_, N_, W_)                                                                                          \
+    {                                                                                                                    \
+        CK(cudaFuncSetAttribute(nwb_batch_bp_kernel<M_, N_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        nwb_batch_bp_kernel<M_, N_, W_><<<grid, 32 * warps, smem, st>>>(pp);                                               \
+        launched = 1;                                                                                                    \
+    }
 #define NWB_BP_GO(M_, N_)                                                                                            \
     if (b->pc.a_match == M_ && b->pc.a_mis == N_) {                                                                  \
-        CK(cudaFuncSetAttribute(nwb_batch_bp_kernel<M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        nwb_batch_bp_kernel<M_, N_><<<grid, 32 * warps, smem, st>>>(pp);                                               \
-        launched = 1;                                                                                                \
+        if (nw == 2) NWB_BP_GO_W(M_, N_, 2) else if (nw == 4) NWB_BP_GO_W(M_, N_, 4) else NWB_BP_GO_W(M_, N_, 8)        \
     }
+        const int nw = nwb_bp_words(b->max_A); /* 64-, 128- or 256-bit row vectors */
         NWB_BP_GO(1, 0) NWB_BP_GO(1, 1) NWB_BP_GO(2, 0) NWB_BP_GO(2, 1) NWB_BP_GO(2, 2)
         NWB_BP_GO(3, 0) NWB_BP_GO(3, 1) NWB_BP_GO(3, 2) NWB_BP_GO(3, 3)
+#undef NWB_BP_GO_W
 #undef NWB_BP_GO
         if (!launched) return NWB_ERR_UNSUPPORTED;
         CK(cudaGetLastError());

@@ -34,7 +34,9 @@
 #pragma once
 #include "nwb_batch.cuh"
 
-#define NWB_BP_NW 8     /* 32-bit words per row vector: up to 256 columns */
+#define NWB_BP_NW 8     /* 32-bit words per row vector, at most: up to 256 columns (instantiated: 2, 4, 8) */
+#define NWB_BP_MIN_AUTO 0  /* top strings up to this length keep the warp kernels unless asked (nwb_tune batch_bp = 1); measured:
+                            * 32 x 32 pairs already run 7x faster here than in nwb_batch_bx_kernel */
 #define NWB_BP_NSYM 4   /* letters with a match vector */
 #define NWB_BP_MAXM 3   /* instantiated difference ranges */
 #define NWB_BP_WARPS 16  /* at most, per block (128 registers per thread) */
@@ -69,6 +71,9 @@ static inline bool nwb_bp_usable(const NwbPkConsts &pc, long long max_A)
     return pc.a_match >= 1 && pc.a_match <= NWB_BP_MAXM && pc.a_mis >= 0 && pc.a_mis <= pc.a_match && max_A <= 32 * NWB_BP_NW;
 }
 
+/* words per row vector for a batch whose longest top string has max_A letters */
+static inline int nwb_bp_words(long long max_A) { return max_A <= 64 ? 2 : (max_A <= 128 ? 4 : 8); }
+
 /* Warps per block: every group of 32 pairs costs the same, so the groups are worked off in rounds of
  * grid x warps; among the block sizes that need the fewest rounds take the smallest (the last round is the
  * fullest, and fewer resident warps leave each one more of the SM). */
@@ -83,8 +88,8 @@ static inline int nwb_bp_choose_warps(long long groups, int grid)
 }
 
 /* [x >= k] of a bit-sliced value (pl[0] = least significant plane); k is a compile-time constant after unrolling */
-template <int NB>
-__device__ __forceinline__ unsigned nwb_bp_ge(const unsigned (&pl)[NB][NWB_BP_NW], const int k, const int w)
+template <int NB, int NW>
+__device__ __forceinline__ unsigned nwb_bp_ge(const unsigned (&pl)[NB][NW], const int k, const int w)
 {
     if (k <= 0) return 0xFFFFFFFFu;
     if (k >= (1 << NB)) return 0u;
@@ -94,37 +99,53 @@ __device__ __forceinline__ unsigned nwb_bp_ge(const unsigned (&pl)[NB][NWB_BP_NW
     return res;
 }
 
-/* s = a + b over NWB_BP_NW words (one carry chain) */
-__device__ __forceinline__ void nwb_bp_add(unsigned (&s)[NWB_BP_NW], const unsigned (&a)[NWB_BP_NW], const unsigned (&b)[NWB_BP_NW])
+/* s = a + b over NW words (one carry chain) */
+template <int NW>
+__device__ __forceinline__ void nwb_bp_add(unsigned (&s)[NW], const unsigned (&a)[NW], const unsigned (&b)[NW])
 {
 #ifdef NWB_EMU
     unsigned long long c = 0ull;
-    for (int w = 0; w < NWB_BP_NW; w++) {
+    for (int w = 0; w < NW; w++) {
         c += (unsigned long long)a[w] + b[w];
         s[w] = (unsigned)c;
         c >>= 32;
     }
 #else
-    asm("add.cc.u32 %0, %8, %16;\n\t"
-        "addc.cc.u32 %1, %9, %17;\n\t"
-        "addc.cc.u32 %2, %10, %18;\n\t"
-        "addc.cc.u32 %3, %11, %19;\n\t"
-        "addc.cc.u32 %4, %12, %20;\n\t"
-        "addc.cc.u32 %5, %13, %21;\n\t"
-        "addc.cc.u32 %6, %14, %22;\n\t"
-        "addc.u32 %7, %15, %23;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
-          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    static_assert(NW == 2 || NW == 4 || NW == 8, "row vectors of 64, 128 or 256 bits");
+    if constexpr (NW == 8) {
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+              "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    } else if constexpr (NW == 4) {
+        asm("add.cc.u32 %0, %4, %8;\n\t"
+            "addc.cc.u32 %1, %5, %9;\n\t"
+            "addc.cc.u32 %2, %6, %10;\n\t"
+            "addc.u32 %3, %7, %11;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    } else {
+        asm("add.cc.u32 %0, %2, %4;\n\t"
+            "addc.u32 %1, %3, %5;"
+            : "=r"(s[0]), "=r"(s[1])
+            : "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]));
+    }
 #endif
 }
 
 /* binary planes of a level-set (thermometer) code th[1..M] */
-template <int M, int NB>
-__device__ __forceinline__ void nwb_bp_binary(unsigned (&out)[NB][NWB_BP_NW], const unsigned (&th)[M + 2][NWB_BP_NW])
+template <int M, int NB, int NW>
+__device__ __forceinline__ void nwb_bp_binary(unsigned (&out)[NB][NW], const unsigned (&th)[M + 2][NW])
 {
 #pragma unroll
-    for (int w = 0; w < NWB_BP_NW; w++) {
+    for (int w = 0; w < NW; w++) {
 #pragma unroll
         for (int t = 0; t < NB; t++) {
             unsigned p = 0u;
@@ -173,11 +194,10 @@ __device__ __forceinline__ unsigned nwb_bp_lut(const unsigned *mylut, const unsi
 
 /* One row of one pair: E = match vector of the row's side letter, uu = u of the row above (bit-sliced; replaced by
  * this row's u).  Out: D = DIAG plane, Ln = NOT LEFT (u != 0), Un = NOT UP (v != 0). */
-template <int M, int N, int NB>
-__device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsigned (&uu)[NB][NWB_BP_NW], unsigned (&D)[NWB_BP_NW],
-                                            unsigned (&Ln)[NWB_BP_NW], unsigned (&Un)[NWB_BP_NW])
+template <int M, int N, int NB, int NW>
+__device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NW], unsigned (&uu)[NB][NW], unsigned (&D)[NW],
+                                            unsigned (&Ln)[NW], unsigned (&Un)[NW])
 {
-    constexpr int NW = NWB_BP_NW;
     if constexpr (M == 3 && N == 1) {
         /* DNA 1/1/1, written out so that every intermediate is a function of three words, one LOP3 each (the
          * look-up tables are spelled out: the compiler does not find them from the generic expressions):
@@ -246,8 +266,8 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsig
         unsigned Pp[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            const unsigned Pw = ~nwb_bp_ge<NB>(uu, 1, w);
-            const unsigned Pn = (w + 1 < NW) ? ~nwb_bp_ge<NB>(uu, 1, w + 1) : 0u;
+            const unsigned Pw = ~nwb_bp_ge<NB, NW>(uu, 1, w);
+            const unsigned Pn = (w + 1 < NW) ? ~nwb_bp_ge<NB, NW>(uu, 1, w + 1) : 0u;
             Pp[w] = __funnelshift_r(Pw, Pn, 1);
         }
         unsigned V[M + 2][NW], Vs[M + 2][NW];
@@ -258,10 +278,10 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsig
             unsigned S[NW], T[NW], sum[NW];
 #pragma unroll
             for (int w = 0; w < NW; w++) {
-                unsigned y = E[w] & ~nwb_bp_ge<NB>(uu, M - k + 1, w);
-                if (k <= N) y |= ~E[w] & ~nwb_bp_ge<NB>(uu, N - k + 1, w);
+                unsigned y = E[w] & ~nwb_bp_ge<NB, NW>(uu, M - k + 1, w);
+                if (k <= N) y |= ~E[w] & ~nwb_bp_ge<NB, NW>(uu, N - k + 1, w);
 #pragma unroll
-                for (int t = 1; t <= M - k; t++) y |= Vs[k + t][w] & ~nwb_bp_ge<NB>(uu, t + 1, w);
+                for (int t = 1; t <= M - k; t++) y |= Vs[k + t][w] & ~nwb_bp_ge<NB, NW>(uu, t + 1, w);
                 S[w] = y;
                 T[w] = y & Pp[w];
             }
@@ -272,8 +292,8 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsig
             for (int w = 0; w < NW; w++) Vs[k][w] = (w > 0) ? __funnelshift_l(V[k][w - 1], V[k][w], 1) : (V[k][0] << 1);
         }
         unsigned v[NB][NW], vl[NB][NW];
-        nwb_bp_binary<M, NB>(v, V);
-        nwb_bp_binary<M, NB>(vl, Vs);
+        nwb_bp_binary<M, NB, NW>(v, V);
+        nwb_bp_binary<M, NB, NW>(vl, Vs);
 #pragma unroll
         for (int w = 0; w < NW; w++) {
             /* u of this row = v + uU - vL (mod 2^NB: the result lies in [0, M]); z = v + uU */
@@ -307,13 +327,12 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NWB_BP_NW], unsig
 /* The rows of one group of 32 pairs (lane = pair).  FULL: every pair of the group is 256 columns wide and all have
  * the same number of rows: no column masks, no per-pair row count at the stores, tables evenly spaced.  A
  * warp-uniform choice made outside the row loop, so that the common case carries no selects. */
-template <int M, int N, int NB, bool FULL>
+template <int M, int N, int NB, int NW, bool FULL>
 __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, const unsigned *peq, uint4 *stage, uint8_t *side_sm,
                                              const uint2 *meta, const unsigned *mylut, const int lane, const int A, const int Brun,
                                              const int maxB, const long long s0, const bool s_al, const unsigned l0,
                                              const unsigned l1, const unsigned l2, const unsigned l3, unsigned &branches, int &rsum)
 {
-    constexpr int NW = NWB_BP_NW;
     unsigned uu[NB][NW]; /* u of the row above, bit-sliced */
 #pragma unroll
     for (int t = 0; t < NB; t++)
@@ -326,8 +345,9 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
     uint4 *st_w[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) st_w[w] = stage + lane * 8 + (w ^ (lane & 7));
-    const int ch = lane & 7, h = lane >> 3;
-    const uint4 *st_r0 = stage + h * 8 + (ch ^ h), *st_r1 = stage + (h + 4) * 8 + (ch ^ (h + 4));
+    /* NW lanes store the row of one pair: lane = h * NW + ch, pair 32 / NW * i + h in round i */
+    const int ch = lane & (NW - 1), h = lane / NW;
+    const uint4 *st_r0 = stage + h * 8 + (ch ^ h), *st_r1 = stage + (h + 4) * 8 + (ch ^ (h + 4)); /* NW == 8: (L & 7) = h or h + 4 */
     const unsigned k2 = bp.k2, k4 = bp.k4;
 
 #pragma unroll 1
@@ -361,7 +381,7 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
 
         /* one row: the arrow planes (LEFT and UP inverted) and u of this row */
         unsigned Dp[NW], Ln[NW], Un[NW];
-        nwb_bp_row<M, N, NB>(E, uu, Dp, Ln, Un);
+        nwb_bp_row<M, N, NB, NW>(E, uu, Dp, Ln, Un);
         unsigned rowbr = 0u;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
@@ -400,11 +420,12 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
             *st_w[w] = make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
-        /* lanes 8h..8h+7 store the row of pair 4i + h: whole 128-byte lines */
+        /* lanes h * NW .. h * NW + NW - 1 store the row of pair 32 / NW * i + h: whole 16 * NW-byte row pieces (NW = 8:
+         * whole 128-byte lines) */
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int L = 4 * i + h; /* (L & 7) = h or h + 4 */
-            const uint4 val = ((i & 1) ? st_r1 : st_r0)[(i >> 1) * 64];
+        for (int i = 0; i < NW; i++) {
+            const int L = (32 / NW) * i + h;
+            const uint4 val = (NW == 8) ? ((i & 1) ? st_r1 : st_r0)[(i >> 1) * 64] : stage[L * 8 + (ch ^ (L & 7))];
             if (FULL) {
                 gdst[(unsigned)L * (unsigned)(8 * maxB) + (unsigned)(8 * j + ch)] = val;
             } else {
@@ -416,11 +437,10 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
     }
 }
 
-template <int M, int N>
+template <int M, int N, int NW>
 __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(const NwbBpParams bp)
 {
     constexpr int NB = (M >= 4) ? 3 : ((M >= 2) ? 2 : 1);
-    constexpr int NW = NWB_BP_NW;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = (int)(blockDim.x >> 5);
@@ -533,8 +553,8 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         meta[lane] = make_uint2(valid ? (unsigned)((bp.arrow_off[p] - off0) >> 4) : 0u, (unsigned)Brun);
         __syncwarp();
         uint4 *gdst = reinterpret_cast<uint4 *>(bp.arrows + off0);
-        if (full) nwb_bp_rows<M, N, NB, true>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
-        else nwb_bp_rows<M, N, NB, false>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
+        if (full) nwb_bp_rows<M, N, NB, NW, true>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
+        else nwb_bp_rows<M, N, NB, NW, false>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
         if (Brun > 0) {
             bp.out_score[p] = rsum - bp.d * (A + B);
             if (bp.out_branch) bp.out_branch[p] = branches;

@@ -194,9 +194,10 @@ def fill_batch(tops, sides, m, k, d, *, grid=1, bx=-1, count=False):
                 counts=counts)
 
 
-def fill_batch_bp(tops, sides, m, k, d, *, grid=1, warps=2):
+def fill_batch_bp(tops, sides, m, k, d, *, grid=1, warps=2, words=0):
     """nwb_batch_bp_kernel (csrc/nwb_batch_bp.cuh: bit-parallel rows, one thread per pair) under the emulator,
-    followed by nwb_batch_pk_kernel over the pairs it left over.  Returns None when the batch does not qualify."""
+    followed by nwb_batch_pk_kernel over the pairs it left over.  words: 0 = as the library picks them (2, 4 or 8 per row
+    vector by the longest top string), or 2 / 4 / 8.  Returns None when the batch does not qualify."""
     build()
     L = lib()
     n = len(tops)
@@ -215,9 +216,9 @@ def fill_batch_bp(tops, sides, m, k, d, *, grid=1, warps=2):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     L.emu_fill_batch_bp.restype = C.c_int
     L.emu_fill_batch_bp.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
-                                    C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]
+                                    C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]
     # the kernels read up to 3 bytes past a string (aligned word loads): pad like the product's device buffers
-    rc = L.emu_fill_batch_bp(b"".join(tops) + b"\0" * 16, p(toff), b"".join(sides) + b"\0" * 16, p(soff), n, m, k, d, grid, warps,
+    rc = L.emu_fill_batch_bp(b"".join(tops) + b"\0" * 16, p(toff), b"".join(sides) + b"\0" * 16, p(soff), n, m, k, d, grid, warps, words,
                              p(arrows), p(aoff), p(scores), p(branches), C.byref(nfb))
     if rc == -6:
         return None

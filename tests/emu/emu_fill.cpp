@@ -35,17 +35,24 @@ static void run_pk_emu(unsigned grid, int warps, const NwbStripParams &p, const 
                [&]() { nwb_fill_pk_kernel<K, R, COUNT>(p, pc); });
 }
 
-template <int M>
-static bool emu_bp_go(int N, unsigned grid, int warps, const NwbBpParams &p)
+template <int M, int NW>
+static bool emu_bp_go_w(int N, unsigned grid, int warps, const NwbBpParams &p)
 {
     const size_t smem = NWB_BP_SMEM_BYTES(warps);
     switch (N) {
-    case 0: emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, 0>(p); }); return true;
-    case 1: if (M >= 1) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 1 ? 1 : 0)>(p); }); return true; } break;
-    case 2: if (M >= 2) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 2 ? 2 : 0)>(p); }); return true; } break;
-    case 3: if (M >= 3) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 3 ? 3 : 0)>(p); }); return true; } break;
+    case 0: emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, 0, NW>(p); }); return true;
+    case 1: if (M >= 1) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 1 ? 1 : 0), NW>(p); }); return true; } break;
+    case 2: if (M >= 2) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 2 ? 2 : 0), NW>(p); }); return true; } break;
+    case 3: if (M >= 3) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 3 ? 3 : 0), NW>(p); }); return true; } break;
     }
     return false;
+}
+template <int M>
+static bool emu_bp_go(int N, int nw, unsigned grid, int warps, const NwbBpParams &p)
+{
+    if (nw == 2) return emu_bp_go_w<M, 2>(N, grid, warps, p);
+    if (nw == 4) return emu_bp_go_w<M, 4>(N, grid, warps, p);
+    return emu_bp_go_w<M, 8>(N, grid, warps, p);
 }
 
 extern "C" {
@@ -569,8 +576,8 @@ int emu_fill_batch(const char *tops, const long long *top_off, const char *sides
  * nwb_batch_pk_kernel over the pairs it left on its list (more than four distinct letters in the top string).
  * *n_fallback reports how many those were.  -6: the batch does not qualify. */
 int emu_fill_batch_bp(const char *tops, const long long *top_off, const char *sides, const long long *side_off,
-                      long long n, int m, int k, int d, unsigned grid, int warps, uint8_t *arrows, long long *arrow_off,
-                      int *scores, unsigned *branches, long long *n_fallback)
+                      long long n, int m, int k, int d, unsigned grid, int warps, int force_words, uint8_t *arrows,
+                      long long *arrow_off, int *scores, unsigned *branches, long long *n_fallback)
 {
     NwbPkConsts pc;
     if (!nwb_pk_supported(m, k, d, &pc)) return -5;
@@ -593,10 +600,12 @@ int emu_fill_batch_bp(const char *tops, const long long *top_off, const char *si
     p.n_pairs = n; p.d = d; p.arrows = arrows; p.arrow_off = arrow_off; p.out_score = scores; p.out_branch = branches;
     p.fb_list = fb.data(); p.fb_count = &fbn; p.k2 = 2u; p.k4 = 4u;
     bool ok = false;
+    const int nw = force_words > 0 ? force_words : nwb_bp_words(maxA);
+    if (32 * nw < maxA) return -6;
     switch (pc.a_match) {
-    case 1: ok = emu_bp_go<1>(pc.a_mis, grid, warps, p); break;
-    case 2: ok = emu_bp_go<2>(pc.a_mis, grid, warps, p); break;
-    case 3: ok = emu_bp_go<3>(pc.a_mis, grid, warps, p); break;
+    case 1: ok = emu_bp_go<1>(pc.a_mis, nw, grid, warps, p); break;
+    case 2: ok = emu_bp_go<2>(pc.a_mis, nw, grid, warps, p); break;
+    case 3: ok = emu_bp_go<3>(pc.a_mis, nw, grid, warps, p); break;
     }
     if (!ok) return -6;
     if (n_fallback) *n_fallback = fbn;

@@ -23,6 +23,7 @@ def _check(oracle, tops, sides, m, k, d, *, grid=1, warps=2, expect_fallback=Non
     assert r is not None
     if expect_fallback is not None:
         assert r["n_fallback"] == expect_fallback
+    amax = max(len(t) for t in tops)
     for i, (t, s) in enumerate(zip(tops, sides)):
         o = oracle.fill(t, s, m, k, d, want_codes=True)
         assert r["scores"][i] == o.final_score, (i, len(t), len(s))
@@ -30,9 +31,10 @@ def _check(oracle, tops, sides, m, k, d, *, grid=1, warps=2, expect_fallback=Non
         if len(t) and len(s):
             got = emu.unpack_arrows(r["tables"][i], len(t)) & 7
             assert np.array_equal(got, o.codes[1:, 1:] & 7), (i, len(t), len(s))
-            # cells beyond the top string: no arrows at all (pairs this kernel computed itself)
-            if len(t) < 256 and len(set(t)) <= 4:
-                assert not (emu.unpack_arrows(r["tables"][i], 256)[:, len(t):] & 7).any(), i
+            # cells beyond the top string, as far as the row vectors reach: no arrows at all (pairs this kernel computed itself)
+            width = 64 if amax <= 64 else (128 if amax <= 128 else 256)
+            if len(t) < width and len(set(t)) <= 4:
+                assert not (emu.unpack_arrows(r["tables"][i], width)[:, len(t):] & 7).any(), i
     return r
 
 
@@ -109,6 +111,30 @@ def test_bp_every_small_scheme(oracle):
                 seen.add((M, N))
                 _check(oracle, tops, sides, m, k, d)
     assert len(seen) == 9   # every instantiated (M, N)
+
+
+def test_bp_narrow_tables(oracle):
+    """Row vectors of 64 and 128 bits (top strings of at most 64 / 128 letters), as the library picks them and forced
+    wider; uniform groups (the instantiation without masks) and ragged ones."""
+    rng = random.Random(31)
+    for amax, n in ((64, 40), (128, 36), (33, 34), (100, 35)):
+        lens = [(amax, 50)] * 33 + [(rng.randint(1, amax), rng.randint(1, 90)) for _ in range(n - 33)] if n > 33 else []
+        lens = lens or [(amax, 50)] * n
+        tops = [_rand(rng, b"ACGT", a) for a, _ in lens]
+        sides = [_rand(rng, b"ACGT", b) for _, b in lens]
+        for words in (0, 8) if amax > 64 else (0, 4):
+            r = emu.fill_batch_bp(tops, sides, 1, 1, 1, grid=1, warps=2, words=words)
+            assert r is not None and r["n_fallback"] == 0
+            for i, (t, s) in enumerate(zip(tops, sides)):
+                o = oracle.fill(t, s, 1, 1, 1, want_codes=True)
+                assert (r["scores"][i], r["branches"][i]) == (o.final_score, o.branch_count), (amax, words, i)
+                assert np.array_equal(emu.unpack_arrows(r["tables"][i], len(t)) & 7, o.codes[1:, 1:] & 7), (amax, words, i)
+    # other schemes on the narrow instantiations
+    tops = [_rand(rng, b"ACGT", a) for a in (64, 40, 13, 1, 57)]
+    sides = [_rand(rng, b"ACGT", b) for b in (60, 90, 33, 12, 1)]
+    for m, k, d in ((0, 0, 1), (1, -1, 0), (3, 0, 0), (0, 1, 1), (1, 2, 1)):
+        _check(oracle, tops, sides, m, k, d)
+    assert emu.fill_batch_bp([b"A" * 100], [b"A" * 10], 1, 1, 1, words=2) is None   # does not fit 64 bits
 
 
 def test_bp_refuses_what_it_cannot_do():

@@ -468,6 +468,25 @@ def test_batch_bit_parallel(oracle, nwb):
         res[knob] = (bt.digest(0)[:3], bt.opt_score(997), bt.branch_count(n - 1))
         bt.close()
     assert res[1] == res[0]
+    # narrow tables: row vectors of 64 and 128 bits (uniform groups and ragged ones)
+    for amax, n in ((64, 3000), (128, 3000), (100, 2500), (40, 2000)):
+        lens = [(amax, 70)] * 1500 + [(rng.randint(1, amax), rng.randint(1, 200)) for _ in range(n - 1500)]
+        tops = [bytes(rng.choice(b"ACGT") for _ in range(a)) for a, _ in lens]
+        sides = [bytes(rng.choice(b"ACGT") for _ in range(b)) for _, b in lens]
+        with nwb.tuned(batch_bp=1):
+            bt = nwb.Batch(tops, sides, 1, 1, 1, nwb.WANT_ARROWS_HOST | nwb.WANT_COUNT)
+        assert bt.kernel_name() == "nwb_batch_bp_kernel"
+        bt.run()
+        bt.fetch()
+        _batch_check(oracle, nwb, bt, tops, sides, 1, 1, 1, [0, 1, 1499, 1500, n - 1] + rng.sample(range(n), 40))
+        dg = bt.digest(0)
+        bt.close()
+        with nwb.tuned(batch_bp=0):
+            b0 = nwb.Batch(tops, sides, 1, 1, 1, nwb.WANT_COUNT)
+        b0.run()
+        b0.fetch()
+        assert b0.digest(0) == dg, amax
+        b0.close()
     # not for this kernel: 2d + m > 3, strings wider than a strip
     with nwb.tuned(batch_bp=1):
         bt = nwb.Batch(tops[:4], sides[:4], 2, 1, 2, 0)
