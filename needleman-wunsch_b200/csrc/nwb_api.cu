@@ -209,6 +209,7 @@ struct nwb_plan {
     DevBuf<uint16_t> side_pre;
     DevBuf<unsigned long long> digest;
     int count_path = 0;
+    bool suppress_count = false; /* nwb_fill_on(): a strip group fills first and tries the sparse count on its last rank */
     DevBuf<int> progress;
     DevBuf<NwbDevSummary> summary;
     Inbox inbox = {};
@@ -404,6 +405,7 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     unsigned flags = p->flags;
     if (flags & NWB_WANT_COUNT_MATRIX) flags |= NWB_WANT_COUNT;
     if (flags & NWB_WANT_COUNT_DIGEST) flags |= NWB_WANT_COUNT;
+    if (p->suppress_count && !(flags & (NWB_WANT_COUNT_MATRIX | NWB_WANT_COUNT_DIGEST))) flags &= ~(unsigned)NWB_WANT_COUNT;
     const NwbTune tn = g_tune;
 
     NwbPkConsts pc;
@@ -1025,6 +1027,35 @@ extern "C" void nwb_cache_clear(void)
     for (NwbPlanSet *c : drop) planset_destroy(c);
 }
 
+/* The count of a strip group, tried on the rank that owns column A before anything else: the sparse backward sweep
+ * (nwb_count_sparse.cuh) over that rank's own arrow columns.  On the BASELINE inputs the live cells die after ~1000
+ * rows, long before the band reaches the rank's first column; if flow does get there the sweep gives up and the
+ * caller runs the group's dense sweep.  Blocking. */
+static int plan_group_sparse_count(nwb_plan *p, int *state, unsigned long long *count, unsigned *rows)
+{
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->last_stream ? p->last_stream : p->stream;
+    NwbSparseCountParams sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.arrows = p->arrows.p;
+    sc.pitch = p->L.pitch;
+    sc.A = p->A; sc.B = p->B;
+    sc.out_count = &p->summary.p->count;
+    sc.out_state = &p->summary.p->count_state;
+    sc.out_rows = &p->summary.p->sparse_rows;
+    sc.min_col = p->strip_begin * p->L.strip_w + 1;
+    nwb_sparse_count_kernel<<<1, 32, 0, st>>>(sc);
+    CK(cudaGetLastError());
+    p->launches += 1;
+    NwbDevSummary h;
+    CK(cudaMemcpyAsync(&h, p->summary.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *state = h.count_state;
+    *count = h.count;
+    *rows = h.sparse_rows;
+    return NWB_OK;
+}
+
 extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int side_len,
                            int m, int k, int d, unsigned flags, int device, int num_gpus,
                            nwb_table **out)
@@ -1053,7 +1084,37 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
     }
     const std::vector<nwb_plan *> &plans = ps->plans;
     for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_upload(plans[g], top, top_len, side, side_len);
+    /* -s on a strip group: fill first, then the sparse count on the rank that owns column A; only if that gives up
+     * (flow reaches the rank's first column, band wider than the window) the group runs again with its dense sweep */
+    const bool group_sparse = num_gpus > 1 && (flags & NWB_WANT_COUNT) && !(flags & (NWB_WANT_COUNT_MATRIX | NWB_WANT_COUNT_DIGEST)) &&
+                              g_tune.count_mode == 0 && top_len > 0 && side_len > 0;
+    int gs_state = NWB_SPC_NONE;
+    unsigned long long gs_count = 0ull;
+    unsigned gs_rows = 0u;
+    for (nwb_plan *p : plans) p->suppress_count = group_sparse;
     for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_run(plans[g], m, k, d, nullptr);
+    if (group_sparse && rc == NWB_OK) {
+        nwb_plan *plast = nullptr;
+        for (nwb_plan *p : plans)
+            if (p->strip_end == p->L.n_strips && p->strip_end > p->strip_begin) plast = p;
+        /* the fill of every rank must be over (and clean) before the arrow codes are read */
+        for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
+            nwb_summary s0;
+            rc = nwb_plan_summary(plans[g], &s0);
+        }
+        if (rc == NWB_OK && plast) rc = plan_group_sparse_count(plast, &gs_state, &gs_count, &gs_rows);
+        if (rc == NWB_OK && gs_state != NWB_SPC_DONE) {
+            for (nwb_plan *p : plans) p->suppress_count = false;
+            for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_reset_inbox(plans[g], nullptr);
+            for (int g = 0; g < num_gpus && rc == NWB_OK; g++) {
+                cudaSetDevice(plans[g]->device);
+                cudaError_t e = cudaStreamSynchronize(plans[g]->stream);
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+            }
+            for (int g = 0; g < num_gpus && rc == NWB_OK; g++) rc = nwb_plan_run(plans[g], m, k, d, nullptr);
+        }
+    }
+    for (nwb_plan *p : plans) p->suppress_count = false;
     /* summaries: score/count live on the rank that owns column A (the last
      * non-empty one); branch counts and abs maxima are combined */
     memset(&t->sum, 0, sizeof(t->sum));
@@ -1072,6 +1133,15 @@ extern "C" int nwb_fill_on(const char *top, int top_len, const char *side, int s
             t->sum.count = s.count;
             t->sum.count_path = s.count_path;
             t->sum.count_rows = s.count_rows;
+            if (group_sparse) { /* which sweep delivered the group's count */
+                if (gs_state == NWB_SPC_DONE) {
+                    t->sum.count = gs_count;
+                    t->sum.count_path = NWB_CNT_SPARSE;
+                } else {
+                    t->sum.count_path = NWB_CNT_SPARSE_BAILED;
+                }
+                t->sum.count_rows = gs_rows;
+            }
         }
         t->sum.partial_r += s.partial_r;
         const float ms = nwb_plan_kernel_ms(p);

@@ -44,13 +44,16 @@ struct NwbSparseCountParams {
     int *out_state;                /* NWB_SPC_*                                             */
     unsigned *out_rows;            /* rows visited before the live set died (or NULL)       */
     int mode;                      /* tests: 1 = skip the 64-column attempt, 2 = skip the 256-column attempt */
+    int min_col;                   /* 0 / 1: the whole table is here.  c > 1 (c - 1 a multiple of 256): `arrows` holds columns
+                                    * c .. A only -- the last rank of a strip group; flow that would leave to the left of
+                                    * column c makes the sweep give up instead of being counted at the border */
 };
 
 /* the CPL arrow nibbles of unit `unit` (CPL consecutive columns) in row j; 0 outside the table */
 template <int CPL>
-__device__ __forceinline__ unsigned nwb_spc_load(const uint8_t *arrows, size_t pitch, int j, int unit, unsigned colmask)
+__device__ __forceinline__ unsigned nwb_spc_load(const uint8_t *arrows, size_t pitch, int j, int unit, unsigned colmask, int umin)
 {
-    if (j < 1 || unit < 0) return 0u;
+    if (j < 1 || unit < umin) return 0u;
     const int col0 = unit * CPL; /* 0-based first column of the unit */
     const unsigned *q = reinterpret_cast<const unsigned *>(arrows + (size_t)(j - 1) * pitch) + (col0 >> 3);
 #ifdef NWB_EMU
@@ -67,8 +70,9 @@ __device__ __forceinline__ unsigned long long nwb_spc_sel(unsigned flag, unsigne
  * NWB_SPC_BAILED (uniform); *count and *rows valid in every lane. */
 template <int CPL>
 __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, const size_t pitch, const int A, const int B,
-                                                     const int lane, unsigned long long *count, unsigned *rows)
+                                                     const int min_col, const int lane, unsigned long long *count, unsigned *rows)
 {
+    const int umin = (min_col > 1) ? (min_col - 1) / CPL : 0; /* first unit that is present */
     const unsigned FULL = (CPL == 8) ? 0x77777777u : (0x77777777u & ((1u << (4 * CPL)) - 1u));
     const int rb0 = (A - 1) / CPL;                /* unit of column A */
     int myb = rb0 - ((rb0 - lane) & 31);          /* my unit: == lane (mod 32), inside [rb0-31, rb0]; < 0: none */
@@ -90,7 +94,7 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
     unsigned w[NWB_SPC_CHUNK], wn[NWB_SPC_CHUNK];
     int jtop = B;
 #pragma unroll
-    for (int t = 0; t < NWB_SPC_CHUNK; t++) w[t] = nwb_spc_load<CPL>(arrows, pitch, jtop - t, myb, colmask_of(myb));
+    for (int t = 0; t < NWB_SPC_CHUNK; t++) w[t] = nwb_spc_load<CPL>(arrows, pitch, jtop - t, myb, colmask_of(myb), umin);
     int rlb = rb0; /* rightmost live unit */
     int state = NWB_SPC_NONE;
     unsigned nrows = 0;
@@ -101,7 +105,7 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
         {
             const unsigned cm = colmask_of(nextb);
 #pragma unroll
-            for (int t = 0; t < NWB_SPC_CHUNK; t++) wn[t] = nwb_spc_load<CPL>(arrows, pitch, jtop - NWB_SPC_CHUNK - t, nextb, cm);
+            for (int t = 0; t < NWB_SPC_CHUNK; t++) wn[t] = nwb_spc_load<CPL>(arrows, pitch, jtop - NWB_SPC_CHUNK - t, nextb, cm, umin);
         }
         const int nbb = __shfl_sync(NWB_FULL_MASK, myb, right);
         const bool adjacent = (nbb == myb + 1);
@@ -119,7 +123,11 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
                 d = nwb_spc_sel((x >> (4 * k + 1)) & 1u, P[k]);
             }
             for (;;) {
-                if (myb == 0) { total += d; d = 0ull; } /* LEFT out of column 1: the border column */
+                if (myb == umin) { /* LEFT out of column 1: the border column -- or out of this rank's columns */
+                    if (umin == 0) total += d;
+                    else bad = bad || (d != 0ull);
+                    d = 0ull;
+                }
                 const unsigned long long cin = __shfl_sync(NWB_FULL_MASK, d, right);
                 /* a carry that arrives from a lane which does not own the unit to my right has left the window: it is
                  * dropped (so it cannot circulate) and the sweep is given up at the end of the chunk */
@@ -135,7 +143,11 @@ __device__ __forceinline__ int nwb_sparse_count_pair(const uint8_t *arrows, cons
             }
             /* flow into row j-1: UP keeps the column, DIAG moves one to the left */
             unsigned long long dg = nwb_spc_sel(x & 1u, P[0]);
-            if (myb == 0) { total += dg; dg = 0ull; } /* DIAG out of column 1 */
+            if (myb == umin) { /* DIAG out of column 1 (or out of this rank's columns) */
+                if (umin == 0) total += dg;
+                else bad = bad || (dg != 0ull);
+                dg = 0ull;
+            }
             const unsigned long long dgin = __shfl_sync(NWB_FULL_MASK, dg, right);
             bad = bad || (dgin != 0ull && !adjacent);
 #pragma unroll
@@ -186,9 +198,9 @@ __global__ void __launch_bounds__(32, 1) nwb_sparse_count_kernel(const NwbSparse
     unsigned long long count = 0ull;
     unsigned rows = 0u, rows2 = 0u;
     int state = NWB_SPC_BAILED;
-    if (!(p.mode & 1)) state = nwb_sparse_count_pair<2>(p.arrows, p.pitch, p.A, p.B, lane, &count, &rows);
+    if (!(p.mode & 1)) state = nwb_sparse_count_pair<2>(p.arrows, p.pitch, p.A, p.B, p.min_col, lane, &count, &rows);
     if (state != NWB_SPC_DONE && !(p.mode & 2)) {
-        state = nwb_sparse_count_pair<8>(p.arrows, p.pitch, p.A, p.B, lane, &count, &rows2);
+        state = nwb_sparse_count_pair<8>(p.arrows, p.pitch, p.A, p.B, p.min_col, lane, &count, &rows2);
         rows += rows2;
     }
     if (lane == 0) {

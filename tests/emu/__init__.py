@@ -93,18 +93,19 @@ def fill_pk(top, side, m, k, d, *, K=4, R=1, grid=2, split=0, warps=4, count=Fal
                 dig_row=out.dig_row, dig_col=out.dig_col)
 
 
-def sparse_count(packed: np.ndarray, a: int, mode: int = 0) -> dict:
+def sparse_count(packed: np.ndarray, a: int, mode: int = 0, min_col: int = 0) -> dict:
     """nwb_sparse_count_kernel (csrc/nwb_count_sparse.cuh) over a (B, pitch) nibble table in the include/nwb.h
-    layout.  state: 1 = done (count is final), 2 = gave up (the dense sweep would run)."""
+    layout.  state: 1 = done (count is final), 2 = gave up (the dense sweep would run).  min_col > 1: the table holds
+    columns min_col .. a only (the last rank of a strip group); flow that leaves to the left makes the sweep give up."""
     packed = np.ascontiguousarray(packed, np.uint8)
     b, pitch = packed.shape
     assert pitch % 4 == 0 and pitch * 2 >= a
     res = (C.c_ulonglong * 3)()
     L = lib()
     L.emu_sparse_count.restype = C.c_int
-    L.emu_sparse_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+    L.emu_sparse_count.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
     # mode: 0 = as the product (64-column window first, then 256), 1 = 256-column window only, 2 = 64-column only
-    assert L.emu_sparse_count(packed.ctypes.data_as(C.c_void_p), pitch, a, b, mode, res) == 0
+    assert L.emu_sparse_count(packed.ctypes.data_as(C.c_void_p), pitch, a, b, mode, min_col, res) == 0
     return dict(count=int(res[0]), state=int(res[1]), rows=int(res[2]))
 
 

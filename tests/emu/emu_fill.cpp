@@ -307,7 +307,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
 
 /* The sparse backward count (nwb_count_sparse.cuh) over a finished nibble table in the include/nwb.h layout.
  * res = {count, state (NWB_SPC_*), rows visited}. */
-int emu_sparse_count(const uint8_t *arrows, size_t pitch, int A, int B, int mode, unsigned long long *res)
+int emu_sparse_count(const uint8_t *arrows, size_t pitch, int A, int B, int mode, int min_col, unsigned long long *res)
 {
     unsigned long long count = 0ull;
     int state = 0;
@@ -317,6 +317,7 @@ int emu_sparse_count(const uint8_t *arrows, size_t pitch, int A, int B, int mode
     sc.arrows = arrows; sc.pitch = pitch; sc.A = A; sc.B = B;
     sc.out_count = &count; sc.out_state = &state; sc.out_rows = &rows;
     sc.mode = mode;
+    sc.min_col = min_col;
     emu_launch(1, 32, 0, [&]() { nwb_sparse_count_kernel(sc); });
     res[0] = count; res[1] = (unsigned long long)state; res[2] = rows;
     return 0;

@@ -1,5 +1,7 @@
 """The sparse backward count (csrc/nwb_count_sparse.cuh) and the digest kernels (csrc/nwb_digest.cuh), run
 under the SIMT emulator on the CPU and compared with the oracle's dense forward DP / digests."""
+import random
+
 import numpy as np
 import pytest
 
@@ -157,3 +159,29 @@ def test_sparse_count_random_sweep():
                 assert r["count"] == o.count, (it, a, b, mkd, mode)
                 done += mode == 0
     assert done >= 40
+
+
+def test_sparse_count_on_the_last_rank_of_a_strip_group(oracle):
+    """min_col > 1: the arrow columns left of min_col live on another GPU (here: overwritten with garbage).  The sweep
+    either finishes inside its own columns with the right count or gives up -- it never reads the foreign columns into
+    a result."""
+    rng = random.Random(77)
+    done = gave_up = 0
+    for (a, b, seed) in ((1500, 1500, 1), (1500, 1500, 2), (1300, 1400, 3), (900, 2000, 4), (600, 600, 5)):
+        t, s = oracle.generate_pair(0x5EED7000 + seed, a, b)
+        o = oracle.fill(t, s, 1, 1, 1, want_packed=True, pitch=oracle.packed_pitch(a))
+        full = emu.sparse_count(o.packed, a)
+        assert full["state"] == 1 and full["count"] == o.count
+        for min_col in (257, 513, 1025):
+            if min_col > a:
+                continue
+            tab = o.packed.copy()
+            tab[:, :(min_col - 1) // 2] = rng.choice([0x77, 0x22, 0x11, 0x55])     # not this rank's columns
+            r = emu.sparse_count(tab, a, min_col=min_col)
+            if r["state"] == 1:
+                assert r["count"] == o.count, (a, b, min_col)
+                done += 1
+            else:
+                assert r["state"] == 2
+                gave_up += 1
+    assert done >= 3 and gave_up >= 3

@@ -202,7 +202,9 @@ def test_two_gpu_strips_match_one(oracle, nwb):
 
 def test_strip_group_full_size_digests(oracle, nwb):
     """Column strips over 2 (and 4, 8 when present) GPUs of one process at full size: EVERY arrow set (the ranks' table
-    digests add up to the oracle's), score, branch count and the count (dense sweep handed from GPU to GPU)."""
+    digests add up to the oracle's), score, branch count and the count (the sparse backward sweep on the rank that owns
+    column A -- on these inputs the live cells die long before the band reaches that rank's first column -- and, with
+    nwb_tune count_mode = 2, the dense sweep handed from GPU to GPU)."""
     ndev = nwb.device_count()
     if ndev < 2:
         pytest.skip("needs 2 GPUs")
@@ -215,9 +217,31 @@ def test_strip_group_full_size_digests(oracle, nwb):
             tab = nwb.fill(t, s, *mkd, nwb.WANT_DIGEST | nwb.WANT_COUNT, num_gpus=world)
             assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"]), (name, world)
             assert tab.arrow_digest() == int(g["arrow_digest"], 16), (name, world)
-            assert tab.summary().count_path == nwb.COUNT_DENSE
+            assert tab.summary().count_path == nwb.COUNT_SPARSE, (name, world, tab.summary().count_path)
             tab.close()
+            if world == 2:
+                with nwb.tuned(count_mode=2):
+                    tab = nwb.fill(t, s, *mkd, nwb.WANT_COUNT, num_gpus=world)
+                assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"]), (name, world)
+                assert tab.summary().count_path == nwb.COUNT_DENSE
+                tab.close()
             nwb.cache_clear()
+
+
+def test_strip_group_count_falls_back_to_the_dense_sweep(oracle, nwb):
+    """A string against a mutated copy of itself on 2 GPUs: the count is not 0 mod 2^64, the live band runs through all
+    30,000 rows and leaves the last rank's columns, so the sparse sweep on that rank gives up and the group's dense
+    sweep delivers the count."""
+    if nwb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = [c for c in golden("golden_big.json") if c["name"] == "mutated_dna_30k"][0]
+    (t, s), (m, k, d) = _mutated("mutated_dna_30k")
+    tab = nwb.fill(t, s, m, k, d, nwb.WANT_COUNT | nwb.WANT_DIGEST, num_gpus=2)
+    assert (tab.opt_score, tab.branch_count, tab.count) == (g["final_score"], g["branch_count"], g["count_u64"])
+    assert tab.arrow_digest() == int(g["arrow_digest"], 16)
+    assert tab.summary().count_path == nwb.COUNT_SPARSE_BAILED
+    tab.close()
+    nwb.cache_clear()
 
 
 # ---- batch of independent pairs (BASELINE config 4) ---------------------------------
