@@ -98,6 +98,7 @@ struct NwbTune {
     int cx_warps = 0;    /* 0 = auto (12); 16                                                                */
     int batch_bp = -1;   /* -1 = auto; 0 = never nwb_batch_bp_kernel (bit-parallel rows, one thread per pair)      */
     int bp_warps = 0;    /* 0 = auto; warps per block of nwb_batch_bp_kernel (1..16)                          */
+    int bp_aligned = -1; /* -1 = auto; 0 = never the 64 KB-aligned look-up table (one PRMT per look-up address)     */
     int batch_lcount = -1; /* -1 = auto; 0 = never nwb_batch_lcount_kernel (sparse count, one thread per pair)      */
     int lc_warps = 0;    /* 0 = auto; warps per block of nwb_batch_lcount_kernel                              */
     int watchdog_ms = 4000; /* device-side spin loops give up after this long without progress               */
@@ -136,7 +137,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"count_mode", &g_tune.count_mode}, {"cnt_cpl", &g_tune.cnt_cpl}, {"batch_bx", &g_tune.batch_bx},
         {"batch_cx", &g_tune.batch_cx}, {"bcnt_chain", &g_tune.bcnt_chain},
         {"cx_warps", &g_tune.cx_warps}, {"batch_bp", &g_tune.batch_bp}, {"bp_warps", &g_tune.bp_warps},
-        {"batch_lcount", &g_tune.batch_lcount}, {"lc_warps", &g_tune.lc_warps},
+        {"bp_aligned", &g_tune.bp_aligned}, {"batch_lcount", &g_tune.batch_lcount}, {"lc_warps", &g_tune.lc_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
 #ifdef NWB_EXPERIMENTS
         {"pk_hy", &g_tune.pk_hy}, {"pk_hz", &g_tune.pk_hz}, {"debug_nowait", &g_tune.debug_nowait},

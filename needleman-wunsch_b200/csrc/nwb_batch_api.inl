@@ -351,14 +351,16 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
         pp.fb_list = b->fb_list.p + c0; pp.fb_count = fbc; pp.k2 = 2u; pp.k4 = 4u;
         int warps = g_tune.bp_warps > 0 ? g_tune.bp_warps : nwb_bp_choose_warps((c1 - c0 + 31) / 32, grid);
         if (warps > NWB_BP_WARPS) warps = NWB_BP_WARPS;
-        const size_t smem = NWB_BP_SMEM_BYTES(warps);
+        const bool aligned = warps >= NWB_BP_ALIGNED_MIN_WARPS && g_tune.bp_aligned != 0;
+        const size_t smem = aligned ? (size_t)NWB_BP_SMEM_MAX : NWB_BP_SMEM_BYTES(warps);
         int launched = 0;
-#define NWB_BP_GO_W(M_, N_, W_)                                                                                          \
-    {                                                                                                                    \
-        CK(cudaFuncSetAttribute(nwb_batch_bp_kernel<M_, N_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        nwb_batch_bp_kernel<M_, N_, W_><<<grid, 32 * warps, smem, st>>>(pp);                                               \
-        launched = 1;                                                                                                    \
+#define NWB_BP_GO_A(M_, N_, W_, A_)                                                                                        \
+    {                                                                                                                       \
+        CK(cudaFuncSetAttribute(nwb_batch_bp_kernel<M_, N_, W_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        nwb_batch_bp_kernel<M_, N_, W_, A_><<<grid, 32 * warps, smem, st>>>(pp);                                               \
+        launched = 1;                                                                                                       \
     }
+#define NWB_BP_GO_W(M_, N_, W_) { if (aligned) NWB_BP_GO_A(M_, N_, W_, true) else NWB_BP_GO_A(M_, N_, W_, false) }
 #define NWB_BP_GO(M_, N_)                                                                                            \
     if (b->pc.a_match == M_ && b->pc.a_mis == N_) {                                                                  \
         if (nw == 2) NWB_BP_GO_W(M_, N_, 2) else if (nw == 4) NWB_BP_GO_W(M_, N_, 4) else NWB_BP_GO_W(M_, N_, 8)        \
@@ -367,6 +369,7 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
         NWB_BP_GO(1, 0) NWB_BP_GO(1, 1) NWB_BP_GO(2, 0) NWB_BP_GO(2, 1) NWB_BP_GO(2, 2)
         NWB_BP_GO(3, 0) NWB_BP_GO(3, 1) NWB_BP_GO(3, 2) NWB_BP_GO(3, 3)
 #undef NWB_BP_GO_W
+#undef NWB_BP_GO_A
 #undef NWB_BP_GO
         if (!launched) return NWB_ERR_UNSUPPORTED;
         CK(cudaGetLastError());

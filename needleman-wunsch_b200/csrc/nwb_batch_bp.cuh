@@ -39,15 +39,23 @@
                             * 32 x 32 pairs already run 7x faster here than in nwb_batch_bx_kernel */
 #define NWB_BP_NSYM 4   /* letters with a match vector */
 #define NWB_BP_MAXM 3   /* instantiated difference ranges */
-#define NWB_BP_WARPS 16  /* at most, per block (128 registers per thread) */
-#define NWB_BP_SIDE_ROWS 64
-#define NWB_BP_LUT_BYTES (256 * 32 * 4)
+#define NWB_BP_WARPS 15  /* at most, per block (128 registers per thread; shared memory, see below) */
+#define NWB_BP_SIDE_ROWS 32
+#define NWB_BP_LUT_BYTES (256 * 256) /* entry x: 256 bytes = 32 lanes x {T[x]} then 32 lanes x {T[~x]} */
 #define NWB_BP_PEQ_BYTES ((NWB_BP_NSYM + 1) * NWB_BP_NW * 32 * 4)
 #define NWB_BP_STAGE_BYTES (32 * 128)
 #define NWB_BP_SIDE_BYTES (NWB_BP_SIDE_ROWS * 32)
 #define NWB_BP_META_BYTES (32 * 8)
 #define NWB_BP_WARP_SMEM (NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES + NWB_BP_SIDE_BYTES + NWB_BP_META_BYTES)
-#define NWB_BP_SMEM_BYTES(warps) ((size_t)NWB_BP_LUT_BYTES + (size_t)(warps) * NWB_BP_WARP_SMEM)
+/* The table sits at a 64 KB-aligned address of the shared window so that ONE PRMT forms a look-up address (byte of
+ * the plane word into bits 8..15 of {table | lane * 4}).  Such a block asks for all of the SM's shared memory; the
+ * warps' own areas (10.25 KB each) fill what lies in front of and behind the table: 15 warps fit whether the window of
+ * the dynamic part starts at 0 or behind a reserved kilobyte. */
+#define NWB_BP_SMEM_MAX 232448
+#define NWB_BP_SMEM_BYTES(warps) ((size_t)NWB_BP_LUT_BYTES + (size_t)(warps) * NWB_BP_WARP_SMEM) /* table not aligned */
+/* the aligned table for launches that fill the SMs on their own; a chunk of a refill (a few warps per SM) takes the
+ * other instantiation, whose blocks are small enough for two of them to share an SM */
+#define NWB_BP_ALIGNED_MIN_WARPS 8
 
 struct NwbBpParams {
     const uint8_t *tops;
@@ -184,13 +192,32 @@ __device__ __forceinline__ unsigned nwb_lop3(const unsigned a, const unsigned b,
 #endif
 }
 
-/* entry (byte q of x, or of ~x) of the lane's copy of the byte -> nibbles table */
-template <bool INV>
-__device__ __forceinline__ unsigned nwb_bp_lut(const unsigned *mylut, const unsigned x, const int q)
+/* entry (byte q of x, or of ~x) of the lane's copy of the byte -> nibbles table.  lanetab: the shared-window address
+ * of the lane's word of entry 0 (entry of ~x: + 128), bits 8..15 zero; the PRMT drops byte q of x into them. */
+#ifdef NWB_EMU
+typedef const unsigned *nwb_bp_tab;
+template <bool INV, bool AL>
+__device__ __forceinline__ unsigned nwb_bp_lut(nwb_bp_tab lanetab, const unsigned x, const int q)
 {
-    const int idx = (int)__byte_perm(x, 0u, 0x4440u + (unsigned)q); /* one PRMT */
-    return INV ? mylut[255 * 32 - idx * 32] : mylut[idx * 32];          /* INV: the entry of ~x */
+    const unsigned idx = (x >> (8 * q)) & 0xFFu;
+    return lanetab[idx * 64 + (INV ? 32 : 0)];
 }
+#else
+typedef unsigned nwb_bp_tab;
+template <bool INV, bool AL>
+__device__ __forceinline__ unsigned nwb_bp_lut(nwb_bp_tab lanetab, const unsigned x, const int q)
+{
+    unsigned addr;
+    if (AL) { /* the table is 64 KB-aligned: one PRMT */
+        addr = __byte_perm(lanetab + (INV ? 128u : 0u), x, 0x3240u + ((unsigned)q << 4));
+    } else {  /* anywhere: byte extraction (PRMT) and a multiply-add */
+        addr = __byte_perm(x, 0u, 0x4440u + (unsigned)q) * 256u + (lanetab + (INV ? 128u : 0u));
+    }
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+#endif
 
 /* One row of one pair: E = match vector of the row's side letter, uu = u of the row above (bit-sliced; replaced by
  * this row's u).  Out: D = DIAG plane, Ln = NOT LEFT (u != 0), Un = NOT UP (v != 0). */
@@ -327,9 +354,9 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NW], unsigned (&u
 /* The rows of one group of 32 pairs (lane = pair).  FULL: every pair of the group is 256 columns wide and all have
  * the same number of rows: no column masks, no per-pair row count at the stores, tables evenly spaced.  A
  * warp-uniform choice made outside the row loop, so that the common case carries no selects. */
-template <int M, int N, int NB, int NW, bool FULL>
+template <int M, int N, int NB, int NW, bool FULL, bool AL>
 __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, const unsigned *peq, uint4 *stage, uint8_t *side_sm,
-                                             const uint2 *meta, const unsigned *mylut, const int lane, const int A, const int Brun,
+                                             const uint2 *meta, const nwb_bp_tab mylut, const int lane, const int A, const int Brun,
                                              const int maxB, const long long s0, const bool s_al, const unsigned l0,
                                              const unsigned l1, const unsigned l2, const unsigned l3, unsigned &branches, int &rsum)
 {
@@ -414,7 +441,7 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
             unsigned o[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const unsigned td = nwb_bp_lut<false>(mylut, Dp[w], q), tl = nwb_bp_lut<true>(mylut, Ln[w], q), tu = nwb_bp_lut<true>(mylut, Un[w], q);
+                const unsigned td = nwb_bp_lut<false, AL>(mylut, Dp[w], q), tl = nwb_bp_lut<true, AL>(mylut, Ln[w], q), tu = nwb_bp_lut<true, AL>(mylut, Un[w], q);
                 o[q] = tu * k4 + (tl * k2 + td);
             }
             *st_w[w] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -437,7 +464,7 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
     }
 }
 
-template <int M, int N, int NW>
+template <int M, int N, int NW, bool AL>
 __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(const NwbBpParams bp)
 {
     constexpr int NB = (M >= 4) ? 3 : ((M >= 2) ? 2 : 1);
@@ -447,24 +474,40 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
     const long long nwarps = (long long)gridDim.x * wpb;
     const long long gwarp = (long long)blockIdx.x * wpb + warp;
     unsigned char *smem = NWB_SMEM_BASE();
-    unsigned *lut = reinterpret_cast<unsigned *>(smem);
+#ifdef NWB_EMU
+    unsigned char *lutp = smem;
     unsigned char *mine = smem + NWB_BP_LUT_BYTES + (size_t)warp * NWB_BP_WARP_SMEM;
+#else
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned before = AL ? ((sbase + 0xFFFFu) & ~0xFFFFu) - sbase : 0u; /* bytes in front of the (64 KB-aligned) table */
+    const int nbefore = (int)(before / NWB_BP_WARP_SMEM);
+    unsigned char *lutp = smem + before;
+    unsigned char *mine = (warp < nbefore) ? smem + (size_t)warp * NWB_BP_WARP_SMEM
+                                           : lutp + NWB_BP_LUT_BYTES + (size_t)(warp - nbefore) * NWB_BP_WARP_SMEM;
+    if (AL && before + NWB_BP_LUT_BYTES + (size_t)(wpb - (nbefore < wpb ? nbefore : wpb)) * NWB_BP_WARP_SMEM > NWB_BP_SMEM_MAX) __trap();
+#endif
+    unsigned *lut = reinterpret_cast<unsigned *>(lutp);
     unsigned *peq = reinterpret_cast<unsigned *>(mine);                                  /* [letter 0..4][word][lane] */
     uint4 *stage = reinterpret_cast<uint4 *>(mine + NWB_BP_PEQ_BYTES);                  /* [lane][8 swizzled 16-byte chunks] */
-    uint8_t *side_sm = mine + NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES;                    /* [row & 63][lane] */
+    uint8_t *side_sm = mine + NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES;                    /* [row & 31][lane] */
     uint2 *meta = reinterpret_cast<uint2 *>(mine + NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES + NWB_BP_SIDE_BYTES); /* {table row 0 / 128, rows} */
 
-    /* byte -> 8 nibbles (bit i -> bit 4i), one copy per lane: entry x of lane l sits in bank l */
+    /* byte -> 8 nibbles (bit i -> bit 4i), of x and of ~x, one copy per lane: the words of lane l sit in bank l */
     for (int x = warp; x < 256; x += wpb) {
         unsigned v = 0u;
 #pragma unroll
         for (int i = 0; i < 8; i++) v |= ((unsigned)(x >> i) & 1u) << (4 * i);
-        lut[x * 32 + lane] = v;
+        lut[x * 64 + lane] = v;
+        lut[x * 64 + 32 + lane] = 0x11111111u - v;
     }
 #pragma unroll
     for (int w = 0; w < NW; w++) peq[(NWB_BP_NSYM * NW + w) * 32 + lane] = 0u; /* a side letter the top string does not have */
     __syncthreads();
-    const unsigned *mylut = lut + lane;
+#ifdef NWB_EMU
+    const nwb_bp_tab mylut = lut + lane;
+#else
+    const nwb_bp_tab mylut = sbase + before + 4u * (unsigned)lane;
+#endif
 
     const long long groups = (bp.n_pairs + 31) / 32;
     for (long long g = gwarp; g < groups; g += nwarps) {
@@ -553,8 +596,8 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         meta[lane] = make_uint2(valid ? (unsigned)((bp.arrow_off[p] - off0) >> 4) : 0u, (unsigned)Brun);
         __syncwarp();
         uint4 *gdst = reinterpret_cast<uint4 *>(bp.arrows + off0);
-        if (full) nwb_bp_rows<M, N, NB, NW, true>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
-        else nwb_bp_rows<M, N, NB, NW, false>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
+        if (full) nwb_bp_rows<M, N, NB, NW, true, AL>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
+        else nwb_bp_rows<M, N, NB, NW, false, AL>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
         if (Brun > 0) {
             bp.out_score[p] = rsum - bp.d * (A + B);
             if (bp.out_branch) bp.out_branch[p] = branches;

@@ -40,10 +40,10 @@ static bool emu_bp_go_w(int N, unsigned grid, int warps, const NwbBpParams &p)
 {
     const size_t smem = NWB_BP_SMEM_BYTES(warps);
     switch (N) {
-    case 0: emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, 0, NW>(p); }); return true;
-    case 1: if (M >= 1) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 1 ? 1 : 0), NW>(p); }); return true; } break;
-    case 2: if (M >= 2) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 2 ? 2 : 0), NW>(p); }); return true; } break;
-    case 3: if (M >= 3) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 3 ? 3 : 0), NW>(p); }); return true; } break;
+    case 0: emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, 0, NW, false>(p); }); return true;
+    case 1: if (M >= 1) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 1 ? 1 : 0), NW, false>(p); }); return true; } break;
+    case 2: if (M >= 2) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 2 ? 2 : 0), NW, false>(p); }); return true; } break;
+    case 3: if (M >= 3) { emu_launch(grid, 32 * warps, smem, [&]() { nwb_batch_bp_kernel<M, (M >= 3 ? 3 : 0), NW, false>(p); }); return true; } break;
     }
     return false;
 }

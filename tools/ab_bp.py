@@ -40,7 +40,8 @@ if n == 125000 and (A, B) == (256, 256):
 tpin, spin = nwb.PinnedBuffer(tcat), nwb.PinnedBuffer(scat)
 ok = True
 ref = None
-runs = [("cx", dict(batch_bp=0))] + [(f"bp warps={w}", dict(batch_bp=1, bp_warps=int(w))) for w in args.warps.split(",")]
+runs = [("cx", dict(batch_bp=0))] + [(f"bp warps={w}", dict(batch_bp=1, bp_warps=int(w))) for w in args.warps.split(",")] + \
+       [("bp table anywhere", dict(batch_bp=1, bp_aligned=0))]
 for name, knobs in runs:
     with nwb.tuned(**knobs):
         b = nwb.Batch.from_arrays(tcat, off, scat, soff, 1, 1, 1, 0)
