@@ -19,7 +19,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=125000)
 ap.add_argument("--warps", default="0")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--lib", default=None, help="another build of libnwb.so (variant A/B on the same box)")
 args = ap.parse_args()
+if args.lib:
+    nwb.LIB_PATH = os.path.abspath(args.lib)
 n = args.pairs
 tcat = nwb.generate(0x5EED4000, 256, nwb.DNA, count=n, seed_stride=2)
 scat = nwb.generate(0x5EED4001, 256, nwb.DNA, count=n, seed_stride=2)
