@@ -1,6 +1,6 @@
 /*
  * nwb_batch_bp.cuh -- bit-parallel batch fill ("bp"): one THREAD per pair, a table row is a handful of
- * 256-bit vectors, one addition per difference level resolves a whole row.
+ * bit-vectors (64, 128 or 256 bits by the longest top string), one addition per difference level resolves a whole row.
  *
  * Same results as the reference's score_cell() (needleman-wunsch.c:418-510: the recurrence and "every tie
  * gets its arrow", :485-503) for top strings of up to 256 characters with at most four distinct letters,
@@ -17,14 +17,14 @@
  * and "seeds S run through the runs of P" is ONE multi-word addition (the carry does the running, as in
  * Myers' bit-vector algorithm):  V_k = S_k | (((S_k & P') + P') ^ P'),  P' = P >> 1.  M additions per
  * row, levels from M down to 1; u of the new row = v + uU - vL in bit-sliced binary, the three arrow
- * planes are zero tests on the same vectors: 23 logic instructions, 4 shifts and 3 additions per 32 cells
+ * planes are zero tests on the same vectors: 22 logic instructions, 4 shifts and 3 additions per 32 cells
  * for DNA 1/1/1 (nwb_bp_row), against ~200 instructions for the packed-difference kernels.
  *
  * Mapping: lane = pair.  A warp sweeps 32 pairs row by row; every lane keeps its row state (u as binary
  * bit-planes, 8 words each) in registers, the match vectors of its top string (one per letter) in shared
  * memory, and needs no shuffle and no carry from any other lane.  The arrow planes become the ABI's
  * 4-bit codes (include/nwb.h) through a byte -> 8-nibble table in shared memory (one copy per lane, so
- * no bank conflicts), and a row of the warp (32 pairs x 128 bytes) leaves through a swizzled staging
+ * no bank conflicts; at a 64 KB-aligned address, so that one PRMT forms a look-up address), and a row of the warp (32 pairs x 128 bytes) leaves through a swizzled staging
  * buffer so that every store instruction writes whole 128-byte lines.
  *
  * Pairs whose top string has more than four distinct letters are not computed here: they are put on a
