@@ -304,7 +304,7 @@ float nwb_batch_kernel_ms(const nwb_batch *b);
 int64_t nwb_batch_launches(const nwb_batch *b);
 /* Name of the kernel nwb_batch_run() launches for this batch: "nwb_batch_bp_kernel" (bit-parallel rows, one thread
  * per pair: top strings of at most 256 characters and 2d + m <= 3, e.g. DNA 1/1/1; pairs whose top string has more
- * than four distinct letters are worked off by nwb_batch_pk_kernel right behind it), "nwb_batch_bx_kernel" (two
+ * than five distinct letters are worked off by nwb_batch_pk_kernel right behind it), "nwb_batch_bx_kernel" (two
  * pairs per warp: top strings of at most 256 characters and 2d + m <= 7), "nwb_batch_cx_kernel" (the same, pairs
  * swept back to back: every pair has the same shape and the side length is a multiple of 32),
  * "nwb_batch_i32_kernel" (any m / k / d, scores), "nwb_batch_pk_kernel" otherwise.  For logs and profiles. */

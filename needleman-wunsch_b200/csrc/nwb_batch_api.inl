@@ -338,7 +338,7 @@ static int batch_fill_pass(nwb_batch *b, cudaStream_t st, int64_t c0, int64_t c1
     memset(&bp, 0, sizeof(bp));
     const int grid = b->sm_count;
     if (b->use_bp) {
-        /* one thread per pair; whatever it cannot take (more than four letters in a top string) lands on a list
+        /* one thread per pair; whatever it cannot take (more than five letters in a top string) lands on a list
          * that the one-warp-per-pair kernel works off right behind it (a launch that finds the list empty returns) */
         unsigned *fbc = b->fb_count.p + chunk; /* every chunk of a refill has its own list and counter */
         CK(cudaMemsetAsync(fbc, 0, sizeof(unsigned), st));

@@ -3,7 +3,7 @@
  * bit-vectors (64, 128 or 256 bits by the longest top string), one addition per difference level resolves a whole row.
  *
  * Same results as the reference's score_cell() (needleman-wunsch.c:418-510: the recurrence and "every tie
- * gets its arrow", :485-503) for top strings of up to 256 characters with at most four distinct letters,
+ * gets its arrow", :485-503) for top strings of up to 256 characters with at most five distinct letters,
  * when the per-cell differences are small (M = 2d + m <= 3: DNA 1/1/1 has M = 3).
  *
  * With r(i,j) = score(i,j) + d(i+j) (nwb_fill_pk.cuh) the differences u = r(i,j) - r(i-1,j) and
@@ -27,7 +27,7 @@
  * no bank conflicts; at a 64 KB-aligned address, so that one PRMT forms a look-up address), and a row of the warp (32 pairs x 128 bytes) leaves through a swizzled staging
  * buffer so that every store instruction writes whole 128-byte lines.
  *
- * Pairs whose top string has more than four distinct letters are not computed here: they are put on a
+ * Pairs whose top string has more than five distinct letters are not computed here: they are put on a
  * list that nwb_batch_pk_kernel works off afterwards (nwb_batch_api.inl).  tools/bp_proto.py is the
  * executable statement of the formulation (Python integers as bit-vectors, checked against the oracle).
  */
@@ -37,12 +37,13 @@
 #define NWB_BP_NW 8     /* 32-bit words per row vector, at most: up to 256 columns (instantiated: 2, 4, 8) */
 #define NWB_BP_MIN_AUTO 0  /* top strings up to this length keep the warp kernels unless asked (nwb_tune batch_bp = 1); measured:
                             * 32 x 32 pairs already run 7x faster here than in nwb_batch_bx_kernel */
-#define NWB_BP_NSYM 4   /* letters with a match vector */
+#define NWB_BP_NSYM 5   /* letters with a match vector (DNA with N) */
 #define NWB_BP_MAXM 3   /* instantiated difference ranges */
 #define NWB_BP_WARPS 15  /* at most, per block (128 registers per thread; shared memory, see below) */
 #define NWB_BP_SIDE_ROWS 32
 #define NWB_BP_LUT_BYTES (256 * 256) /* entry x: 256 bytes = 32 lanes x {T[x]} then 32 lanes x {T[~x]} */
-#define NWB_BP_PEQ_BYTES ((NWB_BP_NSYM + 1) * NWB_BP_NW * 32 * 4)
+#define NWB_BP_PEQ_BYTES (NWB_BP_NSYM * NWB_BP_NW * 32 * 4)
+#define NWB_BP_ZERO_BYTES (NWB_BP_NW * 32 * 4) /* one all-zero match vector per block: a side letter the top string does not have */
 #define NWB_BP_STAGE_BYTES (32 * 128)
 #define NWB_BP_SIDE_BYTES (NWB_BP_SIDE_ROWS * 32)
 #define NWB_BP_META_BYTES (32 * 8)
@@ -52,7 +53,7 @@
  * warps' own areas (10.25 KB each) fill what lies in front of and behind the table: 15 warps fit whether the window of
  * the dynamic part starts at 0 or behind a reserved kilobyte. */
 #define NWB_BP_SMEM_MAX 232448
-#define NWB_BP_SMEM_BYTES(warps) ((size_t)NWB_BP_LUT_BYTES + (size_t)(warps) * NWB_BP_WARP_SMEM) /* table not aligned */
+#define NWB_BP_SMEM_BYTES(warps) ((size_t)NWB_BP_LUT_BYTES + NWB_BP_ZERO_BYTES + (size_t)(warps) * NWB_BP_WARP_SMEM) /* table not aligned */
 /* the aligned table for launches that fill the SMs on their own; a chunk of a refill (a few warps per SM) takes the
  * other instantiation, whose blocks are small enough for two of them to share an SM */
 #define NWB_BP_ALIGNED_MIN_WARPS 8
@@ -68,7 +69,7 @@ struct NwbBpParams {
     const long long *arrow_off; /* byte offset of pair p's table, a multiple of 128 */
     int *out_score;             /* [n_pairs] */
     unsigned *out_branch;       /* [n_pairs] or NULL */
-    long long *fb_list;         /* pairs this kernel leaves to nwb_batch_pk_kernel (more than 4 letters) */
+    long long *fb_list;         /* pairs this kernel leaves to nwb_batch_pk_kernel (more than 5 letters) */
     unsigned *fb_count;
     unsigned k2, k4;            /* 2 and 4, as run-time values (see nwb_bp_rows) */
 };
@@ -357,8 +358,9 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NW], unsigned (&u
 template <int M, int N, int NB, int NW, bool FULL, bool AL>
 __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, const unsigned *peq, uint4 *stage, uint8_t *side_sm,
                                              const uint2 *meta, const nwb_bp_tab mylut, const int lane, const int A, const int Brun,
-                                             const int maxB, const long long s0, const bool s_al, const unsigned l0,
-                                             const unsigned l1, const unsigned l2, const unsigned l3, unsigned &branches, int &rsum)
+                                             const int maxB, const long long s0, const bool s_al, const int nomatch,
+                                             const unsigned l0, const unsigned l1, const unsigned l2, const unsigned l3, const unsigned l4,
+                                             unsigned &branches, int &rsum)
 {
     unsigned uu[NB][NW]; /* u of the row above, bit-sliced */
 #pragma unroll
@@ -400,8 +402,9 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
             }
         }
         const unsigned c = side_sm[(j & (NWB_BP_SIDE_ROWS - 1)) * 32 + lane];
-        const int slot = (c == l0) ? 0 : ((c == l1) ? 1 : ((c == l2) ? 2 : ((c == l3) ? 3 : NWB_BP_NSYM)));
-        const unsigned *pe = peq + slot * (NW * 32) + lane;
+        /* word offset of the letter's match vector; a letter my top string does not have: the all-zero vector */
+        const int voff = (c == l0) ? 0 : ((c == l1) ? NW * 32 : ((c == l2) ? 2 * NW * 32 : ((c == l3) ? 3 * NW * 32 : ((c == l4) ? 4 * NW * 32 : nomatch))));
+        const unsigned *pe = peq + voff + lane;
         unsigned E[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) E[w] = pe[w * 32];
@@ -476,17 +479,23 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
     unsigned char *smem = NWB_SMEM_BASE();
 #ifdef NWB_EMU
     unsigned char *lutp = smem;
-    unsigned char *mine = smem + NWB_BP_LUT_BYTES + (size_t)warp * NWB_BP_WARP_SMEM;
+    unsigned char *zerop = smem + NWB_BP_LUT_BYTES;
+    unsigned char *mine = zerop + NWB_BP_ZERO_BYTES + (size_t)warp * NWB_BP_WARP_SMEM;
 #else
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned before = AL ? ((sbase + 0xFFFFu) & ~0xFFFFu) - sbase : 0u; /* bytes in front of the (64 KB-aligned) table */
-    const int nbefore = (int)(before / NWB_BP_WARP_SMEM);
     unsigned char *lutp = smem + before;
-    unsigned char *mine = (warp < nbefore) ? smem + (size_t)warp * NWB_BP_WARP_SMEM
-                                           : lutp + NWB_BP_LUT_BYTES + (size_t)(warp - nbefore) * NWB_BP_WARP_SMEM;
-    if (AL && before + NWB_BP_LUT_BYTES + (size_t)(wpb - (nbefore < wpb ? nbefore : wpb)) * NWB_BP_WARP_SMEM > NWB_BP_SMEM_MAX) __trap();
+    /* the block's zero vector and the first warps in front of the table, the others behind it */
+    const bool zfront = before >= NWB_BP_ZERO_BYTES;
+    const int nbefore = zfront ? (int)((before - NWB_BP_ZERO_BYTES) / NWB_BP_WARP_SMEM) : 0;
+    unsigned char *zerop = zfront ? smem : lutp + NWB_BP_LUT_BYTES;
+    unsigned char *behind = lutp + NWB_BP_LUT_BYTES + (zfront ? 0 : NWB_BP_ZERO_BYTES);
+    unsigned char *mine = (warp < nbefore) ? smem + NWB_BP_ZERO_BYTES + (size_t)warp * NWB_BP_WARP_SMEM
+                                           : behind + (size_t)(warp - nbefore) * NWB_BP_WARP_SMEM;
+    if (AL && (size_t)(behind - smem) + (size_t)(wpb - (nbefore < wpb ? nbefore : wpb)) * NWB_BP_WARP_SMEM > NWB_BP_SMEM_MAX) __trap();
 #endif
     unsigned *lut = reinterpret_cast<unsigned *>(lutp);
+    unsigned *zero = reinterpret_cast<unsigned *>(zerop);                                /* [word][lane], all zero */
     unsigned *peq = reinterpret_cast<unsigned *>(mine);                                  /* [letter 0..4][word][lane] */
     uint4 *stage = reinterpret_cast<uint4 *>(mine + NWB_BP_PEQ_BYTES);                  /* [lane][8 swizzled 16-byte chunks] */
     uint8_t *side_sm = mine + NWB_BP_PEQ_BYTES + NWB_BP_STAGE_BYTES;                    /* [row & 31][lane] */
@@ -500,8 +509,10 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         lut[x * 64 + lane] = v;
         lut[x * 64 + 32 + lane] = 0x11111111u - v;
     }
+    if (warp == 0) {
 #pragma unroll
-    for (int w = 0; w < NW; w++) peq[(NWB_BP_NSYM * NW + w) * 32 + lane] = 0u; /* a side letter the top string does not have */
+        for (int w = 0; w < NW; w++) zero[w * 32 + lane] = 0u;
+    }
     __syncthreads();
 #ifdef NWB_EMU
     const nwb_bp_tab mylut = lut + lane;
@@ -521,8 +532,8 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
             A = (int)(bp.top_off[p + 1] - t0);
             B = (int)(bp.side_off[p + 1] - s0);
         }
-        /* ---- match vectors of my top string: at most four distinct letters ---- */
-        unsigned l0 = 0x100u, l1 = 0x101u, l2 = 0x102u, l3 = 0x103u; /* no byte equals an unassigned letter */
+        /* ---- match vectors of my top string: at most five distinct letters ---- */
+        unsigned l0 = 0x100u, l1 = 0x101u, l2 = 0x102u, l3 = 0x103u, l4 = 0x104u; /* no byte equals an unassigned letter */
         int nlet = 0;
         bool over = false;
         const bool t_al = __all_sync(NWB_FULL_MASK, (t0 & 3) == 0);
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         }
 #pragma unroll 1
         for (int w = 0; w < NW; w++) {
-            unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+            unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u, a4 = 0u;
             if (32 * w < maxA) {
 #pragma unroll 1
                 for (int q = 0; q < 8; q++) {
@@ -545,12 +556,13 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
                     for (int e = 0; e < 4; e++) {
                         const unsigned c = (word >> (8 * e)) & 0xFFu;
                         if (col + e < A) {
-                            bool h0 = c == l0, h1 = c == l1, h2 = c == l2, h3 = c == l3;
-                            if (!(h0 || h1 || h2 || h3)) {
+                            bool h0 = c == l0, h1 = c == l1, h2 = c == l2, h3 = c == l3, h4 = c == l4;
+                            if (!(h0 || h1 || h2 || h3 || h4)) {
                                 if (nlet == 0) { l0 = c; h0 = true; }
                                 else if (nlet == 1) { l1 = c; h1 = true; }
                                 else if (nlet == 2) { l2 = c; h2 = true; }
                                 else if (nlet == 3) { l3 = c; h3 = true; }
+                                else if (nlet == 4) { l4 = c; h4 = true; }
                                 else over = true;
                                 nlet++;
                             }
@@ -559,6 +571,7 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
                             if (h1) a1 |= bit;
                             if (h2) a2 |= bit;
                             if (h3) a3 |= bit;
+                            if (h4) a4 |= bit;
                         }
                     }
                 }
@@ -567,6 +580,7 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
             peq[(1 * NW + w) * 32 + lane] = a1;
             peq[(2 * NW + w) * 32 + lane] = a2;
             peq[(3 * NW + w) * 32 + lane] = a3;
+            peq[(4 * NW + w) * 32 + lane] = a4;
         }
         if (valid && over) { /* not mine: the general batch kernel takes this pair */
             const unsigned pos = atomicAdd(bp.fb_count, 1u);
@@ -596,8 +610,8 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         meta[lane] = make_uint2(valid ? (unsigned)((bp.arrow_off[p] - off0) >> 4) : 0u, (unsigned)Brun);
         __syncwarp();
         uint4 *gdst = reinterpret_cast<uint4 *>(bp.arrows + off0);
-        if (full) nwb_bp_rows<M, N, NB, NW, true, AL>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
-        else nwb_bp_rows<M, N, NB, NW, false, AL>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, l0, l1, l2, l3, branches, rsum);
+        if (full) nwb_bp_rows<M, N, NB, NW, true, AL>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, (int)(zero - peq), l0, l1, l2, l3, l4, branches, rsum);
+        else nwb_bp_rows<M, N, NB, NW, false, AL>(bp, gdst, peq, stage, side_sm, meta, mylut, lane, A, Brun, maxB, s0, s_al, (int)(zero - peq), l0, l1, l2, l3, l4, branches, rsum);
         if (Brun > 0) {
             bp.out_score[p] = rsum - bp.d * (A + B);
             if (bp.out_branch) bp.out_branch[p] = branches;

@@ -425,7 +425,7 @@ def test_batch_uniform_pairs_back_to_back(oracle, nwb, monkeypatch):
 def test_batch_bit_parallel(oracle, nwb):
     """csrc/nwb_batch_bp.cuh nwb_batch_bp_kernel: one thread per pair, rows as bit-vectors (2d + m <= 3, top strings of
     at most 256 characters).  Config 4's goldens, ragged shapes, empty strings, unaligned offsets, more groups of 32
-    pairs than warps, side letters the top string does not have, top strings with more than four letters (worked off
+    pairs than warps, side letters the top string does not have, top strings with more than five letters (worked off
     by nwb_batch_pk_kernel from the kernel's list), every instantiated (2d + m, 2d - k); the same batches through
     the packed-difference kernels (nwb_tune batch_bp = 0) must agree on every pair."""
     rng = random.Random(37)
@@ -454,11 +454,11 @@ def test_batch_bit_parallel(oracle, nwb):
             (256, 31), (100, 300), (5, 0), (8, 32), (9, 33), (249, 63), (250, 64), (7, 65), (1, 200), (256, 2),
             (0, 0), (31, 31), (130, 95), (96, 128), (256, 1000)] + \
            [(rng.randint(1, 256), rng.randint(1, 400)) for _ in range(6000)]
-    alphas = [b"ACGT"] * 6 + [b"ACGTN", b"AC", bytes(range(1, 256)), b"ARNDCQEGHILKMFPSTWYV"]
+    alphas = [b"ACGT"] * 6 + [b"ACGTN", b"ACGTNR", b"AC", bytes(range(1, 256)), b"ARNDCQEGHILKMFPSTWYV"]
     tops = [bytes(rng.choice(rng.choice(alphas)) for _ in range(a)) for a, _ in lens]
     sides = [bytes(rng.choice(b"ACGTNX") for _ in range(b)) for _, b in lens]
     sample = list(range(25)) + rng.sample(range(25, len(lens)), 150) + [len(lens) - 1]
-    sample += [i for i in range(25, 400) if len(set(tops[i])) > 4][:20]
+    sample += [i for i in range(25, 400) if len(set(tops[i])) > 5][:20] + [i for i in range(25, 400) if len(set(tops[i])) == 5][:10]
     for m, k, d in ((1, 1, 1), (0, 0, 1), (1, -1, 0), (3, 0, 0), (1, 2, 1), (0, 1, 1), (2, -1, 0)):
         with nwb.tuned(batch_bp=1):
             bt = nwb.Batch(tops, sides, m, k, d, nwb.WANT_ARROWS_HOST)
@@ -480,8 +480,8 @@ def test_batch_bit_parallel(oracle, nwb):
     tcat = nwb.generate(0x5EED4000, 256, nwb.DNA, count=n, seed_stride=2)
     scat = nwb.generate(0x5EED4001, 256, nwb.DNA, count=n, seed_stride=2)
     tmix = bytearray(tcat)
-    for p in range(0, n, 997):      # some pairs with five letters in the top string
-        tmix[p * 256:p * 256 + 5] = b"ACGTN"
+    for p in range(0, n, 997):      # some pairs with six letters in the top string
+        tmix[p * 256:p * 256 + 6] = b"ACGTNR"
     off = np.arange(n + 1, dtype=np.int64) * 256
     res = {}
     for knob in (1, 0):

@@ -64,7 +64,7 @@ for (a,b,n) in ((256,256,3),(40,64,61),(255,96,27)):
 # loads at the end of the string buffers; the left-over list) and the per-lane sparse count (16-byte loads around the
 # window, the dense kernel over its left-over list)
 lens=[(256,256)]*33+[(200,90),(256,31),(17,130),(1,1),(64,64),(0,3),(5,0),(255,77),(129,300),(3,3),(256,1)]*3
-tops=[bytes(random.choice(b"ACGTN" if i%13==5 else b"ACGT") for _ in range(a)) for i,(a,_) in enumerate(lens)]
+tops=[bytes(random.choice(b"ACGTNR" if i%13==5 else (b"ACGTN" if i%13==6 else b"ACGT")) for _ in range(a)) for i,(a,_) in enumerate(lens)]
 sides=[bytes(random.choice(b"ACGTX") for _ in range(b)) for _,b in lens]
 r=emu.fill_batch_bp(tops,sides,1,1,1,grid=2,warps=2)
 assert r is not None and r['n_fallback']>=1

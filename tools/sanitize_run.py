@@ -42,11 +42,11 @@ for p in range(40):
 bt.close()
 # the bit-parallel batch kernel (one thread per pair; its left-over list through nwb_batch_pk_kernel) and the per-lane
 # sparse count (its left-over list through nwb_batch_count_kernel): uniform and ragged groups, unaligned offsets,
-# a top string with five letters, empty strings
+# top strings with five and six letters, empty strings
 import random  # noqa: E402
 rng = random.Random(3)
 shapes = [(256, 256)] * 40 + [(200, 90), (256, 31), (17, 130), (1, 1), (64, 64), (0, 3), (5, 0), (255, 77), (129, 300)] * 4
-tops = [bytes(rng.choice(b"ACGTN" if i % 11 == 0 else b"ACGT") for _ in range(a)) for i, (a, b) in enumerate(shapes)]
+tops = [bytes(rng.choice(b"ACGTNR" if i % 11 == 0 else (b"ACGTN" if i % 11 == 1 else b"ACGT")) for _ in range(a)) for i, (a, b) in enumerate(shapes)]
 sides = [bytes(rng.choice(b"ACGTX") for _ in range(b)) for a, b in shapes]
 for flags in (nwb.WANT_ARROWS_HOST, nwb.WANT_COUNT):
     with nwb.tuned(batch_bp=1, batch_lcount=1):
