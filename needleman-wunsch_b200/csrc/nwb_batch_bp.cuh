@@ -352,6 +352,17 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NW], unsigned (&u
     }
 }
 
+/* the arrow codes are written once and read much later, if at all: streaming stores (st.global.cs; 1.2 % on the
+ * config 4 shard) */
+__device__ __forceinline__ void nwb_bp_store(uint4 *p, const uint4 v)
+{
+#ifdef NWB_EMU
+    *p = v;
+#else
+    __stcs(p, v);
+#endif
+}
+
 /* The rows of one group of 32 pairs (lane = pair).  FULL: every pair of the group is 256 columns wide and all have
  * the same number of rows: no column masks, no per-pair row count at the stores, tables evenly spaced.  A
  * warp-uniform choice made outside the row loop, so that the common case carries no selects. */
@@ -457,10 +468,10 @@ __device__ __forceinline__ void nwb_bp_rows(const NwbBpParams &bp, uint4 *gdst, 
             const int L = (32 / NW) * i + h;
             const uint4 val = (NW == 8) ? ((i & 1) ? st_r1 : st_r0)[(i >> 1) * 64] : stage[L * 8 + (ch ^ (L & 7))];
             if (FULL) {
-                gdst[(unsigned)L * (unsigned)(8 * maxB) + (unsigned)(8 * j + ch)] = val;
+                nwb_bp_store(gdst + ((unsigned)L * (unsigned)(8 * maxB) + (unsigned)(8 * j + ch)), val);
             } else {
                 const uint2 mt = meta[L];
-                if ((unsigned)j < mt.y) gdst[mt.x + (unsigned)(8 * j + ch)] = val;
+                if ((unsigned)j < mt.y) nwb_bp_store(gdst + (mt.x + (unsigned)(8 * j + ch)), val);
             }
         }
         __syncwarp();
