@@ -352,6 +352,36 @@ __device__ __forceinline__ void nwb_bp_row(const unsigned (&E)[NW], unsigned (&u
     }
 }
 
+/* the distinct letters of a top string found so far */
+struct NwbBpLetters {
+    unsigned l[NWB_BP_NSYM];
+    int nlet;
+    bool over; /* a sixth letter: the pair is not for this kernel */
+};
+
+/* Up to four letters (the low `n` bytes of `word`, n >= 1) one at a time: new letters get the next free slot; bit
+ * `bit0 + e` of acc[k] is set where letter e of the word is letter k.  The rare path of the match-vector build. */
+__device__ __noinline__ void nwb_bp_letters_slow(NwbBpLetters &lt, const unsigned word, const int n, const int bit0,
+                                                 unsigned (&acc)[NWB_BP_NSYM])
+{
+    for (int e = 0; e < 4 && e < n; e++) {
+        const unsigned c = (word >> (8 * e)) & 0xFFu;
+        int k = -1;
+        for (int i = 0; i < NWB_BP_NSYM; i++)
+            if (c == lt.l[i]) k = i;
+        if (k < 0) {
+            if (lt.nlet < NWB_BP_NSYM) {
+                k = lt.nlet;
+                lt.l[k] = c;
+            } else {
+                lt.over = true;
+            }
+            lt.nlet++;
+        }
+        if (k >= 0) acc[k] |= 1u << (bit0 + e);
+    }
+}
+
 /* the arrow codes are written once and read much later, if at all: streaming stores (st.global.cs; 1.2 % on the
  * config 4 shard) */
 __device__ __forceinline__ void nwb_bp_store(uint4 *p, const uint4 v)
@@ -544,10 +574,12 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
             B = (int)(bp.side_off[p + 1] - s0);
         }
         /* ---- match vectors of my top string: at most five distinct letters ---- */
-        unsigned l0 = 0x100u, l1 = 0x101u, l2 = 0x102u, l3 = 0x103u, l4 = 0x104u; /* no byte equals an unassigned letter */
-        int nlet = 0;
-        bool over = false;
+        NwbBpLetters lt;
+        lt.l[0] = 0x100u; lt.l[1] = 0x101u; lt.l[2] = 0x102u; lt.l[3] = 0x103u; lt.l[4] = 0x104u; /* no byte equals an unassigned letter */
+        lt.nlet = 0;
+        lt.over = false;
         const bool t_al = __all_sync(NWB_FULL_MASK, (t0 & 3) == 0);
+        const bool t_al16 = __all_sync(NWB_FULL_MASK, (t0 & 15) == 0);
         int maxA = A;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -556,43 +588,55 @@ __global__ void __launch_bounds__(32 * NWB_BP_WARPS, 1) nwb_batch_bp_kernel(cons
         }
 #pragma unroll 1
         for (int w = 0; w < NW; w++) {
-            unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u, a4 = 0u;
-            if (32 * w < maxA) {
-#pragma unroll 1
-                for (int q = 0; q < 8; q++) {
-                    const int col = 32 * w + 4 * q;
-                    unsigned word = 0u;
-                    if (col < A) word = nwb_bp_load_word(bp.tops, t0 + col, t_al);
+            unsigned acc[NWB_BP_NSYM];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const unsigned c = (word >> (8 * e)) & 0xFFu;
-                        if (col + e < A) {
-                            bool h0 = c == l0, h1 = c == l1, h2 = c == l2, h3 = c == l3, h4 = c == l4;
-                            if (!(h0 || h1 || h2 || h3 || h4)) {
-                                if (nlet == 0) { l0 = c; h0 = true; }
-                                else if (nlet == 1) { l1 = c; h1 = true; }
-                                else if (nlet == 2) { l2 = c; h2 = true; }
-                                else if (nlet == 3) { l3 = c; h3 = true; }
-                                else if (nlet == 4) { l4 = c; h4 = true; }
-                                else over = true;
-                                nlet++;
-                            }
-                            const unsigned bit = 1u << (4 * q + e);
-                            if (h0) a0 |= bit;
-                            if (h1) a1 |= bit;
-                            if (h2) a2 |= bit;
-                            if (h3) a3 |= bit;
-                            if (h4) a4 |= bit;
-                        }
+            for (int k = 0; k < NWB_BP_NSYM; k++) acc[k] = 0u;
+            if (32 * w < maxA) {
+                /* the 32 letters of this word: all loads first */
+                unsigned wd[8];
+                if (t_al16) {
+#pragma unroll
+                    for (int hq = 0; hq < 2; hq++) {
+                        const int col = 32 * w + 16 * hq;
+                        uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+                        if (col < A) v4 = *reinterpret_cast<const uint4 *>(bp.tops + t0 + col);
+                        wd[4 * hq + 0] = v4.x; wd[4 * hq + 1] = v4.y; wd[4 * hq + 2] = v4.z; wd[4 * hq + 3] = v4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int col = 32 * w + 4 * q;
+                        wd[q] = (col < A) ? nwb_bp_load_word(bp.tops, t0 + col, t_al) : 0u;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    /* four letters at a time: per known letter the bytes of the word that equal it (exact zero-byte
+                     * test of word ^ letter x 0x01010101), gathered into four bits by a multiplication.  A word with a
+                     * letter not seen before (the first few of a string) or with its end in it goes letter by letter. */
+                    const int col = 32 * w + 4 * q;
+                    const unsigned word = wd[q];
+                    unsigned z[NWB_BP_NSYM], zall = 0u;
+#pragma unroll
+                    for (int k = 0; k < NWB_BP_NSYM; k++) {
+                        const unsigned t = word ^ (lt.l[k] * 0x01010101u);
+                        z[k] = (k < lt.nlet) ? (~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u) : 0u; /* slots in use only */
+                        zall |= z[k];
+                    }
+                    if (col + 4 <= A && zall == 0x80808080u) {
+#pragma unroll
+                        for (int k = 0; k < NWB_BP_NSYM; k++)
+                            acc[k] |= ((((z[k] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+                    } else if (col < A) {
+                        nwb_bp_letters_slow(lt, word, A - col, 4 * q, acc);
                     }
                 }
             }
-            peq[(0 * NW + w) * 32 + lane] = a0;
-            peq[(1 * NW + w) * 32 + lane] = a1;
-            peq[(2 * NW + w) * 32 + lane] = a2;
-            peq[(3 * NW + w) * 32 + lane] = a3;
-            peq[(4 * NW + w) * 32 + lane] = a4;
+#pragma unroll
+            for (int k = 0; k < NWB_BP_NSYM; k++) peq[(k * NW + w) * 32 + lane] = acc[k];
         }
+        const unsigned l0 = lt.l[0], l1 = lt.l[1], l2 = lt.l[2], l3 = lt.l[3], l4 = lt.l[4];
+        const bool over = lt.over;
         if (valid && over) { /* not mine: the general batch kernel takes this pair */
             const unsigned pos = atomicAdd(bp.fb_count, 1u);
             bp.fb_list[pos] = p;

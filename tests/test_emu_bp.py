@@ -97,6 +97,17 @@ def test_bp_foreign_letters_and_fallback(oracle):
     assert r["n_fallback"] >= 2
 
 
+def test_bp_low_byte_values(oracle):
+    # letters 0x00 / 0x01 / 0x02 ... must not be mistaken for the patterns of letter slots that are not in use yet
+    rng = random.Random(59)
+    tops, sides = [], []
+    for alpha in (b"\x00\x01", b"\x01", b"\x00", b"\x01\x02\x03\x04", b"\x00\x01\x02\x03\x04", b"\x01\x00\xff"):
+        for n in (5, 64, 200, 256):
+            tops.append(_rand(rng, alpha, n))
+            sides.append(_rand(rng, alpha + b"\x01\x00", 70))
+    _check(oracle, tops, sides, 1, 1, 1, expect_fallback=0)
+
+
 def test_bp_every_small_scheme(oracle):
     rng = random.Random(29)
     tops = [_rand(rng, b"ACGT", a) for a in (256, 40, 130, 1, 77)]
