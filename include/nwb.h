@@ -248,6 +248,19 @@ int32_t nwb_strip_group_score(int64_t partial_r_sum, int top_len, int side_len, 
 /* Re-arm the inbound boundary flag before the next run of a strip group
  * (all ranks must do this, then synchronise, before any rank runs again). */
 int nwb_plan_reset_inbox(nwb_plan *p, void *stream);
+/* A strip group working through a QUEUE of fills (one rank per GPU): like nwb_plan_run(), but consecutive runs need
+ * neither nwb_plan_reset_inbox() nor a barrier between the ranks, so rank r starts fill e + 1 while the ranks to its
+ * right are still on fill e (the group's throughput is bounded by one rank's share of a fill, not by the
+ * whole strip-to-strip wavefront; the reference's analogue is its -p workers picking up the next column set,
+ * needleman-wunsch.c:557-574, across consecutive needleman_wunsch() calls, :654-689).  The inbox is double-buffered
+ * (fill e streams into copy e & 1 of the right neighbour's inbox) and a rank re-uses a copy only after the neighbour
+ * has acknowledged, through a word in its HBM, that it is done with it; that wait is watchdog-bounded (NWB_ERR_CUDA
+ * from nwb_plan_summary()).  Every rank of the group must make the same sequence of calls; after any nwb_plan_run()
+ * on the same plans call nwb_plan_reset_inbox() on every rank and synchronise before the first pipelined run. */
+int nwb_plan_run_pipelined(nwb_plan *p, int m, int k, int d, void *stream);
+/* Same-process strip group (one host thread driving several GPUs): make `right`'s inbox the target of `p`'s last
+ * strip through CUDA peer access (the in-process counterpart of nwb_plan_ipc_attach_right()). */
+int nwb_plan_attach_right(nwb_plan *p, nwb_plan *right);
 /* Multi-process column strips: export this rank's inbound boundary buffer as
  * an opaque CUDA IPC blob (nwb_plan_ipc_size() bytes) and attach the right
  * neighbour's blob so this rank's last strip streams its boundary column

@@ -110,6 +110,8 @@ _SIGS = {
     "nwb_plan_kernel_ms": (C.c_float, [C.c_void_p]),
     "nwb_plan_strip_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nwb_plan_reset_inbox": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nwb_plan_run_pipelined": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nwb_plan_attach_right": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nwb_plan_ipc_size": (C.c_size_t, []),
     "nwb_plan_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nwb_plan_ipc_attach_right": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -460,6 +462,14 @@ class Plan:
         _ck(load_library().nwb_plan_download_arrows(self._h, out.ctypes.data_as(C.c_void_p), pitch,
                                                     row_begin, row_end), "nwb_plan_download_arrows")
         return out
+
+    def run_pipelined(self, m: int, k: int, d: int, stream: int | None = None) -> None:
+        """One fill of a queue of fills of a strip group: no reset_inbox / barrier between consecutive runs."""
+        _ck(load_library().nwb_plan_run_pipelined(self._h, m, k, d, C.c_void_p(stream or 0)), "nwb_plan_run_pipelined")
+
+    def attach_right(self, right: "Plan") -> None:
+        """Same process, another GPU: my last strip streams into `right`'s inbox (peer access)."""
+        _ck(load_library().nwb_plan_attach_right(self._h, right._h), "nwb_plan_attach_right")
 
     def reset_inbox(self, stream: int | None = None) -> None:
         _ck(load_library().nwb_plan_reset_inbox(self._h, C.c_void_p(stream or 0)), "nwb_plan_reset_inbox")

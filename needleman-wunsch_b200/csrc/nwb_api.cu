@@ -214,6 +214,10 @@ struct nwb_plan {
     DevBuf<int> progress;
     DevBuf<NwbDevSummary> summary;
     Inbox inbox = {};
+    /* Pipelined runs (nwb_plan_run_pipelined): the inbox allocation holds TWO copies of the inbox arrays (run e uses
+     * copy e & 1) and, behind them, the acknowledgement word: the number of pipelined runs whose inbox copy this rank
+     * has finished with and zeroed again. */
+    long long epoch = 0;
     /* right neighbour's inbox (peer memory), if attached */
     unsigned char *right_base = nullptr;
     bool right_is_ipc = false;
@@ -231,6 +235,11 @@ struct nwb_plan {
     bool pk_hz = false; /* ... with packing warps as well, two strips per SM (nwb_fill_hz.cuh) */
     bool count_pass = false; /* the count runs as a second sweep over the arrow codes (nwb_count.cuh) */
 };
+
+/* the allocation behind an inbox: two copies of its arrays (pipelined runs alternate) + the acknowledgement word */
+#define NWB_INBOX_ACK_BYTES 256
+#define NWB_INBOX_ALLOC_BYTES(ib) (2 * (ib).bytes + NWB_INBOX_ACK_BYTES)
+#define NWB_INBOX_ACK(ib_base, ib) (reinterpret_cast<unsigned *>((ib_base) + 2 * (ib).bytes))
 
 static void make_inbox_layout(Inbox &ib, size_t bpitch)
 {
@@ -283,11 +292,11 @@ extern "C" int nwb_plan_create(int max_top, int max_side, unsigned flags, int de
         /* inbox sized for the longest side string; allocated once so that it
          * can be exported through CUDA IPC before any fill */
         make_inbox_layout(p->inbox, nwb_round_up((size_t)max_side + 1 + 64 + 512, 32));
-        e = cudaMalloc((void **)&p->inbox.base, p->inbox.bytes);
+        e = cudaMalloc((void **)&p->inbox.base, NWB_INBOX_ALLOC_BYTES(p->inbox));
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(inbox)");
         else {
             /* on the plan's own (non-blocking) stream, then wait: nothing else orders it against the first run */
-            e = cudaMemsetAsync(p->inbox.base, 0, p->inbox.bytes, p->stream);
+            e = cudaMemsetAsync(p->inbox.base, 0, NWB_INBOX_ALLOC_BYTES(p->inbox), p->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
         }
         if (rc == NWB_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaMemset(inbox)");
@@ -395,9 +404,56 @@ __global__ void __launch_bounds__(256) nwb_zero_unless_done_kernel(const int *st
 /* where the count behind -s comes from (nwb_summary.count_path) */
 enum { NWB_CNT_NONE = 0, NWB_CNT_FUSED = 1, NWB_CNT_DENSE = 2, NWB_CNT_SPARSE = 3, NWB_CNT_SPARSE_BAILED = 4 };
 
+/* ---- pipelined strip groups: flow control between neighbouring ranks ---------------------------------------
+ * Consecutive fills of a strip group overlap: rank r starts fill e + 1 while the ranks to its right are still on
+ * fill e.  Fill e streams into copy e & 1 of the right neighbour's inbox; the neighbour zeroes that copy when its
+ * own fill e is done and then posts e + 1 in its acknowledgement word (stream order: fill, memset, this kernel).
+ * Before fill e + 2 the left rank's stream waits in the gate kernel until the word says so -- in steady state it
+ * already does.  The wait is watchdog-bounded like every other device-side wait. */
+__global__ void nwb_inbox_ack_kernel(unsigned *ack, unsigned value)
+{
+    if (threadIdx.x == 0) nwb_st_release_sys(reinterpret_cast<int *>(ack), (int)value);
+}
+__global__ void __launch_bounds__(32) nwb_inbox_gate_kernel(const unsigned *peer_ack, unsigned need, int *err,
+                                                           unsigned long long limit_ns)
+{
+    NwbWatchdog wd;
+    for (;;) {
+        const unsigned v = nwb_ld_relaxed_u32(peer_ack, true);
+        if (__all_sync(NWB_FULL_MASK, (int)(v - need) >= 0)) break;
+        if (wd.tick(err, limit_ns)) return;
+        __nanosleep(200);
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
+static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pipelined);
+
 extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
 {
     if (!p) return NWB_ERR_INVALID;
+    return plan_run_body(p, m, k, d, stream, false);
+}
+
+extern "C" int nwb_plan_run_pipelined(nwb_plan *p, int m, int k, int d, void *stream)
+{
+    if (!p) return NWB_ERR_INVALID;
+    int rc = plan_run_body(p, m, k, d, stream, true);
+    if (rc != NWB_OK) return rc;
+    if (p->inbox.base) {
+        /* my copy of the inbox is free again: zero it, then tell the left neighbour */
+        cudaStream_t st = p->last_stream;
+        CK(cudaMemsetAsync(p->inbox.base + (size_t)(p->epoch & 1) * p->inbox.bytes, 0, p->inbox.bytes, st));
+        nwb_inbox_ack_kernel<<<1, 32, 0, st>>>(NWB_INBOX_ACK(p->inbox.base, p->inbox), (unsigned)(p->epoch + 1));
+        CK(cudaGetLastError());
+        p->launches += 1;
+    }
+    p->epoch++;
+    return NWB_OK;
+}
+
+static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pipelined)
+{
     CK(cudaSetDevice(p->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
     p->last_stream = st;
@@ -545,19 +601,30 @@ extern "C" int nwb_plan_run(nwb_plan *p, int m, int k, int d, void *stream)
     sp.debug_nowait |= tn.debug_nowait;
 #endif
     sp.watchdog_ns = (unsigned long long)(tn.watchdog_ms > 0 ? tn.watchdog_ms : 4000) * 1000000ull;
+    /* a pipelined run e works with copy e & 1 of the inboxes (its own and the right neighbour's) */
+    const size_t copy = pipelined ? (size_t)(p->epoch & 1) : 0;
     if (p->strip_begin > 0) {
         if (!p->inbox.base || L.bpitch > p->inbox.bpitch) return NWB_ERR_INVALID;
-        sp.in_bnd_s = (const int32_t *)(p->inbox.base + p->inbox.off_s);
-        sp.in_bnd_c = (const unsigned long long *)(p->inbox.base + p->inbox.off_c);
-        sp.in_bnd_w = (const uint32_t *)(p->inbox.base + p->inbox.off_w);
-        sp.in_progress = (const int *)(p->inbox.base + p->inbox.off_flag);
+        const unsigned char *ib = p->inbox.base + copy * p->inbox.bytes;
+        sp.in_bnd_s = (const int32_t *)(ib + p->inbox.off_s);
+        sp.in_bnd_c = (const unsigned long long *)(ib + p->inbox.off_c);
+        sp.in_bnd_w = (const uint32_t *)(ib + p->inbox.off_w);
+        sp.in_progress = (const int *)(ib + p->inbox.off_flag);
     }
     if (p->strip_end < L.n_strips) {
         if (!p->right_base || L.bpitch > p->right.bpitch) return NWB_ERR_INVALID;
-        sp.out_bnd_s = (int32_t *)(p->right_base + p->right.off_s);
-        sp.out_bnd_c = (unsigned long long *)(p->right_base + p->right.off_c);
-        sp.out_bnd_w = (uint32_t *)(p->right_base + p->right.off_w);
-        sp.out_progress = (int *)(p->right_base + p->right.off_flag);
+        unsigned char *ob = p->right_base + copy * p->right.bytes;
+        sp.out_bnd_s = (int32_t *)(ob + p->right.off_s);
+        sp.out_bnd_c = (unsigned long long *)(ob + p->right.off_c);
+        sp.out_bnd_w = (uint32_t *)(ob + p->right.off_w);
+        sp.out_progress = (int *)(ob + p->right.off_flag);
+        if (pipelined && p->epoch >= 2) {
+            /* that copy carried fill e - 2: wait until the neighbour has finished with it and zeroed it */
+            nwb_inbox_gate_kernel<<<1, 32, 0, st>>>(NWB_INBOX_ACK(p->right_base, p->right), (unsigned)(p->epoch - 1),
+                                                   &p->summary.p->error, sp.watchdog_ns);
+            CK(cudaGetLastError());
+            p->launches += 1;
+        }
     }
 
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
@@ -681,7 +748,8 @@ extern "C" int nwb_plan_reset_inbox(nwb_plan *p, void *stream)
     if (!p->inbox.base) return NWB_OK;
     CK(cudaSetDevice(p->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-    CK(cudaMemsetAsync(p->inbox.base, 0, p->inbox.bytes, st));
+    CK(cudaMemsetAsync(p->inbox.base, 0, NWB_INBOX_ALLOC_BYTES(p->inbox), st));
+    p->epoch = 0; /* both copies and the acknowledgement word start over (every rank of the group does this) */
     return NWB_OK;
 }
 
@@ -863,6 +931,12 @@ extern "C" int nwb_plan_ipc_attach_right(nwb_plan *p, const void *blob)
 }
 
 /* same-process variant: `right` lives on another device of this process */
+static int plan_attach_right_local(nwb_plan *p, nwb_plan *right);
+extern "C" int nwb_plan_attach_right(nwb_plan *p, nwb_plan *right)
+{
+    if (!p || !right || !right->inbox.base || p->device == right->device) return NWB_ERR_INVALID;
+    return plan_attach_right_local(p, right);
+}
 static int plan_attach_right_local(nwb_plan *p, nwb_plan *right)
 {
     CK(cudaSetDevice(p->device));

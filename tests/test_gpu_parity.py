@@ -200,6 +200,61 @@ def test_two_gpu_strips_match_one(oracle, nwb):
     full_check(oracle, nwb, t, s, 2, 1, 2, nwb.FORCE_GENERAL, num_gpus=2)
 
 
+def _rank_share(pl):
+    sm = pl.summary()                           # waits for this rank's last fill only
+    return (sm.partial_r, sm.branch_count, pl.arrow_digest(), sm.count, sm.opt_score, sm.kernel_kind)
+
+
+def _group_result(nwb, shares, A, B, d):
+    """(score, branch count, table digest, count) of a strip group from its ranks' shares (what bench.py all-reduces)."""
+    score = nwb.strip_group_score(sum(x[0] for x in shares), A, B, d) if shares[0][5] == 1 else shares[-1][4]
+    return (score, sum(x[1] for x in shares) & 0xFFFFFFFF, sum(x[2] for x in shares) & 0xFFFFFFFFFFFFFFFF, shares[-1][3])
+
+
+def test_pipelined_strip_group(oracle, nwb):
+    """nwb_plan_run_pipelined: a strip group works through a queue of DIFFERENT fills with no barrier and no inbox reset
+    between them (double-buffered inboxes + acknowledgement word).  Rank g collects its share of fill e and launches
+    fill e + 1 before rank g + 1 has been looked at, so neighbouring ranks are on different fills; every fill of the
+    queue is checked (score, branch count, digest of every rank's arrow columns, count) against the one-GPU fill of the
+    same pair, whose results the other tests pin to the oracle.  Then one pair is filled 12 times back to back with
+    nothing on the host between the launches, and the last fill is checked."""
+    ndev = nwb.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    for world in [w for w in (2, 4, 8) if w <= ndev]:
+        for (A, B, mkd, flags) in ((10000, 10000, (1, 1, 1), 0), (6000, 9000, (2, 1, 2), 0), (3000, 2500, (5, 4, 3), 0),
+                                   (5000, 6000, (1, 1, 1), nwb.WANT_COUNT), (3000, 2500, (1, 3, 1), nwb.FORCE_GENERAL)):
+            pairs = [oracle.generate_pair(0x5EED0C00 + 16 * i, A, B) for i in range(3)]
+            want = []
+            for (t, s) in pairs:
+                tab = nwb.fill(t, s, *mkd, flags | nwb.WANT_DIGEST)
+                want.append((tab.opt_score, tab.branch_count, tab.arrow_digest(), tab.count))
+                tab.close()
+            plans = [nwb.Plan(A, B, flags, device=g, strip_rank=g, strip_world=world) for g in range(world)]
+            for g in range(world - 1):
+                plans[g].attach_right(plans[g + 1])
+            queue = [0, 1, 2, 1, 0, 2, 2]
+            for step in range(len(queue) + 1):
+                shares = []
+                for pl in plans:
+                    if step > 0:
+                        shares.append(_rank_share(pl))
+                    if step < len(queue):
+                        pl.upload(*pairs[queue[step]])
+                        pl.run_pipelined(*mkd)
+                if step > 0:
+                    assert _group_result(nwb, shares, A, B, mkd[2]) == want[queue[step - 1]], (world, A, B, mkd, step)
+            for pl in plans:
+                pl.upload(*pairs[1])
+            for _ in range(12):
+                for pl in plans:
+                    pl.run_pipelined(*mkd)
+            assert _group_result(nwb, [_rank_share(pl) for pl in plans], A, B, mkd[2]) == want[1], (world, A, B, mkd, "back to back")
+            for pl in plans:
+                pl.close()
+    nwb.cache_clear()
+
+
 def test_strip_group_full_size_digests(oracle, nwb):
     """Column strips over 2 (and 4, 8 when present) GPUs of one process at full size: EVERY arrow set (the ranks' table
     digests add up to the oracle's), score, branch count and the count (the sparse backward sweep on the rank that owns
