@@ -368,29 +368,39 @@ def run_ours(args) -> None:
     gold = goldens()
     g3 = gold["config3_dna_100k"]
     t, s = nwb.generate_pair(SEED, A, B)  # the package's own SURVEY 8d generator (checked against the oracle's in tests/)
-    flags = 0
-    plan = nwb.Plan(A, B, flags, device=local, strip_rank=rank, strip_world=world)
+    # One step = one fill of the whole 100k x 100k table.  The K steps are taken as a QUEUE of fills: NQ plans (device
+    # workspaces, each with its own arrow table and stream) take the steps round robin, so consecutive fills overlap -- on one
+    # GPU the next fill's blocks move onto SMs as this fill's leave them (NWB_QUEUE: ticketed blocks, no co-residency needed);
+    # in a strip group (world > 1, every table is cut into column strips over ALL the GPUs) rank r also starts fill e + 1
+    # while the ranks to its right are still on fill e (nwb_plan_run_pipelined: double-buffered inboxes, no barrier or
+    # inbox reset between steps).  The timed region is bracketed by barriers as the contract says; the time ONE fill takes
+    # from launch to completion is measured separately (`latency`).
+    n_strips = (A + 255) // 256
+    nloc = -(-n_strips // world)
+    NQ = args.queue if args.queue > 0 else min(10, max(2, -(-148 // -(-nloc // 3)) + 1))
+    flags = nwb.QUEUE
+    plans = [nwb.Plan(A, B, flags, device=local, strip_rank=rank, strip_world=world) for _ in range(NQ)]
     if world > 1:
         blobs = [None] * world
-        dist.all_gather_object(blobs, plan.ipc_export())
+        dist.all_gather_object(blobs, [pl.ipc_export() for pl in plans])
         if rank + 1 < world:
-            plan.ipc_attach_right(blobs[rank + 1])
-    plan.upload(t, s)
-    # a non-default torch stream: the C ABI treats a NULL stream as "the plan's own",
-    # and torch.cuda.Event only sees torch's current stream
-    tstream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
+            for q, pl in enumerate(plans):
+                pl.ipc_attach_right(blobs[rank + 1][q])
+    for pl in plans:
+        pl.upload(t, s)
+    # non-default torch streams: the C ABI treats a NULL stream as "the plan's own", and torch.cuda.Event wants a torch stream
+    tstreams = [torch.cuda.Stream(device=local) for _ in range(NQ)]
+    torch.cuda.set_stream(tstreams[0])
+    nstep = [0]
 
-    # One step = one fill of the whole table.  A strip group (world > 1) takes its steps as a QUEUE of fills
-    # (nwb_plan_run_pipelined): no barrier and no inbox reset between consecutive steps, so rank r starts fill e + 1 while the
-    # ranks to its right are still on fill e -- the timed region is bracketed by barriers as the contract says, and the
-    # latency of ONE fill across the group is measured separately below (barrier-bracketed single steps).
     def step():
+        q = nstep[0] % NQ
+        nstep[0] += 1
         if world > 1:
-            plan.run_pipelined(M_, K_, D_, stream)
+            plans[q].run_pipelined(M_, K_, D_, tstreams[q].cuda_stream)
         else:
-            plan.run(M_, K_, D_, stream)
+            plans[q].run(M_, K_, D_, tstreams[q].cuda_stream)
+        return q
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -400,89 +410,120 @@ def run_ours(args) -> None:
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    # ---- device-resident timing: K steps, CUDA events on the launching streams
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    ev_start.record(tstreams[0])                     # every stream is idle here
     for i in range(args.steps):
-        ev[i][0].record()
+        q = nstep[0] % NQ
+        ev[i][0].record(tstreams[q])
         step()
-        ev[i][1].record()
+        ev[i][1].record(tstreams[q])
+    for q in range(1, NQ):
+        tstreams[0].wait_stream(tstreams[q])
+    ev_end.record(tstreams[0])                       # ... and the last of the K fills is done here
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = ev[0][0].elapsed_time(ev[-1][1])      # first launch to the end of this rank's last fill
-    fill_latency_ms = None
+    total_ms = ev_start.elapsed_time(ev_end)
     if world > 1:
         tt = torch.tensor([total_ms], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-        # latency of one fill across the group: every rank starts together, the last rank's end counts
-        lat = []
-        for _ in range(3):
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            step()
-            b.record()
-            barrier()
-            lat.append(a.elapsed_time(b))
-        tt = torch.tensor([sum(lat) / len(lat)], device="cuda")
+    # latency of one fill, nothing else on the GPUs: every rank starts together, the last rank's end counts
+    lat = []
+    for _ in range(3):
+        barrier()
+        q = nstep[0] % NQ
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(tstreams[q])
+        step()
+        b.record(tstreams[q])
+        barrier()
+        lat.append(a.elapsed_time(b))
+    fill_latency_ms = sum(lat) / len(lat)
+    if world > 1:
+        tt = torch.tensor([fill_latency_ms], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         fill_latency_ms = float(tt.item())
-    last_kernel_ms = plan.kernel_ms()
-    kernel_name = plan.kernel_name()
-    summ = plan.summary()
-    launches_per_step = plan.launches() // (warm + args.steps + (3 if world > 1 else 0))
-    digest = plan.arrow_digest()          # this rank's share of the table, digested on the device
+    kernel_name = plans[0].kernel_name()
+    launches_per_step = sum(pl.launches() for pl in plans) // nstep[0]
+    # every plan's table (this rank's share of it), digested on the device
+    shares = []
+    for pl in plans:
+        sm = pl.summary()
+        shares.append((sm.partial_r, sm.branch_count, pl.arrow_digest(), sm.kernel_kind, sm.opt_score))
 
-    # ---- end to end with HOST strings
+    # ---- end to end with HOST strings: per step the H2D copy of the two strings, the fill, and the D2H read of the step's
+    # summary block -- which is read when the plan comes round again (NQ steps later), i.e. the host keeps NQ fills in flight
     barrier()
-    if world == 1:
-        nwb.fill(t, s, M_, K_, D_, flags, device=local).close()      # first call creates the cached workspace
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            tab = nwb.fill(t, s, M_, K_, D_, flags, device=local)    # H2D + fill + D2H summary, one blocking call
-            e2e_score = tab.opt_score
-            tab.close()
-        e2e_s = time.perf_counter() - t0
-        e2e_call = "nwb_fill() (host strings -> table handle; workspace cached between calls)"
-        nwb.cache_clear()
-    else:
-        t0 = time.perf_counter()
-        shares = set()
-        for _ in range(args.steps):
-            plan.upload(t, s)            # H2D of this step's inputs
-            plan.run_pipelined(M_, K_, D_, stream)
-            summ = plan.summary()        # D2H of the step's result (waits for this rank's fill)
-            shares.add((summ.partial_r, summ.branch_count))
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        e2e_score = None
-        e2e_steps_agree = len(shares) == 1   # every step left the same share on this rank; the last one is checked against the goldens
-        e2e_call = ("per rank: nwb_plan_upload + nwb_plan_run_pipelined + nwb_plan_summary (one process per GPU; consecutive "
-                    "fills overlap across the ranks)")
+    in_flight = [False] * NQ
+    e2e_shares = set()
+
+    def collect(q):
+        sm = plans[q].summary()          # D2H of that step's result (waits for this rank's share of that fill only)
+        e2e_shares.add((sm.partial_r, sm.branch_count, sm.opt_score))
+        in_flight[q] = False
+
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        q = nstep[0] % NQ
+        if in_flight[q]:
+            collect(q)
+        plans[q].upload(t, s)            # H2D of this step's inputs
+        step()
+        in_flight[q] = True
+    for q in range(NQ):
+        if in_flight[q]:
+            collect(q)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_steps_agree = len(e2e_shares) == 1 and (shares[0][0], shares[0][1], shares[0][4]) in e2e_shares
+    e2e_call = (f"per step: nwb_plan_upload + nwb_plan_run{'_pipelined' if world > 1 else ''} on plan (step mod {NQ}), nwb_plan_summary "
+                f"of that plan's previous fill when it comes round again (the host keeps {NQ} fills in flight)")
+    if world > 1:
         tt = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    clocks = sampler.stop() if rank == 0 else None
-    opt_score = summ.opt_score
-    branch_total = summ.branch_count
-    if world > 1:
-        # a strip group's score is the sum of the ranks' bottom-row shares (include/nwb.h nwb_summary); branch
-        # counts and digests add up (the digest mod 2^64: two 32-bit halves so that the int64 reduction cannot overflow)
-        tt = torch.tensor([summ.partial_r, summ.branch_count, digest & 0xFFFFFFFF, digest >> 32], device="cuda", dtype=torch.int64)
-        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        if summ.kernel_kind == 1:
-            opt_score = nwb.strip_group_score(int(tt[0].item()), A, B, D_)
-        branch_total = int(tt[1].item()) & 0xFFFFFFFF
-        digest = (int(tt[2].item()) + (int(tt[3].item()) << 32)) & M64
-    golden_ok = (opt_score, branch_total, digest) == (g3["final_score"], g3["branch_count"], int(g3["arrow_digest"], 16))
+    # the one-call path a CLI run takes: nwb_fill(), blocking, host strings in, table handle out (no queue)
+    blocking = None
     if world == 1:
-        golden_ok = golden_ok and e2e_score == g3["final_score"]
-    else:
-        tt = torch.tensor([1 if e2e_steps_agree else 0], device="cuda")
+        for pl in plans[1:]:
+            pl.close()
+        plans = plans[:1]
+        nwb.fill(t, s, M_, K_, D_, 0, device=local).close()          # first call creates the cached workspace
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            tab = nwb.fill(t, s, M_, K_, D_, 0, device=local)        # H2D + fill + D2H summary, one blocking call
+            e2e_score = tab.opt_score
+            blocking_kernel_ms = tab.kernel_ms
+            tab.close()
+        blocking_s = time.perf_counter() - t1
+        nwb.cache_clear()
+        blocking = {"call": "nwb_fill() (host strings -> table handle; workspace cached between calls), one fill at a time",
+                    "ms_per_fill": blocking_s / args.steps * 1e3, "gcups": A * B * args.steps / blocking_s / 1e9,
+                    "kernel_ms": blocking_kernel_ms, "score_ok": e2e_score == g3["final_score"]}
+    clocks = sampler.stop() if rank == 0 else None
+    # golden check of EVERY plan's table: a strip group's score is the sum of the ranks' bottom-row shares (include/nwb.h
+    # nwb_summary); branch counts and digests add up (the digest mod 2^64 as two 32-bit halves: no int64 overflow)
+    golden_ok = True
+    want = (g3["final_score"], g3["branch_count"], int(g3["arrow_digest"], 16))
+    for (partial_r, branches, dig, kind, score) in shares:
+        if world > 1:
+            tt = torch.tensor([partial_r, branches, dig & 0xFFFFFFFF, dig >> 32], device="cuda", dtype=torch.int64)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            if kind == 1:
+                score = nwb.strip_group_score(int(tt[0].item()), A, B, D_)
+            branches = int(tt[1].item()) & 0xFFFFFFFF
+            dig = (int(tt[2].item()) + (int(tt[3].item()) << 32)) & M64
+        golden_ok = golden_ok and (score, branches, dig) == want
+        opt_score, branch_total, digest, kernel_kind = score, branches, dig, kind
+    tt = torch.tensor([1 if e2e_steps_agree else 0], device="cuda")
+    if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MIN)
-        golden_ok = golden_ok and int(tt.item()) == 1
-    plan.close()
+    golden_ok = golden_ok and int(tt.item()) == 1 and (blocking is None or blocking["score_ok"])
+    for pl in plans:
+        pl.close()
 
     extras, extras_ok = (None, True)
     if not args.no_extras:
@@ -502,7 +543,7 @@ def run_ours(args) -> None:
         peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
         f_mhz = float(peaks.get("sm_max_mhz", SM_MAX_MHZ_FALLBACK))
         peak_ops = props.multi_processor_count * r_per_clk * f_mhz * 1e6          # thread-results/s at max clock
-        k_ms = last_kernel_ms if world == 1 else ms_per_step
+        k_ms = ms_per_step  # the fills of a queue overlap: one table's share of the device time, not the span of one launch
         achieved_ops = cells * OPS_PER_CELL / (k_ms * 1e-3)
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = cells * 0.5 + A + B
@@ -522,7 +563,7 @@ def run_ours(args) -> None:
         line = {
             "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u16x2" if summ.kernel_kind == 1 else "int32",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u16x2" if kernel_kind == 1 else "int32",
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "int_issue", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tops/s (algorithmic INT ops, 10 per cell)", "frac": achieved_ops / peak_ops,
@@ -532,7 +573,11 @@ def run_ours(args) -> None:
                                         f"{props.multi_processor_count} SMs x {f_mhz:.0f} MHz "
                                         f"({'MEASURED_PEAKS.json' if peaks else 'fallback'} sm_max_mhz)",
                          "kernel": kernel_name,
-                         "kernel_ms": k_ms},
+                         "kernel_ms": k_ms,
+                         "kernel_ms_is": "device time per table over the timed region (the launches of consecutive fills overlap); one "
+                                         "fill alone: latency.fill_latency_ms, frac_one_fill_alone",
+                         "frac_one_fill_alone": cells * OPS_PER_CELL / (fill_latency_ms * 1e-3) / peak_ops,
+                         "note": "10 ops per cell is SURVEY 8d's counting convention, not a ceiling: one DPX instruction updates two cells"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                              "algorithmic_bytes": alg_bytes,
@@ -543,24 +588,32 @@ def run_ours(args) -> None:
             "launches_per_step": {"per_rank": launches_per_step,
                                   "kernels": ("nwb_pk_prep_side_kernel, " + kernel_name + ", nwb_pk_stream_sum_kernel"
                                               + (", nwb_inbox_gate_kernel, nwb_inbox_ack_kernel" if world > 1 else ""))
-                                  if summ.kernel_kind == 1 else kernel_name},
+                                  if kernel_kind == 1 else kernel_name},
             "clocks": clocks,
             "golden_ok": bool(golden_ok and extras_ok),
             "result": {"opt_score": opt_score, "branch_count": branch_total, "arrow_digest": f"{digest:016x}",
-                       "kernel_kind": summ.kernel_kind, "headline_golden_ok": bool(golden_ok),
+                       "kernel_kind": kernel_kind, "headline_golden_ok": bool(golden_ok),
                        "golden": "tests/golden/golden_big.json config3_dna_100k: score, branch count and the digest of the whole "
                                  "arrow table (every cell, summed over the ranks)"},
             "step_ms": [round(x, 3) for x in step_ms],
         }
-        if world > 1:
-            line["pipelined"] = {
-                "what": "the K timed steps are a queue of fills (nwb_plan_run_pipelined): rank r starts fill e + 1 while the ranks "
-                        "to its right are still on fill e; no barrier or inbox reset between steps, barriers on both sides of the "
-                        "timed region; value = K tables / (first launch .. last rank done, max over ranks)",
-                "fill_latency_ms": fill_latency_ms,
-                "fill_latency_gcups": cells / (fill_latency_ms * 1e-3) / 1e9,
-                "step_ms_is": "rank 0's own share of each fill (its kernels only)",
-            }
+        line["queue"] = {
+            "plans_in_flight": NQ,
+            "what": f"the K timed steps are a queue of fills taken round robin by {NQ} plans (workspaces with their own arrow table and "
+                    "stream) per GPU: consecutive fills overlap on the device (NWB_QUEUE: ticketed blocks sweeping adjacent strips, the "
+                    "next fill's blocks move onto SMs as this one's leave)"
+                    + ("; every table is cut into column strips over all the GPUs and rank r starts fill e + 1 while the ranks to its "
+                       "right are still on fill e (nwb_plan_run_pipelined)" if world > 1 else "")
+                    + "; no barrier between steps, barriers on both sides of the timed region; value = K tables / (first launch .. last "
+                      "fill done, max over ranks); every plan's table is checked against the goldens",
+            "step_ms_is": "rank 0: launch-to-completion span of each fill's kernels (they overlap)",
+        }
+        line["latency"] = {
+            "fill_latency_ms": fill_latency_ms,
+            "fill_latency_gcups": cells / (fill_latency_ms * 1e-3) / 1e9,
+            "how": "one fill in queue mode with nothing else on the GPUs, barrier on both sides, max over ranks, mean of 3",
+            "blocking_call": blocking,
+        }
         if extras is not None:
             line["extras"] = extras
         if world == 1 and not args.no_cpu:
@@ -587,9 +640,10 @@ def run_ours(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queue", type=int, default=0, help="plans (fills in flight) per GPU; 0 = as many as fill the SMs")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (2, 4, 5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--cpu-legs", action="store_true", help=argparse.SUPPRESS)

@@ -73,6 +73,12 @@ extern "C" {
 #define NWB_WANT_COUNT_DIGEST 0x80u
 /* nwb_fill()/nwb_fill_on(): compute the arrow-table digest on the device before returning (nwb_arrow_digest()). */
 #define NWB_WANT_DIGEST 0x100u
+/* nwb_plan_create(): this plan is one of several on the same GPU that work through a QUEUE of fills (fill e on plan
+ * e mod n, each plan on its own stream).  The single-pair kernel is then launched so that consecutive fills overlap:
+ * its blocks draw tickets and sweep adjacent strips, need no co-residency, and the next fill's blocks move onto SMs as
+ * this fill's leave them.  One fill alone is ~5 % slower this way; a queue runs at the rate at which the SMs sweep
+ * strips instead of the rate of one strip-to-strip wavefront. */
+#define NWB_QUEUE 0x200u
 
 /* ---- error codes ---------------------------------------------------------- */
 #define NWB_OK 0

@@ -36,6 +36,7 @@ WANT_COUNT_MATRIX = 0x20
 NO_BRANCH_COUNT = 0x40
 WANT_COUNT_DIGEST = 0x80
 WANT_DIGEST = 0x100
+QUEUE = 0x200          # Plan(): one of several plans on a GPU working through a queue of fills (consecutive fills overlap)
 KIND_I32, KIND_PK = 0, 1
 # nwb_summary.count_path
 COUNT_NONE, COUNT_FUSED, COUNT_DENSE, COUNT_SPARSE, COUNT_SPARSE_BAILED = 0, 1, 2, 3, 4

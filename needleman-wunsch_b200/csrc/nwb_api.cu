@@ -104,6 +104,7 @@ struct NwbTune {
     int watchdog_ms = 4000; /* device-side spin loops give up after this long without progress               */
     int inject_fault = 0;   /* test only: 1 = the fill's strips do not publish their boundary streams        */
     int plan_cache = 1;     /* 0 = nwb_fill()/nwb_fill_on() create and destroy their device workspace per call */
+    int hx_spb = 0;         /* 1..3: the hx kernel in queue mode (see NWB_QUEUE) with that many adjacent strips per block */
 #ifdef NWB_EXPERIMENTS
     int pk_hy = 0;
     int pk_hz = 0;
@@ -139,6 +140,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"cx_warps", &g_tune.cx_warps}, {"batch_bp", &g_tune.batch_bp}, {"bp_warps", &g_tune.bp_warps},
         {"bp_aligned", &g_tune.bp_aligned}, {"batch_lcount", &g_tune.batch_lcount}, {"lc_warps", &g_tune.lc_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
+        {"hx_spb", &g_tune.hx_spb},
 #ifdef NWB_EXPERIMENTS
         {"pk_hy", &g_tune.pk_hy}, {"pk_hz", &g_tune.pk_hz}, {"debug_nowait", &g_tune.debug_nowait},
 #endif
@@ -629,6 +631,14 @@ static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pi
 
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
     const bool hx = (p->kind == NWB_KIND_PK) && p->pk_hx;
+    int hx_grid = grid;
+    if (hx && (pipelined || (p->flags & NWB_QUEUE) || tn.hx_spb > 0)) {
+        /* queue mode (nwb_fill_hx.cuh): blocks draw tickets and sweep three adjacent strips each -- as many blocks as
+         * that takes, resident or not, so that the fills of other plans share the GPU with this one */
+        int spb = (tn.hx_spb >= 1 && tn.hx_spb <= NWB_HX_CRIT) ? tn.hx_spb : NWB_HX_CRIT;
+        sp.hx_spb = spb;
+        hx_grid = (nloc + spb - 1) / spb;
+    }
 #ifdef NWB_EXPERIMENTS
     /* every strip of this launch can have an SM half (sweeping warp + packing warp + flush warp) to itself */
     p->pk_hz = hx && !p->pk_hy && tn.pk_hz != 0 && nwb_hz_usable(nloc, p->sm_count);
@@ -652,15 +662,15 @@ static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pi
      * not guaranteed by CUDA -- the sweep's waits are bounded by the watchdog. */
     const int cnt_grid_wanted = (cp.strip_end - cp.strip_begin + NWB_CNT_WARPS - 1) / NWB_CNT_WARPS;
     const bool overlap = hx && cpath == NWB_CNT_DENSE && tn.count_mode == 3 && cnt_cpl == 8 && cp.strip_end > cp.strip_begin &&
-                         !(flags & NWB_WANT_COUNT_DIGEST) && grid + cnt_grid_wanted <= p->sm_count;
+                         !(flags & NWB_WANT_COUNT_DIGEST) && grid + cnt_grid_wanted <= p->sm_count && sp.hx_spb == 0;
     sp.publish_rows = overlap ? 1 : 0;
     if (overlap) CK(cudaEventRecord(p->ev_fork, st)); /* buffers are zeroed, strings uploaded */
     if (hx) {
 #ifdef NWB_EXPERIMENTS
         rc = p->pk_hy ? nwb_hy_launch(sp, pc, grid, st, cuda_fail)
-                      : (p->pk_hz ? nwb_hz_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, grid, st, cuda_fail));
+                      : (p->pk_hz ? nwb_hz_launch(sp, pc, grid, st, cuda_fail) : nwb_hx_launch(sp, pc, hx_grid, st, cuda_fail));
 #else
-        rc = nwb_hx_launch(sp, pc, grid, st, cuda_fail);
+        rc = nwb_hx_launch(sp, pc, hx_grid, st, cuda_fail);
 #endif
     } else if (p->kind == NWB_KIND_PK) rc = run_pk(p, sp, pc, fused_count, grid, pk_warps, st);
     else rc = run_i32(p, kflags, sp, grid, st);

@@ -284,7 +284,7 @@ struct NwbDevSummary {
     int count_state;      /* NWB_SPC_* (nwb_count_sparse.cuh): 1 = the sparse backward sweep produced `count` */
     unsigned sparse_rows; /* rows the sparse sweep visited before its live set died                            */
     int error;            /* != 0: a device-side watchdog gave up waiting (NWB_DEVERR_*); results are invalid  */
-    int pad;
+    int ticket;           /* nwb_fill_hx_kernel: the next block id (blocks draw their ids as they start)                */
     unsigned long long dig_row; /* dense count sweep with digests: sum_i mix64(i, cnt(i,B)) over this rank's columns */
     unsigned long long dig_col; /* ... sum_j mix64(j, cnt(A,j)) (the rank that owns column A)                        */
 };
@@ -332,6 +332,8 @@ struct NwbStripParams {
     int *out_progress;
     NwbDevSummary *summary;
     int count_branches; /* packed kernel: count cells with >= 2 arrows while flushing rows */
+    int hx_spb;         /* hx kernel: 0 = strips dealt out cyclically over a resident grid (one fill as fast as possible);
+                         * 1..3 = queue mode, blocks draw tickets and sweep that many adjacent strips (nwb_fill_hx.cuh) */
     int publish_rows;   /* hx kernel: publish in progress[] how many arrow rows of each strip are in memory
                          * (the count sweep of nwb_count.cuh trails the fill on a second stream) */
     int debug_nowait; /* bit 2 (value 4): fault injection for the watchdog test -- the strips' boundary streams are

@@ -348,14 +348,14 @@ __device__ __forceinline__ void nwb_hx_flush_slot(const uint4 w, unsigned &pc0, 
     pc1 = c1;
 }
 
-template <bool PUBLISH, int NCRIT = NWB_HX_CRIT>
-__device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int wslot, const unsigned char *ring,
-                                              volatile int *ready, volatile int *done, const int lane,
-                                              unsigned &branches)
+/* worker / nworkers: the first strip (relative to strip_begin) and the strip stride of the sweeping warp this warp
+ * flushes for */
+template <bool PUBLISH>
+__device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int worker, const int nworkers,
+                                              const unsigned char *ring, volatile int *ready, volatile int *done,
+                                              const int lane, unsigned &branches)
 {
     const int B = p.B, A = p.A;
-    const int nworkers = (int)gridDim.x * NCRIT; /* sweeping warps per block: 3 here, 2 in nwb_fill_hz.cuh */
-    const int worker = wslot * (int)gridDim.x + (int)blockIdx.x;
     const int ngroups = (B + 1) / 2;
     const int nfull = B / 2; /* groups with both rows inside the table */
     const int nblocks = (ngroups + 63 + 31) / 32;
@@ -453,7 +453,7 @@ __device__ __forceinline__ void nwb_hx_flush(const NwbStripParams &p, const int 
 /* PUBLISH: the flush warps also publish in p.progress[] how many arrow rows of each strip are in memory, for a
  * count sweep (nwb_count.cuh) that trails the fill on another stream.  A separate instantiation: the sweeping
  * warps' instruction schedule is sensitive to any code added to the kernel. */
-template <bool PUBLISH>
+template <bool PUBLISH, bool QUEUE = false>
 __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const NwbStripParams p, const NwbPkConsts pc)
 {
     const int lane = threadIdx.x & 31;
@@ -461,13 +461,28 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
     unsigned char *smem = NWB_SMEM_BASE();
     volatile int *flags = reinterpret_cast<volatile int *>(smem + (size_t)NWB_HX_CRIT * NWB_HX_RING_BYTES);
     if (threadIdx.x < 2 * NWB_HX_CRIT) flags[threadIdx.x] = 0;
+    /* Two ways of dealing the strips out (p.hx_spb):
+     * 0: strips b, b + G, b + 2G for block b of a grid of G <= SMs blocks that are all resident (cooperative launch) --
+     *    the three sweeping warps of an SM are far apart in the table and the first G strips have an SM each to
+     *    themselves: the shortest time for ONE fill.
+     * 1..3 (queue mode): block ids are TICKETS drawn as the blocks start and a block sweeps that many ADJACENT strips.
+     *    A strip then only ever waits for strips of blocks with smaller tickets, i.e. blocks that are already running
+     *    or done, so the launch needs no co-residency guarantee, a table may have more blocks than the GPU has SMs,
+     *    and the blocks of the NEXT fill (another plan, another stream) move onto SMs as this fill's blocks leave
+     *    them: consecutive fills overlap. */
+    /* QUEUE is a template parameter: the instantiation for one fill alone is the code it was before queue mode
+     * existed (the sweeping warp's schedule is sensitive to anything added to the kernel: +2 % with a run-time switch) */
+    const bool queue = QUEUE;
+    if (QUEUE && threadIdx.x == 0) flags[2 * NWB_HX_CRIT] = p.summary ? atomicAdd(&p.summary->ticket, 1) : (int)blockIdx.x;
     __syncthreads();
-    const int crit_slot = (warp < NWB_HX_CRIT) ? warp : -1;
-    const int flush_slot = ((warp & 3) == 3 && (warp >> 2) < NWB_HX_CRIT) ? (warp >> 2) : -1;
+    const int bid = QUEUE ? flags[2 * NWB_HX_CRIT] : (int)blockIdx.x;
+    const int spb = (QUEUE && p.hx_spb >= 1 && p.hx_spb <= NWB_HX_CRIT) ? p.hx_spb : NWB_HX_CRIT; /* sweeping warps of this block */
+    const int nworkers = (int)gridDim.x * spb;
+    const int crit_slot = (warp < spb) ? warp : -1;
+    const int flush_slot = ((warp & 3) == 3 && (warp >> 2) < spb) ? (warp >> 2) : -1;
     if (crit_slot >= 0) {
         /* sweeping warp */
-        const int nworkers = (int)gridDim.x * NWB_HX_CRIT;
-        const int worker = crit_slot * (int)gridDim.x + (int)blockIdx.x;
+        const int worker = queue ? bid * spb + crit_slot : crit_slot * (int)gridDim.x + bid;
         unsigned char *ring = smem + (size_t)crit_slot * NWB_HX_RING_BYTES;
         long long rsum = 0;
         int seq = 0;
@@ -481,7 +496,7 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
         /* flush warp of sweeping warp flush_slot */
         const int wslot = flush_slot;
         unsigned branches = 0;
-        nwb_hx_flush<PUBLISH>(p, wslot, smem + (size_t)wslot * NWB_HX_RING_BYTES, flags + wslot,
+        nwb_hx_flush<PUBLISH>(p, queue ? bid * spb + wslot : wslot * (int)gridDim.x + bid, nworkers, smem + (size_t)wslot * NWB_HX_RING_BYTES, flags + wslot,
                               flags + NWB_HX_CRIT + wslot, lane, branches);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) branches += __shfl_xor_sync(NWB_FULL_MASK, branches, o);
@@ -490,12 +505,19 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
 }
 
 #ifndef NWB_EMU
-template <bool PUBLISH>
+template <bool PUBLISH, bool QUEUE>
 static int nwb_hx_launch_t(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st, nwb_fail_fn fail)
 {
-    auto kernel = nwb_fill_hx_kernel<PUBLISH>;
+    auto kernel = nwb_fill_hx_kernel<PUBLISH, QUEUE>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NWB_HX_SMEM_BYTES);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
+    if (QUEUE) {
+        /* an ordinary launch: the blocks' tickets make it deadlock-free without co-residency (see the kernel) */
+        kernel<<<dim3(grid), dim3(32 * NWB_HX_WARPS), NWB_HX_SMEM_BYTES, st>>>(sp, pc);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(e, "nwb_fill_hx_kernel launch");
+        return 0;
+    }
     void *args[] = {(void *)&sp, (void *)&pc};
     e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(32 * NWB_HX_WARPS), args, NWB_HX_SMEM_BYTES, st);
     if (e != cudaSuccess) return fail(e, "cudaLaunchCooperativeKernel");
@@ -503,6 +525,8 @@ static int nwb_hx_launch_t(const NwbStripParams &sp, const NwbPkConsts &pc, int 
 }
 static inline int nwb_hx_launch(const NwbStripParams &sp, const NwbPkConsts &pc, int grid, cudaStream_t st, nwb_fail_fn fail)
 {
-    return sp.publish_rows ? nwb_hx_launch_t<true>(sp, pc, grid, st, fail) : nwb_hx_launch_t<false>(sp, pc, grid, st, fail);
+    if (sp.hx_spb > 0) /* queue mode; the count sweep that trails the fill (publish_rows) belongs to the one-fill mode */
+        return nwb_hx_launch_t<false, true>(sp, pc, grid, st, fail);
+    return sp.publish_rows ? nwb_hx_launch_t<true, false>(sp, pc, grid, st, fail) : nwb_hx_launch_t<false, false>(sp, pc, grid, st, fail);
 }
 #endif

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(32 * NWB_HZ_WARPS, 1) nwb_fill_hz_kernel(const
         nwb_hz_pack(p, wslot, raw_ring, ring, f + 0, f + 1, f + 2, f + 3, lane);
     } else if (role == 3) {
         unsigned branches = 0;
-        nwb_hx_flush<PUBLISH, NWB_HZ_CRIT>(p, wslot, ring, f + 2, f + 3, lane, branches);
+        nwb_hx_flush<PUBLISH>(p, wslot * (int)gridDim.x + (int)blockIdx.x, (int)gridDim.x * NWB_HZ_CRIT, ring, f + 2, f + 3, lane, branches);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) branches += __shfl_xor_sync(NWB_FULL_MASK, branches, o);
         if (lane == 0 && branches) atomicAdd(&p.summary->branch_count, branches);

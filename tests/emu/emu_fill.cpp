@@ -198,13 +198,17 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
     emu_launch(2, 64, 0, [&]() { nwb_pk_prep_side_kernel((const uint8_t *)side, B, pc.shift, side_pre.data()); });
     p.side_pre = side_pre.data();
     const uint32_t *last_stream = nullptr; /* the stream consumed by the last strip, when it is not in bnd_w */
+    if (hx >= 4) p.hx_spb = hx - 3; /* hx = 4, 5, 6: queue mode of nwb_fill_hx_kernel with 1, 2, 3 adjacent strips per block */
     auto launch = [&](const NwbStripParams &q) {
+        sum.ticket = 0; /* the hx blocks draw their ids from here; nwb_plan_run() zeroes the summary block per launch */
         if (hx == 3) { /* sweeping + packing + flush warps, two strips per block (nwb_fill_hz.cuh) */
             if (q.publish_rows) emu_launch(grid, 32 * NWB_HZ_WARPS, NWB_HZ_SMEM_BYTES, [&]() { nwb_fill_hz_kernel<true>(q, pc); });
             else emu_launch(grid, 32 * NWB_HZ_WARPS, NWB_HZ_SMEM_BYTES, [&]() { nwb_fill_hz_kernel<false>(q, pc); });
         } else if (hx == 2) { /* one row of skew per virtual lane (nwb_fill_hy.cuh) */
             if (q.publish_rows) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<true>(q, pc); });
             else emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<false>(q, pc); });
+        } else if (hx >= 4) {
+            emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false, true>(q, pc); });
         } else if (hx) {
             if (q.publish_rows) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<true>(q, pc); });
             else emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false>(q, pc); });
@@ -264,7 +268,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         int inbox_flag = 0;
         std::vector<uint32_t> bnd1((size_t)L.n_strips * L.bpitch, 0u);
         std::vector<int> prog1v((size_t)L.n_strips, 0);
-        if (hx && count >= 2) { p0.publish_rows = 1; p1.publish_rows = 1; prog0 = progress.data(); prog1 = prog1v.data(); }
+        if (hx && hx < 4 && count >= 2) { p0.publish_rows = 1; p1.publish_rows = 1; prog0 = progress.data(); prog1 = prog1v.data(); }
         p0.strip_end = split;
         p0.out_bnd_w = inbox_w.data();
         p0.out_bnd_c = inbox_cc.data();
@@ -282,7 +286,7 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         last_stream = (split == L.n_strips - 1) ? inbox_w.data() : bnd1.data() + (size_t)(L.n_strips - 2 - split) * L.bpitch;
         emu_launch(2, 64, 0, [&]() { nwb_pk_stream_sum_kernel(last_stream, B, R, &sum.rsum); });
     } else {
-        if (hx && count >= 2) { p.publish_rows = 1; prog0 = progress.data(); }
+        if (hx && hx < 4 && count >= 2) { p.publish_rows = 1; prog0 = progress.data(); }
         launch(p);
         if (count >= 2) run_count(count, 0, nullptr, nullptr);
         if (L.n_strips >= 2) {

@@ -14,7 +14,8 @@ import emu
 SCHEMES = [(1, 1, 1), (2, 1, 2), (0, 0, 0), (1, 2, 3), (1, 0, 0), (3, -1, 0), (3, 1, 2), (1, 1, 3)]
 
 
-VARIANTS = (1, 2, 3)   # 1 = nwb_fill_hx.cuh, 2 = nwb_fill_hy.cuh (experiment), 3 = nwb_fill_hz.cuh (packing warps, two strips per block)
+VARIANTS = (1, 2, 3, 4, 5, 6)   # 1 = nwb_fill_hx.cuh, 2 = nwb_fill_hy.cuh (experiment), 3 = nwb_fill_hz.cuh (packing warps, two strips per block),
+                                # 4 / 5 / 6 = nwb_fill_hx.cuh in queue mode (ticketed blocks, 1 / 2 / 3 adjacent strips each)
 
 
 def check(oracle, t, s, m, k, d, grid=2, split=0):

@@ -200,6 +200,41 @@ def test_two_gpu_strips_match_one(oracle, nwb):
     full_check(oracle, nwb, t, s, 2, 1, 2, nwb.FORCE_GENERAL, num_gpus=2)
 
 
+def test_queue_mode_on_one_gpu(oracle, nwb):
+    """NWB_QUEUE: several plans on one GPU take a queue of different fills round robin, each on its own stream, so that
+    consecutive fills overlap (ticketed blocks sweeping adjacent strips, ordinary launches).  Every fill is compared
+    with the one-call fill of the same pair (score, branch count, digest of the whole arrow table); one shape has more
+    blocks than the GPU has SMs (157 blocks of three strips: the late blocks start when earlier ones have left), one
+    has a ragged last block, one runs the count behind the fill; nwb_tune hx_spb = 1, 2 puts fewer strips in a block."""
+    for (A, B, mkd, flags, spb) in ((120400, 4200, (1, 1, 1), 0, 0), (30000, 20000, (2, 1, 2), 0, 0), (5100, 9000, (1, 1, 1), nwb.WANT_COUNT, 0),
+                                    (20000, 6000, (1, 1, 1), 0, 1), (20000, 6000, (1, 1, 2), 0, 2)):
+        pairs = [oracle.generate_pair(0x5EED0D00 + 16 * i, A, B) for i in range(3)]
+        want = []
+        for (t, s) in pairs:
+            tab = nwb.fill(t, s, *mkd, flags | nwb.WANT_DIGEST)
+            want.append((tab.opt_score, tab.branch_count, tab.arrow_digest(), tab.count))
+            tab.close()
+        nwb.cache_clear()
+        with nwb.tuned(hx_spb=spb):
+            plans = [nwb.Plan(A, B, flags | nwb.QUEUE) for _ in range(3)]
+            queue = [0, 1, 2, 2, 0, 1, 1, 0, 2, 0, 1]
+            which = [None] * len(plans)
+            for step, q in enumerate(queue + [None] * len(plans)):
+                pl = plans[step % len(plans)]
+                if which[step % len(plans)] is not None:        # the fill this plan took three steps ago
+                    sm = pl.summary()
+                    assert sm.kernel_kind == 1 and pl.kernel_name() == "nwb_fill_hx_kernel"
+                    got = (sm.opt_score, sm.branch_count, pl.arrow_digest(), sm.count)
+                    assert got == want[which[step % len(plans)]], (A, B, mkd, step)
+                    which[step % len(plans)] = None
+                if q is not None:
+                    pl.upload(*pairs[q])
+                    pl.run(*mkd)
+                    which[step % len(plans)] = q
+            for pl in plans:
+                pl.close()
+
+
 def _rank_share(pl):
     sm = pl.summary()                           # waits for this rank's last fill only
     return (sm.partial_r, sm.branch_count, pl.arrow_digest(), sm.count, sm.opt_score, sm.kernel_kind)
