@@ -367,6 +367,8 @@ def run_ours(args) -> None:
 
     gold = goldens()
     g3 = gold["config3_dna_100k"]
+    if os.environ.get("NWB_BENCH_NOGATE"):
+        nwb.tune("pipe_gate", 0)   # diagnostics only
     t, s = nwb.generate_pair(SEED, A, B)  # the package's own SURVEY 8d generator (checked against the oracle's in tests/)
     # One step = one fill of the whole 100k x 100k table.  The K steps are taken as a QUEUE of fills: NQ plans (device
     # workspaces, each with its own arrow table and stream) take the steps round robin, so consecutive fills overlap -- on one
@@ -377,7 +379,11 @@ def run_ours(args) -> None:
     # from launch to completion is measured separately (`latency`).
     n_strips = (A + 255) // 256
     nloc = -(-n_strips // world)
-    NQ = args.queue if args.queue > 0 else min(10, max(2, -(-148 // -(-nloc // 3)) + 1))
+    # plans per GPU: as many fills as fit on the SMs at once (a fill's share is ceil(nloc / 3) blocks, one block per SM) plus
+    # one whose blocks move in as others leave; measured (tools/sweep_queue.sh): more than that and the ranks of a strip group
+    # drift apart in what they have resident
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    NQ = args.queue if args.queue > 0 else min(12, max(3, sms // -(-nloc // 3) + 1))
     flags = nwb.QUEUE
     plans = [nwb.Plan(A, B, flags, device=local, strip_rank=rank, strip_world=world) for _ in range(NQ)]
     if world > 1:
@@ -402,7 +408,7 @@ def run_ours(args) -> None:
             plans[q].run(M_, K_, D_, tstreams[q].cuda_stream)
         return q
 
-    warm = max(args.warmup, 3)
+    warm = max(args.warmup, 3, NQ)   # every plan's first fill (first touch of its 5 GB table) is a warm-up step
     for _ in range(warm):
         step()
     barrier()
@@ -415,17 +421,35 @@ def run_ours(args) -> None:
     ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev_start.record(tstreams[0])                     # every stream is idle here
+    host_t, hbase = [], time.perf_counter()
     for i in range(args.steps):
         q = nstep[0] % NQ
+        h0 = time.perf_counter()
+        if args.pace and i >= NQ:
+            tstreams[q].synchronize()                # host pacing: at most NQ fills launched ahead (what the e2e loop does by reading results)
+        h1 = time.perf_counter()
         ev[i][0].record(tstreams[q])
         step()
         ev[i][1].record(tstreams[q])
+        host_t.append((round((h0 - hbase) * 1e3, 3), round((h1 - hbase) * 1e3, 3), round((time.perf_counter() - hbase) * 1e3, 3)))
     for q in range(1, NQ):
         tstreams[0].wait_stream(tstreams[q])
     ev_end.record(tstreams[0])                       # ... and the last of the K fills is done here
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = ev_start.elapsed_time(ev_end)
+    if args.trace:
+        # diagnostics: when each fill started / ended on each rank, in ms after the start of the timed region
+        tl = [(round(ev_start.elapsed_time(a), 3), round(ev_start.elapsed_time(b), 3)) for a, b in ev]
+        if world > 1:
+            allt = [None] * world
+            dist.all_gather_object(allt, [tl, host_t])
+        else:
+            allt = [[tl, host_t]]
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump({"n_gpus": world, "plans": NQ, "steps": args.steps, "by_rank_device_start_end_and_host_sync_begin_end_launched": allt},
+                      open(os.path.join(ROOT, "gpurun_out", f"queue_trace_n{world}.json"), "w"))
     if world > 1:
         tt = torch.tensor([total_ms], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -644,6 +668,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queue", type=int, default=0, help="plans (fills in flight) per GPU; 0 = as many as fill the SMs")
+    ap.add_argument("--pace", type=int, default=1, help="1: the host waits for a plan's previous fill before it launches the next one on it")
+    ap.add_argument("--trace", action="store_true", help="dump each fill's start / end per rank to gpurun_out/queue_trace_nN.json")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (2, 4, 5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--cpu-legs", action="store_true", help=argparse.SUPPRESS)

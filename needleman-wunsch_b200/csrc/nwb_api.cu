@@ -105,6 +105,7 @@ struct NwbTune {
     int inject_fault = 0;   /* test only: 1 = the fill's strips do not publish their boundary streams        */
     int plan_cache = 1;     /* 0 = nwb_fill()/nwb_fill_on() create and destroy their device workspace per call */
     int hx_spb = 0;         /* 1..3: the hx kernel in queue mode (see NWB_QUEUE) with that many adjacent strips per block */
+    int pipe_gate = 1;      /* diagnostics: 0 = pipelined runs do not wait for the neighbour's acknowledgement (unsafe) */
 #ifdef NWB_EXPERIMENTS
     int pk_hy = 0;
     int pk_hz = 0;
@@ -140,7 +141,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"cx_warps", &g_tune.cx_warps}, {"batch_bp", &g_tune.batch_bp}, {"bp_warps", &g_tune.bp_warps},
         {"bp_aligned", &g_tune.bp_aligned}, {"batch_lcount", &g_tune.batch_lcount}, {"lc_warps", &g_tune.lc_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
-        {"hx_spb", &g_tune.hx_spb},
+        {"hx_spb", &g_tune.hx_spb}, {"pipe_gate", &g_tune.pipe_gate},
 #ifdef NWB_EXPERIMENTS
         {"pk_hy", &g_tune.pk_hy}, {"pk_hz", &g_tune.pk_hz}, {"debug_nowait", &g_tune.debug_nowait},
 #endif
@@ -416,6 +417,14 @@ __global__ void nwb_inbox_ack_kernel(unsigned *ack, unsigned value)
 {
     if (threadIdx.x == 0) nwb_st_release_sys(reinterpret_cast<int *>(ack), (int)value);
 }
+/* The inbox copy is zeroed by a kernel, not by cudaMemsetAsync: a memset queued behind a running fill sits in a
+ * copy-engine queue until that fill is done, and the memsets / the summary upload with which the NEXT fills of the
+ * other plans begin queue up behind it (measured: with five plans per GPU the fills ran in waves of four). */
+__global__ void __launch_bounds__(128) nwb_inbox_zero_kernel(uint4 *dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = make_uint4(0u, 0u, 0u, 0u);
+}
 __global__ void __launch_bounds__(32) nwb_inbox_gate_kernel(const unsigned *peer_ack, unsigned need, int *err,
                                                            unsigned long long limit_ns)
 {
@@ -445,7 +454,9 @@ extern "C" int nwb_plan_run_pipelined(nwb_plan *p, int m, int k, int d, void *st
     if (p->inbox.base) {
         /* my copy of the inbox is free again: zero it, then tell the left neighbour */
         cudaStream_t st = p->last_stream;
-        CK(cudaMemsetAsync(p->inbox.base + (size_t)(p->epoch & 1) * p->inbox.bytes, 0, p->inbox.bytes, st));
+        nwb_inbox_zero_kernel<<<64, 128, 0, st>>>(reinterpret_cast<uint4 *>(p->inbox.base + (size_t)(p->epoch & 1) * p->inbox.bytes),
+                                                 p->inbox.bytes / 16);
+        CK(cudaGetLastError());
         nwb_inbox_ack_kernel<<<1, 32, 0, st>>>(NWB_INBOX_ACK(p->inbox.base, p->inbox), (unsigned)(p->epoch + 1));
         CK(cudaGetLastError());
         p->launches += 1;
@@ -620,14 +631,11 @@ static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pi
         sp.out_bnd_c = (unsigned long long *)(ob + p->right.off_c);
         sp.out_bnd_w = (uint32_t *)(ob + p->right.off_w);
         sp.out_progress = (int *)(ob + p->right.off_flag);
-        if (pipelined && p->epoch >= 2) {
-            /* that copy carried fill e - 2: wait until the neighbour has finished with it and zeroed it */
-            nwb_inbox_gate_kernel<<<1, 32, 0, st>>>(NWB_INBOX_ACK(p->right_base, p->right), (unsigned)(p->epoch - 1),
-                                                   &p->summary.p->error, sp.watchdog_ns);
-            CK(cudaGetLastError());
-            p->launches += 1;
-        }
     }
+    /* the copy of the neighbour's inbox this run writes into carried fill e - 2: the neighbour must have finished with
+     * it and zeroed it.  The hx kernel in queue mode waits for that itself (its last strip, before its first remote
+     * store); every other kernel gets the wait as a small kernel in front of it. */
+    const bool need_gate = pipelined && p->strip_end < L.n_strips && p->epoch >= 2 && tn.pipe_gate != 0;
 
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
     const bool hx = (p->kind == NWB_KIND_PK) && p->pk_hx;
@@ -638,6 +646,16 @@ static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pi
         int spb = (tn.hx_spb >= 1 && tn.hx_spb <= NWB_HX_CRIT) ? tn.hx_spb : NWB_HX_CRIT;
         sp.hx_spb = spb;
         hx_grid = (nloc + spb - 1) / spb;
+        if (need_gate) {
+            sp.gate_ack = NWB_INBOX_ACK(p->right_base, p->right);
+            sp.gate_need = (unsigned)(p->epoch - 1);
+        }
+    }
+    if (need_gate && !sp.gate_ack) {
+        nwb_inbox_gate_kernel<<<1, 32, 0, st>>>(NWB_INBOX_ACK(p->right_base, p->right), (unsigned)(p->epoch - 1),
+                                               &p->summary.p->error, sp.watchdog_ns);
+        CK(cudaGetLastError());
+        p->launches += 1;
     }
 #ifdef NWB_EXPERIMENTS
     /* every strip of this launch can have an SM half (sweeping warp + packing warp + flush warp) to itself */

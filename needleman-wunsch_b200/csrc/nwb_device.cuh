@@ -332,6 +332,8 @@ struct NwbStripParams {
     int *out_progress;
     NwbDevSummary *summary;
     int count_branches; /* packed kernel: count cells with >= 2 arrows while flushing rows */
+    const uint32_t *gate_ack; /* hx kernel in queue mode, pipelined strip group: the right neighbour's acknowledgement word ... */
+    unsigned gate_need;       /* ... and the value it must have reached before this launch writes into the neighbour's inbox   */
     int hx_spb;         /* hx kernel: 0 = strips dealt out cyclically over a resident grid (one fill as fast as possible);
                          * 1..3 = queue mode, blocks draw tickets and sweep that many adjacent strips (nwb_fill_hx.cuh) */
     int publish_rows;   /* hx kernel: publish in progress[] how many arrow rows of each strip are in memory

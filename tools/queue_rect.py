@@ -1,0 +1,37 @@
+"""Queue mode on ONE GPU with a table the width of one rank's share of an 8-way strip group (49 strips x 100,000 rows):
+how much do fills of different plans slow one another down when they share the SMs?  (run under gpurun)
+usage: python tools/queue_rect.py [A] [B] [steps]"""
+import sys, os, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import nw_b200 as nwb
+
+A = int(sys.argv[1]) if len(sys.argv) > 1 else 12544
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+t, s = nwb.generate_pair(0x5EED0030, A, B)
+for NQ in (1, 2, 4, 8, 9, 12):
+    plans = [nwb.Plan(A, B, nwb.QUEUE) for _ in range(NQ)]
+    streams = [torch.cuda.Stream() for _ in range(NQ)]
+    for pl in plans:
+        pl.upload(t, s)
+    for i in range(NQ):
+        plans[i].run(1, 1, 1, streams[i].cuda_stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(streams[0])
+    for i in range(K):
+        q = i % NQ
+        ev[i][0].record(streams[q])
+        plans[q].run(1, 1, 1, streams[q].cuda_stream)
+        ev[i][1].record(streams[q])
+    for q in range(1, NQ):
+        streams[0].wait_stream(streams[q])
+    b.record(streams[0])
+    torch.cuda.synchronize()
+    tot = a.elapsed_time(b)
+    spans = [x.elapsed_time(y) for x, y in ev]
+    print(f"A={A} B={B} NQ={NQ:2d}  {tot / K:7.3f} ms per table  {A * B * K / tot / 1e6:8.1f} GCUPS   spans first {[round(x, 2) for x in spans[:NQ + 2]]} last {[round(x, 2) for x in spans[-3:]]}", flush=True)
+    for pl in plans:
+        pl.close()
