@@ -367,8 +367,6 @@ def run_ours(args) -> None:
 
     gold = goldens()
     g3 = gold["config3_dna_100k"]
-    if os.environ.get("NWB_BENCH_NOGATE"):
-        nwb.tune("pipe_gate", 0)   # diagnostics only
     t, s = nwb.generate_pair(SEED, A, B)  # the package's own SURVEY 8d generator (checked against the oracle's in tests/)
     # One step = one fill of the whole 100k x 100k table.  The K steps are taken as a QUEUE of fills: NQ plans (device
     # workspaces, each with its own arrow table and stream) take the steps round robin, so consecutive fills overlap -- on one

@@ -92,7 +92,8 @@ const char *nwb_strerror(int err);
 /* Explicit overrides for tests and measurements; the library reads NO environment variables.  Every key
  * selects between kernels that produce identical results ("pk_k", "pk_r", "pk_warps", "pk_hx", "count_mode"
  * 0 auto / 1 fused into the fill / 2 dense sweep after the fill / 3 dense sweep trailing the fill on a second
- * stream, "cnt_cpl", "batch_bx", "batch_cx", "batch_bp", "bp_warps", "bp_aligned", "batch_lcount", "lc_warps", "bcnt_chain", "cx_warps"; 0 or -1 = automatic,
+ * stream, "cnt_cpl", "batch_bx", "batch_cx", "batch_bp", "bp_warps", "bp_aligned", "batch_lcount", "lc_warps", "bcnt_chain", "cx_warps",
+ * "hx_spb" 1..3 = the single-pair kernel in queue mode -- see NWB_QUEUE -- with that many adjacent strips per block; 0 or -1 = automatic,
  * see nwb_api.cu) except "watchdog_ms" (how long a device-side wait may see no progress before the fill
  * fails with NWB_ERR_CUDA; default 4000) and "inject_fault" (test only: 1 makes the next fills lose a
  * strip's boundary stream so that the watchdog path can be exercised -- the fill FAILS, it never returns a

@@ -105,7 +105,6 @@ struct NwbTune {
     int inject_fault = 0;   /* test only: 1 = the fill's strips do not publish their boundary streams        */
     int plan_cache = 1;     /* 0 = nwb_fill()/nwb_fill_on() create and destroy their device workspace per call */
     int hx_spb = 0;         /* 1..3: the hx kernel in queue mode (see NWB_QUEUE) with that many adjacent strips per block */
-    int pipe_gate = 1;      /* diagnostics: 0 = pipelined runs do not wait for the neighbour's acknowledgement (unsafe) */
 #ifdef NWB_EXPERIMENTS
     int pk_hy = 0;
     int pk_hz = 0;
@@ -141,7 +140,7 @@ extern "C" int nwb_tune(const char *key, int value)
         {"cx_warps", &g_tune.cx_warps}, {"batch_bp", &g_tune.batch_bp}, {"bp_warps", &g_tune.bp_warps},
         {"bp_aligned", &g_tune.bp_aligned}, {"batch_lcount", &g_tune.batch_lcount}, {"lc_warps", &g_tune.lc_warps},
         {"watchdog_ms", &g_tune.watchdog_ms}, {"inject_fault", &g_tune.inject_fault}, {"plan_cache", &g_tune.plan_cache},
-        {"hx_spb", &g_tune.hx_spb}, {"pipe_gate", &g_tune.pipe_gate},
+        {"hx_spb", &g_tune.hx_spb},
 #ifdef NWB_EXPERIMENTS
         {"pk_hy", &g_tune.pk_hy}, {"pk_hz", &g_tune.pk_hz}, {"debug_nowait", &g_tune.debug_nowait},
 #endif
@@ -635,7 +634,7 @@ static int plan_run_body(nwb_plan *p, int m, int k, int d, void *stream, bool pi
     /* the copy of the neighbour's inbox this run writes into carried fill e - 2: the neighbour must have finished with
      * it and zeroed it.  The hx kernel in queue mode waits for that itself (its last strip, before its first remote
      * store); every other kernel gets the wait as a small kernel in front of it. */
-    const bool need_gate = pipelined && p->strip_end < L.n_strips && p->epoch >= 2 && tn.pipe_gate != 0;
+    const bool need_gate = pipelined && p->strip_end < L.n_strips && p->epoch >= 2;
 
     int grid = nloc < p->sm_count ? nloc : p->sm_count;
     const bool hx = (p->kind == NWB_KIND_PK) && p->pk_hx;
