@@ -319,6 +319,32 @@ def run_extras(nwb, torch, dist, world, rank, local, barrier, gold) -> tuple[dic
             rec[label]["e2e_ms"] = e2e * 1e3
             rec[label]["e2e_gcups"] = n * n / e2e / 1e9
             rec[label]["golden_ok"] = bool(rec[label]["golden_ok"] and okf)
+        # a QUEUE of such fills (NWB_QUEUE: plans take the fills round robin and consecutive fills overlap on the GPU; DESIGN.md
+        # 5.2): device-resident, wall clock from the first launch to the last completion, launches included
+        if n < A:
+            blocks = -(-(-(-n // 256)) // 3)
+            nq = min(12, max(2, torch.cuda.get_device_properties(local).multi_processor_count // blocks + 1))
+            for label, flags in (("fill", 0), ("q_s", nwb.WANT_COUNT)):
+                plans = [nwb.Plan(n, n, flags | nwb.QUEUE, device=local) for _ in range(nq)]
+                for pl in plans:
+                    pl.upload(t, s)
+                    pl.run(*mkd)
+                torch.cuda.synchronize()
+                kq = 6 * nq
+                t0 = time.perf_counter()
+                for i in range(kq):
+                    plans[i % nq].run(*mkd)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                okq = True
+                for pl in plans:
+                    sm = pl.summary()
+                    okq = okq and (sm.opt_score, sm.branch_count) == (g["final_score"], g["branch_count"]) \
+                        and pl.arrow_digest() == int(g["arrow_digest"], 16) and (not flags or sm.count == g["count_u64"])
+                    pl.close()
+                rec[label]["queue"] = {"plans": nq, "fills": kq, "ms_per_table": dt / kq * 1e3, "gcups": n * n * kq / dt / 1e9,
+                                       "golden_ok": bool(okq)}
+                rec[label]["golden_ok"] = bool(rec[label]["golden_ok"] and okq)
         # every count of the dense sweep's last row and column (the final count is 0 mod 2^64 on these inputs)
         plan = nwb.Plan(n, n, nwb.WANT_COUNT_DIGEST, device=local)
         plan.upload(t, s)
