@@ -598,12 +598,12 @@ def run_ours(args) -> None:
         # dram bytes of the fill kernel: NOT measured in this run (ncu cannot run inside a timed bench); taken from the
         # committed ncu --set full capture of the same kernel and command
         traffic, traffic_src = None, None
-        for cand in ("r02_fill_hx_ncu_summary.json", "r01_fill_hx_ncu_summary.json"):
+        for cand in ("r02_fill_hx_queue_ncu_summary.json", "r02_fill_hx_ncu_summary.json", "r01_fill_hx_ncu_summary.json"):
             tpath = os.path.join(ROOT, "profiles", cand)
             if kernel_name == "nwb_fill_hx_kernel" and world == 1 and os.path.exists(tpath):
                 try:
                     traffic = json.load(open(tpath)).get("dram_bytes_total")
-                    traffic_src = f"profiles/{cand} (ncu --set full, one launch of the same kernel; not measured in this run)"
+                    traffic_src = f"profiles/{cand} (ncu --set full, one launch of the same kernel, per launch = per table; not measured in this run)"
                 except Exception:
                     traffic = None
                 if traffic is not None:

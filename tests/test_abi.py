@@ -53,3 +53,6 @@ def test_error_strings(lib):
     assert lib.nwb_strerror(0) == b"ok"
     assert b"no CPU fallback" in lib.nwb_strerror(-4)
     assert lib.nwb_abi_version() >= 1
+    # the queue entry points refuse a missing plan like every other plan call (no device needed to say so)
+    assert lib.nwb_plan_run_pipelined(None, 1, 1, 1, None) == -1
+    assert lib.nwb_plan_attach_right(None, None) == -1
