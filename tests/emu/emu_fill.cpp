@@ -280,6 +280,10 @@ int emu_fill_pk(const char *top, int A, const char *side, int B, int m, int k, i
         p1.in_progress = &inbox_flag;
         p1.bnd_w = bnd1.data();
         p1.progress = prog1v.data();
+        /* queue mode in a pipelined strip group: the last local strip looks at the right neighbour's acknowledgement
+         * word before its first store into the neighbour's inbox (here: already granted) */
+        uint32_t ack_word = 9u;
+        if (hx >= 4) { p0.gate_ack = &ack_word; p0.gate_need = 7u; }
         launch(p0);
         launch(p1);
         if (count >= 2) run_count(count, split, p0.out_bnd_c, p1.in_bnd_c);
