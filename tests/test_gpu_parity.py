@@ -235,6 +235,35 @@ def test_queue_mode_on_one_gpu(oracle, nwb):
                 pl.close()
 
 
+def test_queue_mode_small_tables(oracle, nwb):
+    """Queue mode on small tables forced onto the hx kernel (nwb_tune pk_hx = 1): 1 / 2 / 3 adjacent strips per block,
+    ragged last blocks, a table smaller than one strip, the count behind the fill; two plans, every fill against the
+    ORACLE (score, branch count, digest of every arrow set, count)."""
+    with nwb.tuned(pk_hx=1):
+        for spb in (0, 1, 2):
+            nwb.tune("hx_spb", spb)
+            for (a, b, flags) in ((1500, 300, 0), (700, 260, nwb.WANT_COUNT), (2100, 64, 0), (7, 7, 0)):
+                pairs = [oracle.generate_pair(0x5EED0F80 + 2 * i + a, a, b) for i in range(2)]
+                want = []
+                for t, s in pairs:
+                    o = oracle.fill(t, s, 2, 1, 2)
+                    want.append((o.final_score, o.branch_count, o.arrow_digest, o.count if flags else 0))
+                plans = [nwb.Plan(a, b, flags | nwb.QUEUE) for _ in range(2)]
+                took = [None, None]
+                for step, q in enumerate([0, 1, 1, 0, 0, None, None]):
+                    pl = plans[step % 2]
+                    if took[step % 2] is not None:
+                        sm = pl.summary()
+                        assert pl.kernel_name() == "nwb_fill_hx_kernel", pl.kernel_name()
+                        assert (sm.opt_score, sm.branch_count, pl.arrow_digest(), sm.count) == want[took[step % 2]], (spb, a, b, step)
+                    if q is not None:
+                        pl.upload(*pairs[q])
+                        pl.run(2, 1, 2)
+                    took[step % 2] = q
+                for pl in plans:
+                    pl.close()
+
+
 def _rank_share(pl):
     sm = pl.summary()                           # waits for this rank's last fill only
     b, e = pl.strip_range()
