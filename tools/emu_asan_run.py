@@ -26,6 +26,11 @@ for (a,b) in [(7,7),(300,100),(513,70),(600,260),(90,700)]:
     for cpl in (0,2,4,8):
         r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=2,count=cpl,hx=True)
         assert r['opt_score']==o.final_score and (cpl==0 or r['count']==o.count)
+    # queue mode of the same kernel: ticketed blocks, 1 / 2 / 3 adjacent strips per block, the acknowledgement check
+    # of a pipelined strip group in front of the last local strip's remote stores (split)
+    for hxq in (4,5,6):
+        r=emu.fill_pk(t,s,1,1,1,K=4,R=2,grid=2,hx=hxq,split=(1 if a>256 else 0))
+        assert r['opt_score']==o.final_score and r['branch_count']==o.branch_count
     # the three-rows-per-lane geometry (nwb_fill_hy.cuh): stream words from step 0 on, 47 groups early; per-lane row parity
     for cpl in (0,8):
         r=emu.fill_pk(t,s,2,1,2,K=4,R=2,grid=2,count=cpl,hx=2,split=(1 if a>256 else 0))
