@@ -1,6 +1,6 @@
 """Queue mode on ONE GPU with a table the width of one rank's share of an 8-way strip group (49 strips x 100,000 rows):
 how much do fills of different plans slow one another down when they share the SMs?  (run under gpurun)
-usage: python tools/queue_rect.py [A] [B] [steps]"""
+usage: python tools/queue_rect.py [A] [B] [steps] [hx_spb] [NQ,NQ,...]"""
 import sys, os, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
@@ -9,8 +9,11 @@ import nw_b200 as nwb
 A = int(sys.argv[1]) if len(sys.argv) > 1 else 12544
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+SPB = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # nwb_tune hx_spb: adjacent strips per block (0 = 3)
+NQS = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [1, 2, 4, 8, 9, 12]
+nwb.tune("hx_spb", SPB)
 t, s = nwb.generate_pair(0x5EED0030, A, B)
-for NQ in (1, 2, 4, 8, 9, 12):
+for NQ in NQS:
     plans = [nwb.Plan(A, B, nwb.QUEUE) for _ in range(NQ)]
     streams = [torch.cuda.Stream() for _ in range(NQ)]
     for pl in plans:
@@ -32,6 +35,6 @@ for NQ in (1, 2, 4, 8, 9, 12):
     torch.cuda.synchronize()
     tot = a.elapsed_time(b)
     spans = [x.elapsed_time(y) for x, y in ev]
-    print(f"A={A} B={B} NQ={NQ:2d}  {tot / K:7.3f} ms per table  {A * B * K / tot / 1e6:8.1f} GCUPS   spans first {[round(x, 2) for x in spans[:NQ + 2]]} last {[round(x, 2) for x in spans[-3:]]}", flush=True)
+    print(f"A={A} B={B} spb={SPB} NQ={NQ:2d}  {tot / K:7.3f} ms per table  {A * B * K / tot / 1e6:8.1f} GCUPS   spans first {[round(x, 2) for x in spans[:NQ + 2]]} last {[round(x, 2) for x in spans[-3:]]}", flush=True)
     for pl in plans:
         pl.close()
