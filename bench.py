@@ -7,15 +7,22 @@ Workload (BASELINE.json): config 3, one pair of 100,000 x 100,000 synthetic DNA
 (SplitMix64 seeds 0x5EED0030/31), m=k=d=1 -- the configuration the target
 ("the 100k x 100k fill at >= 50% of the INT/DPX issue roofline") is quoted on.
 A step = one fill of the whole table (scores in registers, every arrow set
-written as 4-bit codes).  At N > 1 the table is cut into column strips across
-the ranks (boundary columns stream rank-to-rank through CUDA-IPC peer memory
-over NVLink), total work fixed -> "scaling": "strong".
+written as 4-bit codes).  The K steps are a QUEUE of fills: a few plans per GPU
+(workspaces with their own 5 GB arrow table and stream) take them round robin
+and consecutive fills overlap on the device (NWB_QUEUE).  At
+N > 1 EVERY table is cut into column strips across the ranks (boundary columns
+stream rank-to-rank through CUDA-IPC peer memory over NVLink; rank r starts fill
+e + 1 while the ranks to its right are still on fill e, nwb_plan_run_pipelined);
+total work fixed -> "scaling": "strong".
 
-value  = interior cells / device time, strings resident in HBM (CUDA events on
-         the launching stream, max over ranks);
-e2e    = the same through the host-buffer C-ABI call: nwb_fill() with HOST strings
-         (H2D + fill + D2H of the summary inside the timed region); at N > 1 the
-         per-rank plan calls (upload + run + summary).
+value   = interior cells of K tables / device time from the first launch to the
+          last completion, strings resident in HBM (CUDA events, max over ranks;
+          barrier + synchronize on both sides, none between the steps);
+e2e     = the same through the C ABI with HOST strings, wall clock: per step
+          nwb_plan_upload (H2D) + nwb_plan_run[_pipelined], and nwb_plan_summary
+          (D2H) of every step's result;
+latency = what ONE fill takes from launch to completion (nothing else on the
+          GPUs), and the one-call path nwb_fill() that a CLI run takes.
 
 Every result is checked against tests/golden/golden_big.json -- score, branch
 count and the digest of the WHOLE arrow table, computed on the device and summed
@@ -404,8 +411,7 @@ def run_ours(args) -> None:
     n_strips = (A + 255) // 256
     nloc = -(-n_strips // world)
     # plans per GPU: as many fills as fit on the SMs at once (a fill's share is ceil(nloc / 3) blocks, one block per SM) plus
-    # one whose blocks move in as others leave; measured (tools/sweep_queue.sh): more than that and the ranks of a strip group
-    # drift apart in what they have resident
+    # one whose blocks move in as others leave (tools/sweep_queue.sh, profiles/r02_queue_sweep.txt: more plans change nothing)
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     NQ = args.queue if args.queue > 0 else min(12, max(3, sms // -(-nloc // 3) + 1))
     flags = nwb.QUEUE
