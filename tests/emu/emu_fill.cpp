@@ -389,6 +389,13 @@ int emu_fill_pk_rank(const char *top, int A, const char *side, int B, int m, int
     p.side_pre = side_pre.data();
     if (hx == 3) emu_launch(grid, 32 * NWB_HZ_WARPS, NWB_HZ_SMEM_BYTES, [&]() { nwb_fill_hz_kernel<false>(p, pc); });
     else if (hx == 2) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hy_kernel<false>(p, pc); });
+    else if (hx >= 4) { /* queue mode: ticketed blocks of hx - 3 adjacent strips; a rank that publishes checks its neighbour's
+                         * acknowledgement word first (the caller has waited for the acknowledgement: granted) */
+        uint32_t ack_word = 3u;
+        p.hx_spb = hx - 3;
+        if (se < L.n_strips) { p.gate_ack = &ack_word; p.gate_need = 3u; }
+        emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false, true>(p, pc); });
+    }
     else if (hx) emu_launch(grid, 32 * NWB_HX_WARPS, NWB_HX_SMEM_BYTES, [&]() { nwb_fill_hx_kernel<false>(p, pc); });
     else run_pk_emu<4, 2, false>(grid, 4, p, pc);
     { /* the counter fused into the flush and the stand-alone pass over this rank's columns must agree */

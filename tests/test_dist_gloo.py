@@ -117,6 +117,70 @@ def test_column_strips_three_ranks_uneven():
     _run(3, _strips_rank, 0x5EED0A03, 1000, 70, (1, 1, 1), 2)
 
 
+# ----------------------------------------------------------------------------- a queue of fills through a strip group
+def _pipelined_rank(rank, world, seeds, a, b, mkd):
+    """The protocol of nwb_plan_run_pipelined() with one process per rank: fill e streams into copy e & 1 of the right
+    neighbour's inbox; the neighbour clears a copy when its own fill e is done and acknowledges e + 1; before fill e + 2
+    a rank waits for that acknowledgement.  No barrier between the fills: rank 0 is on fill e + 1 while rank 1 sweeps
+    fill e.  The sweeps are the queue-mode hx kernel (ticketed blocks of adjacent strips) under the emulator."""
+    import emu
+    import nw_b200 as nwb
+    import oracle
+    m, k, d = mkd
+    c0, c1 = nwb.strip_partition(a, rank, world)
+    bp = emu.bpitch_pk(a, b)
+    copies = [torch.zeros(bp, dtype=torch.int32), torch.zeros(bp, dtype=torch.int32)]
+    acks, mine_sum, want = [], [], []
+    acked = 0          # fills the right neighbour has acknowledged
+    for e, seed in enumerate(seeds):
+        t, s = oracle.generate_pair(seed, a, b)
+        inbox = None
+        if rank > 0:
+            assert int(copies[e & 1].abs().sum()) == 0, "the inbox copy was not cleared after fill e - 2"
+            dist.recv(copies[e & 1], src=rank - 1, tag=e)
+            inbox = copies[e & 1].numpy().view(np.uint32)
+        if rank + 1 < world:
+            while acked < e - 1:          # copy e & 1 of the neighbour's inbox carried fill e - 2
+                ack = torch.zeros(1, dtype=torch.int64)
+                dist.recv(ack, src=rank + 1, tag=1000 + acked)
+                assert int(ack) == acked + 1
+                acked += 1
+        r = emu.fill_pk_rank(t, s, m, k, d, rank=rank, world=world, inbox=inbox, hx=6)
+        if rank + 1 < world:
+            dist.send(torch.from_numpy(r["outbox"].view(np.int32).copy()), dst=rank + 1, tag=e)
+        if rank > 0:
+            copies[e & 1].zero_()
+            acks.append(dist.isend(torch.tensor([e + 1], dtype=torch.int64), dst=rank - 1, tag=1000 + e))
+        o = oracle.fill(t, s, m, k, d, want_codes=True)
+        mine = emu.unpack_arrows(r["arrows"], a)[:, c0:c1] & 7
+        assert np.array_equal(mine, o.codes[1:, 1 + c0:1 + c1] & 7), f"rank {rank}, fill {e}: arrows differ"
+        mine_sum.append((r["partial_r"], r["branch_count"]))
+        want.append((o.final_score, o.branch_count))
+    if rank + 1 < world:                  # drain the acknowledgements still in flight
+        while acked < len(seeds):
+            ack = torch.zeros(1, dtype=torch.int64)
+            dist.recv(ack, src=rank + 1, tag=1000 + acked)
+            acked += 1
+    for w in acks:
+        w.wait()
+    # the summaries are combined at the end (a collective of the CHECK; nothing synchronises the ranks between the fills)
+    shares = [None] * world
+    dist.all_gather_object(shares, mine_sum)
+    for e in range(len(seeds)):
+        assert nwb.strip_group_score(sum(x[e][0] for x in shares), a, b, d) == want[e][0], e
+        assert sum(x[e][1] for x in shares) & 0xFFFFFFFF == want[e][1], e
+
+
+def test_pipelined_queue_of_fills_two_ranks():
+    # 5 strips (3 + 2), four different fills back to back
+    _run(2, _pipelined_rank, [0x5EED0A21, 0x5EED0A23, 0x5EED0A25, 0x5EED0A27], 1200, 90, (1, 1, 1))
+
+
+def test_pipelined_queue_of_fills_three_ranks():
+    # 7 strips (3 + 3 + 1), protein scheme
+    _run(3, _pipelined_rank, [0x5EED0A31, 0x5EED0A33, 0x5EED0A35], 1700, 70, (2, 1, 2))
+
+
 # ----------------------------------------------------------------------------- batch of pairs, no communication
 def _batch_rank(rank, world, n_pairs):
     import emu
