@@ -147,6 +147,24 @@ __device__ __forceinline__ void nwb_hx_step(NwbHxState &st, const NwbPkConsts &p
 
 /* A sweeping warp's strip: nwb_pk_strip<4, 2> without the write-back.  seq counts this warp's
  * 32-step blocks over all its strips; ring slot of a step = (32 * seq + step in block) mod 128. */
+/* Pipelined strip group (nwb_plan_run_pipelined): the strip that streams into the right neighbour's inbox writes
+ * into copy e & 1 of it, which carried fill e - 2: wait until the neighbour says it is done with that fill (in steady
+ * state it long is).  In the kernel, not as a kernel of its own in front of the fill: a spinning kernel at the head of
+ * a stream held up the other plans' streams (measured: the fills of a queue ran in waves).  Not inlined, and called
+ * before the warp's strip loop: the sweeping loop's instruction schedule must not depend on it. */
+__device__ __noinline__ bool nwb_hx_gate(const uint32_t *ack, const unsigned need, int *err, const unsigned long long limit_ns)
+{
+    NwbWatchdog wd;
+    for (;;) {
+        const unsigned v = nwb_ld_relaxed_u32(ack, true);
+        if (__all_sync(NWB_FULL_MASK, (int)(v - need) >= 0)) return true;
+        if (wd.tick(err, limit_ns)) return false;
+#ifdef NWB_EMU
+        nwb_pause();
+#endif
+    }
+}
+
 template <bool QUEUE>
 __device__ __forceinline__ bool nwb_hx_strip(const NwbStripParams &p, const NwbPkConsts &pc, const int c,
                                               unsigned char *ring, volatile int *ready, volatile int *done,
@@ -187,22 +205,6 @@ __device__ __forceinline__ bool nwb_hx_strip(const NwbStripParams &p, const NwbP
     const bool pub31 = publish && (lane == 31) && !NWB_FAULT_INJECTED(p);
     const bool is_last = (c == p.n_strips - 1);
     const uint16_t *sp_lane = p.side_pre + NWB_PK_SPAD + 1 - 2 * R * lane;
-    if (QUEUE && out_remote && p.gate_ack) {
-        /* pipelined strip group: this strip streams into copy e & 1 of the right neighbour's inbox, which carried
-         * fill e - 2: wait until the neighbour says it is done with that fill (nwb_plan_run_pipelined; in steady state
-         * it long is).  In the kernel, not as a kernel of its own in front of the fill: a spinning kernel at the head
-         * of a stream held up the other plans' streams (measured: the fills of a queue ran in waves). */
-        NwbWatchdog wd;
-        for (;;) {
-            const unsigned v = nwb_ld_relaxed_u32(p.gate_ack, true);
-            if (__all_sync(NWB_FULL_MASK, (int)(v - p.gate_need) >= 0)) break;
-            if (wd.tick(NWB_ERR_WORD(p), p.watchdog_ns)) return false;
-#ifdef NWB_EMU
-            nwb_pause();
-#endif
-        }
-    }
-
     const unsigned VMASK = 0x7FFF7FFFu;
     unsigned bq = 0u, bq_next = 0u;
     if (has_left && lane < NWB_PK_SUB && lane < ngroups) bq_next = nwb_ld_relaxed_u32(in_w + lane, left_remote);
@@ -502,6 +504,13 @@ __global__ void __launch_bounds__(32 * NWB_HX_WARPS, 1) nwb_fill_hx_kernel(const
         unsigned char *ring = smem + (size_t)crit_slot * NWB_HX_RING_BYTES;
         long long rsum = 0;
         int seq = 0;
+        if (QUEUE && p.gate_ack && p.strip_end < p.n_strips) {
+            /* am I the warp that sweeps this launch's last strip? */
+            const int last = p.strip_end - 1 - p.strip_begin;
+            if (last >= worker && (last - worker) % nworkers == 0 &&
+                !nwb_hx_gate(p.gate_ack, p.gate_need, NWB_ERR_WORD(p), p.watchdog_ns))
+                return;
+        }
         for (int c = p.strip_begin + worker; c < p.strip_end; c += nworkers)
             if (!nwb_hx_strip<QUEUE>(p, pc, c, ring, flags + crit_slot, flags + NWB_HX_CRIT + crit_slot, seq, lane, rsum))
                 return; /* watchdog: summary->error is set, the host reports NWB_ERR_CUDA */

@@ -13,6 +13,17 @@ SPB = int(sys.argv[4]) if len(sys.argv) > 4 else 0      # nwb_tune hx_spb: adjac
 NQS = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [1, 2, 4, 8, 9, 12]
 nwb.tune("hx_spb", SPB)
 t, s = nwb.generate_pair(0x5EED0030, A, B)
+# one fill alone, the kernel's own time (events around prep + fill inside the library): one-fill launch vs queue mode
+for flags, name in ((0, "cooperative launch, strips dealt out cyclically"), (nwb.QUEUE, f"queue mode, hx_spb={SPB}")):
+    pl = nwb.Plan(A, B, flags)
+    pl.upload(t, s)
+    ks = []
+    for _ in range(4):
+        pl.run(1, 1, 1)
+        pl.summary()
+        ks.append(round(pl.kernel_ms(), 3))
+    print(f"A={A} B={B} one fill alone, {name}: kernel_ms {ks}", flush=True)
+    pl.close()
 for NQ in NQS:
     plans = [nwb.Plan(A, B, nwb.QUEUE) for _ in range(NQ)]
     streams = [torch.cuda.Stream() for _ in range(NQ)]
