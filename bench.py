@@ -617,6 +617,20 @@ def run_ours(args) -> None:
                     traffic = None
                 if traffic is not None:
                     break
+        # a ceiling that cannot be exceeded: the SMs' issue slots (4 schedulers per SM, one warp instruction per clock each);
+        # warp instructions per table from the committed ncu capture of the kernel (not measured in this run)
+        issue = None
+        try:
+            wi = json.load(open(os.path.join(ROOT, "profiles", "r02_fill_hx_queue_ncu_summary.json"))).get("smsp__inst_executed.sum")
+            if wi and kernel_name == "nwb_fill_hx_kernel":
+                peak_slots = props.multi_processor_count * 4 * f_mhz * 1e6 * world
+                issue = {"warp_instructions_per_table": wi, "achieved_per_s": wi / (ms_per_step * 1e-3), "peak_per_s": peak_slots,
+                         "frac": wi / (ms_per_step * 1e-3) / peak_slots,
+                         "frac_one_fill_alone": wi / (fill_latency_ms * 1e-3) / peak_slots,
+                         "source": "smsp__inst_executed.sum of profiles/r02_fill_hx_queue_ncu_summary.json (sweeping + flush warps, "
+                                   "flag polls included) / device time per table; peak = SMs x 4 schedulers x sm_max_mhz x GPUs"}
+        except Exception:
+            issue = None
         line = {
             "metric": METRIC, "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -634,7 +648,9 @@ def run_ours(args) -> None:
                          "kernel_ms_is": "device time per table over the timed region (the launches of consecutive fills overlap); one "
                                          "fill alone: latency.fill_latency_ms, frac_one_fill_alone",
                          "frac_one_fill_alone": cells * OPS_PER_CELL / (fill_latency_ms * 1e-3) / peak_ops,
-                         "note": "10 ops per cell is SURVEY 8d's counting convention, not a ceiling: one DPX instruction updates two cells"},
+                         "note": "10 ops per cell is SURVEY 8d's counting convention, not a ceiling: one DPX instruction updates two cells; "
+                                 "issue_slots is the ceiling that cannot be exceeded",
+                         "issue_slots": issue},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                              "algorithmic_bytes": alg_bytes,
