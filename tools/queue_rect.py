@@ -15,6 +15,7 @@ nwb.tune("hx_spb", SPB)
 t, s = nwb.generate_pair(0x5EED0030, A, B)
 # one fill alone, the kernel's own time (events around prep + fill inside the library): one-fill launch vs queue mode
 for flags, name in ((0, "cooperative launch, strips dealt out cyclically"), (nwb.QUEUE, f"queue mode, hx_spb={SPB}")):
+    nwb.tune("hx_spb", SPB if flags else 0)      # the override is read at every run: none for the one-fill launch
     pl = nwb.Plan(A, B, flags)
     pl.upload(t, s)
     ks = []
@@ -24,6 +25,7 @@ for flags, name in ((0, "cooperative launch, strips dealt out cyclically"), (nwb
         ks.append(round(pl.kernel_ms(), 3))
     print(f"A={A} B={B} one fill alone, {name}: kernel_ms {ks}", flush=True)
     pl.close()
+nwb.tune("hx_spb", SPB)
 for NQ in NQS:
     plans = [nwb.Plan(A, B, nwb.QUEUE) for _ in range(NQ)]
     streams = [torch.cuda.Stream() for _ in range(NQ)]
