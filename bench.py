@@ -54,6 +54,16 @@ CPU_SAMPLE_N = 8000        # the reference arm and cpu_baseline time the same 80
 M64 = (1 << 64) - 1
 
 
+def queue_depth(top_len: int, world: int, sms: int) -> int:
+    """Plans (fills in flight) per GPU for the queue of fills: as many fills as fit on the SMs at once -- a fill's share of a
+    rank is ceil(strips of the rank / 3) blocks of nwb_fill_hx_kernel, one block per SM -- plus one whose blocks move in as
+    others leave (tools/sweep_queue.sh, profiles/r02_queue_sweep.txt: more plans change nothing)."""
+    n_strips = (top_len + 255) // 256
+    nloc = -(-n_strips // world)
+    blocks = max(1, -(-nloc // 3))
+    return min(12, max(3, sms // blocks + 1))
+
+
 def workload_config(n_gpus: int) -> dict:
     return {"workload": "config3: single pair 100000x100000 synthetic DNA (seeds 0x5EED0030/31), m=1 k=1 d=1, "
                         "fill + 4-bit arrow table, no count",
@@ -408,12 +418,8 @@ def run_ours(args) -> None:
     # while the ranks to its right are still on fill e (nwb_plan_run_pipelined: double-buffered inboxes, no barrier or
     # inbox reset between steps).  The timed region is bracketed by barriers as the contract says; the time ONE fill takes
     # from launch to completion is measured separately (`latency`).
-    n_strips = (A + 255) // 256
-    nloc = -(-n_strips // world)
-    # plans per GPU: as many fills as fit on the SMs at once (a fill's share is ceil(nloc / 3) blocks, one block per SM) plus
-    # one whose blocks move in as others leave (tools/sweep_queue.sh, profiles/r02_queue_sweep.txt: more plans change nothing)
     sms = torch.cuda.get_device_properties(local).multi_processor_count
-    NQ = args.queue if args.queue > 0 else min(12, max(3, sms // -(-nloc // 3) + 1))
+    NQ = args.queue if args.queue > 0 else queue_depth(A, world, sms)
     flags = nwb.QUEUE
     plans = [nwb.Plan(A, B, flags, device=local, strip_rank=rank, strip_world=world) for _ in range(NQ)]
     if world > 1:
